@@ -1,0 +1,122 @@
+/* kvmatch_gpu.h — C ABI of libkvmatch_gpu.so: KV-match phase-2 candidate verification and
+ * IndexBuilder's sliding-window mean pass on one NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE hot path of DSM-fudan/KV-match.  The reference has no
+ * native interface (phase 2 is inline Java), so each entry point below states the reference
+ * loop it replaces.  K/ = src/main/java/cn/edu/fudan/dsm/kvmatch/ in the reference tree.
+ *
+ * Conventions
+ *   - plain C, no C++ types, no exceptions; every call returns KVM_OK (0) or a negative code and
+ *     records a message retrievable with kvm_last_error().
+ *   - offsets are the reference's: 1-based int32 positions in the whole series of length n.
+ *   - arithmetic is IEEE binary64 without FMA contraction wherever a value is reported or decides
+ *     an answer, so results equal the reference's Java loops (see DESIGN.md "Parity").
+ *   - inputs are caller-owned and only read during the call.  Result buffers are library-owned
+ *     pinned host memory, valid until the next call on the same ctx or kvm_result_free().
+ *   - one kvm_ctx = one GPU = one engine instance; a ctx is not re-entrant; distinct ctxs are
+ *     independent.  Multi-GPU: one process (or ctx) per GPU, each holding an offset range of the
+ *     series plus a halo (kvm_load_series_host's `first`), answers merged by the host.
+ *   - NO CPU FALLBACK: without a usable sm_100 device kvm_create fails with KVM_E_NODEVICE.
+ */
+#ifndef KVMATCH_GPU_H_
+#define KVMATCH_GPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KVM_ABI_VERSION 1
+
+enum {
+  KVM_OK = 0,
+  KVM_E_NODEVICE = -1, /* no CUDA device / not compute capability 10.x */
+  KVM_E_ARG = -2,      /* invalid argument */
+  KVM_E_OOM = -3,      /* device or pinned-host allocation failed */
+  KVM_E_CUDA = -4,     /* CUDA runtime error (message has the detail) */
+  KVM_E_IO = -5,       /* series file could not be read */
+  KVM_E_STATE = -6,    /* no series loaded */
+  KVM_E_RANGE = -7     /* an interval needs samples outside [1,n] or outside this ctx's shard; the
+                          reference throws IllegalArgumentException for the former
+                          (K/operator/file/TimeSeriesFileOperator.java:55-57) */
+};
+
+typedef struct kvm_ctx kvm_ctx;
+
+/* Answers of one verification call, in ascending offset order (= the reference's scan order; the
+ * Java caller then stable-sorts by distance, K/QueryEngine.java:373). */
+typedef struct kvm_result {
+  int64_t count;           /* #answers */
+  const int32_t* offsets;  /* 1-based window starts */
+  const double* distances; /* sqrt(dist^2), K/QueryEngine.java:359 */
+  int64_t cnt_candidate;   /* sum(right-left+1) over the intervals, unclamped: the reference's #candidates */
+  int64_t n_verified;      /* window starts examined (after clamping to [1,n]) */
+  int64_t s_total;         /* series samples those windows cover, each counted once per interval */
+  int64_t n_gate_pass;     /* cNSM: windows passing the exact alpha/beta gate */
+  int64_t n_lb_pass;       /* DTW: windows surviving the GPU lower bounds, i.e. full DTWs computed */
+  int64_t n_exact;         /* ED: windows re-evaluated by the sequential reference-order path */
+  double kernel_ms;        /* device time of this call's kernels (CUDA events on the ctx stream) */
+  int32_t n_launches;      /* kernels launched by this call */
+  int32_t reserved;
+} kvm_result;
+
+/* IndexBuilder step-1 output for one window width w: the (key, first, last) intervals in the order
+ * K/IndexBuilder.java:268-286 appends them; last-first <= 254. */
+typedef struct kvm_runs {
+  int64_t count;
+  const double* keys;   /* MeanIntervalUtils.toRound(mean), K/utils/MeanIntervalUtils.java:51-61 */
+  const int32_t* first; /* 1-based */
+  const int32_t* last;
+  double kernel_ms;
+  int32_t n_launches;
+  int32_t reserved;
+} kvm_runs;
+
+int kvm_abi_version(void);
+
+/* Create a context on CUDA device `device_id`.  Replaces the engines' constructor choice of a
+ * TimeSeriesOperator (K/QueryEngine.java:70-96): the series lives in HBM for the ctx lifetime. */
+int kvm_create(kvm_ctx** out, int device_id);
+void kvm_destroy(kvm_ctx* ctx);
+const char* kvm_last_error(const kvm_ctx* ctx); /* ctx may be NULL: last kvm_create error */
+
+/* Load samples [first, first+count-1] (1-based) of a series whose total length is n.
+ * first=1,count=n loads everything (single GPU).  Replaces TimeSeriesOperator.readTimeSeries
+ * (K/operator/TimeSeriesOperator.java:38) as the data feed of phase 2. */
+int kvm_load_series_host(kvm_ctx* ctx, const double* samples, int64_t n, int64_t first, int64_t count);
+/* Same, from a reference data file files/data-N: N big-endian IEEE-754 doubles, no header
+ * (K/DataGenerator.java:102-113); the byte swap runs on the device. */
+int kvm_load_series_file(kvm_ctx* ctx, const char* path, int64_t n, int64_t first, int64_t count);
+
+/* Phase-2 verification.  q: raw query (length m); lr: K merged intervals (left,right) as produced
+ * by sortAndMergeIntervals (K/QueryEngine.java:664-693), sorted by left; shift =
+ * (lastSegment-1)*25.  Each interval p is scanned over samples
+ * [max(left-shift,1), min(right-shift+m-1, n)]; running statistics restart per interval.
+ *
+ * kvm_verify_ed       replaces K/QueryEngine.java:341-363        (RSM-ED)
+ * kvm_verify_cnsm_ed  replaces K/NormQueryEngine.java:432-528    (cNSM-ED)
+ * kvm_verify_dtw      replaces K/QueryEngineDtw.java:349-452     (RSM-DTW, rho = Sakoe-Chiba radius)
+ * kvm_verify_cnsm_dtw replaces K/NormQueryEngineDtw.java:457-603 (cNSM-DTW)
+ */
+int kvm_verify_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, const int32_t* lr, int32_t K,
+                  int32_t shift, kvm_result* out);
+int kvm_verify_cnsm_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, double alpha, double beta,
+                       const int32_t* lr, int32_t K, int32_t shift, kvm_result* out);
+int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int32_t rho, const int32_t* lr,
+                   int32_t K, int32_t shift, kvm_result* out);
+int kvm_verify_cnsm_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int32_t rho, double alpha,
+                        double beta, const int32_t* lr, int32_t K, int32_t shift, kvm_result* out);
+
+/* IndexBuilder step 1 for window width w (K/IndexBuilder.java:194-301): sliding mean with the
+ * reference's EPOCH=100000 restart structure, toRound key, run-length intervals split at 255.
+ * Needs the whole series on this ctx (first == 1, count == n). */
+int kvm_window_mean_runs(kvm_ctx* ctx, int32_t w, kvm_runs* out);
+
+void kvm_result_free(kvm_ctx* ctx, kvm_result* r);
+void kvm_runs_free(kvm_ctx* ctx, kvm_runs* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVMATCH_GPU_H_ */

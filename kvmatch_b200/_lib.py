@@ -1,0 +1,122 @@
+"""ctypes binding of libkvmatch_gpu.so (include/kvmatch_gpu.h).
+
+This is the same C ABI a JNI / Panama shim binds from the reference's Java classes.
+There is no CPU fallback: a missing library or a missing B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkvmatch_gpu.so")
+
+KVM_OK = 0
+KVM_E_NODEVICE = -1
+KVM_E_ARG = -2
+KVM_E_OOM = -3
+KVM_E_CUDA = -4
+KVM_E_IO = -5
+KVM_E_STATE = -6
+KVM_E_RANGE = -7
+
+ERROR_NAMES = {
+    KVM_E_NODEVICE: "KVM_E_NODEVICE", KVM_E_ARG: "KVM_E_ARG", KVM_E_OOM: "KVM_E_OOM", KVM_E_CUDA: "KVM_E_CUDA",
+    KVM_E_IO: "KVM_E_IO", KVM_E_STATE: "KVM_E_STATE", KVM_E_RANGE: "KVM_E_RANGE",
+}
+
+# every symbol include/kvmatch_gpu.h declares
+EXPORTS = [
+    "kvm_abi_version", "kvm_create", "kvm_destroy", "kvm_last_error", "kvm_load_series_host", "kvm_load_series_file",
+    "kvm_verify_ed", "kvm_verify_cnsm_ed", "kvm_verify_dtw", "kvm_verify_cnsm_dtw", "kvm_window_mean_runs",
+    "kvm_result_free", "kvm_runs_free",
+]
+
+
+class KvmError(RuntimeError):
+    """Non-zero return code of the C ABI.  The Java shim maps this to IOException (engines' query() throws it)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+class KvmResult(C.Structure):
+    _fields_ = [
+        ("count", C.c_int64),
+        ("offsets", C.POINTER(C.c_int32)),
+        ("distances", C.POINTER(C.c_double)),
+        ("cnt_candidate", C.c_int64),
+        ("n_verified", C.c_int64),
+        ("s_total", C.c_int64),
+        ("n_gate_pass", C.c_int64),
+        ("n_lb_pass", C.c_int64),
+        ("n_exact", C.c_int64),
+        ("kernel_ms", C.c_double),
+        ("n_launches", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class KvmRuns(C.Structure):
+    _fields_ = [
+        ("count", C.c_int64),
+        ("keys", C.POINTER(C.c_double)),
+        ("first", C.POINTER(C.c_int32)),
+        ("last", C.POINTER(C.c_int32)),
+        ("kernel_ms", C.c_double),
+        ("n_launches", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+def load():
+    """dlopen the library and declare the prototypes.  Does not touch the GPU."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: build it with `make -C kvmatch_b200/csrc` (or __graft_entry__.build()). "
+            "kvmatch_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    R = C.POINTER(KvmResult)
+    L.kvm_abi_version.restype = C.c_int
+    L.kvm_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.kvm_destroy.argtypes = [vp]
+    L.kvm_destroy.restype = None
+    L.kvm_last_error.argtypes = [vp]
+    L.kvm_last_error.restype = C.c_char_p
+    L.kvm_load_series_host.argtypes = [vp, _dp, C.c_int64, C.c_int64, C.c_int64]
+    L.kvm_load_series_file.argtypes = [vp, C.c_char_p, C.c_int64, C.c_int64, C.c_int64]
+    L.kvm_verify_ed.argtypes = [vp, _dp, C.c_int32, C.c_double, _ip, C.c_int32, C.c_int32, R]
+    L.kvm_verify_cnsm_ed.argtypes = [vp, _dp, C.c_int32, C.c_double, C.c_double, C.c_double, _ip, C.c_int32, C.c_int32,
+                                     R]
+    L.kvm_verify_dtw.argtypes = [vp, _dp, C.c_int32, C.c_double, C.c_int32, _ip, C.c_int32, C.c_int32, R]
+    L.kvm_verify_cnsm_dtw.argtypes = [vp, _dp, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_double, _ip,
+                                      C.c_int32, C.c_int32, R]
+    L.kvm_window_mean_runs.argtypes = [vp, C.c_int32, C.POINTER(KvmRuns)]
+    L.kvm_result_free.argtypes = [vp, R]
+    L.kvm_result_free.restype = None
+    L.kvm_runs_free.argtypes = [vp, C.POINTER(KvmRuns)]
+    L.kvm_runs_free.restype = None
+    _lib = L
+    return L
+
+
+def as_f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+def as_intervals(intervals):
+    lr = np.ascontiguousarray(np.asarray(intervals, dtype=np.int32).reshape(-1, 2))
+    return lr, lr.ctypes.data_as(_ip), int(lr.shape[0])

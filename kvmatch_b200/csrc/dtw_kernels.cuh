@@ -1,0 +1,241 @@
+// dtw_kernels.cuh — Sakoe-Chiba banded DTW verification with the LB_Kim / LB_Keogh cascade.
+// Replaces K/QueryEngineDtw.java:349-452, K/NormQueryEngineDtw.java:457-603 and
+// K/utils/DtwUtils.java:149-337.
+//
+// Stage 1 (one thread per candidate, lanes = consecutive window starts -> coalesced):
+//   LB_KimFL (3 points at each end) and LB_Keogh against the query envelope, in fast FMA arithmetic,
+//   pruning only when the bound exceeds eps^2*(1+1e-9).  Both are valid lower bounds of the band DTW
+//   (m >= 6), so pruning never changes the answer set; survivors are appended to a candidate list.
+// Stage 2 (one warp per survivor): the DTW matrix is swept along anti-diagonals.  Cell (i,j) lives on
+//   diagonal d = i+j at band coordinate u = i-j+rho in [0, 2 rho]; on one diagonal only every second u
+//   is populated, so a lane owns R consecutive (even,odd) u-pairs in registers and needs one 64-bit
+//   shuffle per step for the pair that straddles its neighbour.  Every cell is
+//   min(min(x,y),z) + (a-b)^2 with unfused binary64 ops on the same operands as the reference's
+//   row sweep, so the result is bit-identical to DtwUtils.dtw() whenever that does not abandon
+//   (out-of-band / out-of-matrix neighbours are the reference's INF = 1e20).
+#pragma once
+#include "cnsm_kernels.cuh"
+#include "ed_kernels.cuh"
+
+namespace kvm {
+
+struct LbQuery {
+  const double* __restrict__ q;   // query in natural order (raw for RSM, z-normalised for cNSM)
+  const double* __restrict__ uq;  // upper envelope of q, radius rho
+  const double* __restrict__ lq;  // lower envelope
+  int m;
+  double eps2_hi;
+};
+
+__device__ __forceinline__ double fsq(double a, double b) {
+  const double d = a - b;
+  return d * d;
+}
+
+// true = the candidate may still be an answer
+__device__ __forceinline__ bool lb_cascade(const double* __restrict__ w, const LbQuery& Q, double rstd, double nmr) {
+  const int m = Q.m;
+  const double* __restrict__ q = Q.q;
+  double lb = 0.0;
+  if (m >= 6) {  // LB_KimFL, K/utils/DtwUtils.java:149-189 (all five stages, no early return)
+    const double x0 = __fma_rn(w[0], rstd, nmr), x1 = __fma_rn(w[1], rstd, nmr), x2 = __fma_rn(w[2], rstd, nmr);
+    const double y0 = __fma_rn(w[m - 1], rstd, nmr), y1 = __fma_rn(w[m - 2], rstd, nmr),
+                 y2 = __fma_rn(w[m - 3], rstd, nmr);
+    const double q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+    const double p0 = __ldg(q + m - 1), p1 = __ldg(q + m - 2), p2 = __ldg(q + m - 3);
+    lb = fsq(x0, q0) + fsq(y0, p0);
+    lb += fmin(fmin(fsq(x1, q0), fsq(x0, q1)), fsq(x1, q1));
+    lb += fmin(fmin(fsq(y1, p0), fsq(y0, p1)), fsq(y1, p1));
+    lb += fmin(fmin(fmin(fsq(x0, q2), fsq(x1, q2)), fsq(x2, q2)), fmin(fsq(x2, q1), fsq(x2, q0)));
+    lb += fmin(fmin(fmin(fsq(y0, p2), fsq(y1, p2)), fsq(y2, p2)), fmin(fsq(y2, p1), fsq(y2, p0)));
+    if (!(lb <= Q.eps2_hi)) return false;
+  }
+  // LB_Keogh on the query envelope, K/utils/DtwUtils.java:206-222
+  lb = 0.0;
+  bool alive = true;
+  int k = 0;
+  for (; k + 4 <= m && alive; k += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const double x = __fma_rn(w[k + u], rstd, nmr);
+      const double up = __ldg(Q.uq + k + u), lo = __ldg(Q.lq + k + u);
+      const double d = (x > up) ? (x - up) : ((x < lo) ? (x - lo) : 0.0);
+      lb = __fma_rn(d, d, lb);
+    }
+    alive = lb <= Q.eps2_hi;
+  }
+  if (alive) {
+    for (; k < m; k++) {
+      const double x = __fma_rn(w[k], rstd, nmr);
+      const double up = __ldg(Q.uq + k), lo = __ldg(Q.lq + k);
+      const double d = (x > up) ? (x - up) : ((x < lo) ? (x - lo) : 0.0);
+      lb = __fma_rn(d, d, lb);
+    }
+  }
+  return lb <= Q.eps2_hi;
+}
+
+__device__ __forceinline__ void cand_append(const CandList& L, int32_t off, double mean, double stdv) {
+  const unsigned long long slot = atomicAdd(L.count, 1ULL);
+  if ((long long)slot < L.cap) {
+    L.off[slot] = off;
+    L.mean[slot] = mean;
+    L.stdv[slot] = stdv;
+  }
+}
+
+// RSM-DTW stage 1: candidates enumerated from the interval tiles (same tiling as ed_verify_kernel).
+struct LbRawParams {
+  const double* __restrict__ T;
+  const int32_t* __restrict__ cbegin;
+  const int32_t* __restrict__ ncand;
+  const int32_t* __restrict__ tile_prefix;
+  int K;
+  int32_t first_global;
+  LbQuery Q;
+  CandList out;
+};
+
+__global__ void __launch_bounds__(kEdTile) dtw_lb_raw_kernel(LbRawParams P) {
+  __shared__ int s_p;
+  if (threadIdx.x == 0) s_p = find_segment<int32_t>(P.tile_prefix, P.K + 1, (int32_t)blockIdx.x);
+  __syncthreads();
+  const int p = s_p;
+  const int c = ((int)blockIdx.x - P.tile_prefix[p]) * kEdTile + (int)threadIdx.x;
+  if (c >= P.ncand[p]) return;
+  const int start = P.cbegin[p] + c;
+  if (lb_cascade(P.T + start, P.Q, 1.0, 0.0)) cand_append(P.out, P.first_global + start, 0.0, 1.0);
+}
+
+// cNSM-DTW stage 1: work-list entries from cnsm_walk_kernel -> exact gate -> lower bounds.
+struct LbNormParams {
+  EvalParams E;  // work list + exact gate parameters (zq/order/eps fields unused)
+  LbQuery Q;
+};
+
+__global__ void __launch_bounds__(kEvalTile) cnsm_dtw_lb_kernel(LbNormParams P) {
+  __shared__ int s_r;
+  __shared__ unsigned int s_gate;
+  if (threadIdx.x == 0) s_gate = 0;
+  const EvalParams& E = P.E;
+  const int n_tiles = (int)E.totals[0];
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_r = find_segment<int32_t>(E.tile_prefix, E.n_regions + 1, t);
+    __syncthreads();
+    const int r = s_r;
+    const int i = (t - E.tile_prefix[r]) * kEvalTile + (int)threadIdx.x;
+    bool live = i < E.region_count[r];
+    double mean = 0.0, stdv = 1.0;
+    int32_t off = 0;
+    if (live) {
+      const long long e = E.region_base[r] + i;
+      off = E.e_off[e];
+      live = cnsm_exact_gate(E.e_ex[e], E.e_ex2[e], E.m, E.meanQ, E.stdQ, E.alpha, E.inv_alpha, E.beta, mean, stdv);
+    }
+    const unsigned gmask = __ballot_sync(kFullMask, live);
+    if ((threadIdx.x & 31) == 0 && gmask) atomicAdd(&s_gate, (unsigned)__popc(gmask));
+    if (!live) continue;
+    const double rstd = 1.0 / stdv;
+    if (lb_cascade(E.T + (off - E.first_global), P.Q, rstd, -mean * rstd)) cand_append(E.out, off, mean, stdv);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_gate) atomicAdd(E.gate_pass, (unsigned long long)s_gate);
+}
+
+struct DtwParams {
+  const double* __restrict__ T;
+  int32_t first_global;
+  int m;
+  int rho;
+  const double* __restrict__ q;  // natural order
+  double eps2;
+  CandList in;
+  AnswerSink sink;
+};
+
+template <int R>
+__global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
+  extern __shared__ double dtw_smem[];
+  const int m = P.m, rho = P.rho;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  double* B = dtw_smem;                          // query
+  double* A = dtw_smem + (size_t)(warp + 1) * m; // this warp's (normalised) window
+  for (int k = threadIdx.x; k < m; k += blockDim.x) B[k] = P.q[k];
+  __syncthreads();
+
+  unsigned long long n = *P.in.count;
+  if ((long long)n > P.in.cap) n = (unsigned long long)P.in.cap;
+  const int tgt_u = rho;  // final cell (m-1, m-1): i-j = 0
+  const int tgt_pair = tgt_u >> 1;
+
+  for (unsigned long long e = (unsigned long long)blockIdx.x * n_warps + warp; e < n;
+       e += (unsigned long long)gridDim.x * n_warps) {
+    const int32_t off = P.in.off[e];
+    const double mean = P.in.mean[e], stdv = P.in.stdv[e];
+    const double* __restrict__ w = P.T + (off - P.first_global);
+    __syncwarp();
+    for (int k = lane; k < m; k += 32) A[k] = xdiv(xsub(w[k], mean), stdv);  // NormQueryEngineDtw.java:564-567
+    __syncwarp();
+
+    double Ev[R], Od[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      Ev[r] = kDtwInf;
+      Od[r] = kDtwInf;
+    }
+    const int u0 = 2 * lane * R;  // band coordinate of this lane's first even cell
+    const int last = 2 * m - 2;
+    for (int d = 0; d <= last; d++) {
+      if (((d + rho) & 1) == 0) {
+        double left = __shfl_up_sync(kFullMask, Od[R - 1], 1);
+        if (lane == 0) left = kDtwInf;
+        // i = (d + u - rho)/2, j = d - i ; consecutive pairs: i+1, j-1
+        const int s = d + u0 - rho;
+        const int i0 = s >> 1;  // s is even here
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const int i = i0 + r, j = d - i;
+          const bool valid = (u0 + 2 * r <= 2 * rho) && i >= 0 && j >= 0 && i < m && j < m && s + 2 * r >= 0;
+          double v = kDtwInf;
+          if (valid) {
+            const double c = xsqdist(A[i], B[j]);
+            const double x = (r == 0) ? left : Od[r - 1];
+            const double y = Od[r];
+            const double z = Ev[r];
+            v = (d == 0) ? c : xadd(xmin(xmin(x, y), z), c);
+          }
+          Ev[r] = v;
+        }
+      } else {
+        double right = __shfl_down_sync(kFullMask, Ev[0], 1);
+        if (lane == 31) right = kDtwInf;
+        const int s = d + u0 + 1 - rho;
+        const int i0 = s >> 1;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const int i = i0 + r, j = d - i;
+          const bool valid = (u0 + 2 * r + 1 <= 2 * rho) && i >= 0 && j >= 0 && i < m && j < m && s + 2 * r >= 0;
+          double v = kDtwInf;
+          if (valid) {
+            const double c = xsqdist(A[i], B[j]);
+            const double x = Ev[r];
+            const double y = (r == R - 1) ? right : Ev[r + 1];
+            const double z = Od[r];
+            v = (d == 0) ? c : xadd(xmin(xmin(x, y), z), c);
+          }
+          Od[r] = v;
+        }
+      }
+    }
+    double res = kDtwInf;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      if (lane * R + r == tgt_pair) res = (tgt_u & 1) ? Od[r] : Ev[r];
+    }
+    res = __shfl_sync(kFullMask, res, tgt_pair / R);
+    if (lane == 0 && res <= P.eps2) P.sink.emit(off, xsqrt(res));
+  }
+}
+
+}  // namespace kvm

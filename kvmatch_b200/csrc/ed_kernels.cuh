@@ -1,0 +1,62 @@
+// ed_kernels.cuh — RSM-ED phase-2 verification (replaces K/QueryEngine.java:341-363).
+//
+// One thread per candidate window start; the lanes of a warp hold 32 consecutive starts, so every
+// load T[start + j] is a coalesced 256-byte row and the query value q[j] is a warp-uniform
+// broadcast.  Each thread accumulates sum (d-q)^2 in the reference's natural order with unfused
+// binary64 ops, so an accepted distance is bit-identical to the Java loop's.  The early-abandon test
+// `dist <= eps^2` is evaluated once per 8 terms instead of per term: partial sums are monotone
+// non-decreasing, so this changes neither the accept decision nor any accepted value.
+//
+// HBM traffic: the series is streamed once (8 B per verified subsequence on a full scan); the
+// re-reads by neighbouring lanes hit L1.
+#pragma once
+#include "common.cuh"
+
+namespace kvm {
+
+constexpr int kEdTile = 256;  // candidates per CTA
+
+struct EdParams {
+  const double* __restrict__ T;          // local shard, element 0 = global sample `first_global`
+  const double* __restrict__ q;          // raw query, length m
+  const int32_t* __restrict__ cbegin;    // per interval: local 0-based index of its first sample
+  const int32_t* __restrict__ ncand;     // per interval: number of window starts
+  const int32_t* __restrict__ tile_prefix;  // K+1 exclusive prefix of ceil(ncand/kEdTile)
+  int K;
+  int m;
+  double eps2;
+  int32_t first_global;  // 1-based global offset of T[0]
+  AnswerSink sink;
+};
+
+__global__ void __launch_bounds__(kEdTile) ed_verify_kernel(EdParams P) {
+  __shared__ int s_p;
+  if (threadIdx.x == 0) s_p = find_segment<int32_t>(P.tile_prefix, P.K + 1, (int32_t)blockIdx.x);
+  __syncthreads();
+  const int p = s_p;
+  const int c = ((int)blockIdx.x - P.tile_prefix[p]) * kEdTile + (int)threadIdx.x;
+  if (c >= P.ncand[p]) return;
+  const int start = P.cbegin[p] + c;
+  const double* __restrict__ w = P.T + start;
+  const double* __restrict__ q = P.q;
+  const int m = P.m;
+  const double eps2 = P.eps2;
+
+  double dist = 0.0;
+  bool alive = true;
+  int j = 0;
+  for (; j + 8 <= m && alive; j += 8) {
+    double t[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) t[u] = xsqdist(w[j + u], __ldg(q + j + u));
+#pragma unroll
+    for (int u = 0; u < 8; u++) dist = xadd(dist, t[u]);
+    alive = dist <= eps2;
+  }
+  if (alive) {
+    for (; j < m; j++) dist = xadd(dist, xsqdist(w[j], __ldg(q + j)));
+  }
+  if (dist <= eps2) P.sink.emit(P.first_global + start, xsqrt(dist));
+}
+
+}  // namespace kvm

@@ -1,0 +1,949 @@
+// kvmatch_gpu.cu — C ABI (include/kvmatch_gpu.h) and host orchestration of libkvmatch_gpu.so.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared ...
+// (see Makefile).  -fmad=false plus the __d*_rn intrinsics in the exact paths keep every reported
+// value free of FMA contraction; the fast paths request FMA explicitly with __fma_rn.
+//
+// There is NO CPU fallback in this file: every verification result is produced by the kernels in
+// ed_kernels.cuh / cnsm_kernels.cuh / dtw_kernels.cuh / index_kernels.cuh.  The host side only
+// clamps intervals, prepares the query (statistics, z-normalisation, |z| ordering, envelope — all
+// O(m), as the reference does before its phase-2 loop), and sorts the sparse answers by offset.
+#include "../../include/kvmatch_gpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dtw_kernels.cuh"
+#include "index_kernels.cuh"
+
+using namespace kvm;
+
+struct kvm_ctx;
+int launch_dtw(kvm_ctx* ctx, const DtwParams& D);
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Packs small host arrays into one pinned staging block that is uploaded with a single H2D copy.
+struct Arena {
+  std::vector<unsigned char> host;
+  size_t add(const void* src, size_t bytes) {
+    size_t off = (host.size() + 255) & ~size_t(255);
+    host.resize(off + bytes);
+    if (bytes) std::memcpy(host.data() + off, src, bytes);
+    return off;
+  }
+};
+
+enum Counter { kCntAnswers = 0, kCntCand = 1, kCntGate = 2, kCntTiles = 3, kCntEntries = 4, kCntFlag = 5, kNumCounters = 8 };
+
+}  // namespace
+
+struct kvm_ctx {
+  int device = 0;
+  int n_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+
+  DevBuf series;
+  int64_t n = 0, first = 0, count = 0;  // global length; 1-based offset of series[0]; samples held
+
+  DevBuf arena, counters, wl_off, wl_ex, wl_ex2, region_count, tile_prefix;
+  DevBuf cand_off, cand_mean, cand_std, ans_off, ans_dist;
+  DevBuf seg_b, seg_first, seg_last, chain_count, chain_prefix, run_key, run_b, run_first, run_last;
+  long long cand_cap = 0, ans_cap = 0;
+  PinBuf stage, h_counters, h_off, h_dist, h_key, h_first, h_last, h_b;
+  std::vector<int32_t> res_off, run_first_v, run_last_v;
+  std::vector<double> res_dist, run_key_v;
+};
+
+namespace {
+
+int fail(kvm_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define KVM_CUDA(ctx, expr)                                                                         \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      cudaGetLastError();                                                                           \
+      return fail(ctx, _e == cudaErrorMemoryAllocation ? KVM_E_OOM : KVM_E_CUDA, "%s: %s", #expr,   \
+                  cudaGetErrorString(_e));                                                          \
+    }                                                                                               \
+  } while (0)
+
+// ---- Java-compatible helpers used for the O(m) query preparation --------------------------------
+inline uint64_t java_bits(double v) {
+  if (v != v) return 0x7ff8000000000000ULL;
+  uint64_t b;
+  std::memcpy(&b, &v, 8);
+  return b;
+}
+inline int java_double_compare(double a, double b) {
+  if (a < b) return -1;
+  if (a > b) return 1;
+  const int64_t x = (int64_t)java_bits(a), y = (int64_t)java_bits(b);
+  return x == y ? 0 : (x < y ? -1 : 1);
+}
+
+// K/NormQueryEngine.java:192-198
+void query_stats(const double* q, int m, double* meanQ, double* stdQ) {
+  double ex = 0, ex2 = 0;
+  for (int i = 0; i < m; i++) {
+    ex += q[i];
+    ex2 += q[i] * q[i];
+  }
+  *meanQ = ex / m;
+  *stdQ = std::sqrt(ex2 / m - *meanQ * *meanQ);
+}
+
+// Clamped sliding min/max of radius r — what DtwUtils.lowerUpperLemire computes (K/utils/DtwUtils.java:50-91).
+void envelope(const std::vector<double>& t, int r, std::vector<double>& lo, std::vector<double>& up) {
+  const int n = (int)t.size();
+  lo.resize(n);
+  up.resize(n);
+  std::vector<int> dq_max(n), dq_min(n);
+  int hmax = 0, tmax = 0, hmin = 0, tmin = 0;
+  int next = 0;
+  for (int i = 0; i < n; i++) {
+    const int hi = std::min(n - 1, i + r);
+    for (; next <= hi; next++) {
+      while (tmax > hmax && t[dq_max[tmax - 1]] <= t[next]) tmax--;
+      dq_max[tmax++] = next;
+      while (tmin > hmin && t[dq_min[tmin - 1]] >= t[next]) tmin--;
+      dq_min[tmin++] = next;
+    }
+    const int lo_i = std::max(0, i - r);
+    while (dq_max[hmax] < lo_i) hmax++;
+    while (dq_min[hmin] < lo_i) hmin++;
+    up[i] = t[dq_max[hmax]];
+    lo[i] = t[dq_min[hmin]];
+  }
+}
+
+// One interval after the reference's shift / clamp (K/QueryEngine.java:345-349).
+struct Plan {
+  std::vector<int32_t> cbegin, nsamp, ncand;
+  int64_t cnt_candidate = 0, V = 0, S = 0;
+};
+
+int make_plan(kvm_ctx* ctx, const int32_t* lr, int K, int shift, int m, Plan* P) {
+  P->cbegin.resize(K);
+  P->nsamp.resize(K);
+  P->ncand.resize(K);
+  const int64_t lo = ctx->first, hi = ctx->first + ctx->count - 1;
+  for (int p = 0; p < K; p++) {
+    const int64_t left = lr[2 * p], right = lr[2 * p + 1];
+    P->cnt_candidate += right - left + 1;
+    int64_t begin = left - shift, end = right - shift + (int64_t)m - 1;
+    if (begin < 1) begin = 1;
+    if (end > ctx->n) end = ctx->n;
+    if (end < begin)
+      return fail(ctx, KVM_E_RANGE, "interval %d [%lld,%lld] shift %d lies outside [1,%lld] (the reference throws)", p,
+                  (long long)left, (long long)right, shift, (long long)ctx->n);
+    if (begin < lo || end > hi)
+      return fail(ctx, KVM_E_RANGE, "interval %d needs samples [%lld,%lld]; this ctx holds [%lld,%lld]", p,
+                  (long long)begin, (long long)end, (long long)lo, (long long)hi);
+    const int64_t ns = end - begin + 1;
+    const int64_t nc = ns >= m ? ns - m + 1 : 0;
+    P->cbegin[p] = (int32_t)(begin - lo);
+    P->nsamp[p] = (int32_t)ns;
+    P->ncand[p] = (int32_t)nc;
+    P->S += ns;
+    P->V += nc;
+  }
+  return KVM_OK;
+}
+
+int check_common(kvm_ctx* ctx, const double* q, int m, double epsilon, const int32_t* lr, int K, kvm_result* out) {
+  if (!ctx) return KVM_E_ARG;
+  if (!out || !q || m < 1 || K < 0 || (K > 0 && !lr)) return fail(ctx, KVM_E_ARG, "null/invalid argument");
+  if (!(epsilon == epsilon)) return fail(ctx, KVM_E_ARG, "epsilon is NaN");
+  if (!ctx->series.p) return fail(ctx, KVM_E_STATE, "no series loaded");
+  std::memset(out, 0, sizeof(*out));
+  return KVM_OK;
+}
+
+int ensure_answers(kvm_ctx* ctx, long long cap) {
+  if (cap <= ctx->ans_cap) return KVM_OK;
+  KVM_CUDA(ctx, ctx->ans_off.ensure(sizeof(int32_t) * cap));
+  KVM_CUDA(ctx, ctx->ans_dist.ensure(sizeof(double) * cap));
+  ctx->ans_cap = cap;
+  return KVM_OK;
+}
+
+int ensure_cands(kvm_ctx* ctx, long long cap) {
+  if (cap <= ctx->cand_cap) return KVM_OK;
+  KVM_CUDA(ctx, ctx->cand_off.ensure(sizeof(int32_t) * cap));
+  KVM_CUDA(ctx, ctx->cand_mean.ensure(sizeof(double) * cap));
+  KVM_CUDA(ctx, ctx->cand_std.ensure(sizeof(double) * cap));
+  ctx->cand_cap = cap;
+  return KVM_OK;
+}
+
+AnswerSink sink_of(kvm_ctx* ctx) {
+  return AnswerSink{ctx->ans_off.as<int32_t>(), ctx->ans_dist.as<double>(),
+                    ctx->counters.as<unsigned long long>() + kCntAnswers, ctx->ans_cap};
+}
+CandList cands_of(kvm_ctx* ctx) {
+  return CandList{ctx->cand_off.as<int32_t>(), ctx->cand_mean.as<double>(), ctx->cand_std.as<double>(),
+                  ctx->counters.as<unsigned long long>() + kCntCand, ctx->cand_cap};
+}
+
+int upload_arena(kvm_ctx* ctx, const Arena& A) {
+  KVM_CUDA(ctx, ctx->stage.ensure(A.host.size() + 256));
+  KVM_CUDA(ctx, ctx->arena.ensure(A.host.size() + 256));
+  std::memcpy(ctx->stage.p, A.host.data(), A.host.size());
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->arena.p, ctx->stage.p, A.host.size(), cudaMemcpyHostToDevice, ctx->stream));
+  return KVM_OK;
+}
+
+int read_counters(kvm_ctx* ctx, unsigned long long* out) {
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters.p, ctx->counters.p, sizeof(unsigned long long) * kNumCounters,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::memcpy(out, ctx->h_counters.p, sizeof(unsigned long long) * kNumCounters);
+  return KVM_OK;
+}
+
+// Copy the sparse answers back and put them in ascending offset order (the reference's scan order).
+int fetch_answers(kvm_ctx* ctx, long long count, kvm_result* out) {
+  ctx->res_off.resize((size_t)count);
+  ctx->res_dist.resize((size_t)count);
+  if (count > 0) {
+    KVM_CUDA(ctx, ctx->h_off.ensure(sizeof(int32_t) * count));
+    KVM_CUDA(ctx, ctx->h_dist.ensure(sizeof(double) * count));
+    KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_off.p, ctx->ans_off.p, sizeof(int32_t) * count, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_dist.p, ctx->ans_dist.p, sizeof(double) * count, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int32_t* ho = ctx->h_off.as<int32_t>();
+    const double* hd = ctx->h_dist.as<double>();
+    std::vector<int64_t> idx((size_t)count);
+    for (int64_t i = 0; i < count; i++) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return ho[a] < ho[b]; });
+    for (int64_t i = 0; i < count; i++) {
+      ctx->res_off[i] = ho[idx[i]];
+      ctx->res_dist[i] = hd[idx[i]];
+    }
+  }
+  out->count = count;
+  out->offsets = ctx->res_off.data();
+  out->distances = ctx->res_dist.data();
+  return KVM_OK;
+}
+
+int begin_call(kvm_ctx* ctx) {
+  KVM_CUDA(ctx, cudaSetDevice(ctx->device));
+  KVM_CUDA(ctx, ctx->counters.ensure(sizeof(unsigned long long) * kNumCounters));
+  KVM_CUDA(ctx, ctx->h_counters.ensure(sizeof(unsigned long long) * kNumCounters));
+  return KVM_OK;
+}
+
+int zero_counters(kvm_ctx* ctx) {
+  KVM_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * kNumCounters, ctx->stream));
+  return KVM_OK;
+}
+
+// Tile prefix for kernels that enumerate candidates straight from the intervals.
+std::vector<int32_t> tile_prefix_of(const Plan& P, int tile, int64_t* n_tiles) {
+  std::vector<int32_t> tp(P.ncand.size() + 1);
+  int64_t acc = 0;
+  for (size_t p = 0; p < P.ncand.size(); p++) {
+    tp[p] = (int32_t)acc;
+    acc += (P.ncand[p] + tile - 1) / tile;
+  }
+  tp[P.ncand.size()] = (int32_t)acc;
+  *n_tiles = acc;
+  return tp;
+}
+
+// Everything the cNSM engines share: query statistics, pre-gate constants, walker + planner launch.
+struct NormSetup {
+  double meanQ = 0, stdQ = 0, inv_alpha = 0;
+  int n_regions = 0;
+  bool degenerate = false;  // stdQ is 0/NaN: no window can pass the gate
+};
+
+int launch_walker(kvm_ctx* ctx, const Plan& P, int K, int m, double alpha, double beta, const NormSetup& S,
+                  size_t off_cbegin, size_t off_nsamp, size_t off_region_base, int* launches) {
+  const unsigned char* base = ctx->arena.as<unsigned char>();
+  WalkParams W;
+  W.T = ctx->series.as<double>();
+  W.cbegin = reinterpret_cast<const int32_t*>(base + off_cbegin);
+  W.cnsamp = reinterpret_cast<const int32_t*>(base + off_nsamp);
+  W.region_base = reinterpret_cast<const long long*>(base + off_region_base);
+  W.K = K;
+  W.m = m;
+  W.first_global = (int32_t)ctx->first;
+  W.inv_m = 1.0 / (double)m;
+  W.meanQ = S.meanQ;
+  // Conservative pre-gate: a superset of the exact gate (rounding of ex/m, ex2/m - mean^2 is far below
+  // these slacks); the exact gate is re-evaluated with the reference's arithmetic by the evaluators.
+  const double amq = std::fabs(S.meanQ) + std::fabs(beta);
+  const double hi2 = (alpha * S.stdQ) * (alpha * S.stdQ), lo2 = (S.stdQ * S.inv_alpha) * (S.stdQ * S.inv_alpha);
+  const double d2 = 1e-13 * (hi2 + 2.0 * amq * amq) + 1e-290;
+  W.beta_hi = beta + 1e-14 * amq + 1e-290;
+  W.var_hi = hi2 * (1.0 + 1e-12) + d2;
+  W.var_lo = lo2 * (1.0 - 1e-12) - d2;
+  W.e_off = ctx->wl_off.as<int32_t>();
+  W.e_ex = ctx->wl_ex.as<double>();
+  W.e_ex2 = ctx->wl_ex2.as<double>();
+  W.region_count = ctx->region_count.as<int32_t>();
+  const int n_blocks = (K + kWalkWarps * 32 - 1) / (kWalkWarps * 32);
+  const size_t smem = sizeof(double) * kWalkSmemDoublesPerWarp * kWalkWarps;
+  cnsm_walk_kernel<<<n_blocks, kWalkWarps * 32, smem, ctx->stream>>>(W);
+  cnsm_plan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->region_count.as<int32_t>(), S.n_regions,
+                                                ctx->tile_prefix.as<int32_t>(),
+                                                ctx->counters.as<unsigned long long>() + kCntTiles);
+  *launches += 2;
+  KVM_CUDA(ctx, cudaGetLastError());
+  return KVM_OK;
+}
+
+double elapsed_ms(kvm_ctx* ctx) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  return (double)ms;
+}
+
+enum class Mode { kEd, kDtw };
+
+// cNSM-ED and cNSM-DTW share everything up to the evaluator.
+int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon, int rho, double alpha, double beta,
+                const int32_t* lr, int K, int shift, kvm_result* out) {
+  int rc = check_common(ctx, q, m, epsilon, lr, K, out);
+  if (rc) return rc;
+  if (mode == Mode::kDtw && (rho < 0 || m < 3)) return fail(ctx, KVM_E_ARG, "DTW needs rho >= 0 and m >= 3");
+  if ((rc = begin_call(ctx))) return rc;
+  Plan P;
+  if ((rc = make_plan(ctx, lr, K, shift, m, &P))) return rc;
+  out->cnt_candidate = P.cnt_candidate;
+  out->n_verified = P.V;
+  out->s_total = P.S;
+
+  NormSetup S;
+  query_stats(q, m, &S.meanQ, &S.stdQ);
+  S.inv_alpha = 1.0 / alpha;
+  S.degenerate = !(S.stdQ > 0.0) || !(S.stdQ < INFINITY);
+  if (P.V == 0 || S.degenerate) return fetch_answers(ctx, 0, out);
+
+  // query arrays: z-normalised; ED: sorted by |z| descending (stable), DTW: natural order + envelope
+  std::vector<double> z(m), zq(m), uq, lq;
+  std::vector<int32_t> order(m);
+  for (int i = 0; i < m; i++) z[i] = (q[i] - S.meanQ) / S.stdQ;  // K/NormQueryEngine.java:438-441
+  for (int i = 0; i < m; i++) order[i] = i;
+  if (mode == Mode::kEd) {
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+      return java_double_compare(std::fabs(z[b]), std::fabs(z[a])) < 0;  // :448
+    });
+    for (int i = 0; i < m; i++) zq[i] = z[order[i]];
+  } else {
+    zq = z;
+    envelope(z, rho, lq, uq);  // K/NormQueryEngineDtw.java:469
+  }
+
+  // chains -> walker regions (one region per walker warp = 32 chains)
+  const int n_regions = (K + 31) / 32;
+  S.n_regions = n_regions;
+  std::vector<long long> region_base(n_regions + 1);
+  long long acc = 0;
+  for (int r = 0; r < n_regions; r++) {
+    region_base[r] = acc;
+    for (int c = r * 32; c < std::min(K, r * 32 + 32); c++) acc += P.ncand[c];
+  }
+  region_base[n_regions] = acc;
+  std::vector<int32_t> walk_nsamp(K);
+  for (int c = 0; c < K; c++) walk_nsamp[c] = P.ncand[c] > 0 ? P.nsamp[c] : 0;
+
+  Arena A;
+  const size_t o_zq = A.add(zq.data(), sizeof(double) * m);
+  const size_t o_order = A.add(order.data(), sizeof(int32_t) * m);
+  const size_t o_uq = A.add(uq.data(), sizeof(double) * uq.size());
+  const size_t o_lq = A.add(lq.data(), sizeof(double) * lq.size());
+  const size_t o_cbegin = A.add(P.cbegin.data(), sizeof(int32_t) * K);
+  const size_t o_nsamp = A.add(walk_nsamp.data(), sizeof(int32_t) * K);
+  const size_t o_rbase = A.add(region_base.data(), sizeof(long long) * (n_regions + 1));
+  if ((rc = upload_arena(ctx, A))) return rc;
+
+  KVM_CUDA(ctx, ctx->wl_off.ensure(sizeof(int32_t) * (size_t)P.V));
+  KVM_CUDA(ctx, ctx->wl_ex.ensure(sizeof(double) * (size_t)P.V));
+  KVM_CUDA(ctx, ctx->wl_ex2.ensure(sizeof(double) * (size_t)P.V));
+  KVM_CUDA(ctx, ctx->region_count.ensure(sizeof(int32_t) * (n_regions + 1)));
+  KVM_CUDA(ctx, ctx->tile_prefix.ensure(sizeof(int32_t) * (n_regions + 2)));
+  if ((rc = ensure_answers(ctx, std::max<long long>(ctx->ans_cap, 1 << 16)))) return rc;
+  if ((rc = ensure_cands(ctx, std::max<long long>(ctx->cand_cap, 1 << 18)))) return rc;
+
+  const unsigned char* base = ctx->arena.as<unsigned char>();
+  const double eps2 = epsilon * epsilon;
+  unsigned long long cnt[kNumCounters];
+  double total_ms = 0;
+  for (int attempt = 0; attempt < 8; attempt++) {
+    int launches = 0;
+    if ((rc = zero_counters(ctx))) return rc;
+    KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if ((rc = launch_walker(ctx, P, K, m, alpha, beta, S, o_cbegin, o_nsamp, o_rbase, &launches))) return rc;
+
+    EvalParams E;
+    E.T = ctx->series.as<double>();
+    E.first_global = (int32_t)ctx->first;
+    E.m = m;
+    E.e_off = ctx->wl_off.as<int32_t>();
+    E.e_ex = ctx->wl_ex.as<double>();
+    E.e_ex2 = ctx->wl_ex2.as<double>();
+    E.region_base = reinterpret_cast<const long long*>(base + o_rbase);
+    E.region_count = ctx->region_count.as<int32_t>();
+    E.tile_prefix = ctx->tile_prefix.as<int32_t>();
+    E.totals = ctx->counters.as<unsigned long long>() + kCntTiles;
+    E.n_regions = n_regions;
+    E.zq = reinterpret_cast<const double*>(base + o_zq);
+    E.order = reinterpret_cast<const int32_t*>(base + o_order);
+    E.meanQ = S.meanQ;
+    E.stdQ = S.stdQ;
+    E.alpha = alpha;
+    E.inv_alpha = S.inv_alpha;
+    E.beta = beta;
+    E.eps2 = eps2;
+    E.eps2_hi = eps2 * (1.0 + 1e-9) + 1e-18;
+    E.out = cands_of(ctx);
+    E.gate_pass = ctx->counters.as<unsigned long long>() + kCntGate;
+    const int eval_grid = ctx->n_sms * 16;
+    if (mode == Mode::kEd) {
+      cnsm_ed_eval_kernel<<<eval_grid, kEvalTile, 0, ctx->stream>>>(E);
+      ExactEdParams X;
+      X.T = E.T;
+      X.first_global = E.first_global;
+      X.m = m;
+      X.zq = E.zq;
+      X.order = E.order;
+      X.eps2 = eps2;
+      X.in = E.out;
+      X.sink = sink_of(ctx);
+      cnsm_ed_exact_kernel<<<ctx->n_sms * 4, 128, 0, ctx->stream>>>(X);
+      launches += 2;
+    } else {
+      LbNormParams L;
+      L.E = E;
+      L.Q = LbQuery{E.zq, reinterpret_cast<const double*>(base + o_uq), reinterpret_cast<const double*>(base + o_lq),
+                    m, E.eps2_hi};
+      cnsm_dtw_lb_kernel<<<eval_grid, kEvalTile, 0, ctx->stream>>>(L);
+      launches += 1;
+      DtwParams D;
+      D.T = E.T;
+      D.first_global = E.first_global;
+      D.m = m;
+      D.rho = rho;
+      D.q = E.zq;
+      D.eps2 = eps2;
+      D.in = E.out;
+      D.sink = sink_of(ctx);
+      if ((rc = launch_dtw(ctx, D))) return rc;
+      launches += 1;
+    }
+    KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    KVM_CUDA(ctx, cudaGetLastError());
+    if ((rc = read_counters(ctx, cnt))) return rc;
+    total_ms += elapsed_ms(ctx);
+    out->n_launches += launches;
+    const bool cand_over = (long long)cnt[kCntCand] > ctx->cand_cap, ans_over = (long long)cnt[kCntAnswers] > ctx->ans_cap;
+    if (!cand_over && !ans_over) break;
+    if (attempt == 7) return fail(ctx, KVM_E_OOM, "result buffers kept overflowing");
+    if (cand_over && (rc = ensure_cands(ctx, (long long)cnt[kCntCand] + 1024))) return rc;
+    if (ans_over && (rc = ensure_answers(ctx, (long long)cnt[kCntAnswers] + 1024))) return rc;
+  }
+  out->kernel_ms = total_ms;
+  out->n_gate_pass = (int64_t)cnt[kCntGate];
+  if (mode == Mode::kEd) out->n_exact = (int64_t)cnt[kCntCand]; else out->n_lb_pass = (int64_t)cnt[kCntCand];
+  return fetch_answers(ctx, (long long)cnt[kCntAnswers], out);
+}
+
+}  // namespace
+
+int launch_dtw(kvm_ctx* ctx, const DtwParams& D) {
+  const int need = (D.rho + 1 + 31) / 32;  // (even,odd) pairs per lane
+  const size_t bytes_per_row = sizeof(double) * (size_t)D.m;
+  const size_t smem_budget = 200 * 1024;
+  if (2 * bytes_per_row > smem_budget)
+    return fail(ctx, KVM_E_ARG, "DTW query length %d exceeds the shared-memory staging limit (%zu)", D.m,
+                smem_budget / 16);
+  int warps = (int)std::min<size_t>(8, smem_budget / bytes_per_row - 1);
+  const size_t smem = bytes_per_row * (warps + 1);
+  const int grid = ctx->n_sms * std::max(1, (int)(smem_budget / smem));
+#define KVM_DTW_CASE(R)                                                                                        \
+  if (need <= R) {                                                                                             \
+    KVM_CUDA(ctx, cudaFuncSetAttribute(dtw_band_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    dtw_band_kernel<R><<<grid, warps * 32, smem, ctx->stream>>>(D);                                            \
+    return KVM_OK;                                                                                             \
+  }
+  KVM_DTW_CASE(1)
+  KVM_DTW_CASE(2)
+  KVM_DTW_CASE(3)
+  KVM_DTW_CASE(4)
+  KVM_DTW_CASE(6)
+  KVM_DTW_CASE(8)
+  KVM_DTW_CASE(10)
+  KVM_DTW_CASE(13)
+  KVM_DTW_CASE(16)
+#undef KVM_DTW_CASE
+  return fail(ctx, KVM_E_ARG, "Sakoe-Chiba radius %d exceeds the supported maximum 511", D.rho);
+}
+
+extern "C" {
+
+int kvm_abi_version(void) { return KVM_ABI_VERSION; }
+
+const char* kvm_last_error(const kvm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int kvm_create(kvm_ctx** out, int device_id) {
+  if (!out) return fail(nullptr, KVM_E_ARG, "out is null");
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, KVM_E_NODEVICE, "no CUDA device (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device_id < 0 || device_id >= n_dev) return fail(nullptr, KVM_E_ARG, "device %d of %d", device_id, n_dev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess || prop.major != 10)
+    return fail(nullptr, KVM_E_NODEVICE, "device %d is not compute capability 10.x (B200); kernels are sm_100a only",
+                device_id);
+  kvm_ctx* ctx = new kvm_ctx();
+  ctx->device = device_id;
+  ctx->n_sms = prop.multiProcessorCount;
+  if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    const char* msg = cudaGetErrorString(cudaGetLastError());
+    delete ctx;
+    return fail(nullptr, KVM_E_CUDA, "stream/event creation failed: %s", msg);
+  }
+  const int walk_smem = (int)(sizeof(double) * kWalkSmemDoublesPerWarp * kWalkWarps);
+  const int mean_smem = (int)(sizeof(double) * kMeanSmemDoublesPerWarp * kWalkWarps);
+  if (cudaFuncSetAttribute(cnsm_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, walk_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(mean_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem) != cudaSuccess) {
+    const char* msg = cudaGetErrorString(cudaGetLastError());
+    kvm_destroy(ctx);
+    return fail(nullptr, KVM_E_CUDA, "cudaFuncSetAttribute failed: %s", msg);
+  }
+  *out = ctx;
+  return KVM_OK;
+}
+
+void kvm_destroy(kvm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  DevBuf* dev[] = {&ctx->series, &ctx->arena, &ctx->counters, &ctx->wl_off, &ctx->wl_ex, &ctx->wl_ex2,
+                   &ctx->region_count, &ctx->tile_prefix, &ctx->cand_off, &ctx->cand_mean, &ctx->cand_std,
+                   &ctx->ans_off, &ctx->ans_dist, &ctx->seg_b, &ctx->seg_first, &ctx->seg_last, &ctx->chain_count,
+                   &ctx->chain_prefix, &ctx->run_key, &ctx->run_b, &ctx->run_first, &ctx->run_last};
+  for (DevBuf* b : dev) b->release();
+  PinBuf* pin[] = {&ctx->stage, &ctx->h_counters, &ctx->h_off, &ctx->h_dist, &ctx->h_key, &ctx->h_first, &ctx->h_last,
+                   &ctx->h_b};
+  for (PinBuf* b : pin) b->release();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+static int alloc_series(kvm_ctx* ctx, int64_t n, int64_t first, int64_t count) {
+  if (n < 1 || first < 1 || count < 1 || first + count - 1 > n)
+    return fail(ctx, KVM_E_ARG, "series range first=%lld count=%lld n=%lld", (long long)first, (long long)count,
+                (long long)n);
+  if (n > 2147483647LL) return fail(ctx, KVM_E_ARG, "n exceeds the reference's int32 offsets");
+  KVM_CUDA(ctx, cudaSetDevice(ctx->device));
+  // +128 zero samples: the index-build path reproduces the reference's zero padding of the last
+  // 1000-byte block (K/operator/file/TimeSeriesNodeIterator.java:55-59).
+  KVM_CUDA(ctx, ctx->series.ensure(sizeof(double) * (size_t)(count + 128)));
+  KVM_CUDA(ctx, cudaMemsetAsync(ctx->series.as<double>() + count, 0, sizeof(double) * 128, ctx->stream));
+  ctx->n = n;
+  ctx->first = first;
+  ctx->count = count;
+  return KVM_OK;
+}
+
+int kvm_load_series_host(kvm_ctx* ctx, const double* samples, int64_t n, int64_t first, int64_t count) {
+  if (!ctx) return KVM_E_ARG;
+  if (!samples) return fail(ctx, KVM_E_ARG, "samples is null");
+  int rc = alloc_series(ctx, n, first, count);
+  if (rc) return rc;
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->series.p, samples, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice,
+                                ctx->stream));
+  KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KVM_OK;
+}
+
+int kvm_load_series_file(kvm_ctx* ctx, const char* path, int64_t n, int64_t first, int64_t count) {
+  if (!ctx) return KVM_E_ARG;
+  if (!path) return fail(ctx, KVM_E_ARG, "path is null");
+  int rc = alloc_series(ctx, n, first, count);
+  if (rc) return rc;
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return fail(ctx, KVM_E_IO, "cannot open %s", path);
+  const size_t chunk = size_t(8) << 20;  // doubles per staged block (64 MiB)
+  if (cudaSuccess != ctx->stage.ensure(sizeof(double) * std::min<size_t>(chunk, (size_t)count))) {
+    std::fclose(f);
+    return fail(ctx, KVM_E_OOM, "pinned staging allocation failed");
+  }
+  if (fseeko(f, (off_t)(8 * (first - 1)), SEEK_SET) != 0) {
+    std::fclose(f);
+    return fail(ctx, KVM_E_IO, "seek failed in %s", path);
+  }
+  int64_t done = 0;
+  while (done < count) {
+    const size_t c = (size_t)std::min<int64_t>((int64_t)chunk, count - done);
+    if (std::fread(ctx->stage.p, 8, c, f) != c) {
+      std::fclose(f);
+      return fail(ctx, KVM_E_IO, "%s is shorter than %lld doubles", path, (long long)(first - 1 + count));
+    }
+    cudaError_t e = cudaMemcpyAsync(ctx->series.as<double>() + done, ctx->stage.p, 8 * c, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      std::fclose(f);
+      return fail(ctx, KVM_E_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    }
+    done += (int64_t)c;
+  }
+  std::fclose(f);
+  bswap64_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(ctx->series.as<unsigned long long>(), (long long)count);
+  KVM_CUDA(ctx, cudaGetLastError());
+  KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KVM_OK;
+}
+
+int kvm_verify_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, const int32_t* lr, int32_t K, int32_t shift,
+                  kvm_result* out) {
+  int rc = check_common(ctx, q, m, epsilon, lr, K, out);
+  if (rc) return rc;
+  if ((rc = begin_call(ctx))) return rc;
+  Plan P;
+  if ((rc = make_plan(ctx, lr, K, shift, m, &P))) return rc;
+  out->cnt_candidate = P.cnt_candidate;
+  out->n_verified = P.V;
+  out->s_total = P.S;
+  if (P.V == 0) return fetch_answers(ctx, 0, out);
+  int64_t n_tiles = 0;
+  std::vector<int32_t> tp = tile_prefix_of(P, kEdTile, &n_tiles);
+  Arena A;
+  const size_t o_q = A.add(q, sizeof(double) * m);
+  const size_t o_cbegin = A.add(P.cbegin.data(), sizeof(int32_t) * K);
+  const size_t o_ncand = A.add(P.ncand.data(), sizeof(int32_t) * K);
+  const size_t o_tp = A.add(tp.data(), sizeof(int32_t) * (K + 1));
+  if ((rc = upload_arena(ctx, A))) return rc;
+  if ((rc = ensure_answers(ctx, std::max<long long>(ctx->ans_cap, 1 << 16)))) return rc;
+  const unsigned char* base = ctx->arena.as<unsigned char>();
+  unsigned long long cnt[kNumCounters];
+  for (int attempt = 0; attempt < 8; attempt++) {
+    if ((rc = zero_counters(ctx))) return rc;
+    EdParams E;
+    E.T = ctx->series.as<double>();
+    E.q = reinterpret_cast<const double*>(base + o_q);
+    E.cbegin = reinterpret_cast<const int32_t*>(base + o_cbegin);
+    E.ncand = reinterpret_cast<const int32_t*>(base + o_ncand);
+    E.tile_prefix = reinterpret_cast<const int32_t*>(base + o_tp);
+    E.K = K;
+    E.m = m;
+    E.eps2 = epsilon * epsilon;
+    E.first_global = (int32_t)ctx->first;
+    E.sink = sink_of(ctx);
+    KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    ed_verify_kernel<<<(unsigned)n_tiles, kEdTile, 0, ctx->stream>>>(E);
+    KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    KVM_CUDA(ctx, cudaGetLastError());
+    if ((rc = read_counters(ctx, cnt))) return rc;
+    out->kernel_ms += elapsed_ms(ctx);
+    out->n_launches += 1;
+    if ((long long)cnt[kCntAnswers] <= ctx->ans_cap) break;
+    if (attempt == 7) return fail(ctx, KVM_E_OOM, "answer buffer kept overflowing");
+    if ((rc = ensure_answers(ctx, (long long)cnt[kCntAnswers] + 1024))) return rc;
+  }
+  out->n_exact = P.V;
+  return fetch_answers(ctx, (long long)cnt[kCntAnswers], out);
+}
+
+int kvm_verify_cnsm_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, double alpha, double beta,
+                       const int32_t* lr, int32_t K, int32_t shift, kvm_result* out) {
+  return verify_norm(ctx, Mode::kEd, q, m, epsilon, 0, alpha, beta, lr, K, shift, out);
+}
+
+int kvm_verify_cnsm_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int32_t rho, double alpha, double beta,
+                        const int32_t* lr, int32_t K, int32_t shift, kvm_result* out) {
+  return verify_norm(ctx, Mode::kDtw, q, m, epsilon, rho, alpha, beta, lr, K, shift, out);
+}
+
+int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int32_t rho, const int32_t* lr, int32_t K,
+                   int32_t shift, kvm_result* out) {
+  int rc = check_common(ctx, q, m, epsilon, lr, K, out);
+  if (rc) return rc;
+  if (rho < 0 || m < 3) return fail(ctx, KVM_E_ARG, "DTW needs rho >= 0 and m >= 3");
+  if ((rc = begin_call(ctx))) return rc;
+  Plan P;
+  if ((rc = make_plan(ctx, lr, K, shift, m, &P))) return rc;
+  out->cnt_candidate = P.cnt_candidate;
+  out->n_verified = P.V;
+  out->s_total = P.S;
+  if (P.V == 0) return fetch_answers(ctx, 0, out);
+  std::vector<double> qv(q, q + m), uq, lq;
+  envelope(qv, rho, lq, uq);  // K/QueryEngineDtw.java:362
+  int64_t n_tiles = 0;
+  std::vector<int32_t> tp = tile_prefix_of(P, kEdTile, &n_tiles);
+  Arena A;
+  const size_t o_q = A.add(q, sizeof(double) * m);
+  const size_t o_uq = A.add(uq.data(), sizeof(double) * m);
+  const size_t o_lq = A.add(lq.data(), sizeof(double) * m);
+  const size_t o_cbegin = A.add(P.cbegin.data(), sizeof(int32_t) * K);
+  const size_t o_ncand = A.add(P.ncand.data(), sizeof(int32_t) * K);
+  const size_t o_tp = A.add(tp.data(), sizeof(int32_t) * (K + 1));
+  if ((rc = upload_arena(ctx, A))) return rc;
+  if ((rc = ensure_answers(ctx, std::max<long long>(ctx->ans_cap, 1 << 16)))) return rc;
+  if ((rc = ensure_cands(ctx, std::max<long long>(ctx->cand_cap, 1 << 18)))) return rc;
+  const unsigned char* base = ctx->arena.as<unsigned char>();
+  const double eps2 = epsilon * epsilon;
+  unsigned long long cnt[kNumCounters];
+  for (int attempt = 0; attempt < 8; attempt++) {
+    if ((rc = zero_counters(ctx))) return rc;
+    LbRawParams L;
+    L.T = ctx->series.as<double>();
+    L.cbegin = reinterpret_cast<const int32_t*>(base + o_cbegin);
+    L.ncand = reinterpret_cast<const int32_t*>(base + o_ncand);
+    L.tile_prefix = reinterpret_cast<const int32_t*>(base + o_tp);
+    L.K = K;
+    L.first_global = (int32_t)ctx->first;
+    L.Q = LbQuery{reinterpret_cast<const double*>(base + o_q), reinterpret_cast<const double*>(base + o_uq),
+                  reinterpret_cast<const double*>(base + o_lq), m, eps2 * (1.0 + 1e-9) + 1e-18};
+    L.out = cands_of(ctx);
+    DtwParams D;
+    D.T = L.T;
+    D.first_global = L.first_global;
+    D.m = m;
+    D.rho = rho;
+    D.q = L.Q.q;
+    D.eps2 = eps2;
+    D.in = L.out;
+    D.sink = sink_of(ctx);
+    KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    dtw_lb_raw_kernel<<<(unsigned)n_tiles, kEdTile, 0, ctx->stream>>>(L);
+    if ((rc = launch_dtw(ctx, D))) return rc;
+    KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    KVM_CUDA(ctx, cudaGetLastError());
+    if ((rc = read_counters(ctx, cnt))) return rc;
+    out->kernel_ms += elapsed_ms(ctx);
+    out->n_launches += 2;
+    const bool cand_over = (long long)cnt[kCntCand] > ctx->cand_cap, ans_over = (long long)cnt[kCntAnswers] > ctx->ans_cap;
+    if (!cand_over && !ans_over) break;
+    if (attempt == 7) return fail(ctx, KVM_E_OOM, "result buffers kept overflowing");
+    if (cand_over && (rc = ensure_cands(ctx, (long long)cnt[kCntCand] + 1024))) return rc;
+    if (ans_over && (rc = ensure_answers(ctx, (long long)cnt[kCntAnswers] + 1024))) return rc;
+  }
+  out->n_lb_pass = (int64_t)cnt[kCntCand];
+  return fetch_answers(ctx, (long long)cnt[kCntAnswers], out);
+}
+
+int kvm_window_mean_runs(kvm_ctx* ctx, int32_t w, kvm_runs* out) {
+  if (!ctx) return KVM_E_ARG;
+  if (!out) return fail(ctx, KVM_E_ARG, "out is null");
+  std::memset(out, 0, sizeof(*out));
+  constexpr int kEpoch = 100000;  // K/IndexBuilder.java:136
+  if (w < 2 || w > kEpoch) return fail(ctx, KVM_E_ARG, "window width %d", w);
+  if (!ctx->series.p) return fail(ctx, KVM_E_STATE, "no series loaded");
+  if (ctx->first != 1 || ctx->count != ctx->n)
+    return fail(ctx, KVM_E_RANGE, "index build needs the whole series on this ctx");
+  int rc = begin_call(ctx);
+  if (rc) return rc;
+  const int64_t n = ctx->n;
+  // Samples the reference's block iterator feeds (K/IndexBuilder.java:152-180): 125-sample nodes,
+  // the last one zero padded; nextData() counts only within-node advances against n.
+  int64_t fed = 0;
+  {
+    const int64_t n_nodes = (n + 124) / 125;
+    int64_t cnt = 0;
+    for (int64_t b = 0; b < n_nodes; b++) {
+      const int64_t within = std::min<int64_t>(124, std::max<int64_t>(0, n - cnt));
+      fed += 1 + within;
+      cnt += within;
+      if (within < 124) break;  // ++cnt <= n failed inside this node
+    }
+  }
+  std::vector<MeanChain> chains;
+  const int64_t stride = kEpoch - w + 1;
+  long long slot = 0;
+  for (int64_t it = 0;; it++) {
+    const int64_t g0 = it * stride;
+    if (g0 + w - 1 >= fed) break;  // ep <= w-1: nothing new to read
+    const int64_t ep = std::min<int64_t>(kEpoch, fed - g0);
+    const int64_t nwin = std::min<int64_t>(ep - w + 1, n - g0);  // loc = g0 + i - w + 2 <= n
+    if (nwin <= 0) break;
+    chains.push_back(MeanChain{(int32_t)g0, (int32_t)ep, (int32_t)nwin, w, slot});
+    slot += nwin;
+    if (ep < kEpoch) break;
+  }
+  const int n_chains = (int)chains.size();
+  if (n_chains == 0) return KVM_OK;
+  Arena A;
+  const size_t o_chains = A.add(chains.data(), sizeof(MeanChain) * n_chains);
+  if ((rc = upload_arena(ctx, A))) return rc;
+  KVM_CUDA(ctx, ctx->seg_b.ensure(sizeof(int32_t) * (size_t)slot));
+  KVM_CUDA(ctx, ctx->seg_first.ensure(sizeof(int32_t) * (size_t)slot));
+  KVM_CUDA(ctx, ctx->seg_last.ensure(sizeof(int32_t) * (size_t)slot));
+  KVM_CUDA(ctx, ctx->chain_count.ensure(sizeof(int32_t) * n_chains));
+  KVM_CUDA(ctx, ctx->chain_prefix.ensure(sizeof(long long) * (n_chains + 1)));
+  if ((rc = zero_counters(ctx))) return rc;
+  const MeanChain* d_chains = reinterpret_cast<const MeanChain*>(ctx->arena.as<unsigned char>() + o_chains);
+  MeanWalkParams M;
+  M.T = ctx->series.as<double>();
+  M.chains = d_chains;
+  M.n_chains = n_chains;
+  M.seg_b = ctx->seg_b.as<int32_t>();
+  M.seg_first = ctx->seg_first.as<int32_t>();
+  M.seg_last = ctx->seg_last.as<int32_t>();
+  M.chain_count = ctx->chain_count.as<int32_t>();
+  M.overflow = reinterpret_cast<int*>(ctx->counters.as<unsigned long long>() + kCntFlag);
+  const int n_blocks = (n_chains + kWalkWarps * 32 - 1) / (kWalkWarps * 32);
+  const size_t smem = sizeof(double) * kMeanSmemDoublesPerWarp * kWalkWarps;
+  KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  mean_walk_kernel<<<n_blocks, kWalkWarps * 32, smem, ctx->stream>>>(M);
+  mean_scan_kernel<<<1, 1024, 0, ctx->stream>>>(M.chain_count, n_chains, ctx->chain_prefix.as<long long>());
+  KVM_CUDA(ctx, cudaGetLastError());
+  long long total = 0;
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters.p, ctx->chain_prefix.as<long long>() + n_chains, sizeof(long long),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::memcpy(&total, ctx->h_counters.p, sizeof(long long));
+  KVM_CUDA(ctx, ctx->run_key.ensure(sizeof(double) * (size_t)total));
+  KVM_CUDA(ctx, ctx->run_b.ensure(sizeof(int32_t) * (size_t)total));
+  KVM_CUDA(ctx, ctx->run_first.ensure(sizeof(int32_t) * (size_t)total));
+  KVM_CUDA(ctx, ctx->run_last.ensure(sizeof(int32_t) * (size_t)total));
+  mean_gather_kernel<<<n_chains, 256, 0, ctx->stream>>>(d_chains, M.chain_count, ctx->chain_prefix.as<long long>(),
+                                                       M.seg_b, M.seg_first, M.seg_last, ctx->run_key.as<double>(),
+                                                       ctx->run_b.as<int32_t>(), ctx->run_first.as<int32_t>(),
+                                                       ctx->run_last.as<int32_t>());
+  KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  KVM_CUDA(ctx, cudaGetLastError());
+  unsigned long long cnt[kNumCounters];
+  if ((rc = read_counters(ctx, cnt))) return rc;
+  if (cnt[kCntFlag]) return fail(ctx, KVM_E_ARG, "window mean outside the supported key range (|mean| < 1e8)");
+  out->kernel_ms = elapsed_ms(ctx);
+  out->n_launches = 3;
+  KVM_CUDA(ctx, ctx->h_key.ensure(sizeof(double) * (size_t)total));
+  KVM_CUDA(ctx, ctx->h_b.ensure(sizeof(int32_t) * (size_t)total));
+  KVM_CUDA(ctx, ctx->h_first.ensure(sizeof(int32_t) * (size_t)total));
+  KVM_CUDA(ctx, ctx->h_last.ensure(sizeof(int32_t) * (size_t)total));
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_key.p, ctx->run_key.p, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream));
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_b.p, ctx->run_b.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_first.p, ctx->run_first.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_last.p, ctx->run_last.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
+  KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // Stitch segments that continue across an epoch border (the reference's run state persists over
+  // epochs, K/IndexBuilder.java:190-192) and split at 255 positions (:268, MAXIMUM_DIFF - 1).
+  const double* hk = ctx->h_key.as<double>();
+  const int32_t* hb = ctx->h_b.as<int32_t>();
+  const int32_t* hf = ctx->h_first.as<int32_t>();
+  const int32_t* hl = ctx->h_last.as<int32_t>();
+  ctx->run_key_v.clear();
+  ctx->run_first_v.clear();
+  ctx->run_last_v.clear();
+  ctx->run_key_v.reserve((size_t)total + 16);
+  ctx->run_first_v.reserve((size_t)total + 16);
+  ctx->run_last_v.reserve((size_t)total + 16);
+  long long i = 0;
+  while (i < total) {
+    long long j = i;
+    while (j + 1 < total && hb[j + 1] == hb[i]) j++;
+    const int32_t first = hf[i], last = hl[j];
+    for (int64_t f = first; f <= last; f += 255) {
+      ctx->run_key_v.push_back(hk[i]);
+      ctx->run_first_v.push_back((int32_t)f);
+      ctx->run_last_v.push_back((int32_t)std::min<int64_t>(f + 254, last));
+    }
+    i = j + 1;
+  }
+  out->count = (int64_t)ctx->run_key_v.size();
+  out->keys = ctx->run_key_v.data();
+  out->first = ctx->run_first_v.data();
+  out->last = ctx->run_last_v.data();
+  return KVM_OK;
+}
+
+void kvm_result_free(kvm_ctx* ctx, kvm_result* r) {
+  (void)ctx;
+  if (!r) return;
+  r->count = 0;
+  r->offsets = nullptr;
+  r->distances = nullptr;
+}
+
+void kvm_runs_free(kvm_ctx* ctx, kvm_runs* r) {
+  (void)ctx;
+  if (!r) return;
+  r->count = 0;
+  r->keys = nullptr;
+  r->first = r->last = nullptr;
+}
+
+}  // extern "C"

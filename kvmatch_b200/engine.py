@@ -1,0 +1,249 @@
+"""Host-side mirror of the reference's engine classes for the phase-2 path, over the C ABI.
+
+The reference is Java and no JVM exists in this image, so the host side the parity tests and the
+bench drive is this Python mirror (same class names, argument meaning, statistics slots, output
+lines and error behaviour as K/QueryEngine.java, K/NormQueryEngine.java, K/QueryEngineDtw.java,
+K/NormQueryEngineDtw.java and K/IndexBuilder.java for the part of `query()` / `run()` that follows
+`sortAndMergeIntervals`).  Phase 0/1 (query planning, index probing) stay in the Java classes and are
+out of scope: `query()` here takes their output (`valid_positions`, `last_segment`), or scans the whole
+series index-free when none is given.  The Java-side binding is shown in INTEGRATION.md / java/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from .datagen import chain_intervals
+
+logger = logging.getLogger("kvmatch_b200")
+
+WU_LIST = (25, 50, 100, 200, 400)  # K/QueryEngine.java:51
+EPOCH = 100000                     # K/IndexBuilder.java:136
+
+
+@dataclass
+class VerifyResult:
+    offsets: np.ndarray      # int32, 1-based, ascending (= reference scan order)
+    distances: np.ndarray    # float64
+    cnt_candidate: int
+    n_verified: int
+    s_total: int
+    n_gate_pass: int
+    n_lb_pass: int
+    n_exact: int
+    kernel_ms: float
+    n_launches: int
+
+    @property
+    def count(self) -> int:
+        return int(len(self.offsets))
+
+
+class StatisticInfo:
+    """K/statistic/StatisticInfo.java — the six per-query slots the engines append to."""
+
+    def __init__(self):
+        self.values = []
+
+    def append(self, v):
+        self.values.append(float(v))
+
+    def get_average(self):
+        return sum(self.values) / len(self.values) if self.values else 0.0
+
+
+class GpuSeries:
+    """One kvm_ctx: a device-resident offset range [first, first+count-1] of a length-n series.
+    Takes the place of the TimeSeriesOperator the engines read phase-2 data through
+    (K/operator/TimeSeriesOperator.java:38)."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        rc = self._L.kvm_create(C.byref(h), device)
+        if rc != 0:
+            raise _lib.KvmError(rc, self._L.kvm_last_error(None).decode())
+        self._h = h
+        self.n = self.first = self.count = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.kvm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise _lib.KvmError(rc, self._L.kvm_last_error(self._h).decode())
+
+    def load(self, samples, n: int | None = None, first: int = 1):
+        a, p = _lib.as_f64(samples)
+        n = len(a) if n is None else n
+        self._check(self._L.kvm_load_series_host(self._h, p, n, first, len(a)))
+        self.n, self.first, self.count = n, first, len(a)
+        return self
+
+    def load_file(self, path: str, n: int, first: int = 1, count: int | None = None):
+        count = n - first + 1 if count is None else count
+        self._check(self._L.kvm_load_series_file(self._h, path.encode(), n, first, count))
+        self.n, self.first, self.count = n, first, count
+        return self
+
+    def _take(self, r: _lib.KvmResult) -> VerifyResult:
+        c = r.count
+        off = np.ctypeslib.as_array(r.offsets, shape=(c,)).copy() if c else np.zeros(0, np.int32)
+        dist = np.ctypeslib.as_array(r.distances, shape=(c,)).copy() if c else np.zeros(0, np.float64)
+        out = VerifyResult(off, dist, r.cnt_candidate, r.n_verified, r.s_total, r.n_gate_pass, r.n_lb_pass, r.n_exact,
+                           r.kernel_ms, r.n_launches)
+        self._L.kvm_result_free(self._h, C.byref(r))
+        return out
+
+    def verify_ed(self, q, epsilon, intervals, shift=0) -> VerifyResult:
+        q, qp = _lib.as_f64(q)
+        lr, lp, K = _lib.as_intervals(intervals)
+        r = _lib.KvmResult()
+        self._check(self._L.kvm_verify_ed(self._h, qp, len(q), epsilon, lp, K, shift, C.byref(r)))
+        return self._take(r)
+
+    def verify_cnsm_ed(self, q, epsilon, alpha, beta, intervals, shift=0) -> VerifyResult:
+        q, qp = _lib.as_f64(q)
+        lr, lp, K = _lib.as_intervals(intervals)
+        r = _lib.KvmResult()
+        self._check(self._L.kvm_verify_cnsm_ed(self._h, qp, len(q), epsilon, alpha, beta, lp, K, shift, C.byref(r)))
+        return self._take(r)
+
+    def verify_dtw(self, q, epsilon, rho, intervals, shift=0) -> VerifyResult:
+        q, qp = _lib.as_f64(q)
+        lr, lp, K = _lib.as_intervals(intervals)
+        r = _lib.KvmResult()
+        self._check(self._L.kvm_verify_dtw(self._h, qp, len(q), epsilon, rho, lp, K, shift, C.byref(r)))
+        return self._take(r)
+
+    def verify_cnsm_dtw(self, q, epsilon, rho, alpha, beta, intervals, shift=0) -> VerifyResult:
+        q, qp = _lib.as_f64(q)
+        lr, lp, K = _lib.as_intervals(intervals)
+        r = _lib.KvmResult()
+        self._check(self._L.kvm_verify_cnsm_dtw(self._h, qp, len(q), epsilon, rho, alpha, beta, lp, K, shift,
+                                                C.byref(r)))
+        return self._take(r)
+
+    def window_mean_runs(self, w: int):
+        r = _lib.KvmRuns()
+        self._check(self._L.kvm_window_mean_runs(self._h, w, C.byref(r)))
+        c = r.count
+        keys = np.ctypeslib.as_array(r.keys, shape=(c,)).copy() if c else np.zeros(0)
+        first = np.ctypeslib.as_array(r.first, shape=(c,)).copy() if c else np.zeros(0, np.int32)
+        last = np.ctypeslib.as_array(r.last, shape=(c,)).copy() if c else np.zeros(0, np.int32)
+        ms, nl = r.kernel_ms, r.n_launches
+        self._L.kvm_runs_free(self._h, C.byref(r))
+        return keys, first, last, ms, nl
+
+
+def stable_sort_by_distance(offsets, distances):
+    """answers.sort(Comparator.comparing(Pair::getSecond)) — stable, K/QueryEngine.java:373."""
+    order = np.argsort(distances, kind="stable")
+    return offsets[order], distances[order]
+
+
+@dataclass
+class _EngineBase:
+    series: GpuSeries
+    answers: list = field(default_factory=list)   # [(offset, distance)] sorted by distance, as the reference leaves them
+    last: VerifyResult | None = None
+
+    def _positions(self, valid_positions, m, chunk):
+        if valid_positions is None:  # index-free: every window start, cut into statistic chains
+            s = self.series
+            hi = min(s.n - m + 1, s.first + s.count - m)
+            return chain_intervals(s.n, m, chunk or (EPOCH - m + 1), lo=s.first, hi=hi)
+        return np.asarray(valid_positions, dtype=np.int32).reshape(-1, 2)
+
+    def _finish(self, statistics, res: VerifyResult, t0, t1_ms=0.0):
+        t2_ms = (time.perf_counter() - t0) * 1e3
+        off, dist = stable_sort_by_distance(res.offsets, res.distances)
+        self.answers = list(zip(off.tolist(), dist.tolist()))
+        self.last = res
+        if statistics is not None:  # K/QueryEngine.java:366-371
+            for slot, v in enumerate([t1_ms + t2_ms, t1_ms, t2_ms, res.cnt_candidate, res.count, 0]):
+                statistics[slot].append(v)
+        if self.answers:
+            logger.info("Best: %s, distance: %s", self.answers[0][0], self.answers[0][1])  # :376
+        logger.info("T: %d ms, T_1: %d ms, T_2: %d ms, #candidates: %d, #answers: %d", round(t1_ms + t2_ms),
+                    round(t1_ms), round(t2_ms), res.cnt_candidate, res.count)  # :378
+        return bool(self.answers)
+
+
+class QueryEngine(_EngineBase):
+    """RSM-ED — phase 2 of K/QueryEngine.java:162 (lines 341-363)."""
+
+    def query(self, statistics, query_data, epsilon, valid_positions=None, last_segment=1, chunk=None):
+        t0 = time.perf_counter()
+        iv = self._positions(valid_positions, len(query_data), chunk)
+        res = self.series.verify_ed(query_data, epsilon, iv, (last_segment - 1) * WU_LIST[0])
+        return self._finish(statistics, res, t0)
+
+
+class NormQueryEngine(_EngineBase):
+    """cNSM-ED — phase 2 of K/NormQueryEngine.java:177 (lines 432-528)."""
+
+    def query(self, statistics, query_data, epsilon, alpha, beta, valid_positions=None, last_segment=1, chunk=None):
+        t0 = time.perf_counter()
+        iv = self._positions(valid_positions, len(query_data), chunk)
+        res = self.series.verify_cnsm_ed(query_data, epsilon, alpha, beta, iv, (last_segment - 1) * WU_LIST[0])
+        return self._finish(statistics, res, t0)
+
+
+class QueryEngineDtw(_EngineBase):
+    """RSM-DTW — phase 2 of K/QueryEngineDtw.java:172 (lines 349-452)."""
+
+    def query(self, statistics, query_data, epsilon, rho, valid_positions=None, last_segment=1, chunk=None):
+        t0 = time.perf_counter()
+        iv = self._positions(valid_positions, len(query_data), chunk)
+        res = self.series.verify_dtw(query_data, epsilon, rho, iv, (last_segment - 1) * WU_LIST[0])
+        return self._finish(statistics, res, t0)
+
+
+class NormQueryEngineDtw(_EngineBase):
+    """cNSM-DTW — phase 2 of K/NormQueryEngineDtw.java:190 (lines 457-603)."""
+
+    def query(self, statistics, query_data, epsilon, rho, alpha, beta, valid_positions=None, last_segment=1,
+              chunk=None):
+        t0 = time.perf_counter()
+        iv = self._positions(valid_positions, len(query_data), chunk)
+        res = self.series.verify_cnsm_dtw(query_data, epsilon, rho, alpha, beta, iv,
+                                          (last_segment - 1) * WU_LIST[0])
+        return self._finish(statistics, res, t0)
+
+
+def rho_from_prompt(r: float, length: int) -> int:
+    """The `Rho (|Q|%) = ` prompt: r <= 1 is a fraction of the query length (K/QueryEngineDtw.java:134-140)."""
+    return int(np.floor(r * length)) if r <= 1 else int(np.floor(r))
+
+
+class IndexBuilder:
+    """Step 1 of K/IndexBuilder.java SingleIndexBuilder.run (lines 194-301) for each w in WuList."""
+
+    def __init__(self, series: GpuSeries):
+        self.series = series
+
+    def window_mean_runs(self, w: int):
+        keys, first, last, _, _ = self.series.window_mean_runs(w)
+        return keys, first, last
+
+    def build_rows(self, w: int):
+        """{key: [(first, last), ...]} — what the reference's indexNodeMap holds after step 1."""
+        keys, first, last = self.window_mean_runs(w)
+        rows = {}
+        for k, f, l in zip(keys.tolist(), first.tolist(), last.tolist()):
+            rows.setdefault(k, []).append((f, l))
+        return rows

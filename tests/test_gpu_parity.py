@@ -1,0 +1,250 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar: answer offsets and #answers bit-exact; distances bit-exact as well (the exact stages use the
+reference's operation order with unfused binary64 ops), which is stricter than the 1e-9 relative
+north_star asks for.  /root/reference is never read here.
+"""
+import numpy as np
+import pytest
+
+from kvmatch_b200 import datagen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import kvmatch_b200
+    g = kvmatch_b200.GpuSeries(0)
+    yield g
+    g.close()
+
+
+@pytest.fixture(scope="module")
+def series_1m():
+    return datagen.generate(1_000_000)
+
+
+def assert_same(got, exp, exact_dist=True):
+    assert got.offsets.tolist() == exp.offsets.tolist()
+    if exact_dist:
+        assert got.distances.tolist() == exp.distances.tolist()
+    else:
+        np.testing.assert_allclose(got.distances, exp.distances, rtol=1e-9, atol=0)
+    assert got.cnt_candidate == exp.cnt_candidate
+    assert got.n_verified == exp.n_verified
+    assert got.s_total == exp.s_total
+
+
+def pruned_intervals(n, m, rng, k=200, span=60, around=()):
+    lefts = np.sort(rng.choice(np.arange(1, n - m - span), size=k, replace=False)).tolist()
+    lefts = sorted(set(lefts) | set(around))
+    out, end = [], 0
+    for l in lefts:
+        l = max(int(l), end + 2)
+        r = l + int(rng.integers(0, span))
+        out.append((l, r))
+        end = r
+    return out
+
+
+# ---------------------------------------------------------------- RSM-ED (a1)
+def test_ed_config1_full_scan(gpu, oracle, series_1m):
+    """BASELINE config 1: n=1e6, offset 123456, length 8192, eps 10 -> Best: 123456, distance 0.0."""
+    s = series_1m
+    n, m, off = len(s), 8192, 123456
+    q = s[off - 1:off - 1 + m].copy()
+    gpu.load(s)
+    iv = [(1, n - m + 1)]
+    got = gpu.verify_ed(q, 10.0, iv)
+    exp = oracle.verify_ed(s, q, 10.0, iv)
+    assert_same(got, exp)
+    assert (off, 0.0) in list(zip(got.offsets.tolist(), got.distances.tolist()))
+
+
+@pytest.mark.parametrize("m,eps,shift", [(25, 2.0, 0), (128, 30.0, 25), (1000, 400.0, 75), (8192, 3000.0, 0)])
+def test_ed_pruned_intervals(gpu, oracle, series_1m, m, eps, shift):
+    s = series_1m
+    rng = np.random.default_rng(m)
+    gpu.load(s)
+    off = 400_000
+    q = s[off - 1:off - 1 + m] + rng.normal(scale=0.01, size=m)
+    iv = pruned_intervals(len(s), m, rng, around=(off + shift - 5,))
+    assert_same(gpu.verify_ed(q, eps, iv, shift), oracle.verify_ed(s, q, eps, iv, shift))
+
+
+def test_ed_many_answers_and_clamping(gpu, oracle):
+    s = np.tile(np.array([0.0, 1.0, 0.5, -1.0]), 5000)  # periodic: thousands of exact matches
+    gpu.load(s)
+    q = s[:64].copy()
+    iv = [(1, 300), (9000, len(s))]  # right end far beyond n-m+1: clamped like the reference
+    got = gpu.verify_ed(q, 0.0, iv, 50)
+    exp = oracle.verify_ed(s, q, 0.0, iv, 50)
+    assert_same(got, exp)
+    assert got.count > 1000
+
+
+# ---------------------------------------------------------------- cNSM-ED (a2)
+@pytest.mark.parametrize("m,eps,alpha,beta,chunk", [(128, 4.0, 1.5, 5.0, 4096), (1024, 10.0, 1.5, 5.0, 100000 - 1023),
+                                                    (1024, 5.0, 2.0, 1.0, 20000), (256, 1.0, 1.1, 10.0, 999)])
+def test_cnsm_ed_full_scan(gpu, oracle, series_1m, m, eps, alpha, beta, chunk):
+    s = series_1m
+    gpu.load(s)
+    off = 654_321
+    q = s[off - 1:off - 1 + m].copy()
+    iv = datagen.chain_intervals(len(s), m, chunk)
+    got = gpu.verify_cnsm_ed(q, eps, alpha, beta, iv)
+    exp = oracle.verify_cnsm_ed(s, q, eps, alpha, beta, iv)
+    assert_same(got, exp)
+    assert got.n_gate_pass == exp.n_gate_pass
+    assert off in got.offsets.tolist()
+
+
+def test_cnsm_ed_pruned_intervals_with_shift(gpu, oracle, series_1m):
+    s = series_1m
+    m = 512
+    rng = np.random.default_rng(3)
+    gpu.load(s)
+    off = 222_222
+    q = 1.3 * s[off - 1:off - 1 + m] + 2.0  # scaled + shifted copy: z-normalised distance ~ 0
+    iv = pruned_intervals(len(s), m, rng, k=500, span=300, around=(off + 50 - 7,))
+    got = gpu.verify_cnsm_ed(q, 3.0, 1.5, 5.0, iv, 50)
+    exp = oracle.verify_cnsm_ed(s, q, 3.0, 1.5, 5.0, iv, 50)
+    assert_same(got, exp)
+    assert got.n_gate_pass == exp.n_gate_pass and off in got.offsets.tolist()
+
+
+def test_cnsm_ed_degenerate_query_and_constant_data(gpu, oracle):
+    s = np.concatenate([np.full(3000, 2.5), datagen.generate(5000, seed=8)])
+    gpu.load(s)
+    iv = [(1, len(s) - 63)]
+    # constant query: stdQ == 0 -> every gate comparison is false in the reference
+    assert gpu.verify_cnsm_ed(np.full(64, 1.0), 5.0, 1.5, 5.0, iv).count == 0
+    # constant data windows: std == 0 (or NaN from negative variance) -> silently dropped
+    q = s[4000:4064].copy()
+    assert_same(gpu.verify_cnsm_ed(q, 5.0, 1.5, 5.0, iv), oracle.verify_cnsm_ed(s, q, 5.0, 1.5, 5.0, iv))
+
+
+# ---------------------------------------------------------------- RSM-DTW (a3) / cNSM-DTW (a4)
+@pytest.mark.parametrize("m,rho,eps", [(64, 3, 6.0), (128, 6, 12.0), (512, 25, 40.0), (600, 77, 80.0)])
+def test_dtw_scan(gpu, oracle, m, rho, eps):
+    s = datagen.generate(200_000, seed=21)
+    gpu.load(s)
+    off = 150_000
+    rng = np.random.default_rng(rho)
+    q = s[off - 1:off - 1 + m] + rng.normal(scale=0.05, size=m)
+    iv = [(1, 60_000), (149_000, 151_000), (199_000, len(s) - m + 1)]
+    got = gpu.verify_dtw(q, eps, rho, iv)
+    exp = oracle.verify_dtw(s, q, eps, rho, iv)
+    assert_same(got, exp)
+    assert off in got.offsets.tolist()
+    assert got.n_lb_pass >= exp.n_dtw  # the GPU cascade omits the data-envelope bound: it prunes no more
+
+
+@pytest.mark.parametrize("m,rho,eps,chunk", [(128, 6, 3.0, 5000), (512, 25, 6.0, 100000 - 511),
+                                             (2048, 102, 12.0, 30000)])
+def test_cnsm_dtw_scan(gpu, oracle, m, rho, eps, chunk):
+    s = datagen.generate(300_000, seed=22)
+    gpu.load(s)
+    off = 123_456
+    q = 0.8 * s[off - 1:off - 1 + m] - 1.0
+    iv = datagen.chain_intervals(len(s), m, chunk)
+    got = gpu.verify_cnsm_dtw(q, eps, rho, 1.5, 5.0, iv)
+    exp = oracle.verify_cnsm_dtw(s, q, eps, rho, 1.5, 5.0, iv)
+    assert_same(got, exp)
+    assert got.n_gate_pass == exp.n_gate_pass and off in got.offsets.tolist()
+
+
+def test_dtw_rho0_equals_ed(gpu, series_1m):
+    s = series_1m[:100_000]
+    gpu.load(s)
+    q = s[5000:5128].copy()
+    iv = [(1, len(s) - 127)]
+    a = gpu.verify_dtw(q, 25.0, 0, iv)
+    b = gpu.verify_ed(q, 25.0, iv)
+    assert a.offsets.tolist() == b.offsets.tolist() and a.distances.tolist() == b.distances.tolist()
+
+
+# ---------------------------------------------------------------- IndexBuilder step 1 (a10/a11)
+@pytest.mark.parametrize("w", [25, 50, 100, 200, 400])
+def test_window_mean_runs(gpu, oracle, series_1m, w):
+    gpu.load(series_1m)
+    keys, first, last, _, _ = gpu.window_mean_runs(w)
+    ek, ef, el = oracle.window_mean_runs(series_1m, w)
+    assert first.tolist() == ef.tolist() and last.tolist() == el.tolist()
+    assert keys.view(np.int64).tolist() == ek.view(np.int64).tolist()  # Double.equals: bitwise
+
+
+def test_window_mean_runs_phantom_padding_and_long_runs(gpu, oracle):
+    s = np.concatenate([np.full(2000, 3.0), datagen.generate(1030, seed=4)])  # constant prefix: runs split at 255
+    gpu.load(s)
+    keys, first, last, _, _ = gpu.window_mean_runs(25)
+    ek, ef, el = oracle.window_mean_runs(s, 25)
+    assert first.tolist() == ef.tolist() and last.tolist() == el.tolist() and keys.tolist() == ek.tolist()
+    assert (last - first).max() == 254
+
+
+# ---------------------------------------------------------------- boundary behaviour
+def test_file_loader_big_endian(gpu, oracle, tmp_path):
+    s = datagen.generate(50_000, seed=6)
+    p = str(tmp_path / "data-50000")
+    oracle.write_series_be(p, s)
+    gpu.load_file(p, len(s))
+    q = s[1000:1256].copy()
+    iv = [(1, len(s) - 255)]
+    assert_same(gpu.verify_ed(q, 5.0, iv), oracle.verify_ed(s, q, 5.0, iv))
+    # a shard with halo: samples [20001, 40000] of the same file
+    gpu.load_file(p, len(s), first=20001, count=20000)
+    iv2 = [(20001, 39000)]
+    assert_same(gpu.verify_cnsm_ed(q, 50.0, 2.0, 50.0, iv2), oracle.verify_cnsm_ed(s, q, 50.0, 2.0, 50.0, iv2))
+
+
+def test_error_codes(gpu, series_1m):
+    import kvmatch_b200
+    fresh = kvmatch_b200.GpuSeries(0)
+    with pytest.raises(kvmatch_b200.KvmError) as e:
+        fresh.verify_ed(np.zeros(32), 1.0, [(1, 2)])
+    assert e.value.code == -6  # KVM_E_STATE
+    fresh.load(series_1m[:1000])
+    with pytest.raises(kvmatch_b200.KvmError) as e:
+        fresh.verify_ed(np.zeros(32), 1.0, [(1, 2)], shift=100)  # the reference throws IllegalArgumentException
+    assert e.value.code == -7
+    fresh.load(series_1m[:1000], n=5000, first=2001)
+    with pytest.raises(kvmatch_b200.KvmError) as e:
+        fresh.verify_ed(np.zeros(32), 1.0, [(1, 200)])  # outside this shard
+    assert e.value.code == -7
+    fresh.close()
+
+
+def test_engine_mirror_output(gpu, series_1m, caplog):
+    import logging
+
+    import kvmatch_b200
+    gpu.load(series_1m)
+    q = series_1m[123455:123455 + 8192].copy()
+    stats = [kvmatch_b200.StatisticInfo() for _ in range(6)]
+    eng = kvmatch_b200.QueryEngine(gpu)
+    with caplog.at_level(logging.INFO, logger="kvmatch_b200"):
+        assert eng.query(stats, q, 10.0) is True
+    assert eng.answers[0] == (123456, 0.0)
+    assert "Best: 123456, distance: 0.0" in caplog.text and "#answers: %d" % len(eng.answers) in caplog.text
+    assert stats[4].values == [float(len(eng.answers))]
+
+
+# ---------------------------------------------------------------- full-size properties (no oracle)
+def test_cnsm_ed_1e7_properties(gpu):
+    n, m = 10_000_000, 1024
+    s = datagen.generate(n, seed=77)
+    gpu.load(s)
+    off = 7_654_321
+    q = s[off - 1:off - 1 + m].copy()
+    iv = datagen.chain_intervals(n, m, 16384)
+    r5 = gpu.verify_cnsm_ed(q, 5.0, 1.5, 5.0, iv)
+    r10 = gpu.verify_cnsm_ed(q, 10.0, 1.5, 5.0, iv)
+    assert off in r5.offsets.tolist()
+    assert np.all(np.diff(r5.offsets) > 0) and np.all(r5.distances <= 5.0)
+    assert set(r5.offsets.tolist()) <= set(r10.offsets.tolist())  # monotone in epsilon
+    assert r5.n_gate_pass == r10.n_gate_pass and r5.n_verified == n - m + 1
+    # idempotent
+    again = gpu.verify_cnsm_ed(q, 5.0, 1.5, 5.0, iv)
+    assert again.offsets.tolist() == r5.offsets.tolist() and again.distances.tolist() == r5.distances.tolist()
