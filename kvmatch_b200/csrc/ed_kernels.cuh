@@ -4,7 +4,7 @@
 // load T[start + j] is a coalesced 256-byte row and the query value q[j] is a warp-uniform
 // broadcast.  Each thread accumulates sum (d-q)^2 in the reference's natural order with unfused
 // binary64 ops, so an accepted distance is bit-identical to the Java loop's.  The early-abandon test
-// `dist <= eps^2` is evaluated once per 8 terms instead of per term: partial sums are monotone
+// `dist <= eps^2` is evaluated after 1, 4, 12, 20, ... terms instead of after every term: partial sums are monotone
 // non-decreasing, so this changes neither the accept decision nor any accepted value.
 //
 // HBM traffic: the series is streamed once (8 B per verified subsequence on a full scan); the
@@ -42,9 +42,17 @@ __global__ void __launch_bounds__(kEdTile) ed_verify_kernel(EdParams P) {
   const int m = P.m;
   const double eps2 = P.eps2;
 
-  double dist = 0.0;
-  bool alive = true;
-  int j = 0;
+  // The first abandon tests come after 1 and 4 terms: on a scan almost every window is hopeless after its
+  // first sample, and each thread then costs 8 bytes of L1 traffic instead of 64.
+  double dist = xsqdist(w[0], __ldg(q));
+  bool alive = dist <= eps2;
+  int j = 1;
+  if (alive && m >= 4) {
+#pragma unroll
+    for (int u = 1; u < 4; u++) dist = xadd(dist, xsqdist(w[u], __ldg(q + u)));
+    alive = dist <= eps2;
+    j = 4;
+  }
   for (; j + 8 <= m && alive; j += 8) {
     double t[8];
 #pragma unroll

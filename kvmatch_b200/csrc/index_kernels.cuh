@@ -36,9 +36,10 @@ struct MeanWalkParams {
   int* overflow;  // set when a bucket does not fit int32
 };
 
+constexpr int kMeanWarps = 4;
 constexpr int kMeanSmemDoublesPerWarp = 2 * 32 * kWalkPitch + 3 * (kFifoDepth * 32) / 2;
 
-__global__ void __launch_bounds__(kWalkWarps * 32) mean_walk_kernel(MeanWalkParams P) {
+__global__ void __launch_bounds__(kMeanWarps * 32) mean_walk_kernel(MeanWalkParams P) {
   extern __shared__ double walk_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* tA = walk_smem + (size_t)warp * kMeanSmemDoublesPerWarp;
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32) mean_walk_kernel(MeanWalkPara
   int32_t* f_first = f_b + kFifoDepth * 32;
   int32_t* f_last = f_first + kFifoDepth * 32;
 
-  const int c = (blockIdx.x * kWalkWarps + warp) * 32 + lane;
+  const int c = (blockIdx.x * kMeanWarps + warp) * 32 + lane;
   MeanChain ch{0, 0, 0, 2, 0};
   if (c < P.n_chains) ch = P.chains[c];
   const int pos = ch.begin, len = ch.nsamp, w = ch.w;

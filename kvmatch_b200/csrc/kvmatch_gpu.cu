@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -101,7 +102,8 @@ struct kvm_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
 
-  DevBuf series;
+  DevBuf series_buf;  // [kFrontPad zeros | samples | kTailPad zeros]
+  double* series = nullptr;  // sample 0
   int64_t n = 0, first = 0, count = 0;  // global length; 1-based offset of series[0]; samples held
 
   DevBuf arena, counters, wl_off, wl_ex, wl_ex2, region_count, tile_prefix;
@@ -141,6 +143,18 @@ inline uint64_t java_bits(double v) {
   uint64_t b;
   std::memcpy(&b, &v, 8);
   return b;
+}
+// developer tuning knobs (tools/quick_bench.py); unset = built-in defaults
+inline int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+// host twin of kvm::hi_key
+inline int host_hi_key(double x) {
+  uint64_t b;
+  std::memcpy(&b, &x, 8);
+  const int h = (int)(uint32_t)(b >> 32);
+  return h ^ ((h >> 31) & 0x7fffffff);
 }
 inline int java_double_compare(double a, double b) {
   if (a < b) return -1;
@@ -222,7 +236,7 @@ int check_common(kvm_ctx* ctx, const double* q, int m, double epsilon, const int
   if (!ctx) return KVM_E_ARG;
   if (!out || !q || m < 1 || K < 0 || (K > 0 && !lr)) return fail(ctx, KVM_E_ARG, "null/invalid argument");
   if (!(epsilon == epsilon)) return fail(ctx, KVM_E_ARG, "epsilon is NaN");
-  if (!ctx->series.p) return fail(ctx, KVM_E_STATE, "no series loaded");
+  if (!ctx->series) return fail(ctx, KVM_E_STATE, "no series loaded");
   std::memset(out, 0, sizeof(*out));
   return KVM_OK;
 }
@@ -333,30 +347,53 @@ int launch_walker(kvm_ctx* ctx, const Plan& P, int K, int m, double alpha, doubl
                   size_t off_cbegin, size_t off_nsamp, size_t off_region_base, int* launches) {
   const unsigned char* base = ctx->arena.as<unsigned char>();
   WalkParams W;
-  W.T = ctx->series.as<double>();
+  W.T = ctx->series;
   W.cbegin = reinterpret_cast<const int32_t*>(base + off_cbegin);
   W.cnsamp = reinterpret_cast<const int32_t*>(base + off_nsamp);
   W.region_base = reinterpret_cast<const long long*>(base + off_region_base);
   W.K = K;
   W.m = m;
   W.first_global = (int32_t)ctx->first;
-  W.inv_m = 1.0 / (double)m;
-  W.meanQ = S.meanQ;
-  // Conservative pre-gate: a superset of the exact gate (rounding of ex/m, ex2/m - mean^2 is far below
-  // these slacks); the exact gate is re-evaluated with the reference's arithmetic by the evaluators.
-  const double amq = std::fabs(S.meanQ) + std::fabs(beta);
-  const double hi2 = (alpha * S.stdQ) * (alpha * S.stdQ), lo2 = (S.stdQ * S.inv_alpha) * (S.stdQ * S.inv_alpha);
-  const double d2 = 1e-13 * (hi2 + 2.0 * amq * amq) + 1e-290;
-  W.beta_hi = beta + 1e-14 * amq + 1e-290;
-  W.var_hi = hi2 * (1.0 + 1e-12) + d2;
-  W.var_lo = lo2 * (1.0 - 1e-12) - d2;
+  W.dm = (double)m;
+  W.idx_hi = (int)((ctx->count + kTailPad - 2) & ~int64_t(1));
+  W.prefetch_tiles = env_int("KVM_WALK_PREFETCH", 0);
+  W.l2_hints = env_int("KVM_WALK_HINTS", 1);
+  // Conservative pre-gate: a superset of the exact gate (rounding of the chain sums' products is far below
+  // these slacks, and the integer keys widen each bound by one high-word unit); the exact gate is
+  // re-evaluated with the reference's arithmetic by the evaluators.
+  {
+    const double dm = (double)m;
+    const double amq = std::fabs(S.meanQ) + std::fabs(beta);
+    const double beta_hi = beta + 1e-14 * amq + 1e-290;
+    const double hi2 = (alpha * S.stdQ) * (alpha * S.stdQ), lo2 = (S.stdQ * S.inv_alpha) * (S.stdQ * S.inv_alpha);
+    const double d2 = 1e-13 * (hi2 + 2.0 * amq * amq) + 1e-290;
+    const double var_hi = hi2 * (1.0 + 1e-12) + d2, var_lo = lo2 * (1.0 - 1e-12) - d2;
+    double e_lo = dm * (S.meanQ - beta_hi), e_hi = dm * (S.meanQ + beta_hi);
+    e_lo -= std::fabs(e_lo) * 1e-12;
+    e_hi += std::fabs(e_hi) * 1e-12;
+    double v_lo = dm * dm * var_lo, v_hi = dm * dm * var_hi;
+    v_lo -= std::fabs(v_lo) * 1e-12;
+    v_hi += std::fabs(v_hi) * 1e-12;
+    const long long mk_lo = (long long)host_hi_key(e_lo) - 1, mk_hi = (long long)host_hi_key(e_hi) + 1;
+    const long long vk_lo = (long long)host_hi_key(v_lo) - 1, vk_hi = (long long)host_hi_key(v_hi) + 1;
+    W.mean_klo = (int)std::max<long long>(mk_lo, INT32_MIN);
+    W.var_klo = (int)std::max<long long>(vk_lo, INT32_MIN);
+    W.mean_kspan = (unsigned)(std::min<long long>(mk_hi, INT32_MAX) - W.mean_klo);
+    W.var_kspan = (unsigned)(std::min<long long>(vk_hi, INT32_MAX) - W.var_klo);
+  }
   W.e_off = ctx->wl_off.as<int32_t>();
   W.e_ex = ctx->wl_ex.as<double>();
   W.e_ex2 = ctx->wl_ex2.as<double>();
   W.region_count = ctx->region_count.as<int32_t>();
-  const int n_blocks = (K + kWalkWarps * 32 - 1) / (kWalkWarps * 32);
-  const size_t smem = sizeof(double) * kWalkSmemDoublesPerWarp * kWalkWarps;
-  cnsm_walk_kernel<<<n_blocks, kWalkWarps * 32, smem, ctx->stream>>>(W);
+  // Deeper tile rings while every walker warp can be resident at once; fewer stages = more warps per SM.
+  int stages = S.n_regions <= ctx->n_sms * 2 ? 4 : (S.n_regions <= ctx->n_sms * 3 ? 3 : 2);
+  stages = env_int("KVM_WALK_STAGES", stages);
+  const bool even_m = (m % 2) == 0;
+#define KVM_WALK(ST, DL) cnsm_walk_kernel<ST, DL><<<S.n_regions, 32, walk_smem_bytes(ST), ctx->stream>>>(W)
+  if (stages == 4) { if (even_m) KVM_WALK(4, 1); else KVM_WALK(4, 0); }
+  else if (stages == 3) { if (even_m) KVM_WALK(3, 1); else KVM_WALK(3, 0); }
+  else { if (even_m) KVM_WALK(2, 1); else KVM_WALK(2, 0); }
+#undef KVM_WALK
   cnsm_plan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->region_count.as<int32_t>(), S.n_regions,
                                                 ctx->tile_prefix.as<int32_t>(),
                                                 ctx->counters.as<unsigned long long>() + kCntTiles);
@@ -449,7 +486,7 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
     if ((rc = launch_walker(ctx, P, K, m, alpha, beta, S, o_cbegin, o_nsamp, o_rbase, &launches))) return rc;
 
     EvalParams E;
-    E.T = ctx->series.as<double>();
+    E.T = ctx->series;
     E.first_global = (int32_t)ctx->first;
     E.m = m;
     E.e_off = ctx->wl_off.as<int32_t>();
@@ -483,7 +520,7 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
       X.eps2 = eps2;
       X.in = E.out;
       X.sink = sink_of(ctx);
-      cnsm_ed_exact_kernel<<<ctx->n_sms * 4, 128, 0, ctx->stream>>>(X);
+      cnsm_ed_exact_kernel<<<ctx->n_sms * 2, 128, sizeof(double) * kExactChunk * 4, ctx->stream>>>(X);
       launches += 2;
     } else {
       LbNormParams L;
@@ -582,9 +619,15 @@ int kvm_create(kvm_ctx** out, int device_id) {
     delete ctx;
     return fail(nullptr, KVM_E_CUDA, "stream/event creation failed: %s", msg);
   }
-  const int walk_smem = (int)(sizeof(double) * kWalkSmemDoublesPerWarp * kWalkWarps);
-  const int mean_smem = (int)(sizeof(double) * kMeanSmemDoublesPerWarp * kWalkWarps);
-  if (cudaFuncSetAttribute(cnsm_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, walk_smem) != cudaSuccess ||
+  const int mean_smem = (int)(sizeof(double) * kMeanSmemDoublesPerWarp * kMeanWarps);
+  const int w2 = (int)walk_smem_bytes(2), w3 = (int)walk_smem_bytes(3), w4 = (int)walk_smem_bytes(4);
+  if (cudaFuncSetAttribute(cnsm_walk_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, w2) != cudaSuccess ||
+      cudaFuncSetAttribute(cnsm_walk_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w2) != cudaSuccess ||
+      cudaFuncSetAttribute(cnsm_walk_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, w3) != cudaSuccess ||
+      cudaFuncSetAttribute(cnsm_walk_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w3) != cudaSuccess ||
+      cudaFuncSetAttribute(cnsm_walk_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4) != cudaSuccess ||
+      cudaFuncSetAttribute(cnsm_walk_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4) != cudaSuccess ||
+      cudaFuncSetAttribute(cnsm_ed_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kExactChunk * 4)) != cudaSuccess ||
       cudaFuncSetAttribute(mean_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem) != cudaSuccess) {
     const char* msg = cudaGetErrorString(cudaGetLastError());
     kvm_destroy(ctx);
@@ -598,7 +641,7 @@ void kvm_destroy(kvm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  DevBuf* dev[] = {&ctx->series, &ctx->arena, &ctx->counters, &ctx->wl_off, &ctx->wl_ex, &ctx->wl_ex2,
+  DevBuf* dev[] = {&ctx->series_buf, &ctx->arena, &ctx->counters, &ctx->wl_off, &ctx->wl_ex, &ctx->wl_ex2,
                    &ctx->region_count, &ctx->tile_prefix, &ctx->cand_off, &ctx->cand_mean, &ctx->cand_std,
                    &ctx->ans_off, &ctx->ans_dist, &ctx->seg_b, &ctx->seg_first, &ctx->seg_last, &ctx->chain_count,
                    &ctx->chain_prefix, &ctx->run_key, &ctx->run_b, &ctx->run_first, &ctx->run_last};
@@ -618,10 +661,14 @@ static int alloc_series(kvm_ctx* ctx, int64_t n, int64_t first, int64_t count) {
                 (long long)n);
   if (n > 2147483647LL) return fail(ctx, KVM_E_ARG, "n exceeds the reference's int32 offsets");
   KVM_CUDA(ctx, cudaSetDevice(ctx->device));
-  // +128 zero samples: the index-build path reproduces the reference's zero padding of the last
-  // 1000-byte block (K/operator/file/TimeSeriesNodeIterator.java:55-59).
-  KVM_CUDA(ctx, ctx->series.ensure(sizeof(double) * (size_t)(count + 128)));
-  KVM_CUDA(ctx, cudaMemsetAsync(ctx->series.as<double>() + count, 0, sizeof(double) * 128, ctx->stream));
+  // Zero pads on both sides: (a) the walkers' whole-row TMA copies may start up to one tile before the
+  // first sample / end one tile after the last; (b) the index-build path reproduces the reference's zero
+  // padding of the last 1000-byte block (K/operator/file/TimeSeriesNodeIterator.java:55-59).
+  ctx->series = nullptr;
+  KVM_CUDA(ctx, ctx->series_buf.ensure(sizeof(double) * (size_t)(count + kFrontPad + kTailPad)));
+  ctx->series = ctx->series_buf.as<double>() + kFrontPad;
+  KVM_CUDA(ctx, cudaMemsetAsync(ctx->series_buf.p, 0, sizeof(double) * kFrontPad, ctx->stream));
+  KVM_CUDA(ctx, cudaMemsetAsync(ctx->series + count, 0, sizeof(double) * kTailPad, ctx->stream));
   ctx->n = n;
   ctx->first = first;
   ctx->count = count;
@@ -633,7 +680,7 @@ int kvm_load_series_host(kvm_ctx* ctx, const double* samples, int64_t n, int64_t
   if (!samples) return fail(ctx, KVM_E_ARG, "samples is null");
   int rc = alloc_series(ctx, n, first, count);
   if (rc) return rc;
-  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->series.p, samples, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice,
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->series, samples, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice,
                                 ctx->stream));
   KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return KVM_OK;
@@ -662,7 +709,7 @@ int kvm_load_series_file(kvm_ctx* ctx, const char* path, int64_t n, int64_t firs
       std::fclose(f);
       return fail(ctx, KVM_E_IO, "%s is shorter than %lld doubles", path, (long long)(first - 1 + count));
     }
-    cudaError_t e = cudaMemcpyAsync(ctx->series.as<double>() + done, ctx->stage.p, 8 * c, cudaMemcpyHostToDevice, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(ctx->series + done, ctx->stage.p, 8 * c, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
       std::fclose(f);
@@ -671,7 +718,7 @@ int kvm_load_series_file(kvm_ctx* ctx, const char* path, int64_t n, int64_t firs
     done += (int64_t)c;
   }
   std::fclose(f);
-  bswap64_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(ctx->series.as<unsigned long long>(), (long long)count);
+  bswap64_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(reinterpret_cast<unsigned long long*>(ctx->series), (long long)count);
   KVM_CUDA(ctx, cudaGetLastError());
   KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return KVM_OK;
@@ -702,7 +749,7 @@ int kvm_verify_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, cons
   for (int attempt = 0; attempt < 8; attempt++) {
     if ((rc = zero_counters(ctx))) return rc;
     EdParams E;
-    E.T = ctx->series.as<double>();
+    E.T = ctx->series;
     E.q = reinterpret_cast<const double*>(base + o_q);
     E.cbegin = reinterpret_cast<const int32_t*>(base + o_cbegin);
     E.ncand = reinterpret_cast<const int32_t*>(base + o_ncand);
@@ -769,7 +816,7 @@ int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int
   for (int attempt = 0; attempt < 8; attempt++) {
     if ((rc = zero_counters(ctx))) return rc;
     LbRawParams L;
-    L.T = ctx->series.as<double>();
+    L.T = ctx->series;
     L.cbegin = reinterpret_cast<const int32_t*>(base + o_cbegin);
     L.ncand = reinterpret_cast<const int32_t*>(base + o_ncand);
     L.tile_prefix = reinterpret_cast<const int32_t*>(base + o_tp);
@@ -811,7 +858,7 @@ int kvm_window_mean_runs(kvm_ctx* ctx, int32_t w, kvm_runs* out) {
   std::memset(out, 0, sizeof(*out));
   constexpr int kEpoch = 100000;  // K/IndexBuilder.java:136
   if (w < 2 || w > kEpoch) return fail(ctx, KVM_E_ARG, "window width %d", w);
-  if (!ctx->series.p) return fail(ctx, KVM_E_STATE, "no series loaded");
+  if (!ctx->series) return fail(ctx, KVM_E_STATE, "no series loaded");
   if (ctx->first != 1 || ctx->count != ctx->n)
     return fail(ctx, KVM_E_RANGE, "index build needs the whole series on this ctx");
   int rc = begin_call(ctx);
@@ -856,7 +903,7 @@ int kvm_window_mean_runs(kvm_ctx* ctx, int32_t w, kvm_runs* out) {
   if ((rc = zero_counters(ctx))) return rc;
   const MeanChain* d_chains = reinterpret_cast<const MeanChain*>(ctx->arena.as<unsigned char>() + o_chains);
   MeanWalkParams M;
-  M.T = ctx->series.as<double>();
+  M.T = ctx->series;
   M.chains = d_chains;
   M.n_chains = n_chains;
   M.seg_b = ctx->seg_b.as<int32_t>();
@@ -864,10 +911,10 @@ int kvm_window_mean_runs(kvm_ctx* ctx, int32_t w, kvm_runs* out) {
   M.seg_last = ctx->seg_last.as<int32_t>();
   M.chain_count = ctx->chain_count.as<int32_t>();
   M.overflow = reinterpret_cast<int*>(ctx->counters.as<unsigned long long>() + kCntFlag);
-  const int n_blocks = (n_chains + kWalkWarps * 32 - 1) / (kWalkWarps * 32);
-  const size_t smem = sizeof(double) * kMeanSmemDoublesPerWarp * kWalkWarps;
+  const int n_blocks = (n_chains + kMeanWarps * 32 - 1) / (kMeanWarps * 32);
+  const size_t smem = sizeof(double) * kMeanSmemDoublesPerWarp * kMeanWarps;
   KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  mean_walk_kernel<<<n_blocks, kWalkWarps * 32, smem, ctx->stream>>>(M);
+  mean_walk_kernel<<<n_blocks, kMeanWarps * 32, smem, ctx->stream>>>(M);
   mean_scan_kernel<<<1, 1024, 0, ctx->stream>>>(M.chain_count, n_chains, ctx->chain_prefix.as<long long>());
   KVM_CUDA(ctx, cudaGetLastError());
   long long total = 0;

@@ -108,8 +108,8 @@ def test_cnsm_ed_pruned_intervals_with_shift(gpu, oracle, series_1m):
     off = 222_222
     q = 1.3 * s[off - 1:off - 1 + m] + 2.0  # scaled + shifted copy: z-normalised distance ~ 0
     iv = pruned_intervals(len(s), m, rng, k=500, span=300, around=(off + 50 - 7,))
-    got = gpu.verify_cnsm_ed(q, 3.0, 1.5, 5.0, iv, 50)
-    exp = oracle.verify_cnsm_ed(s, q, 3.0, 1.5, 5.0, iv, 50)
+    got = gpu.verify_cnsm_ed(q, 3.0, 1.5, 100.0, iv, 50)
+    exp = oracle.verify_cnsm_ed(s, q, 3.0, 1.5, 100.0, iv, 50)
     assert_same(got, exp)
     assert got.n_gate_pass == exp.n_gate_pass and off in got.offsets.tolist()
 
