@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native KV-match phase-2 path.
+
+A "step" is one cNSM-ED verification pass (BASELINE.json configs[1]: NormQueryEngine, query length 1024,
+alpha=1.5, beta=5) of one query over every window start of a DataGenerator-style synthetic series, index-free:
+the merged-interval list handed to the C ABI is [1, n-m+1] cut into statistic chains of --chunk candidates
+(<= 100000-m+1, the reference's own epoch chunking, K/experiments/ucr/UcrDtwQueryExecutor.java:97).
+
+  python bench.py --gpus N --steps K --warmup W              # ours (one process per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU loops (oracle port), rank 0 only
+
+N GPUs: weak scaling — every rank holds its own n_per_gpu samples (+ m-1 halo) of one global series of length
+N*n_per_gpu and verifies its own window starts; the only exchange is the tail (counts, sparse answers, best
+match) over torch.distributed/NCCL.  `value` = window starts verified by all ranks / max-over-ranks device time
+of the K timed steps (CUDA events on the library's stream, series resident in HBM).  `e2e` = the same through
+the C ABI call with host buffers (query + interval list copied in, answers copied out, every step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from kvmatch_b200 import datagen, sharding  # noqa: E402
+
+M = 1024
+ALPHA, BETA = 1.5, 5.0
+EPSILON = 5.0            # middle of the reference's cNSM grid {1,5,10} (NormQueryDtwSelectivityGenerate.java:72-86)
+N_PER_GPU = 100_000_000
+N_QUERIES = 10           # seeded query offsets, cycled over the steps
+SEED = datagen.DEFAULT_SEED
+DEFAULT_CHUNK = 16384    # candidates per statistic chain (see DESIGN.md "chain chunking")
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def query_offsets(n_total, m, k):
+    rng = np.random.default_rng(SEED)
+    return [int(x) for x in rng.integers(1, n_total - m, k)]
+
+
+def query_of(n_total, off, m):
+    return datagen.generate_range(n_total, off - 1, off - 1 + m, SEED)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_sample(series, q, intervals, n_threads):
+    """Time the CPU oracle (the restated reference loops) on `intervals`; n_threads > 1 shards the interval list
+    over Python threads (ctypes releases the GIL) — every chain is still walked by exactly one thread."""
+    from oracle import kvm_oracle
+    kvm_oracle.lib()
+    parts = [p for p in np.array_split(np.asarray(intervals), n_threads) if len(p)]
+    out = [None] * len(parts)
+
+    def run(i):
+        out[i] = kvm_oracle.verify_cnsm_ed(series, q, EPSILON, ALPHA, BETA, parts[i])
+
+    t0 = time.perf_counter()
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(len(parts))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    dt = time.perf_counter() - t0
+    return sum(o.n_verified for o in out), dt, out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  It is Java (no JVM in this image), so
+    this times the C++ restatement in oracle/ on the host cores, rank 0 only; other ranks exit without work."""
+    if rank != 0:
+        return
+    n = N_PER_GPU * world
+    cores = os.cpu_count() or 1
+    chunk = min(args.chunk, 100000 - M + 1)
+    # bounded sample: the first `sample_n` samples of the same series, same chains, same queries
+    sample_n = int(args.ref_sample)
+    series = datagen.generate_range(n, 0, sample_n, SEED)
+    iv = datagen.chain_intervals(sample_n, M, chunk)
+    offs = query_offsets(n, M, N_QUERIES)
+    times, verified = [], 0
+    for step in range(args.warmup + args.steps):
+        q = query_of(n, offs[step % N_QUERIES], M)
+        v, dt, _ = oracle_sample(series, q, iv, cores)
+        if step >= args.warmup:
+            times.append(dt)
+            verified += v
+    total = sum(times)
+    value = verified / total
+    line = {
+        "impl": "reference", "metric": "verified subsequences/sec (cNSM-ED)", "value": value, "unit": "subsequences/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n, chunk, world),
+        "cpu_baseline": {"value": value, "unit": "subsequences/s", "cores": cores, "kind": "port",
+                         "sample": f"first {sample_n} samples ({len(iv)} chains of <= {chunk} candidates) of the same "
+                                   f"series per step, interval list sharded over {cores} threads"},
+        "e2e": {"value": value, "unit": "subsequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is Java 8 with no JVM in this image: timed the line-by-line C++ restatement (oracle/), "
+                "series resident in RAM (kinder than the reference, which re-reads its file per interval)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_total, chunk, world):
+    return {"workload": "cNSM-ED NormQueryEngine phase-2 verification, index-free scan of every window start "
+                        "(BASELINE.json configs[1])",
+            "n_per_gpu": N_PER_GPU, "n_total": n_total, "query_length": M, "alpha": ALPHA, "beta": BETA,
+            "epsilon": EPSILON, "chain_chunk": chunk, "queries": N_QUERIES, "parallelism": f"offset-shard x{world}",
+            "l2": "inputs (800 MB per GPU) exceed the 126 MB L2; no explicit flush between steps"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("KVM_BENCH_CHUNK", DEFAULT_CHUNK)))
+    ap.add_argument("--ref-sample", type=float, default=20_000_000)
+    ap.add_argument("--cpu-sample", type=float, default=20_000_000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import kvmatch_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: kvmatch_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_total = N_PER_GPU * world
+    chunk = min(args.chunk, 100000 - M + 1)
+    shard = sharding.make_shard(n_total, M, rank, world, grid=chunk)
+    t0 = time.perf_counter()
+    local = datagen.generate_range(n_total, shard.first - 1, shard.last, SEED)
+    t_gen = time.perf_counter() - t0
+    g = kvmatch_b200.GpuSeries(local_rank)
+    t0 = time.perf_counter()
+    g.load(local, n=n_total, first=shard.first)
+    t_load = time.perf_counter() - t0
+    all_iv = datagen.chain_intervals(n_total, M, chunk, lo=shard.start_lo, hi=min(shard.start_hi, n_total - M + 1))
+    iv = sharding.assign_intervals(all_iv, 0, M, shard)
+    offs = query_offsets(n_total, M, N_QUERIES)
+    queries = [query_of(n_total, o, M) for o in offs]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(i):
+        t = time.perf_counter()
+        r = g.verify_cnsm_ed(queries[i % N_QUERIES], EPSILON, ALPHA, BETA, iv)  # host buffers in, host answers out
+        return r, time.perf_counter() - t
+
+    for i in range(args.warmup):
+        one_step(i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    dev_ms = walker_ms = wall_s = 0.0
+    verified = launches = answers = s_total = gate = 0
+    lat = []
+    for i in range(args.steps):
+        r, dt = one_step(args.warmup + i)
+        dev_ms += r.kernel_ms
+        walker_ms += r.stage_ms[0]
+        wall_s += dt
+        lat.append(dt)
+        verified += r.n_verified
+        launches += r.n_launches
+        answers += r.count
+        s_total += r.s_total
+        gate += r.n_gate_pass
+        last = r
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+
+    # the multi-GPU tail of one query (not inside the timed kernels): counts, answers, best match
+    offs_m, dists_m, totals, best = sharding.merge_answers(last.offsets, last.distances,
+                                                           {"n_verified": last.n_verified}, device=dev)
+
+    stats = torch.tensor([dev_ms, t_wall, wall_s, walker_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([verified, launches, answers, s_total, gate], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    dev_ms_max, t_wall_max, wall_s_max, walker_ms_max = [float(x) for x in stats.tolist()]
+    verified_all, launches_all, answers_all, s_total_all, gate_all = [float(x) for x in sums.tolist()]
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        k = args.steps
+        value = verified_all / (dev_ms_max * 1e-3)
+        e2e_value = verified_all / wall_s_max
+        # roofline of the dominant kernel (the statistics walker): algorithmic bytes = 8 B per touched sample
+        # (bytes_alg = 8*S_total + 12*#answers), per launch, over its own CUDA-event duration
+        bytes_per_launch = (8.0 * s_total + 12.0 * answers) / k          # rank 0's shard
+        walker_s = (walker_ms / k) * 1e-3
+        achieved = bytes_per_launch / walker_s / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "roofline_r01.json")
+        if os.path.exists(prof):
+            pj = json.load(open(prof))
+            if pj.get("chain_chunk") == chunk and pj.get("n_per_gpu") == N_PER_GPU:
+                traffic = pj.get("walker_dram_bytes_per_launch")
+        line = {
+            "metric": "verified subsequences/sec (cNSM-ED)", "value": value, "unit": "subsequences/s",
+            "n_gpus": world, "steps": k, "warmup": args.warmup, "ms_per_step": dev_ms_max / k,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(n_total, chunk, world),
+            "e2e": {"value": e2e_value, "unit": "subsequences/s",
+                    "h2d_bytes_per_step": int(8 * M + 8 * len(iv)),
+                    "d2h_bytes_per_step": int(12 * answers / k + 64),
+                    "ms_per_step": 1e3 * wall_s_max / k,
+                    "latency_ms_p50": 1e3 * float(np.median(lat)), "latency_ms_p95": 1e3 * float(np.percentile(lat, 95)),
+                    "series_upload_s_once": t_load},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "cnsm_walk_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": walker_ms / k,
+                         "whole_step_frac": (bytes_per_launch / ((dev_ms / k) * 1e-3) / 1e9) / peak},
+            "answers_per_step": answers_all / k, "gate_pass_per_step": gate_all / k,
+            "wall_s_timed_region": t_wall_max, "datagen_s": t_gen,
+            "best_of_last_query": best,
+        }
+        # CPU baseline beside it (N=1 only): the oracle port on 1 core, bounded sample of the same workload
+        if world == 1:
+            sample_n = int(args.cpu_sample)
+            cpu_iv = datagen.chain_intervals(sample_n, M, chunk)
+            v, dt, outs = oracle_sample(local[:sample_n], queries[(args.warmup + k - 1) % N_QUERIES], cpu_iv, 1)
+            line["cpu_baseline"] = {"value": v / dt, "unit": "subsequences/s", "cores": 1, "kind": "port",
+                                    "sample": f"first {sample_n} samples of the same series, last timed query, "
+                                              f"{len(cpu_iv)} chains; {dt:.1f} s on 1 core "
+                                              f"({os.cpu_count()} cores on the box)"}
+            # parity spot check on the sample (the oracle as checker, never as the thing measured)
+            ref = outs[0]
+            keep = last.offsets <= sample_n - M + 1
+            line["parity_on_cpu_sample"] = bool(last.offsets[keep].tolist() == ref.offsets.tolist() and
+                                                last.distances[keep].tolist() == ref.distances.tolist())
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    g.close()
+
+
+if __name__ == "__main__":
+    main()

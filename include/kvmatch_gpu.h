@@ -57,6 +57,9 @@ typedef struct kvm_result {
   int64_t n_lb_pass;       /* DTW: windows surviving the GPU lower bounds, i.e. full DTWs computed */
   int64_t n_exact;         /* ED: windows re-evaluated by the sequential reference-order path */
   double kernel_ms;        /* device time of this call's kernels (CUDA events on the ctx stream) */
+  double stage_ms[4];      /* the same, per stage: [0] streaming kernel (ED scan / statistics walker / raw LB scan),
+                              [1] planner + evaluator (exact gate, fast distance or lower bounds),
+                              [2] exact stage (reference-order ED sum / banded DTW), [3] unused */
   int32_t n_launches;      /* kernels launched by this call */
   int32_t reserved;
 } kvm_result;

@@ -55,6 +55,7 @@ class KvmResult(C.Structure):
         ("n_lb_pass", C.c_int64),
         ("n_exact", C.c_int64),
         ("kernel_ms", C.c_double),
+        ("stage_ms", C.c_double * 4),
         ("n_launches", C.c_int32),
         ("reserved", C.c_int32),
     ]

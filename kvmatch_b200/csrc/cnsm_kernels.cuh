@@ -21,6 +21,8 @@
 //   cnsm_ed_exact_kernel one thread per survivor: the reference's sequential, unfused sum -> the
 //                      accepted distances are bit-identical to the Java loop's
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace kvm {
@@ -31,14 +33,10 @@ constexpr int kFifoDepth = 16;     // per-lane staging of work-list entries betw
 constexpr int kFifoPitch = kFifoDepth + 1;
 constexpr int kFrontPad = 64;      // zero samples the ctx keeps in front of / behind the series so that
 constexpr int kTailPad = 192;      // whole-row bulk copies never leave the allocation
-constexpr int kPrefetchTiles = 16; // L2 prefetch distance of the incoming stream, in tiles
+constexpr int kPrefetchTiles = 12; // L2 prefetch distance of the incoming stream, in tiles
 constexpr int kEvalTile = 128;     // work-list entries per evaluator tile (= evaluator CTA size)
 
 constexpr int walk_tile_doubles(int stages) { return stages * 2 * 32 * kWalkPitch; }
-constexpr size_t walk_smem_bytes(int stages) {
-  return sizeof(double) * (size_t)(walk_tile_doubles(stages) + 2 * 32 * kFifoPitch) + sizeof(int32_t) * 32 * kFifoPitch +
-         16;
-}
 
 // ---- asynchronous global->shared copies (LDGSTS) ----------------------------------------------------
 // Per-lane 256-byte TMA row copies (cp.async.bulk) were measured first: the TMA unit serialises such small
@@ -86,8 +84,6 @@ struct WalkParams {
   int m;
   int32_t first_global;
   int idx_hi;  // last even local index a 16-byte copy may start at (inside the tail pad)
-  int prefetch_tiles;  // L2 prefetch distance of the incoming stream in tiles (0 = off)
-  int l2_hints;        // 1: incoming rows evict_last, outgoing rows evict_first
   // conservative pre-gate on the chain sums (superset of the exact gate; see DESIGN.md "cNSM pre-gate"):
   //   key(ex) in [mean_klo, mean_klo + mean_kspan]   <=>  |ex/m - meanQ| <= beta (+slack)
   //   key(m*ex2 - ex^2) in [var_klo, var_klo + var_kspan]  <=>  (std/stdQ) in [1/alpha, alpha] (+slack)
@@ -100,20 +96,66 @@ struct WalkParams {
   int32_t* region_count;
 };
 
-// One CTA = one warp = 32 chains = one work-list region.  STAGES-deep ring of (incoming, outgoing) tiles,
-// each row = 32 consecutive samples of one chain, filled by 16-byte cp.async copies (half a warp per row,
-// so every copy instruction moves two full 256-byte rows) and read back with lane-private LDS.128.
-// Rows are 16-byte aligned in global memory: the incoming row starts at pos & ~1, and kDelta = 1 when m is
-// even (the outgoing row is then aligned one sample later, so its columns lag the incoming ones by one).
-template <int STAGES, int kDelta>
-__global__ void __launch_bounds__(32) cnsm_walk_kernel(WalkParams P) {
-  extern __shared__ __align__(16) unsigned char walk_smem_raw[];
-  double* tiles = reinterpret_cast<double*>(walk_smem_raw);   // [STAGES][2][32][pitch]
-  double* f_ex = tiles + walk_tile_doubles(STAGES);           // [32][kFifoPitch]
-  double* f_ex2 = f_ex + 32 * kFifoPitch;
-  int32_t* f_off = reinterpret_cast<int32_t*>(f_ex2 + 32 * kFifoPitch);
+// ---- named barriers (producer/consumer hand-off inside a CTA) --------------------------------------
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-  const int lane = threadIdx.x;
+// ---- mbarriers (tile ring hand-off between the loader warp and the chain warp) ----------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// the executing thread's arrival is triggered when all its prior cp.async copies have landed
+__device__ __forceinline__ void mbar_arrive_on_cp_async(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+constexpr int kStageBlocks = 4;   // ring of staged (ex, ex2) blocks between the chain warp and the gate warps
+constexpr int kBlockCols = 16;    // window positions per staged block
+constexpr int kStagePitch = kBlockCols + 1;  // double2 per lane row: conflict-free lane-private 16-byte accesses
+constexpr int kWalkThreads = 128; // warp 0: chain walker; warps 1-2: gate / compaction; warp 3: tile loader
+constexpr size_t walk_smem_bytes(int stages) {
+  return sizeof(double) * (size_t)walk_tile_doubles(stages) + sizeof(double2) * kStageBlocks * 32 * kStagePitch +
+         sizeof(unsigned long long) * 2 * stages + 16;
+}
+
+// One CTA = 32 chains = one work-list region, four specialised warps:
+//   warp 3 (loader)        fills the tile ring: STAGES x (incoming, outgoing) tiles, row = 32 consecutive samples of
+//     one chain, by 16-byte cp.async copies (half a warp per row: every copy instruction moves two full 256-byte
+//     rows) with L2 eviction hints (incoming rows evict_last — they are re-read m-1 steps later as outgoing rows,
+//     which are read evict_first), and lets an mbarrier per stage track their completion.
+//   warp 0 (chain walker)  keeps only the two dependent FP64 recurrences (ex, ex2) in its instruction stream: per
+//     window position 1 LDS.128 per stream per sample pair (register double-buffered), 4 DADD, 2 DMUL and one
+//     STS.128 of the post-add (ex, ex2) into a staging block.  Its pace is the 2 x 8-cycle dependent-DADD latency.
+//   warps 1-2 (gates)      take alternate staged blocks: conservative alpha/beta pre-gate on integer keys of the high
+//     words, then a warp-cooperative, coalesced append of the passing (offset, ex, ex2) to the region's slice of the
+//     work list.  Hand-off is by named barriers (bar.arrive / bar.sync), 4 blocks deep.
+// Rows are 16-byte aligned in global memory: the incoming row starts at pos & ~1; kDelta = 1 when m is even (the
+// outgoing row is then aligned one sample later, so its columns lag the incoming ones by one).
+template <int STAGES, int kDelta>
+__global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
+  extern __shared__ __align__(16) unsigned char walk_smem_raw[];
+  double* tiles = reinterpret_cast<double*>(walk_smem_raw);                      // [STAGES][2][32][pitch]
+  double2* stage_ring = reinterpret_cast<double2*>(tiles + walk_tile_doubles(STAGES));  // [blocks][32][kStagePitch]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(stage_ring + kStageBlocks * 32 * kStagePitch);
+  int* s_rcount = reinterpret_cast<int*>(bars + 2 * STAGES);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int region = blockIdx.x;
   const int c = region * 32 + lane;
   int pos = 0, len = 0;
@@ -123,148 +165,233 @@ __global__ void __launch_bounds__(32) cnsm_walk_kernel(WalkParams P) {
   }
   const int m = P.m;
   const int sha = pos & 1;                 // column of sample 0 in the incoming tiles
-  const int ab = pos - sha;                // 16-byte aligned base of the incoming rows
-  const int ob = pos - (m - 1) - sha + kDelta;  // aligned base of the outgoing rows (parity of m-1 fixed by kDelta)
   const int ntl = (len > 0) ? (len + sha + kWalkTile - 1) / kWalkTile : 0;
   const int ntiles = warp_max_i32(ntl);
-  if (ntiles == 0) {
-    if (lane == 0) P.region_count[region] = 0;
-    return;
-  }
-  const double* __restrict__ T = P.T;
-  const int idx_lo = -kFrontPad, idx_hi = P.idx_hi;  // even bounds of the padded allocation
-
-  // copy i of a tile: lanes 0-15 fill row 2i, lanes 16-31 row 2i+1, 16 bytes each
-  int a_idx[16], o_idx[16];
-  {
-    const int half = lane >> 4, piece = (lane & 15) * 2;
+  const int k_w = (m - 1) / kWalkTile;     // first tile that can contain the end of a complete window
+  const int n_blocks = ntiles > k_w ? 2 * (ntiles - k_w) : 0;
+  const uint32_t bar_ready = smem_u32(bars), bar_free = bar_ready + 8 * STAGES;
+  if (threadIdx.x == 0) {
+    *s_rcount = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-      a_idx[i] = __shfl_sync(kFullMask, ab, 2 * i + half) + piece;
-      o_idx[i] = __shfl_sync(kFullMask, ob, 2 * i + half) + piece;
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(bar_ready + 8 * s, 32);
+      mbar_init(bar_free + 8 * s, 32);
     }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const bool hints = P.l2_hints != 0;
-  const int pf_tiles = P.prefetch_tiles;
-  const unsigned long long pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
-  const uint32_t dst0 = smem_u32(tiles) + (uint32_t)(((lane >> 4) * kWalkPitch + (lane & 15) * 2) * 8);
-  constexpr uint32_t kStageBytes = 2 * 32 * kWalkPitch * 8, kStreamBytes = 32 * kWalkPitch * 8;
-  constexpr uint32_t kPairBytes = 2 * kWalkPitch * 8;
+  __syncthreads();
 
-  auto issue = [&](int k) {
-    const uint32_t dst = dst0 + (uint32_t)(k % STAGES) * kStageBytes;
-    const int koff = k * kWalkTile;
+  if (warp == 3) {
+    // ------------------------------------------------------------------ tile loader
+    const int ab = pos - sha;                     // 16-byte aligned base of the incoming rows
+    const int ob = pos - (m - 1) - sha + kDelta;  // aligned base of the outgoing rows
+    const double* __restrict__ T = P.T;
+    const int idx_lo = -kFrontPad, idx_hi = P.idx_hi;
+    // copy i of a tile: lanes 0-15 fill row 2i, lanes 16-31 row 2i+1, 16 bytes each
+    int a_idx[16], o_idx[16];
+    {
+      const int half = lane >> 4, piece = (lane & 15) * 2;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-      const int ia = max(min(a_idx[i] + koff, idx_hi), idx_lo);
-      const int io = max(min(o_idx[i] + koff, idx_hi), idx_lo);
-      if (hints) {
+      for (int i = 0; i < 16; i++) {
+        a_idx[i] = __shfl_sync(kFullMask, ab, 2 * i + half) + piece;
+        o_idx[i] = __shfl_sync(kFullMask, ob, 2 * i + half) + piece;
+      }
+    }
+    const unsigned long long pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+    const uint32_t dst0 = smem_u32(tiles) + (uint32_t)(((lane >> 4) * kWalkPitch + (lane & 15) * 2) * 8);
+    constexpr uint32_t kStageBytes = 2 * 32 * kWalkPitch * 8, kStreamBytes = 32 * kWalkPitch * 8;
+    constexpr uint32_t kPairBytes = 2 * kWalkPitch * 8;
+    for (int k = 0; k < ntiles; k++) {
+      const int stage = k % STAGES;
+      if (k >= STAGES) mbar_wait(bar_free + 8 * stage, (uint32_t)(((k / STAGES) - 1) & 1));  // chain warp left tile k-STAGES
+      const uint32_t dst = dst0 + (uint32_t)stage * kStageBytes;
+      const int koff = k * kWalkTile;
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int ia = max(min(a_idx[i] + koff, idx_hi), idx_lo);
+        const int io = max(min(o_idx[i] + koff, idx_hi), idx_lo);
         cp_async16_hint(dst + i * kPairBytes, T + ia, pol_keep);
         cp_async16_hint(dst + kStreamBytes + i * kPairBytes, T + io, pol_drop);
-      } else {
-        cp_async16(dst + i * kPairBytes, T + ia);
-        cp_async16(dst + kStreamBytes + i * kPairBytes, T + io);
+      }
+      mbar_arrive_on_cp_async(bar_ready + 8 * stage);
+      // pull this lane's own incoming row kPrefetchTiles tiles ahead into L2 (two 128-byte lines): the copies
+      // above then find their data in L2 and the 4-stage ring covers L2 latency instead of DRAM latency
+      if (k + kPrefetchTiles < ntl) {
+        const double* pf = T + min(ab + (k + kPrefetchTiles) * kWalkTile, idx_hi);
+        l2_prefetch_line(pf);
+        l2_prefetch_line(pf + 16);
       }
     }
-    if (pf_tiles > 0) {
-      const int pf = min(ab + (k + pf_tiles) * kWalkTile, idx_hi);
-      l2_prefetch_line(T + pf);
-      l2_prefetch_line(T + pf + 16);
-    }
-  };
-
-  const long long base = P.region_base[region];
-  int rcount = 0, cnt = 0;
-  double ex = 0.0, ex2 = 0.0, carry = 0.0;
-  const int mean_klo = P.mean_klo, var_klo = P.var_klo;
-  const unsigned mean_kspan = P.mean_kspan, var_kspan = P.var_kspan;
-  const double dm = P.dm;
-  const int32_t off0 = P.first_global + pos - (m - 1);  // window start (1-based, global) of the window ending at sample 0
-
-  // Warp-cooperative flush: entry e of the staged block goes to lane e%32, so the global stores are
-  // coalesced and each chain's entries stay contiguous (the evaluator's lanes then read neighbouring windows).
-  auto flush = [&]() {
-    __syncwarp();
-    const int incl = warp_incl_scan_i32(cnt, lane);
-    const int total = __shfl_sync(kFullMask, incl, 31);
-    const int excl = incl - cnt;
-    for (int e0 = 0; e0 < total; e0 += 32) {
-      const int e = e0 + lane;
-      int owner = 0;
+  } else if (warp == 0) {
+    // ------------------------------------------------------------------ chain walker (producer)
+    // Software pipeline over 16-column blocks: while block j's dependent FP64 chain runs out of one register
+    // set, block j+1's 16 LDS.128 are already in flight into the other (ping-pong, no copies), across tile
+    // borders too (the next tile's mbarrier is polled one block early).
+    double ex = 0.0, ex2 = 0.0, carry = 0.0;
+    double2 A0[8], O0[8], A1[8], O1[8];
+    auto load16 = [&](double2(&Av)[8], double2(&Ov)[8], const double* ra, const double* ro) {
 #pragma unroll
-      for (int step = 16; step > 0; step >>= 1) {
-        const int t = __shfl_sync(kFullMask, excl, owner + step);
-        if (t <= e) owner += step;
+      for (int i = 0; i < 8; i++) {
+        Av[i] = *reinterpret_cast<const double2*>(ra + 2 * i);
+        Ov[i] = *reinterpret_cast<const double2*>(ro + 2 * i);
       }
-      const int j = e - __shfl_sync(kFullMask, excl, owner);
-      if (e < total) {
-        const long long g = base + rcount + e;
-        P.e_off[g] = f_off[owner * kFifoPitch + j];
-        P.e_ex[g] = f_ex[owner * kFifoPitch + j];
-        P.e_ex2[g] = f_ex2[owner * kFifoPitch + j];
-      }
-    }
-    rcount += total;
-    cnt = 0;
-    __syncwarp();
-  };
-
-  double* const my_ex = f_ex + lane * kFifoPitch;
-  double* const my_ex2 = f_ex2 + lane * kFifoPitch;
-  int32_t* const my_off = f_off + lane * kFifoPitch;
-  auto step = [&](int s, double a, double o) {
-    const bool act = (unsigned)s < (unsigned)len;
-    const bool win = act & (s >= m - 1);
-    a = act ? a : 0.0;
-    o = win ? o : 0.0;
-    ex = xadd(ex, a);                 // K/NormQueryEngine.java:498
-    ex2 = xadd(ex2, xmul(a, a));      // :499
-    const double v = __fma_rn(ex2, dm, -(ex * ex));
-    const bool pass = win & ((unsigned)(hi_key(ex) - mean_klo) <= mean_kspan) &
-                      ((unsigned)(hi_key(v) - var_klo) <= var_kspan);
-    if (pass) {
-      my_ex[cnt] = ex;
-      my_ex2[cnt] = ex2;
-      my_off[cnt] = off0 + s;
-      cnt++;
-    }
-    ex = xsub(ex, o);                 // :523
-    ex2 = xsub(ex2, xmul(o, o));      // :524
-  };
-
+    };
+    // 16 window positions from (Av, Ov).  kStore: stage the post-add (ex, ex2) of every position (the store of a
+    // pair is placed after the next pair's arithmetic so it never sits in front of the dependent chain);
+    // kSteady: every lane's columns are inside its chain and past the warm-up -> no per-column selects.
+    auto walk16 = [&](const double2(&Av)[8], const double2(&Ov)[8], double2(&An)[8], double2(&On)[8],
+                      const double* na, const double* no, int s0, double2* st, auto store_tag, auto steady_tag) {
+      constexpr bool kStore = decltype(store_tag)::value, kSteady = decltype(steady_tag)::value;
+      double2 p0 = make_double2(0.0, 0.0), p1 = p0;
 #pragma unroll
-  for (int k = 0; k < STAGES - 1; k++) {
-    if (k < ntiles) issue(k);
-    cp_async_commit();
-  }
-  for (int k = 0; k < ntiles; k++) {
-    if (k + STAGES - 1 < ntiles) issue(k + STAGES - 1);  // refills the stage that tile k-1 used
-    cp_async_commit();
-    cp_async_wait<STAGES - 1>();  // tile k has landed (groups complete in order)
-    __syncwarp();
-    const int stage = k % STAGES;
-    const double* ra = tiles + (size_t)stage * (2 * 32 * kWalkPitch) + lane * kWalkPitch;
-    const double* ro = ra + 32 * kWalkPitch;
-    const int sbase = k * kWalkTile - sha;
-#pragma unroll
-    for (int blk = 0; blk < kWalkTile / 8; blk++) {
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int col = blk * 8 + 2 * i;
-        const double2 A = *reinterpret_cast<const double2*>(ra + col);
-        const double2 O = *reinterpret_cast<const double2*>(ro + col);
-        const double o0 = kDelta ? carry : O.x;
-        const double o1 = kDelta ? O.x : O.y;
+      for (int i = 0; i < 8; i++) {
+        // the next block's sample pair i is fetched here, between the arithmetic of this block's pairs: one
+        // LDS.128 per stream per 2 positions keeps the shared-memory queue shallow and off the FP64 chain
+        if (na != nullptr) {
+          An[i] = *reinterpret_cast<const double2*>(na + 2 * i);
+          On[i] = *reinterpret_cast<const double2*>(no + 2 * i);
+        }
+        const double2 A = Av[i], O = Ov[i];
+        double a0 = A.x, a1 = A.y;
+        double o0 = kDelta ? carry : O.x, o1 = kDelta ? O.x : O.y;
         carry = O.y;
-        step(sbase + col, A.x, o0);
-        step(sbase + col + 1, A.y, o1);
+        if (!kSteady) {
+          const int s = s0 + 2 * i;
+          const bool act0 = (unsigned)s < (unsigned)len, act1 = (unsigned)(s + 1) < (unsigned)len;
+          a0 = act0 ? a0 : 0.0;
+          a1 = act1 ? a1 : 0.0;
+          o0 = (act0 & (s >= m - 1)) ? o0 : 0.0;
+          o1 = (act1 & (s + 1 >= m - 1)) ? o1 : 0.0;
+        }
+        ex = xadd(ex, a0);                  // K/NormQueryEngine.java:498
+        ex2 = xadd(ex2, xmul(a0, a0));      // :499
+        const double2 q0 = make_double2(ex, ex2);
+        ex = xsub(ex, o0);                  // :523
+        ex2 = xsub(ex2, xmul(o0, o0));      // :524
+        ex = xadd(ex, a1);
+        ex2 = xadd(ex2, xmul(a1, a1));
+        const double2 q1 = make_double2(ex, ex2);
+        ex = xsub(ex, o1);
+        ex2 = xsub(ex2, xmul(o1, o1));
+        if (kStore && i > 0) {
+          st[2 * i - 2] = p0;
+          st[2 * i - 1] = p1;
+        }
+        p0 = q0;
+        p1 = q1;
       }
-      if (__any_sync(kFullMask, cnt > kFifoDepth - 8)) flush();
+      if (kStore) {
+        st[14] = p0;
+        st[15] = p1;
+      }
+    };
+    using T_ = std::true_type;
+    using F_ = std::false_type;
+    auto tile_rows = [&](int k, const double*& ra, const double*& ro) {
+      ra = tiles + (size_t)(k % STAGES) * (2 * 32 * kWalkPitch) + lane * kWalkPitch;
+      ro = ra + 32 * kWalkPitch;
+    };
+    int b = 0;
+    // one block: compute from (Av, Ov) while (An, On) is loaded for the block after it
+    auto block = [&](const double2(&Av)[8], const double2(&Ov)[8], double2(&An)[8], double2(&On)[8], int k, int h,
+                     bool steady) {
+      const double* na = nullptr;
+      const double* no = nullptr;
+      if (h == 0) {
+        tile_rows(k, na, no);
+        na += 16;
+        no += 16;
+      } else if (k + 1 < ntiles) {
+        mbar_wait(bar_ready + 8 * ((k + 1) % STAGES), (uint32_t)(((k + 1) / STAGES) & 1));  // tile k+1 has landed
+        tile_rows(k + 1, na, no);
+      }
+      const int s0 = k * kWalkTile - sha + 16 * h;
+      if (k < k_w) {  // warm-up: no complete window ends in this tile
+        walk16(Av, Ov, An, On, na, no, s0, nullptr, F_{}, F_{});
+      } else {
+        const int slot = b % kStageBlocks;
+        if (b >= kStageBlocks) bar_sync(1 + kStageBlocks + slot, 64);  // gate warp has drained this slot
+        double2* st = stage_ring + ((size_t)slot * 32 + lane) * kStagePitch;
+        if (steady) walk16(Av, Ov, An, On, na, no, s0, st, T_{}, T_{});
+        else walk16(Av, Ov, An, On, na, no, s0, st, T_{}, F_{});
+        bar_arrive(1 + slot, 64);  // block is staged
+        b++;
+      }
+    };
+    if (ntiles > 0) {
+      mbar_wait(bar_ready, 0);
+      const double* ra;
+      const double* ro;
+      tile_rows(0, ra, ro);
+      load16(A0, O0, ra, ro);
     }
-    __syncwarp();
+    for (int k = 0; k < ntiles; k++) {
+      const int sbase = k * kWalkTile - sha;
+      const bool steady = __all_sync(kFullMask, (sbase >= m - 1) && (sbase + kWalkTile <= len));
+      block(A0, O0, A1, O1, k, 0, steady);
+      block(A1, O1, A0, O0, k, 1, steady);
+      mbar_arrive(bar_free + 8 * (k % STAGES));  // every read of tile k has completed (its values were consumed)
+    }
+  } else {
+    // ------------------------------------------------------------------ gate warps (consumers)
+    const int g = warp - 1;
+    const long long base = P.region_base[region];
+    const int mean_klo = P.mean_klo, var_klo = P.var_klo;
+    const unsigned mean_kspan = P.mean_kspan, var_kspan = P.var_kspan;
+    const double dm = P.dm;
+    const int32_t off0 = P.first_global + pos - (m - 1) - sha;  // + tile column = 1-based global window start
+    for (int b = g; b < n_blocks; b += 2) {
+      const int slot = b % kStageBlocks;
+      const int col0 = (k_w + (b >> 1)) * kWalkTile + (b & 1) * kBlockCols;  // tile column of the block's first entry
+      bar_sync(1 + slot, 64);  // wait for the chain warp to stage this block
+      const double2* st = stage_ring + ((size_t)slot * 32 + lane) * kStagePitch;
+      unsigned mask = 0;
+#pragma unroll
+      for (int cc = 0; cc < kBlockCols; cc++) {
+        const double2 v2 = st[cc];
+        const int s = col0 + cc - sha;
+        const bool win = ((unsigned)s < (unsigned)len) & (s >= m - 1);
+        const double v = __fma_rn(v2.y, dm, -(v2.x * v2.x));
+        const bool pass = win & ((unsigned)(hi_key(v2.x) - mean_klo) <= mean_kspan) &
+                          ((unsigned)(hi_key(v) - var_klo) <= var_kspan);
+        mask |= pass ? (1u << cc) : 0u;
+      }
+      // warp-cooperative append: entry e of the block goes to lane e%32 -> coalesced stores, and every
+      // chain's entries stay contiguous (the evaluator's lanes then read neighbouring windows)
+      const int cnt = __popc(mask);
+      const int incl = warp_incl_scan_i32(cnt, lane);
+      const int total = __shfl_sync(kFullMask, incl, 31);
+      if (total > 0) {
+        const int excl = incl - cnt;
+        int rbase = 0;
+        if (lane == 0) rbase = atomicAdd(s_rcount, total);
+        rbase = __shfl_sync(kFullMask, rbase, 0);
+        for (int e0 = 0; e0 < total; e0 += 32) {
+          const int e = e0 + lane;
+          int owner = 0;
+#pragma unroll
+          for (int step = 16; step > 0; step >>= 1) {
+            const int t = __shfl_sync(kFullMask, excl, owner + step);
+            if (t <= e) owner += step;
+          }
+          const int j = e - __shfl_sync(kFullMask, excl, owner);
+          const unsigned omask = __shfl_sync(kFullMask, mask, owner);
+          const int32_t ooff = __shfl_sync(kFullMask, off0, owner);
+          if (e < total) {
+            const int cc = (int)__fns(omask, 0, j + 1);
+            const double2 v2 = stage_ring[((size_t)slot * 32 + owner) * kStagePitch + cc];
+            const long long gidx = base + rbase + e;
+            P.e_off[gidx] = ooff + col0 + cc;
+            P.e_ex[gidx] = v2.x;
+            P.e_ex2[gidx] = v2.y;
+          }
+        }
+      }
+      bar_arrive(1 + kStageBlocks + slot, 64);  // slot may be overwritten
+    }
   }
-  flush();
-  if (lane == 0) P.region_count[region] = rcount;
+  __syncthreads();
+  if (threadIdx.x == 0) P.region_count[region] = *s_rcount;
 }
 
 // Single-CTA exclusive scan over regions: tile_prefix[r] = sum_{r'<r} ceil(count[r']/kEvalTile).

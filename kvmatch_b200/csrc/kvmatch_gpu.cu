@@ -100,6 +100,7 @@ struct kvm_ctx {
   int n_sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evs[2] = {nullptr, nullptr};  // stage boundaries inside a call
   std::string err;
 
   DevBuf series_buf;  // [kFrontPad zeros | samples | kTailPad zeros]
@@ -356,8 +357,6 @@ int launch_walker(kvm_ctx* ctx, const Plan& P, int K, int m, double alpha, doubl
   W.first_global = (int32_t)ctx->first;
   W.dm = (double)m;
   W.idx_hi = (int)((ctx->count + kTailPad - 2) & ~int64_t(1));
-  W.prefetch_tiles = env_int("KVM_WALK_PREFETCH", 0);
-  W.l2_hints = env_int("KVM_WALK_HINTS", 1);
   // Conservative pre-gate: a superset of the exact gate (rounding of the chain sums' products is far below
   // these slacks, and the integer keys widen each bound by one high-word unit); the exact gate is
   // re-evaluated with the reference's arithmetic by the evaluators.
@@ -385,21 +384,30 @@ int launch_walker(kvm_ctx* ctx, const Plan& P, int K, int m, double alpha, doubl
   W.e_ex = ctx->wl_ex.as<double>();
   W.e_ex2 = ctx->wl_ex2.as<double>();
   W.region_count = ctx->region_count.as<int32_t>();
-  // Deeper tile rings while every walker warp can be resident at once; fewer stages = more warps per SM.
-  int stages = S.n_regions <= ctx->n_sms * 2 ? 4 : (S.n_regions <= ctx->n_sms * 3 ? 3 : 2);
-  stages = env_int("KVM_WALK_STAGES", stages);
-  const bool even_m = (m % 2) == 0;
-#define KVM_WALK(ST, DL) cnsm_walk_kernel<ST, DL><<<S.n_regions, 32, walk_smem_bytes(ST), ctx->stream>>>(W)
-  if (stages == 4) { if (even_m) KVM_WALK(4, 1); else KVM_WALK(4, 0); }
-  else if (stages == 3) { if (even_m) KVM_WALK(3, 1); else KVM_WALK(3, 0); }
-  else { if (even_m) KVM_WALK(2, 1); else KVM_WALK(2, 0); }
-#undef KVM_WALK
+  // 4-stage tile ring: 104 KB of shared memory per CTA, 2 CTAs (= 64 chains) per SM.  More resident chains
+  // would not help: ~6.5k chains x (m-1) x 8 B of lag windows is what stays L2-resident.
+  // (A 2-stage instantiation is deliberately not built: ptxas 12.9 emits its hinted LDGSTS with an
+  // uninitialised uniform descriptor register -> "illegal instruction"; the Makefile greps for that pattern.)
+  if ((m % 2) == 0) cnsm_walk_kernel<4, 1><<<S.n_regions, kWalkThreads, walk_smem_bytes(4), ctx->stream>>>(W);
+  else cnsm_walk_kernel<4, 0><<<S.n_regions, kWalkThreads, walk_smem_bytes(4), ctx->stream>>>(W);
+  KVM_CUDA(ctx, cudaEventRecord(ctx->evs[0], ctx->stream));
   cnsm_plan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->region_count.as<int32_t>(), S.n_regions,
                                                 ctx->tile_prefix.as<int32_t>(),
                                                 ctx->counters.as<unsigned long long>() + kCntTiles);
   *launches += 2;
   KVM_CUDA(ctx, cudaGetLastError());
   return KVM_OK;
+}
+
+// ev0 -> evs[0] -> evs[1] -> ev1
+void add_stage_ms(kvm_ctx* ctx, kvm_result* out) {
+  float a = 0.f, b = 0.f, c = 0.f;
+  cudaEventElapsedTime(&a, ctx->ev0, ctx->evs[0]);
+  cudaEventElapsedTime(&b, ctx->evs[0], ctx->evs[1]);
+  cudaEventElapsedTime(&c, ctx->evs[1], ctx->ev1);
+  out->stage_ms[0] += a;
+  out->stage_ms[1] += b;
+  out->stage_ms[2] += c;
 }
 
 double elapsed_ms(kvm_ctx* ctx) {
@@ -511,6 +519,7 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
     const int eval_grid = ctx->n_sms * 16;
     if (mode == Mode::kEd) {
       cnsm_ed_eval_kernel<<<eval_grid, kEvalTile, 0, ctx->stream>>>(E);
+      KVM_CUDA(ctx, cudaEventRecord(ctx->evs[1], ctx->stream));
       ExactEdParams X;
       X.T = E.T;
       X.first_global = E.first_global;
@@ -528,6 +537,7 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
       L.Q = LbQuery{E.zq, reinterpret_cast<const double*>(base + o_uq), reinterpret_cast<const double*>(base + o_lq),
                     m, E.eps2_hi};
       cnsm_dtw_lb_kernel<<<eval_grid, kEvalTile, 0, ctx->stream>>>(L);
+      KVM_CUDA(ctx, cudaEventRecord(ctx->evs[1], ctx->stream));
       launches += 1;
       DtwParams D;
       D.T = E.T;
@@ -545,6 +555,7 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
     KVM_CUDA(ctx, cudaGetLastError());
     if ((rc = read_counters(ctx, cnt))) return rc;
     total_ms += elapsed_ms(ctx);
+    add_stage_ms(ctx, out);
     out->n_launches += launches;
     const bool cand_over = (long long)cnt[kCntCand] > ctx->cand_cap, ans_over = (long long)cnt[kCntAnswers] > ctx->ans_cap;
     if (!cand_over && !ans_over) break;
@@ -614,18 +625,15 @@ int kvm_create(kvm_ctx** out, int device_id) {
   ctx->device = device_id;
   ctx->n_sms = prop.multiProcessorCount;
   if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreate(&ctx->evs[0]) != cudaSuccess || cudaEventCreate(&ctx->evs[1]) != cudaSuccess) {
     const char* msg = cudaGetErrorString(cudaGetLastError());
     delete ctx;
     return fail(nullptr, KVM_E_CUDA, "stream/event creation failed: %s", msg);
   }
   const int mean_smem = (int)(sizeof(double) * kMeanSmemDoublesPerWarp * kMeanWarps);
-  const int w2 = (int)walk_smem_bytes(2), w3 = (int)walk_smem_bytes(3), w4 = (int)walk_smem_bytes(4);
-  if (cudaFuncSetAttribute(cnsm_walk_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, w2) != cudaSuccess ||
-      cudaFuncSetAttribute(cnsm_walk_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w2) != cudaSuccess ||
-      cudaFuncSetAttribute(cnsm_walk_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, w3) != cudaSuccess ||
-      cudaFuncSetAttribute(cnsm_walk_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w3) != cudaSuccess ||
-      cudaFuncSetAttribute(cnsm_walk_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4) != cudaSuccess ||
+  const int w4 = (int)walk_smem_bytes(4);
+  if (cudaFuncSetAttribute(cnsm_walk_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4) != cudaSuccess ||
       cudaFuncSetAttribute(cnsm_walk_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4) != cudaSuccess ||
       cudaFuncSetAttribute(cnsm_ed_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kExactChunk * 4)) != cudaSuccess ||
       cudaFuncSetAttribute(mean_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem) != cudaSuccess) {
@@ -651,6 +659,8 @@ void kvm_destroy(kvm_ctx* ctx) {
   for (PinBuf* b : pin) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (cudaEvent_t e : ctx->evs)
+    if (e) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -765,6 +775,7 @@ int kvm_verify_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, cons
     KVM_CUDA(ctx, cudaGetLastError());
     if ((rc = read_counters(ctx, cnt))) return rc;
     out->kernel_ms += elapsed_ms(ctx);
+    out->stage_ms[0] += elapsed_ms(ctx);
     out->n_launches += 1;
     if ((long long)cnt[kCntAnswers] <= ctx->ans_cap) break;
     if (attempt == 7) return fail(ctx, KVM_E_OOM, "answer buffer kept overflowing");
@@ -836,11 +847,14 @@ int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int
     D.sink = sink_of(ctx);
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     dtw_lb_raw_kernel<<<(unsigned)n_tiles, kEdTile, 0, ctx->stream>>>(L);
+    KVM_CUDA(ctx, cudaEventRecord(ctx->evs[0], ctx->stream));
+    KVM_CUDA(ctx, cudaEventRecord(ctx->evs[1], ctx->stream));
     if ((rc = launch_dtw(ctx, D))) return rc;
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     KVM_CUDA(ctx, cudaGetLastError());
     if ((rc = read_counters(ctx, cnt))) return rc;
     out->kernel_ms += elapsed_ms(ctx);
+    add_stage_ms(ctx, out);
     out->n_launches += 2;
     const bool cand_over = (long long)cnt[kCntCand] > ctx->cand_cap, ans_over = (long long)cnt[kCntAnswers] > ctx->ans_cap;
     if (!cand_over && !ans_over) break;

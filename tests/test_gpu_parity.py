@@ -114,6 +114,38 @@ def test_cnsm_ed_pruned_intervals_with_shift(gpu, oracle, series_1m):
     assert got.n_gate_pass == exp.n_gate_pass and off in got.offsets.tolist()
 
 
+@pytest.mark.parametrize("m", [25, 127, 1023, 1025])
+def test_cnsm_ed_odd_lengths_and_ragged_chains(gpu, oracle, series_1m, m):
+    """Odd m (outgoing rows aligned with the incoming ones), chains of very different lengths in one warp,
+    chains shorter than m (no window), chains starting at odd/even offsets and ending at n."""
+    s = series_1m
+    rng = np.random.default_rng(m)
+    gpu.load(s)
+    off = 500_001
+    q = s[off - 1:off - 1 + m].copy()
+    iv = [(1, 3), (10, 10 + 5 * m), (40_000, 40_001), (100_001, 190_000), (300_000, 300_000 + m // 2),
+          (499_990, 500_020), (700_003, 700_004 + 37), (len(s) - m - 5000, len(s))]
+    iv += [(int(a), int(a) + int(rng.integers(0, 2000))) for a in np.arange(800_000, 900_000, 3001)]
+    iv.sort()
+    got = gpu.verify_cnsm_ed(q, 6.0, 2.0, 50.0, iv)
+    exp = oracle.verify_cnsm_ed(s, q, 6.0, 2.0, 50.0, iv)
+    assert_same(got, exp)
+    assert got.n_gate_pass == exp.n_gate_pass and off in got.offsets.tolist()
+
+
+def test_cnsm_ed_many_regions(gpu, oracle, series_1m):
+    """More walker CTAs than can be resident at once (> 2 per SM)."""
+    s = series_1m
+    m = 64
+    gpu.load(s)
+    q = s[250_000:250_000 + m].copy()
+    iv = datagen.chain_intervals(len(s), m, 60)  # 16666 chains -> 521 regions
+    got = gpu.verify_cnsm_ed(q, 2.0, 1.5, 5.0, iv)
+    exp = oracle.verify_cnsm_ed(s, q, 2.0, 1.5, 5.0, iv)
+    assert_same(got, exp)
+    assert got.n_gate_pass == exp.n_gate_pass
+
+
 def test_cnsm_ed_degenerate_query_and_constant_data(gpu, oracle):
     s = np.concatenate([np.full(3000, 2.5), datagen.generate(5000, seed=8)])
     gpu.load(s)
