@@ -34,6 +34,7 @@ constexpr int kFifoPitch = kFifoDepth + 1;
 constexpr int kFrontPad = 64;      // zero samples the ctx keeps in front of / behind the series so that
 constexpr int kTailPad = 192;      // whole-row bulk copies never leave the allocation
 constexpr int kPrefetchTiles = 12; // L2 prefetch distance of the incoming stream, in tiles
+constexpr int kFastTerms = 32;     // terms of the evaluator's fast screen
 constexpr int kEvalTile = 128;     // work-list entries per evaluator tile (= evaluator CTA size)
 
 constexpr int walk_tile_doubles(int stages) { return stages * 2 * 32 * kWalkPitch; }
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
 #pragma unroll
     for (int s = 0; s < STAGES; s++) {
       mbar_init(bar_ready + 8 * s, 32);
-      mbar_init(bar_free + 8 * s, 32);
+      mbar_init(bar_free + 8 * s, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -239,10 +240,42 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
     // 16 window positions from (Av, Ov).  kStore: stage the post-add (ex, ex2) of every position (the store of a
     // pair is placed after the next pair's arithmetic so it never sits in front of the dependent chain);
     // kSteady: every lane's columns are inside its chain and past the warm-up -> no per-column selects.
+    // arrive_id >= 0: signal the previous staged block; sync_id >= 0: wait until this block's slot is drained.
+    // Both happen after the first pair's arithmetic: by then the previous block's last stores were issued two
+    // pair-times ago, so the barrier instructions find no pending shared-memory stores to drain.
     auto walk16 = [&](const double2(&Av)[8], const double2(&Ov)[8], double2(&An)[8], double2(&On)[8],
-                      const double* na, const double* no, int s0, double2* st, auto store_tag, auto steady_tag) {
+                      const double* na, const double* no, int s0, double2* st, int arrive_id, int sync_id,
+                      auto store_tag, auto steady_tag) {
       constexpr bool kStore = decltype(store_tag)::value, kSteady = decltype(steady_tag)::value;
       double2 p0 = make_double2(0.0, 0.0), p1 = p0;
+      // operands of one sample pair: the two incoming / outgoing samples (already zeroed where a column lies
+      // outside the chain or before its first complete window) and their squares
+      struct Pair { double a0, a1, o0, o1, a0s, a1s, o0s, o1s; };
+      auto prep = [&](int i, double& cr) {
+        const double2 A = Av[i], O = Ov[i];
+        Pair q;
+        q.a0 = A.x;
+        q.a1 = A.y;
+        q.o0 = kDelta ? cr : O.x;
+        q.o1 = kDelta ? O.x : O.y;
+        cr = O.y;
+        if (!kSteady) {
+          const int s = s0 + 2 * i;
+          const bool act0 = (unsigned)s < (unsigned)len, act1 = (unsigned)(s + 1) < (unsigned)len;
+          q.a0 = act0 ? q.a0 : 0.0;
+          q.a1 = act1 ? q.a1 : 0.0;
+          q.o0 = (act0 & (s >= m - 1)) ? q.o0 : 0.0;
+          q.o1 = (act1 & (s + 1 >= m - 1)) ? q.o1 : 0.0;
+        }
+        q.a0s = xmul(q.a0, q.a0);
+        q.a1s = xmul(q.a1, q.a1);
+        q.o0s = xmul(q.o0, q.o0);
+        q.o1s = xmul(q.o1, q.o1);
+        return q;
+      };
+      // The squares of pair i+1 are formed while pair i's dependent add/sub chain runs: issued just-in-time
+      // (ptxas's choice otherwise) each DMUL's 8-cycle latency would sit on the chain and double its length.
+      Pair cur = prep(0, carry);
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         // the next block's sample pair i is fetched here, between the arithmetic of this block's pairs: one
@@ -251,34 +284,29 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
           An[i] = *reinterpret_cast<const double2*>(na + 2 * i);
           On[i] = *reinterpret_cast<const double2*>(no + 2 * i);
         }
-        const double2 A = Av[i], O = Ov[i];
-        double a0 = A.x, a1 = A.y;
-        double o0 = kDelta ? carry : O.x, o1 = kDelta ? O.x : O.y;
-        carry = O.y;
-        if (!kSteady) {
-          const int s = s0 + 2 * i;
-          const bool act0 = (unsigned)s < (unsigned)len, act1 = (unsigned)(s + 1) < (unsigned)len;
-          a0 = act0 ? a0 : 0.0;
-          a1 = act1 ? a1 : 0.0;
-          o0 = (act0 & (s >= m - 1)) ? o0 : 0.0;
-          o1 = (act1 & (s + 1 >= m - 1)) ? o1 : 0.0;
-        }
-        ex = xadd(ex, a0);                  // K/NormQueryEngine.java:498
-        ex2 = xadd(ex2, xmul(a0, a0));      // :499
+        Pair nxt = cur;
+        if (i < 7) nxt = prep(i + 1, carry);
+        ex = xadd(ex, cur.a0);              // K/NormQueryEngine.java:498
+        ex2 = xadd(ex2, cur.a0s);           // :499
         const double2 q0 = make_double2(ex, ex2);
-        ex = xsub(ex, o0);                  // :523
-        ex2 = xsub(ex2, xmul(o0, o0));      // :524
-        ex = xadd(ex, a1);
-        ex2 = xadd(ex2, xmul(a1, a1));
+        ex = xsub(ex, cur.o0);              // :523
+        ex2 = xsub(ex2, cur.o0s);           // :524
+        ex = xadd(ex, cur.a1);
+        ex2 = xadd(ex2, cur.a1s);
         const double2 q1 = make_double2(ex, ex2);
-        ex = xsub(ex, o1);
-        ex2 = xsub(ex2, xmul(o1, o1));
+        ex = xsub(ex, cur.o1);
+        ex2 = xsub(ex2, cur.o1s);
+        if (i == 1) {
+          if (arrive_id >= 0) bar_arrive(arrive_id, 64);
+          if (sync_id >= 0) bar_sync(sync_id, 64);
+        }
         if (kStore && i > 0) {
           st[2 * i - 2] = p0;
           st[2 * i - 1] = p1;
         }
         p0 = q0;
         p1 = q1;
+        cur = nxt;
       }
       if (kStore) {
         st[14] = p0;
@@ -291,7 +319,7 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
       ra = tiles + (size_t)(k % STAGES) * (2 * 32 * kWalkPitch) + lane * kWalkPitch;
       ro = ra + 32 * kWalkPitch;
     };
-    int b = 0;
+    int b = 0, pending_slot = -1;
     // one block: compute from (Av, Ov) while (An, On) is loaded for the block after it
     auto block = [&](const double2(&Av)[8], const double2(&Ov)[8], double2(&An)[8], double2(&On)[8], int k, int h,
                      bool steady) {
@@ -307,14 +335,15 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
       }
       const int s0 = k * kWalkTile - sha + 16 * h;
       if (k < k_w) {  // warm-up: no complete window ends in this tile
-        walk16(Av, Ov, An, On, na, no, s0, nullptr, F_{}, F_{});
+        walk16(Av, Ov, An, On, na, no, s0, nullptr, -1, -1, F_{}, F_{});
       } else {
         const int slot = b % kStageBlocks;
-        if (b >= kStageBlocks) bar_sync(1 + kStageBlocks + slot, 64);  // gate warp has drained this slot
+        const int arrive_id = pending_slot >= 0 ? 1 + pending_slot : -1;                 // previous block is staged
+        const int sync_id = b >= kStageBlocks ? 1 + kStageBlocks + slot : -1;             // gate warp drained this slot
         double2* st = stage_ring + ((size_t)slot * 32 + lane) * kStagePitch;
-        if (steady) walk16(Av, Ov, An, On, na, no, s0, st, T_{}, T_{});
-        else walk16(Av, Ov, An, On, na, no, s0, st, T_{}, F_{});
-        bar_arrive(1 + slot, 64);  // block is staged
+        if (steady) walk16(Av, Ov, An, On, na, no, s0, st, arrive_id, sync_id, T_{}, T_{});
+        else walk16(Av, Ov, An, On, na, no, s0, st, arrive_id, sync_id, T_{}, F_{});
+        pending_slot = slot;
         b++;
       }
     };
@@ -330,8 +359,10 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
       const bool steady = __all_sync(kFullMask, (sbase >= m - 1) && (sbase + kWalkTile <= len));
       block(A0, O0, A1, O1, k, 0, steady);
       block(A1, O1, A0, O0, k, 1, steady);
-      mbar_arrive(bar_free + 8 * (k % STAGES));  // every read of tile k has completed (its values were consumed)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_free + 8 * (k % STAGES));  // every lane's reads of tile k have completed
     }
+    if (pending_slot >= 0) bar_arrive(1 + pending_slot, 64);  // the last staged block
   } else {
     // ------------------------------------------------------------------ gate warps (consumers)
     const int g = warp - 1;
@@ -497,22 +528,27 @@ __global__ void __launch_bounds__(kEvalTile) cnsm_ed_eval_kernel(EvalParams P) {
     const double rstd = 1.0 / stdv;
     const double nmr = -mean * rstd;
     const double* __restrict__ w = P.T + (off - P.first_global);
+    // Fast screen: the kFastTerms largest-|zQ| terms (a lower bound of the full distance).  Windows still under
+    // eps^2 after them are rare (near matches); they go to the warp-cooperative exact stage instead of having
+    // one thread chase up to m scattered loads on its own.
     double dist = 0.0;
+    const int kmax = min(m, kFastTerms);
     int k = 0;
     bool alive = true;
-    for (; k + 4 <= m && alive; k += 4) {
+    for (; k + 4 <= kmax && alive; k += 4) {
+      double wv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) wv[u] = w[__ldg(P.order + k + u)];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const double x = __fma_rn(w[__ldg(P.order + k + u)], rstd, nmr);
-        const double df = x - __ldg(P.zq + k + u);
+        const double df = __fma_rn(wv[u], rstd, nmr) - __ldg(P.zq + k + u);
         dist = __fma_rn(df, df, dist);
       }
       alive = dist <= P.eps2_hi;
     }
     if (alive) {
-      for (; k < m; k++) {
-        const double x = __fma_rn(w[__ldg(P.order + k)], rstd, nmr);
-        const double df = x - __ldg(P.zq + k);
+      for (; k < kmax; k++) {
+        const double df = __fma_rn(w[__ldg(P.order + k)], rstd, nmr) - __ldg(P.zq + k);
         dist = __fma_rn(df, df, dist);
       }
     }
@@ -535,12 +571,13 @@ struct ExactEdParams {
   int m;
   const double* __restrict__ zq;
   const int32_t* __restrict__ order;
-  double eps2;
+  double eps2, eps2_hi;
   CandList in;
   AnswerSink sink;
+  unsigned long long* n_exact;  // windows that reached the reference-order summation
 };
 
-constexpr int kExactChunk = 4096;  // terms staged in shared memory per pass (32 KB per warp)
+constexpr int kExactChunk = 1024;  // terms staged in shared memory per pass (8 KB per warp)
 
 // K/NormQueryEngine.java:513-520 verbatim arithmetic: x = (T[order[k]+j]-mean)/std; dist += (x-zQ[k])^2.
 // One warp per survivor: all lanes compute the per-term values (divisions in parallel, each term rounded
@@ -558,14 +595,54 @@ __global__ void __launch_bounds__(128) cnsm_ed_exact_kernel(ExactEdParams P) {
     const int32_t off = P.in.off[e];
     const double mean = P.in.mean[e], stdv = P.in.stdv[e];
     const double* __restrict__ w = P.T + (off - P.first_global);
+    // Tier 2: warp-cooperative fast distance (FMA, reciprocal) over all m terms, 128 terms per round in |zQ|
+    // order, abandoned as soon as the partial sum exceeds eps^2*(1+1e-9).  Only windows that survive every
+    // round reach the reference-order summation below.
+    {
+      const double rstd = 1.0 / stdv, nmr = -mean * rstd;
+      double part = 0.0;
+      bool over = false;
+      for (int k0 = 0; k0 < m && !over; k0 += 128) {
+        double wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int k = k0 + u * 32 + lane;
+          wv[u] = (k < m) ? w[__ldg(P.order + k)] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int k = k0 + u * 32 + lane;
+          if (k < m) {
+            const double df = __fma_rn(wv[u], rstd, nmr) - __ldg(P.zq + k);
+            part = __fma_rn(df, df, part);
+          }
+        }
+        double tot = part;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFullMask, tot, o);
+        over = !(tot <= P.eps2_hi);
+      }
+      if (over) continue;
+    }
+    if (lane == 0) atomicAdd(P.n_exact, 1ULL);
     double dist = 0.0;
     bool alive = true;
     for (int k0 = 0; k0 < m && alive; k0 += kExactChunk) {
       const int kc = min(kExactChunk, m - k0);
       __syncwarp();
-      for (int k = lane; k < kc; k += 32) {
-        const double x = xdiv(xsub(w[__ldg(P.order + k0 + k)], mean), stdv);
-        term[k] = xsqdist(x, __ldg(P.zq + k0 + k));
+      // independent scattered loads, 8 in flight per lane
+      for (int kb = 0; kb < kc; kb += 256) {
+        double wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int k = kb + u * 32 + lane;
+          wv[u] = (k < kc) ? w[__ldg(P.order + k0 + k)] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int k = kb + u * 32 + lane;
+          if (k < kc) term[k] = xsqdist(xdiv(xsub(wv[u], mean), stdv), __ldg(P.zq + k0 + k));
+        }
       }
       __syncwarp();
       if (lane == 0) {

@@ -527,9 +527,11 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
       X.zq = E.zq;
       X.order = E.order;
       X.eps2 = eps2;
+      X.eps2_hi = E.eps2_hi;
+      X.n_exact = ctx->counters.as<unsigned long long>() + kCntFlag;
       X.in = E.out;
       X.sink = sink_of(ctx);
-      cnsm_ed_exact_kernel<<<ctx->n_sms * 2, 128, sizeof(double) * kExactChunk * 4, ctx->stream>>>(X);
+      cnsm_ed_exact_kernel<<<ctx->n_sms * 6, 128, sizeof(double) * kExactChunk * 4, ctx->stream>>>(X);
       launches += 2;
     } else {
       LbNormParams L;
@@ -565,7 +567,7 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
   }
   out->kernel_ms = total_ms;
   out->n_gate_pass = (int64_t)cnt[kCntGate];
-  if (mode == Mode::kEd) out->n_exact = (int64_t)cnt[kCntCand]; else out->n_lb_pass = (int64_t)cnt[kCntCand];
+  if (mode == Mode::kEd) out->n_exact = (int64_t)cnt[kCntFlag]; else out->n_lb_pass = (int64_t)cnt[kCntCand];
   return fetch_answers(ctx, (long long)cnt[kCntAnswers], out);
 }
 
