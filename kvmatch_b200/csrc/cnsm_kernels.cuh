@@ -397,24 +397,46 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
         int rbase = 0;
         if (lane == 0) rbase = atomicAdd(s_rcount, total);
         rbase = __shfl_sync(kFullMask, rbase, 0);
-        for (int e0 = 0; e0 < total; e0 += 32) {
-          const int e = e0 + lane;
-          int owner = 0;
-#pragma unroll
-          for (int step = 16; step > 0; step >>= 1) {
-            const int t = __shfl_sync(kFullMask, excl, owner + step);
-            if (t <= e) owner += step;
+        if (total > 64) {
+          // dense block (a matching region: most lanes pass most columns): two chains per round, half a warp each;
+          // lane c of a half copies column c of its chain's staged row if it passed -> 16 consecutive work-list
+          // slots per half-warp (coalesced), no owner search
+          const unsigned nz = __ballot_sync(kFullMask, cnt > 0);
+          const int hl = lane & 15, hw = lane >> 4;
+          for (int pr = 0; pr < 16; pr++) {
+            if (((nz >> (2 * pr)) & 3u) == 0) continue;
+            const int owner = 2 * pr + hw;
+            const unsigned omask = __shfl_sync(kFullMask, mask, owner);
+            const int oexcl = __shfl_sync(kFullMask, excl, owner);
+            const int32_t ooff = __shfl_sync(kFullMask, off0, owner);
+            if ((omask >> hl) & 1u) {
+              const double2 v2 = stage_ring[((size_t)slot * 32 + owner) * kStagePitch + hl];
+              const long long gidx = base + rbase + oexcl + __popc(omask & ((1u << hl) - 1u));
+              P.e_off[gidx] = ooff + col0 + hl;
+              P.e_ex[gidx] = v2.x;
+              P.e_ex2[gidx] = v2.y;
+            }
           }
-          const int j = e - __shfl_sync(kFullMask, excl, owner);
-          const unsigned omask = __shfl_sync(kFullMask, mask, owner);
-          const int32_t ooff = __shfl_sync(kFullMask, off0, owner);
-          if (e < total) {
-            const int cc = (int)__fns(omask, 0, j + 1);
-            const double2 v2 = stage_ring[((size_t)slot * 32 + owner) * kStagePitch + cc];
-            const long long gidx = base + rbase + e;
-            P.e_off[gidx] = ooff + col0 + cc;
-            P.e_ex[gidx] = v2.x;
-            P.e_ex2[gidx] = v2.y;
+        } else {
+          for (int e0 = 0; e0 < total; e0 += 32) {
+            const int e = e0 + lane;
+            int owner = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+              const int t = __shfl_sync(kFullMask, excl, owner + step);
+              if (t <= e) owner += step;
+            }
+            const int j = e - __shfl_sync(kFullMask, excl, owner);
+            const unsigned omask = __shfl_sync(kFullMask, mask, owner);
+            const int32_t ooff = __shfl_sync(kFullMask, off0, owner);
+            if (e < total) {
+              const int cc = (int)__fns(omask, 0, j + 1);
+              const double2 v2 = stage_ring[((size_t)slot * 32 + owner) * kStagePitch + cc];
+              const long long gidx = base + rbase + e;
+              P.e_off[gidx] = ooff + col0 + cc;
+              P.e_ex[gidx] = v2.x;
+              P.e_ex2[gidx] = v2.y;
+            }
           }
         }
       }
