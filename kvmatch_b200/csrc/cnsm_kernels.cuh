@@ -33,7 +33,6 @@ constexpr int kFifoDepth = 16;     // per-lane staging of work-list entries betw
 constexpr int kFifoPitch = kFifoDepth + 1;
 constexpr int kFrontPad = 64;      // zero samples the ctx keeps in front of / behind the series so that
 constexpr int kTailPad = 192;      // whole-row bulk copies never leave the allocation
-constexpr int kPrefetchTiles = 12; // L2 prefetch distance of the incoming stream, in tiles
 constexpr int kFastTerms = 32;     // terms of the evaluator's fast screen
 constexpr int kEvalTile = 128;     // work-list entries per evaluator tile (= evaluator CTA size)
 
@@ -129,21 +128,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 constexpr int kStageBlocks = 4;   // ring of staged (ex, ex2) blocks between the chain warp and the gate warps
 constexpr int kBlockCols = 16;    // window positions per staged block
 constexpr int kStagePitch = kBlockCols + 1;  // double2 per lane row: conflict-free lane-private 16-byte accesses
-constexpr int kWalkThreads = 128; // warp 0: chain walker; warps 1-2: gate / compaction; warp 3: tile loader
+constexpr int kGateWarps = 3;
+constexpr int kWalkThreads = 32 * (2 + kGateWarps); // warp 0: chain walker; warps 1..kGateWarps: gates; last warp: tile loader
 constexpr size_t walk_smem_bytes(int stages) {
   return sizeof(double) * (size_t)walk_tile_doubles(stages) + sizeof(double2) * kStageBlocks * 32 * kStagePitch +
          sizeof(unsigned long long) * 2 * stages + 16;
 }
 
-// One CTA = 32 chains = one work-list region, four specialised warps:
-//   warp 3 (loader)        fills the tile ring: STAGES x (incoming, outgoing) tiles, row = 32 consecutive samples of
+// One CTA = 32 chains = one work-list region, five specialised warps:
+//   last warp (loader)     fills the tile ring: STAGES x (incoming, outgoing) tiles, row = 32 consecutive samples of
 //     one chain, by 16-byte cp.async copies (half a warp per row: every copy instruction moves two full 256-byte
 //     rows) with L2 eviction hints (incoming rows evict_last — they are re-read m-1 steps later as outgoing rows,
 //     which are read evict_first), and lets an mbarrier per stage track their completion.
 //   warp 0 (chain walker)  keeps only the two dependent FP64 recurrences (ex, ex2) in its instruction stream: per
 //     window position 1 LDS.128 per stream per sample pair (register double-buffered), 4 DADD, 2 DMUL and one
 //     STS.128 of the post-add (ex, ex2) into a staging block.  Its pace is the 2 x 8-cycle dependent-DADD latency.
-//   warps 1-2 (gates)      take alternate staged blocks: conservative alpha/beta pre-gate on integer keys of the high
+//   warps 1-3 (gates)      take staged blocks round-robin: conservative alpha/beta pre-gate on integer keys of the high
 //     words, then a warp-cooperative, coalesced append of the passing (offset, ex, ex2) to the region's slice of the
 //     work list.  Hand-off is by named barriers (bar.arrive / bar.sync), 4 blocks deep.
 // Rows are 16-byte aligned in global memory: the incoming row starts at pos & ~1; kDelta = 1 when m is even (the
@@ -156,7 +156,10 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(stage_ring + kStageBlocks * 32 * kStagePitch);
   int* s_rcount = reinterpret_cast<int*>(bars + 2 * STAGES);
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // keep lane/warp in registers: ptxas otherwise re-reads SR_TID.X (a ~100-cycle S2R) inside the walker's hot loop
+  asm volatile("mov.u32 %0, %0;" : "+r"(lane));
+  asm volatile("mov.u32 %0, %0;" : "+r"(warp));
   const int region = blockIdx.x;
   const int c = region * 32 + lane;
   int pos = 0, len = 0;
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
   }
   __syncthreads();
 
-  if (warp == 3) {
+  if (warp == 1 + kGateWarps) {
     // ------------------------------------------------------------------ tile loader
     const int ab = pos - sha;                     // 16-byte aligned base of the incoming rows
     const int ob = pos - (m - 1) - sha + kDelta;  // aligned base of the outgoing rows
@@ -215,13 +218,6 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
         cp_async16_hint(dst + kStreamBytes + i * kPairBytes, T + io, pol_drop);
       }
       mbar_arrive_on_cp_async(bar_ready + 8 * stage);
-      // pull this lane's own incoming row kPrefetchTiles tiles ahead into L2 (two 128-byte lines): the copies
-      // above then find their data in L2 and the 4-stage ring covers L2 latency instead of DRAM latency
-      if (k + kPrefetchTiles < ntl) {
-        const double* pf = T + min(ab + (k + kPrefetchTiles) * kWalkTile, idx_hi);
-        l2_prefetch_line(pf);
-        l2_prefetch_line(pf + 16);
-      }
     }
   } else if (warp == 0) {
     // ------------------------------------------------------------------ chain walker (producer)
@@ -371,7 +367,7 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
     const unsigned mean_kspan = P.mean_kspan, var_kspan = P.var_kspan;
     const double dm = P.dm;
     const int32_t off0 = P.first_global + pos - (m - 1) - sha;  // + tile column = 1-based global window start
-    for (int b = g; b < n_blocks; b += 2) {
+    for (int b = g; b < n_blocks; b += kGateWarps) {
       const int slot = b % kStageBlocks;
       const int col0 = (k_w + (b >> 1)) * kWalkTile + (b & 1) * kBlockCols;  // tile column of the block's first entry
       bar_sync(1 + slot, 64);  // wait for the chain warp to stage this block
