@@ -94,6 +94,10 @@ struct WalkParams {
   double* e_ex;
   double* e_ex2;
   int32_t* region_count;
+  // kMode == 1 (IndexBuilder window means): per-window bucket ids instead of a work list
+  int32_t* bucket_out;  // bucket_out[local window start] = floor(2 * fl(fl(ex/w) * 10))
+  double c20w;          // 20 / w
+  int* overflow;        // set when a bucket does not fit int32
 };
 
 // ---- named barriers (producer/consumer hand-off inside a CTA) --------------------------------------
@@ -148,7 +152,7 @@ constexpr size_t walk_smem_bytes(int stages) {
 //     work list.  Hand-off is by named barriers (bar.arrive / bar.sync), 4 blocks deep.
 // Rows are 16-byte aligned in global memory: the incoming row starts at pos & ~1; kDelta = 1 when m is even (the
 // outgoing row is then aligned one sample later, so its columns lag the incoming ones by one).
-template <int STAGES, int kDelta>
+template <int STAGES, int kDelta, int kMode = 0>
 __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
   extern __shared__ __align__(16) unsigned char walk_smem_raw[];
   double* tiles = reinterpret_cast<double*>(walk_smem_raw);                      // [STAGES][2][32][pitch]
@@ -372,6 +376,36 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
       const int col0 = (k_w + (b >> 1)) * kWalkTile + (b & 1) * kBlockCols;  // tile column of the block's first entry
       bar_sync(1 + slot, 64);  // wait for the chain warp to stage this block
       const double2* st = stage_ring + ((size_t)slot * 32 + lane) * kStagePitch;
+      if (kMode == 1) {
+        // IndexBuilder step 1 (K/IndexBuilder.java:251-265): key bucket of every window mean.  b is taken from one
+        // multiply when ex*(20/w) is clear of an integer by more than the rounding slack, and from the reference's
+        // exact divide / multiply otherwise (MeanIntervalUtils.toRound, K/utils/MeanIntervalUtils.java:51-61).
+        double exv[kBlockCols];
+#pragma unroll
+        for (int cc = 0; cc < kBlockCols; cc++) exv[cc] = st[cc].x;
+        // release the slot before the global stores: a barrier arrive waits for this warp's pending stores, and
+        // 16 scattered global stores per block would otherwise throttle the chain warp through the ring
+        bar_arrive(1 + kStageBlocks + slot, 64);
+#pragma unroll
+        for (int cc = 0; cc < kBlockCols; cc++) {
+          const double ex = exv[cc];
+          const int s = col0 + cc - sha;
+          const bool win = ((unsigned)s < (unsigned)len) & (s >= m - 1);
+          double v2 = ex * P.c20w;
+          double fl = floor(v2);
+          const double frac = v2 - fl;
+          const double gd = fabs(v2) * 4e-15 + 1e-290;
+          if (win && !(frac >= gd && frac <= 1.0 - gd)) {  // (idle lanes hold ex == 0: keep them off the slow path)
+            const double v = xmul(xdiv(ex, dm), 10.0);
+            fl = floor(xadd(v, v));  // 2v is exact
+          }
+          if (win) {
+            if (!(fabs(fl) < 2147483000.0)) *P.overflow = 1;
+            P.bucket_out[pos + s - (m - 1)] = (int)fl;
+          }
+        }
+        continue;
+      }
       unsigned mask = 0;
 #pragma unroll
       for (int cc = 0; cc < kBlockCols; cc++) {

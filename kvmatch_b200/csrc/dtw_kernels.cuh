@@ -148,10 +148,13 @@ struct DtwParams {
   int32_t first_global;
   int m;
   int rho;
-  const double* __restrict__ q;  // natural order
-  double eps2;
+  const double* __restrict__ q;   // natural order
+  const double* __restrict__ uq;  // query envelope (radius rho), for the cumulative LB_Keogh remainder
+  const double* __restrict__ lq;
+  double eps2, eps2_hi;
   CandList in;
   AnswerSink sink;
+  unsigned long long* n_abandoned;
 };
 
 template <int R>
@@ -159,8 +162,9 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
   extern __shared__ double dtw_smem[];
   const int m = P.m, rho = P.rho;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  double* B = dtw_smem;                          // query
-  double* A = dtw_smem + (size_t)(warp + 1) * m; // this warp's (normalised) window
+  double* B = dtw_smem;                                  // query
+  double* A = dtw_smem + (size_t)(1 + 2 * warp) * m;     // this warp's (normalised) window
+  double* CB = A + m;                                    // cb[k] = sum_{k' >= k} LB_Keogh contribution of A[k']
   for (int k = threadIdx.x; k < m; k += blockDim.x) B[k] = P.q[k];
   __syncthreads();
 
@@ -168,6 +172,7 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
   if ((long long)n > P.in.cap) n = (unsigned long long)P.in.cap;
   const int tgt_u = rho;  // final cell (m-1, m-1): i-j = 0
   const int tgt_pair = tgt_u >> 1;
+  const int per = (m + 31) / 32;  // contiguous span of cb each lane scans
 
   for (unsigned long long e = (unsigned long long)blockIdx.x * n_warps + warp; e < n;
        e += (unsigned long long)gridDim.x * n_warps) {
@@ -175,7 +180,31 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
     const double mean = P.in.mean[e], stdv = P.in.stdv[e];
     const double* __restrict__ w = P.T + (off - P.first_global);
     __syncwarp();
-    for (int k = lane; k < m; k += 32) A[k] = xdiv(xsub(w[k], mean), stdv);  // NormQueryEngineDtw.java:564-567
+    for (int k = lane; k < m; k += 32) {
+      const double a = xdiv(xsub(w[k], mean), stdv);  // NormQueryEngineDtw.java:564-567
+      A[k] = a;
+      const double up = __ldg(P.uq + k), lo = __ldg(P.lq + k);
+      const double d = (a > up) ? (a - up) : ((a < lo) ? (a - lo) : 0.0);
+      CB[k] = d * d;  // K/utils/DtwUtils.java:206-222 contribution of data point k against the query envelope
+    }
+    __syncwarp();
+    {  // suffix sums of CB (the reference's cb, K/QueryEngineDtw.java:430-441): lane-local spans, then a warp scan
+      const int k0 = lane * per, k1 = min(m, k0 + per);
+      double run = 0.0;
+      for (int k = k1 - 1; k >= k0; k--) {
+        run += CB[k];
+        CB[k] = run;
+      }
+      double right = run;  // inclusive sum of this and all lanes to the right, minus own
+      double tot = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_down_sync(kFullMask, tot, o);
+        if (lane + o < 32) tot += t;
+      }
+      right = tot - run;
+      for (int k = k0; k < k1; k++) CB[k] += right;
+    }
     __syncwarp();
 
     double Ev[R], Od[R];
@@ -186,7 +215,25 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
     }
     const int u0 = 2 * lane * R;  // band coordinate of this lane's first even cell
     const int last = 2 * m - 2;
+    bool abandoned = false;
     for (int d = 0; d <= last; d++) {
+      // Early abandon (the reference abandons per row with min_cost + cb[i+r+1], DtwUtils.java:324-326).  On the
+      // wavefront: every warping path crosses one of the two most recent anti-diagonals, cell values only grow
+      // along a path, and data points beyond imax = (d-1+rho)/2 have not been matched yet, so
+      // min(cells on the last two diagonals) + cb[imax+1] is a lower bound of the final distance.
+      if ((d & 15) == 0 && d > 0) {
+        double mn = kDtwInf;
+#pragma unroll
+        for (int r = 0; r < R; r++) mn = fmin(mn, fmin(Ev[r], Od[r]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(kFullMask, mn, o));
+        const int imax = min(m - 1, (d - 1 + rho) >> 1);
+        const double rest = (imax + 1 < m) ? CB[imax + 1] : 0.0;
+        if (mn + rest > P.eps2_hi) {
+          abandoned = true;
+          break;
+        }
+      }
       if (((d + rho) & 1) == 0) {
         double left = __shfl_up_sync(kFullMask, Od[R - 1], 1);
         if (lane == 0) left = kDtwInf;
@@ -227,6 +274,10 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
           Od[r] = v;
         }
       }
+    }
+    if (abandoned) {
+      if (lane == 0) atomicAdd(P.n_abandoned, 1ULL);
+      continue;
     }
     double res = kDtwInf;
 #pragma unroll

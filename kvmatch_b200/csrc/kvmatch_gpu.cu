@@ -547,7 +547,11 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
       D.m = m;
       D.rho = rho;
       D.q = E.zq;
+      D.uq = L.Q.uq;
+      D.lq = L.Q.lq;
       D.eps2 = eps2;
+      D.eps2_hi = E.eps2_hi;
+      D.n_abandoned = ctx->counters.as<unsigned long long>() + kCntFlag;
       D.in = E.out;
       D.sink = sink_of(ctx);
       if ((rc = launch_dtw(ctx, D))) return rc;
@@ -577,11 +581,11 @@ int launch_dtw(kvm_ctx* ctx, const DtwParams& D) {
   const int need = (D.rho + 1 + 31) / 32;  // (even,odd) pairs per lane
   const size_t bytes_per_row = sizeof(double) * (size_t)D.m;
   const size_t smem_budget = 200 * 1024;
-  if (2 * bytes_per_row > smem_budget)
+  if (3 * bytes_per_row > smem_budget)
     return fail(ctx, KVM_E_ARG, "DTW query length %d exceeds the shared-memory staging limit (%zu)", D.m,
-                smem_budget / 16);
-  int warps = (int)std::min<size_t>(8, smem_budget / bytes_per_row - 1);
-  const size_t smem = bytes_per_row * (warps + 1);
+                smem_budget / 24);
+  int warps = (int)std::min<size_t>(8, (smem_budget / bytes_per_row - 1) / 2);
+  const size_t smem = bytes_per_row * (2 * warps + 1);
   const int grid = ctx->n_sms * std::max(1, (int)(smem_budget / smem));
 #define KVM_DTW_CASE(R)                                                                                        \
   if (need <= R) {                                                                                             \
@@ -633,12 +637,12 @@ int kvm_create(kvm_ctx** out, int device_id) {
     delete ctx;
     return fail(nullptr, KVM_E_CUDA, "stream/event creation failed: %s", msg);
   }
-  const int mean_smem = (int)(sizeof(double) * kMeanSmemDoublesPerWarp * kMeanWarps);
   const int w4 = (int)walk_smem_bytes(4);
   if (cudaFuncSetAttribute(cnsm_walk_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4) != cudaSuccess ||
       cudaFuncSetAttribute(cnsm_walk_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4) != cudaSuccess ||
       cudaFuncSetAttribute(cnsm_ed_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kExactChunk * 4)) != cudaSuccess ||
-      cudaFuncSetAttribute(mean_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mean_smem) != cudaSuccess) {
+      cudaFuncSetAttribute(cnsm_walk_kernel<4, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4) != cudaSuccess ||
+      cudaFuncSetAttribute(cnsm_walk_kernel<4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4) != cudaSuccess) {
     const char* msg = cudaGetErrorString(cudaGetLastError());
     kvm_destroy(ctx);
     return fail(nullptr, KVM_E_CUDA, "cudaFuncSetAttribute failed: %s", msg);
@@ -844,7 +848,11 @@ int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int
     D.m = m;
     D.rho = rho;
     D.q = L.Q.q;
+    D.uq = L.Q.uq;
+    D.lq = L.Q.lq;
     D.eps2 = eps2;
+    D.eps2_hi = L.Q.eps2_hi;
+    D.n_abandoned = ctx->counters.as<unsigned long long>() + kCntFlag;
     D.in = L.out;
     D.sink = sink_of(ctx);
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -893,98 +901,95 @@ int kvm_window_mean_runs(kvm_ctx* ctx, int32_t w, kvm_runs* out) {
       if (within < 124) break;  // ++cnt <= n failed inside this node
     }
   }
-  std::vector<MeanChain> chains;
+  // chains = the reference's epochs: epoch `it` starts at sample it*(EPOCH-w+1) and restarts the running sum
+  std::vector<int32_t> cbegin, cnsamp;
   const int64_t stride = kEpoch - w + 1;
-  long long slot = 0;
+  int64_t n_win = 0;
   for (int64_t it = 0;; it++) {
     const int64_t g0 = it * stride;
     if (g0 + w - 1 >= fed) break;  // ep <= w-1: nothing new to read
     const int64_t ep = std::min<int64_t>(kEpoch, fed - g0);
     const int64_t nwin = std::min<int64_t>(ep - w + 1, n - g0);  // loc = g0 + i - w + 2 <= n
     if (nwin <= 0) break;
-    chains.push_back(MeanChain{(int32_t)g0, (int32_t)ep, (int32_t)nwin, w, slot});
-    slot += nwin;
+    cbegin.push_back((int32_t)g0);
+    cnsamp.push_back((int32_t)(w - 1 + nwin));  // samples the chain needs for its nwin windows
+    n_win = g0 + nwin;                            // windows are contiguous: loc 1 .. n_win
     if (ep < kEpoch) break;
   }
-  const int n_chains = (int)chains.size();
+  const int n_chains = (int)cbegin.size();
   if (n_chains == 0) return KVM_OK;
+  const int n_regions = (n_chains + 31) / 32;
+  std::vector<long long> region_base(n_regions + 1, 0);
   Arena A;
-  const size_t o_chains = A.add(chains.data(), sizeof(MeanChain) * n_chains);
+  const size_t o_cbegin = A.add(cbegin.data(), sizeof(int32_t) * n_chains);
+  const size_t o_nsamp = A.add(cnsamp.data(), sizeof(int32_t) * n_chains);
+  const size_t o_rbase = A.add(region_base.data(), sizeof(long long) * (n_regions + 1));
   if ((rc = upload_arena(ctx, A))) return rc;
-  KVM_CUDA(ctx, ctx->seg_b.ensure(sizeof(int32_t) * (size_t)slot));
-  KVM_CUDA(ctx, ctx->seg_first.ensure(sizeof(int32_t) * (size_t)slot));
-  KVM_CUDA(ctx, ctx->seg_last.ensure(sizeof(int32_t) * (size_t)slot));
-  KVM_CUDA(ctx, ctx->chain_count.ensure(sizeof(int32_t) * n_chains));
-  KVM_CUDA(ctx, ctx->chain_prefix.ensure(sizeof(long long) * (n_chains + 1)));
+  const int n_tiles = (int)((n_win + kRleTile - 1) / kRleTile);
+  KVM_CUDA(ctx, ctx->seg_b.ensure(sizeof(int32_t) * (size_t)n_win));
+  KVM_CUDA(ctx, ctx->chain_count.ensure(sizeof(int32_t) * (size_t)n_tiles));
+  KVM_CUDA(ctx, ctx->chain_prefix.ensure(sizeof(long long) * (size_t)(n_tiles + 1)));
+  KVM_CUDA(ctx, ctx->region_count.ensure(sizeof(int32_t) * (n_regions + 1)));
   if ((rc = zero_counters(ctx))) return rc;
-  const MeanChain* d_chains = reinterpret_cast<const MeanChain*>(ctx->arena.as<unsigned char>() + o_chains);
-  MeanWalkParams M;
-  M.T = ctx->series;
-  M.chains = d_chains;
-  M.n_chains = n_chains;
-  M.seg_b = ctx->seg_b.as<int32_t>();
-  M.seg_first = ctx->seg_first.as<int32_t>();
-  M.seg_last = ctx->seg_last.as<int32_t>();
-  M.chain_count = ctx->chain_count.as<int32_t>();
-  M.overflow = reinterpret_cast<int*>(ctx->counters.as<unsigned long long>() + kCntFlag);
-  const int n_blocks = (n_chains + kMeanWarps * 32 - 1) / (kMeanWarps * 32);
-  const size_t smem = sizeof(double) * kMeanSmemDoublesPerWarp * kMeanWarps;
+  const unsigned char* base = ctx->arena.as<unsigned char>();
+  WalkParams W{};
+  W.T = ctx->series;
+  W.cbegin = reinterpret_cast<const int32_t*>(base + o_cbegin);
+  W.cnsamp = reinterpret_cast<const int32_t*>(base + o_nsamp);
+  W.region_base = reinterpret_cast<const long long*>(base + o_rbase);
+  W.K = n_chains;
+  W.m = w;
+  W.first_global = 1;
+  W.idx_hi = (int)((ctx->count + kTailPad - 2) & ~int64_t(1));
+  W.dm = (double)w;
+  W.region_count = ctx->region_count.as<int32_t>();
+  W.bucket_out = ctx->seg_b.as<int32_t>();
+  W.c20w = 20.0 / (double)w;
+  W.overflow = reinterpret_cast<int*>(ctx->counters.as<unsigned long long>() + kCntFlag);
   KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  mean_walk_kernel<<<n_blocks, kMeanWarps * 32, smem, ctx->stream>>>(M);
-  mean_scan_kernel<<<1, 1024, 0, ctx->stream>>>(M.chain_count, n_chains, ctx->chain_prefix.as<long long>());
+  if ((w % 2) == 0) cnsm_walk_kernel<4, 1, 1><<<n_regions, kWalkThreads, walk_smem_bytes(4), ctx->stream>>>(W);
+  else cnsm_walk_kernel<4, 0, 1><<<n_regions, kWalkThreads, walk_smem_bytes(4), ctx->stream>>>(W);
+  rle_count_kernel<<<n_tiles, 256, 0, ctx->stream>>>(W.bucket_out, (long long)n_win, ctx->chain_count.as<int32_t>());
+  rle_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->chain_count.as<int32_t>(), n_tiles, ctx->chain_prefix.as<long long>());
   KVM_CUDA(ctx, cudaGetLastError());
   long long total = 0;
-  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters.p, ctx->chain_prefix.as<long long>() + n_chains, sizeof(long long),
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters.p, ctx->chain_prefix.as<long long>() + n_tiles, sizeof(long long),
                                 cudaMemcpyDeviceToHost, ctx->stream));
   KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   std::memcpy(&total, ctx->h_counters.p, sizeof(long long));
   KVM_CUDA(ctx, ctx->run_key.ensure(sizeof(double) * (size_t)total));
-  KVM_CUDA(ctx, ctx->run_b.ensure(sizeof(int32_t) * (size_t)total));
   KVM_CUDA(ctx, ctx->run_first.ensure(sizeof(int32_t) * (size_t)total));
-  KVM_CUDA(ctx, ctx->run_last.ensure(sizeof(int32_t) * (size_t)total));
-  mean_gather_kernel<<<n_chains, 256, 0, ctx->stream>>>(d_chains, M.chain_count, ctx->chain_prefix.as<long long>(),
-                                                       M.seg_b, M.seg_first, M.seg_last, ctx->run_key.as<double>(),
-                                                       ctx->run_b.as<int32_t>(), ctx->run_first.as<int32_t>(),
-                                                       ctx->run_last.as<int32_t>());
+  rle_emit_kernel<<<n_tiles, 256, 0, ctx->stream>>>(W.bucket_out, (long long)n_win, ctx->chain_prefix.as<long long>(),
+                                                   ctx->run_first.as<int32_t>(), ctx->run_key.as<double>());
   KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   KVM_CUDA(ctx, cudaGetLastError());
   unsigned long long cnt[kNumCounters];
   if ((rc = read_counters(ctx, cnt))) return rc;
   if (cnt[kCntFlag]) return fail(ctx, KVM_E_ARG, "window mean outside the supported key range (|mean| < 1e8)");
   out->kernel_ms = elapsed_ms(ctx);
-  out->n_launches = 3;
+  out->n_launches = 4;
   KVM_CUDA(ctx, ctx->h_key.ensure(sizeof(double) * (size_t)total));
-  KVM_CUDA(ctx, ctx->h_b.ensure(sizeof(int32_t) * (size_t)total));
   KVM_CUDA(ctx, ctx->h_first.ensure(sizeof(int32_t) * (size_t)total));
-  KVM_CUDA(ctx, ctx->h_last.ensure(sizeof(int32_t) * (size_t)total));
   KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_key.p, ctx->run_key.p, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream));
-  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_b.p, ctx->run_b.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
   KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_first.p, ctx->run_first.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
-  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_last.p, ctx->run_last.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
   KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  // Stitch segments that continue across an epoch border (the reference's run state persists over
-  // epochs, K/IndexBuilder.java:190-192) and split at 255 positions (:268, MAXIMUM_DIFF - 1).
+  // split at 255 positions (K/IndexBuilder.java:268, MAXIMUM_DIFF - 1)
   const double* hk = ctx->h_key.as<double>();
-  const int32_t* hb = ctx->h_b.as<int32_t>();
-  const int32_t* hf = ctx->h_first.as<int32_t>();
-  const int32_t* hl = ctx->h_last.as<int32_t>();
+  const int32_t* hs = ctx->h_first.as<int32_t>();
   ctx->run_key_v.clear();
   ctx->run_first_v.clear();
   ctx->run_last_v.clear();
   ctx->run_key_v.reserve((size_t)total + 16);
   ctx->run_first_v.reserve((size_t)total + 16);
   ctx->run_last_v.reserve((size_t)total + 16);
-  long long i = 0;
-  while (i < total) {
-    long long j = i;
-    while (j + 1 < total && hb[j + 1] == hb[i]) j++;
-    const int32_t first = hf[i], last = hl[j];
+  for (long long i = 0; i < total; i++) {
+    const int64_t first = (int64_t)hs[i] + 1;                                   // 1-based loc
+    const int64_t last = (i + 1 < total) ? (int64_t)hs[i + 1] : (int64_t)n_win;  // next run's first - 1
     for (int64_t f = first; f <= last; f += 255) {
       ctx->run_key_v.push_back(hk[i]);
       ctx->run_first_v.push_back((int32_t)f);
       ctx->run_last_v.push_back((int32_t)std::min<int64_t>(f + 254, last));
     }
-    i = j + 1;
   }
   out->count = (int64_t)ctx->run_key_v.size();
   out->keys = ctx->run_key_v.data();
