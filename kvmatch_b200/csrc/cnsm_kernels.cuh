@@ -225,140 +225,118 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
     }
   } else if (warp == 0) {
     // ------------------------------------------------------------------ chain walker (producer)
-    // Software pipeline over 16-column blocks: while block j's dependent FP64 chain runs out of one register
-    // set, block j+1's 16 LDS.128 are already in flight into the other (ping-pong, no copies), across tile
-    // borders too (the next tile's mbarrier is polled one block early).
+    // One tile (16 sample pairs = 32 window positions = 2 staged blocks) per loop iteration, fully unrolled.
+    // Samples come through a 4-pair rolling register window: pair i+4 is loaded (one LDS.128 per stream) while
+    // pair i is consumed, across tile borders too (the next tile's mbarrier is polled at pair 12), so the
+    // shared-memory loads are spread along the dependent FP64 chain instead of bunching at block ends.
     double ex = 0.0, ex2 = 0.0, carry = 0.0;
-    double2 A0[8], O0[8], A1[8], O1[8];
-    auto load16 = [&](double2(&Av)[8], double2(&Ov)[8], const double* ra, const double* ro) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        Av[i] = *reinterpret_cast<const double2*>(ra + 2 * i);
-        Ov[i] = *reinterpret_cast<const double2*>(ro + 2 * i);
-      }
-    };
-    // 16 window positions from (Av, Ov).  kStore: stage the post-add (ex, ex2) of every position (the store of a
-    // pair is placed after the next pair's arithmetic so it never sits in front of the dependent chain);
-    // kSteady: every lane's columns are inside its chain and past the warm-up -> no per-column selects.
-    // arrive_id >= 0: signal the previous staged block; sync_id >= 0: wait until this block's slot is drained.
-    // Both happen after the first pair's arithmetic: by then the previous block's last stores were issued two
-    // pair-times ago, so the barrier instructions find no pending shared-memory stores to drain.
-    auto walk16 = [&](const double2(&Av)[8], const double2(&Ov)[8], double2(&An)[8], double2(&On)[8],
-                      const double* na, const double* no, int s0, double2* st, int arrive_id, int sync_id,
-                      auto store_tag, auto steady_tag) {
-      constexpr bool kStore = decltype(store_tag)::value, kSteady = decltype(steady_tag)::value;
-      double2 p0 = make_double2(0.0, 0.0), p1 = p0;
-      // operands of one sample pair: the two incoming / outgoing samples (already zeroed where a column lies
-      // outside the chain or before its first complete window) and their squares
-      struct Pair { double a0, a1, o0, o1, a0s, a1s, o0s, o1s; };
-      auto prep = [&](int i, double& cr) {
-        const double2 A = Av[i], O = Ov[i];
-        Pair q;
-        q.a0 = A.x;
-        q.a1 = A.y;
-        q.o0 = kDelta ? cr : O.x;
-        q.o1 = kDelta ? O.x : O.y;
-        cr = O.y;
-        if (!kSteady) {
-          const int s = s0 + 2 * i;
-          const bool act0 = (unsigned)s < (unsigned)len, act1 = (unsigned)(s + 1) < (unsigned)len;
-          q.a0 = act0 ? q.a0 : 0.0;
-          q.a1 = act1 ? q.a1 : 0.0;
-          q.o0 = (act0 & (s >= m - 1)) ? q.o0 : 0.0;
-          q.o1 = (act1 & (s + 1 >= m - 1)) ? q.o1 : 0.0;
-        }
-        q.a0s = xmul(q.a0, q.a0);
-        q.a1s = xmul(q.a1, q.a1);
-        q.o0s = xmul(q.o0, q.o0);
-        q.o1s = xmul(q.o1, q.o1);
-        return q;
-      };
-      // The squares of pair i+1 are formed while pair i's dependent add/sub chain runs: issued just-in-time
-      // (ptxas's choice otherwise) each DMUL's 8-cycle latency would sit on the chain and double its length.
-      Pair cur = prep(0, carry);
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        // the next block's sample pair i is fetched here, between the arithmetic of this block's pairs: one
-        // LDS.128 per stream per 2 positions keeps the shared-memory queue shallow and off the FP64 chain
-        if (na != nullptr) {
-          An[i] = *reinterpret_cast<const double2*>(na + 2 * i);
-          On[i] = *reinterpret_cast<const double2*>(no + 2 * i);
-        }
-        Pair nxt = cur;
-        if (i < 7) nxt = prep(i + 1, carry);
-        ex = xadd(ex, cur.a0);              // K/NormQueryEngine.java:498
-        ex2 = xadd(ex2, cur.a0s);           // :499
-        const double2 q0 = make_double2(ex, ex2);
-        ex = xsub(ex, cur.o0);              // :523
-        ex2 = xsub(ex2, cur.o0s);           // :524
-        ex = xadd(ex, cur.a1);
-        ex2 = xadd(ex2, cur.a1s);
-        const double2 q1 = make_double2(ex, ex2);
-        ex = xsub(ex, cur.o1);
-        ex2 = xsub(ex2, cur.o1s);
-        if (i == 1) {
-          if (arrive_id >= 0) bar_arrive(arrive_id, 64);
-          if (sync_id >= 0) bar_sync(sync_id, 64);
-        }
-        if (kStore && i > 0) {
-          st[2 * i - 2] = p0;
-          st[2 * i - 1] = p1;
-        }
-        p0 = q0;
-        p1 = q1;
-        cur = nxt;
-      }
-      if (kStore) {
-        st[14] = p0;
-        st[15] = p1;
-      }
-    };
-    using T_ = std::true_type;
-    using F_ = std::false_type;
+    constexpr int kAhead = 4;
+    double2 RA[kAhead], RO[kAhead];
     auto tile_rows = [&](int k, const double*& ra, const double*& ro) {
       ra = tiles + (size_t)(k % STAGES) * (2 * 32 * kWalkPitch) + lane * kWalkPitch;
       ro = ra + 32 * kWalkPitch;
     };
     int b = 0, pending_slot = -1;
-    // one block: compute from (Av, Ov) while (An, On) is loaded for the block after it
-    auto block = [&](const double2(&Av)[8], const double2(&Ov)[8], double2(&An)[8], double2(&On)[8], int k, int h,
-                     bool steady) {
-      const double* na = nullptr;
+    // kStore: stage the post-add (ex, ex2) of every position; kSteady: every lane's columns are inside its chain
+    // and past the warm-up, so no per-column selects are needed.
+    auto walk_tile = [&](int k, auto store_tag, auto steady_tag) {
+      constexpr bool kStore = decltype(store_tag)::value, kSteady = decltype(steady_tag)::value;
+      const double* ra;
+      const double* ro;
+      tile_rows(k, ra, ro);
+      const double* na = nullptr;  // next tile's rows, valid once its copies have landed
       const double* no = nullptr;
-      if (h == 0) {
-        tile_rows(k, na, no);
-        na += 16;
-        no += 16;
-      } else if (k + 1 < ntiles) {
-        mbar_wait(bar_ready + 8 * ((k + 1) % STAGES), (uint32_t)(((k + 1) / STAGES) & 1));  // tile k+1 has landed
-        tile_rows(k + 1, na, no);
-      }
-      const int s0 = k * kWalkTile - sha + 16 * h;
-      if (k < k_w) {  // warm-up: no complete window ends in this tile
-        walk16(Av, Ov, An, On, na, no, s0, nullptr, -1, -1, F_{}, F_{});
-      } else {
-        const int slot = b % kStageBlocks;
-        const int arrive_id = pending_slot >= 0 ? 1 + pending_slot : -1;                 // previous block is staged
-        const int sync_id = b >= kStageBlocks ? 1 + kStageBlocks + slot : -1;             // gate warp drained this slot
-        double2* st = stage_ring + ((size_t)slot * 32 + lane) * kStagePitch;
-        if (steady) walk16(Av, Ov, An, On, na, no, s0, st, arrive_id, sync_id, T_{}, T_{});
-        else walk16(Av, Ov, An, On, na, no, s0, st, arrive_id, sync_id, T_{}, F_{});
-        pending_slot = slot;
-        b++;
+      const int s0 = k * kWalkTile - sha;
+      double2* st = nullptr;
+      double2 p0 = make_double2(0.0, 0.0), p1 = p0;
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        if (kStore && (i == 0 || i == 8)) {  // a new 16-position block starts: pick its staging slot
+          const int slot = b % kStageBlocks;
+          st = stage_ring + ((size_t)slot * 32 + lane) * kStagePitch;
+        }
+        const double2 A = RA[i % kAhead], O = RO[i % kAhead];
+        // refill this register slot with the pair 4 ahead
+        if (i + kAhead < 16) {
+          RA[i % kAhead] = *reinterpret_cast<const double2*>(ra + 2 * (i + kAhead));
+          RO[i % kAhead] = *reinterpret_cast<const double2*>(ro + 2 * (i + kAhead));
+        } else {
+          if (i + kAhead == 16 && k + 1 < ntiles) {
+            mbar_wait(bar_ready + 8 * ((k + 1) % STAGES), (uint32_t)(((k + 1) / STAGES) & 1));  // tile k+1 has landed
+            tile_rows(k + 1, na, no);
+          }
+          if (na != nullptr) {
+            RA[i % kAhead] = *reinterpret_cast<const double2*>(na + 2 * (i + kAhead - 16));
+            RO[i % kAhead] = *reinterpret_cast<const double2*>(no + 2 * (i + kAhead - 16));
+          }
+        }
+        double a0 = A.x, a1 = A.y;
+        double o0 = kDelta ? carry : O.x, o1 = kDelta ? O.x : O.y;
+        carry = O.y;
+        if (!kSteady) {
+          const int s = s0 + 2 * i;
+          const bool act0 = (unsigned)s < (unsigned)len, act1 = (unsigned)(s + 1) < (unsigned)len;
+          a0 = act0 ? a0 : 0.0;
+          a1 = act1 ? a1 : 0.0;
+          o0 = (act0 & (s >= m - 1)) ? o0 : 0.0;
+          o1 = (act1 & (s + 1 >= m - 1)) ? o1 : 0.0;
+        }
+        const double a0s = xmul(a0, a0), o0s = xmul(o0, o0), a1s = xmul(a1, a1), o1s = xmul(o1, o1);
+        ex = xadd(ex, a0);              // K/NormQueryEngine.java:498
+        ex2 = xadd(ex2, a0s);           // :499
+        const double2 q0 = make_double2(ex, ex2);
+        ex = xsub(ex, o0);              // :523
+        ex2 = xsub(ex2, o0s);           // :524
+        ex = xadd(ex, a1);
+        ex2 = xadd(ex2, a1s);
+        const double2 q1 = make_double2(ex, ex2);
+        ex = xsub(ex, o1);
+        ex2 = xsub(ex2, o1s);
+        if (kStore) {
+          if (i == 1 || i == 9) {
+            // block hand-off, placed after the block's first pair: the previous block's last stores were issued
+            // two pair-times ago, so the barrier instructions find nothing left to drain
+            if (pending_slot >= 0) bar_arrive(1 + pending_slot, 64);            // previous block is staged
+            if (b >= kStageBlocks) bar_sync(1 + kStageBlocks + (b % kStageBlocks), 64);  // this slot is drained
+          }
+          const int j = i & 7;  // pair index inside the block; its stores trail the arithmetic by one pair
+          if (j > 0) {
+            st[2 * j - 2] = p0;
+            st[2 * j - 1] = p1;
+          }
+          if (j == 7) {
+            st[14] = q0;
+            st[15] = q1;
+            pending_slot = b % kStageBlocks;
+            b++;
+          }
+        }
+        p0 = q0;
+        p1 = q1;
       }
     };
+    using T_ = std::true_type;
+    using F_ = std::false_type;
     if (ntiles > 0) {
       mbar_wait(bar_ready, 0);
       const double* ra;
       const double* ro;
       tile_rows(0, ra, ro);
-      load16(A0, O0, ra, ro);
+#pragma unroll
+      for (int i = 0; i < kAhead; i++) {
+        RA[i] = *reinterpret_cast<const double2*>(ra + 2 * i);
+        RO[i] = *reinterpret_cast<const double2*>(ro + 2 * i);
+      }
     }
     for (int k = 0; k < ntiles; k++) {
       const int sbase = k * kWalkTile - sha;
-      const bool steady = __all_sync(kFullMask, (sbase >= m - 1) && (sbase + kWalkTile <= len));
-      block(A0, O0, A1, O1, k, 0, steady);
-      block(A1, O1, A0, O0, k, 1, steady);
+      if (k < k_w) {  // warm-up: no complete window ends in this tile
+        walk_tile(k, F_{}, F_{});
+      } else {
+        const bool steady = __all_sync(kFullMask, (sbase >= m - 1) && (sbase + kWalkTile <= len));
+        if (steady) walk_tile(k, T_{}, T_{});
+        else walk_tile(k, T_{}, F_{});
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_free + 8 * (k % STAGES));  // every lane's reads of tile k have completed
     }
