@@ -96,15 +96,17 @@ struct LbRawParams {
   CandList out;
 };
 
-__global__ void __launch_bounds__(kEdTile) dtw_lb_raw_kernel(LbRawParams P) {
+__global__ void __launch_bounds__(kEdThreads) dtw_lb_raw_kernel(LbRawParams P) {
   __shared__ int s_p;
   if (threadIdx.x == 0) s_p = find_segment<int32_t>(P.tile_prefix, P.K + 1, (int32_t)blockIdx.x);
   __syncthreads();
   const int p = s_p;
-  const int c = ((int)blockIdx.x - P.tile_prefix[p]) * kEdTile + (int)threadIdx.x;
-  if (c >= P.ncand[p]) return;
-  const int start = P.cbegin[p] + c;
-  if (lb_cascade(P.T + start, P.Q, 1.0, 0.0)) cand_append(P.out, P.first_global + start, 0.0, 1.0);
+  const int c0 = ((int)blockIdx.x - P.tile_prefix[p]) * kEdTile;
+  const int ncand = P.ncand[p], cbegin = P.cbegin[p];
+  for (int c = c0 + (int)threadIdx.x; c < min(c0 + kEdTile, ncand); c += kEdThreads) {
+    const int start = cbegin + c;
+    if (lb_cascade(P.T + start, P.Q, 1.0, 0.0)) cand_append(P.out, P.first_global + start, 0.0, 1.0);
+  }
 }
 
 // cNSM-DTW stage 1: work-list entries from cnsm_walk_kernel -> exact gate -> lower bounds.

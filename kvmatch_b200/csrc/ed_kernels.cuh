@@ -14,7 +14,8 @@
 
 namespace kvm {
 
-constexpr int kEdTile = 256;  // candidates per CTA
+constexpr int kEdThreads = 256;
+constexpr int kEdTile = 4096;  // candidates per CTA (16 per thread): amortises the tile -> interval search
 
 struct EdParams {
   const double* __restrict__ T;          // local shard, element 0 = global sample `first_global`
@@ -29,42 +30,45 @@ struct EdParams {
   AnswerSink sink;
 };
 
-__global__ void __launch_bounds__(kEdTile) ed_verify_kernel(EdParams P) {
+__global__ void __launch_bounds__(kEdThreads) ed_verify_kernel(EdParams P) {
   __shared__ int s_p;
   if (threadIdx.x == 0) s_p = find_segment<int32_t>(P.tile_prefix, P.K + 1, (int32_t)blockIdx.x);
   __syncthreads();
   const int p = s_p;
-  const int c = ((int)blockIdx.x - P.tile_prefix[p]) * kEdTile + (int)threadIdx.x;
-  if (c >= P.ncand[p]) return;
-  const int start = P.cbegin[p] + c;
-  const double* __restrict__ w = P.T + start;
+  const int c0 = ((int)blockIdx.x - P.tile_prefix[p]) * kEdTile;
+  const int ncand = P.ncand[p];
+  const int cbegin = P.cbegin[p];
   const double* __restrict__ q = P.q;
   const int m = P.m;
   const double eps2 = P.eps2;
-
-  // The first abandon tests come after 1 and 4 terms: on a scan almost every window is hopeless after its
-  // first sample, and each thread then costs 8 bytes of L1 traffic instead of 64.
-  double dist = xsqdist(w[0], __ldg(q));
-  bool alive = dist <= eps2;
-  int j = 1;
-  if (alive && m >= 4) {
+  const double q0 = __ldg(q);
+  for (int c = c0 + (int)threadIdx.x; c < min(c0 + kEdTile, ncand); c += kEdThreads) {
+    const int start = cbegin + c;
+    const double* __restrict__ w = P.T + start;
+    // The first abandon tests come after 1 and 4 terms: on a scan almost every window is hopeless after its
+    // first sample, and each thread then costs 8 bytes of L1 traffic instead of 64.
+    double dist = xsqdist(w[0], q0);
+    bool alive = dist <= eps2;
+    int j = 1;
+    if (alive && m >= 4) {
 #pragma unroll
-    for (int u = 1; u < 4; u++) dist = xadd(dist, xsqdist(w[u], __ldg(q + u)));
-    alive = dist <= eps2;
-    j = 4;
-  }
-  for (; j + 8 <= m && alive; j += 8) {
-    double t[8];
+      for (int u = 1; u < 4; u++) dist = xadd(dist, xsqdist(w[u], __ldg(q + u)));
+      alive = dist <= eps2;
+      j = 4;
+    }
+    for (; j + 8 <= m && alive; j += 8) {
+      double t[8];
 #pragma unroll
-    for (int u = 0; u < 8; u++) t[u] = xsqdist(w[j + u], __ldg(q + j + u));
+      for (int u = 0; u < 8; u++) t[u] = xsqdist(w[j + u], __ldg(q + j + u));
 #pragma unroll
-    for (int u = 0; u < 8; u++) dist = xadd(dist, t[u]);
-    alive = dist <= eps2;
+      for (int u = 0; u < 8; u++) dist = xadd(dist, t[u]);
+      alive = dist <= eps2;
+    }
+    if (alive) {
+      for (; j < m; j++) dist = xadd(dist, xsqdist(w[j], __ldg(q + j)));
+    }
+    if (dist <= eps2) P.sink.emit(P.first_global + start, xsqrt(dist));
   }
-  if (alive) {
-    for (; j < m; j++) dist = xadd(dist, xsqdist(w[j], __ldg(q + j)));
-  }
-  if (dist <= eps2) P.sink.emit(P.first_global + start, xsqrt(dist));
 }
 
 }  // namespace kvm

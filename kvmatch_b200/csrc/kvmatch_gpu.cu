@@ -776,7 +776,7 @@ int kvm_verify_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, cons
     E.first_global = (int32_t)ctx->first;
     E.sink = sink_of(ctx);
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    ed_verify_kernel<<<(unsigned)n_tiles, kEdTile, 0, ctx->stream>>>(E);
+    ed_verify_kernel<<<(unsigned)n_tiles, kEdThreads, 0, ctx->stream>>>(E);
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     KVM_CUDA(ctx, cudaGetLastError());
     if ((rc = read_counters(ctx, cnt))) return rc;
@@ -856,7 +856,7 @@ int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int
     D.in = L.out;
     D.sink = sink_of(ctx);
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    dtw_lb_raw_kernel<<<(unsigned)n_tiles, kEdTile, 0, ctx->stream>>>(L);
+    dtw_lb_raw_kernel<<<(unsigned)n_tiles, kEdThreads, 0, ctx->stream>>>(L);
     KVM_CUDA(ctx, cudaEventRecord(ctx->evs[0], ctx->stream));
     KVM_CUDA(ctx, cudaEventRecord(ctx->evs[1], ctx->stream));
     if ((rc = launch_dtw(ctx, D))) return rc;
