@@ -145,6 +145,15 @@ __global__ void __launch_bounds__(kEvalTile) cnsm_dtw_lb_kernel(LbNormParams P) 
   if (threadIdx.x == 0 && s_gate) atomicAdd(E.gate_pass, (unsigned long long)s_gate);
 }
 
+// min of two non-negative doubles through their bit patterns (for x, y >= +0 the IEEE order is the unsigned integer
+// order).  DTW costs are sums of squares, never negative and never -0.0, so this equals DtwUtils.min — and it runs on
+// the integer pipe: DMNMX issues at only ~1/5 of the DADD rate on B200 (tools/fp64_peak.cu) and two of them per cell
+// were the kernel's bottleneck.
+__device__ __forceinline__ double umin_pos(double a, double b) {
+  const unsigned long long x = (unsigned long long)__double_as_longlong(a), y = (unsigned long long)__double_as_longlong(b);
+  return __longlong_as_double((long long)(x < y ? x : y));
+}
+
 struct DtwParams {
   const double* __restrict__ T;
   int32_t first_global;
@@ -164,9 +173,12 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
   extern __shared__ double dtw_smem[];
   const int m = P.m, rho = P.rho;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  double* B = dtw_smem;                                  // query
-  double* A = dtw_smem + (size_t)(1 + 2 * warp) * m;     // this warp's (normalised) window
-  double* CB = A + m;                                    // cb[k] = sum_{k' >= k} LB_Keogh contribution of A[k']
+  // per warp: the (normalised) window A[m] and the cumulative LB_Keogh remainder sampled every 8th position
+  const int cbs_len = (m >> 3) + 2;
+  const int warp_doubles = m + ((cbs_len + 1) & ~1);
+  double* B = dtw_smem;                                        // query
+  double* A = dtw_smem + m + (size_t)warp * warp_doubles;      // this warp's window
+  double* CBS = A + m;                                         // CBS[t] = sum_{k >= 8t} contribution of A[k]
   for (int k = threadIdx.x; k < m; k += blockDim.x) B[k] = P.q[k];
   __syncthreads();
 
@@ -174,7 +186,6 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
   if ((long long)n > P.in.cap) n = (unsigned long long)P.in.cap;
   const int tgt_u = rho;  // final cell (m-1, m-1): i-j = 0
   const int tgt_pair = tgt_u >> 1;
-  const int per = (m + 31) / 32;  // contiguous span of cb each lane scans
 
   for (unsigned long long e = (unsigned long long)blockIdx.x * n_warps + warp; e < n;
        e += (unsigned long long)gridDim.x * n_warps) {
@@ -182,30 +193,40 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
     const double mean = P.in.mean[e], stdv = P.in.stdv[e];
     const double* __restrict__ w = P.T + (off - P.first_global);
     __syncwarp();
-    for (int k = lane; k < m; k += 32) {
-      const double a = xdiv(xsub(w[k], mean), stdv);  // NormQueryEngineDtw.java:564-567
-      A[k] = a;
-      const double up = __ldg(P.uq + k), lo = __ldg(P.lq + k);
-      const double d = (a > up) ? (a - up) : ((a < lo) ? (a - lo) : 0.0);
-      CB[k] = d * d;  // K/utils/DtwUtils.java:206-222 contribution of data point k against the query envelope
+    // window -> shared memory; each lane also sums the LB_Keogh contributions (K/utils/DtwUtils.java:206-222) of the
+    // 8-sample groups it owns (group t = samples 8t..8t+7, lane t % 32)
+    for (int t = lane; t < cbs_len; t += 32) {
+      double grp = 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int k = 8 * t + u;
+        if (k < m) {
+          const double a = xdiv(xsub(w[k], mean), stdv);  // NormQueryEngineDtw.java:564-567
+          A[k] = a;
+          const double up = __ldg(P.uq + k), lo = __ldg(P.lq + k);
+          const double dd = (a > up) ? (a - up) : ((a < lo) ? (a - lo) : 0.0);
+          grp += dd * dd;
+        }
+      }
+      CBS[t] = grp;
     }
     __syncwarp();
-    {  // suffix sums of CB (the reference's cb, K/QueryEngineDtw.java:430-441): lane-local spans, then a warp scan
-      const int k0 = lane * per, k1 = min(m, k0 + per);
+    {  // suffix sums over the groups (the reference's cb, K/QueryEngineDtw.java:430-441, at every 8th position)
+      const int per = (cbs_len + 31) / 32;
+      const int t0 = lane * per, t1 = min(cbs_len, t0 + per);
       double run = 0.0;
-      for (int k = k1 - 1; k >= k0; k--) {
-        run += CB[k];
-        CB[k] = run;
+      for (int t = t1 - 1; t >= t0; t--) {
+        run += CBS[t];
+        CBS[t] = run;
       }
-      double right = run;  // inclusive sum of this and all lanes to the right, minus own
       double tot = run;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_down_sync(kFullMask, tot, o);
-        if (lane + o < 32) tot += t;
+        const double tt = __shfl_down_sync(kFullMask, tot, o);
+        if (lane + o < 32) tot += tt;
       }
-      right = tot - run;
-      for (int k = k0; k < k1; k++) CB[k] += right;
+      const double right = tot - run;
+      for (int t = t0; t < t1; t++) CBS[t] += right;
     }
     __syncwarp();
 
@@ -217,6 +238,20 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
     }
     const int u0 = 2 * lane * R;  // band coordinate of this lane's first even cell
     const int last = 2 * m - 2;
+    // Operands in registers: av[r] = A[i0 + r], bv[r] = B[j0 - r] for the lane's R cells of the current step.  Going
+    // from an even to an odd diagonal every i grows by one (av shifts, one new element), from odd to even every j
+    // grows by one (bv shifts) — one LDS per step instead of 2R.
+    double av[R], bv[R];
+    auto ld = [&](const double* base, int idx) { return base[min(max(idx, 0), m - 1)]; };  // clamped: unused when invalid
+    {
+      const int par0 = rho & 1;  // parity of the first step's cells (d = 0)
+      const int i0 = (u0 + par0 - rho) >> 1, j0 = -i0;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        av[r] = ld(A, i0 + r);
+        bv[r] = ld(B, j0 - r);
+      }
+    }
     bool abandoned = false;
     for (int d = 0; d <= last; d++) {
       // Early abandon (the reference abandons per row with min_cost + cb[i+r+1], DtwUtils.java:324-326).  On the
@@ -226,11 +261,11 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
       if ((d & 15) == 0 && d > 0) {
         double mn = kDtwInf;
 #pragma unroll
-        for (int r = 0; r < R; r++) mn = fmin(mn, fmin(Ev[r], Od[r]));
+        for (int r = 0; r < R; r++) mn = umin_pos(mn, umin_pos(Ev[r], Od[r]));
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(kFullMask, mn, o));
+        for (int o = 16; o > 0; o >>= 1) mn = umin_pos(mn, __shfl_xor_sync(kFullMask, mn, o));
         const int imax = min(m - 1, (d - 1 + rho) >> 1);
-        const double rest = (imax + 1 < m) ? CB[imax + 1] : 0.0;
+        const double rest = CBS[(imax + 1 + 7) >> 3];  // first sampled position >= imax+1: a (slightly smaller) valid remainder
         if (mn + rest > P.eps2_hi) {
           abandoned = true;
           break;
@@ -242,17 +277,22 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
         // i = (d + u - rho)/2, j = d - i ; consecutive pairs: i+1, j-1
         const int s = d + u0 - rho;
         const int i0 = s >> 1;  // s is even here
+        if (d > 0) {            // odd -> even: j grows by one
+#pragma unroll
+          for (int r = R - 1; r > 0; r--) bv[r] = bv[r - 1];
+          bv[0] = ld(B, d - i0);
+        }
 #pragma unroll
         for (int r = 0; r < R; r++) {
           const int i = i0 + r, j = d - i;
-          const bool valid = (u0 + 2 * r <= 2 * rho) && i >= 0 && j >= 0 && i < m && j < m && s + 2 * r >= 0;
+          const bool valid = (u0 + 2 * r <= 2 * rho) && i >= 0 && j >= 0 && i < m && j < m;
           double v = kDtwInf;
           if (valid) {
-            const double c = xsqdist(A[i], B[j]);
+            const double c = xsqdist(av[r], bv[r]);
             const double x = (r == 0) ? left : Od[r - 1];
             const double y = Od[r];
             const double z = Ev[r];
-            v = (d == 0) ? c : xadd(xmin(xmin(x, y), z), c);
+            v = (d == 0) ? c : xadd(umin_pos(umin_pos(x, y), z), c);
           }
           Ev[r] = v;
         }
@@ -261,17 +301,22 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
         if (lane == 31) right = kDtwInf;
         const int s = d + u0 + 1 - rho;
         const int i0 = s >> 1;
+        if (d > 0) {            // even -> odd: i grows by one
+#pragma unroll
+          for (int r = 0; r < R - 1; r++) av[r] = av[r + 1];
+          av[R - 1] = ld(A, i0 + R - 1);
+        }
 #pragma unroll
         for (int r = 0; r < R; r++) {
           const int i = i0 + r, j = d - i;
-          const bool valid = (u0 + 2 * r + 1 <= 2 * rho) && i >= 0 && j >= 0 && i < m && j < m && s + 2 * r >= 0;
+          const bool valid = (u0 + 2 * r + 1 <= 2 * rho) && i >= 0 && j >= 0 && i < m && j < m;
           double v = kDtwInf;
           if (valid) {
-            const double c = xsqdist(A[i], B[j]);
+            const double c = xsqdist(av[r], bv[r]);
             const double x = Ev[r];
             const double y = (r == R - 1) ? right : Ev[r + 1];
             const double z = Od[r];
-            v = (d == 0) ? c : xadd(xmin(xmin(x, y), z), c);
+            v = (d == 0) ? c : xadd(umin_pos(umin_pos(x, y), z), c);
           }
           Od[r] = v;
         }

@@ -615,12 +615,13 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
 int launch_dtw(kvm_ctx* ctx, const DtwParams& D) {
   const int need = (D.rho + 1 + 31) / 32;  // (even,odd) pairs per lane
   const size_t bytes_per_row = sizeof(double) * (size_t)D.m;
+  const size_t warp_bytes = sizeof(double) * (size_t)(D.m + ((((D.m >> 3) + 2) + 1) & ~1));  // window + sampled cb
   const size_t smem_budget = 200 * 1024;
-  if (3 * bytes_per_row > smem_budget)
+  if (bytes_per_row + warp_bytes > smem_budget)
     return fail(ctx, KVM_E_ARG, "DTW query length %d exceeds the shared-memory staging limit (%zu)", D.m,
-                smem_budget / 24);
-  int warps = (int)std::min<size_t>(8, (smem_budget / bytes_per_row - 1) / 2);
-  const size_t smem = bytes_per_row * (2 * warps + 1);
+                smem_budget / 17);
+  const int warps = (int)std::min<size_t>(8, (smem_budget - bytes_per_row) / warp_bytes);
+  const size_t smem = bytes_per_row + warp_bytes * warps;
   const int grid = ctx->n_sms * std::max(1, (int)(smem_budget / smem));
 #define KVM_DTW_CASE(R)                                                                                        \
   if (need <= R) {                                                                                             \
