@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkvmatch_gpu.so")
+LIB_PATH = os.environ.get("KVM_LIB") or os.path.join(_HERE, "libkvmatch_gpu.so")  # KVM_LIB: developer A/B builds
 
 KVM_OK = 0
 KVM_E_NODEVICE = -1

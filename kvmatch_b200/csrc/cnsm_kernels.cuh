@@ -129,10 +129,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-constexpr int kStageBlocks = 4;   // ring of staged (ex, ex2) blocks between the chain warp and the gate warps
+#ifndef KVM_STAGE_BLOCKS
+#define KVM_STAGE_BLOCKS 4
+#endif
+#ifndef KVM_WALK_STAGES
+#define KVM_WALK_STAGES 4
+#endif
+constexpr int kWalkStages = KVM_WALK_STAGES;  // tile ring depth
+constexpr int kStageBlocks = KVM_STAGE_BLOCKS;   // ring of staged (ex, ex2) blocks between the chain warp and the gate warps
 constexpr int kBlockCols = 16;    // window positions per staged block
 constexpr int kStagePitch = kBlockCols + 1;  // double2 per lane row: conflict-free lane-private 16-byte accesses
-constexpr int kGateWarps = 3;
+#ifndef KVM_GATE_WARPS
+#define KVM_GATE_WARPS 3
+#endif
+constexpr int kGateWarps = KVM_GATE_WARPS;
+static_assert(kStageBlocks % kGateWarps != 0 ? kStageBlocks > kGateWarps : true, "a slot must not be awaited by two gate warps at once");
 constexpr int kWalkThreads = 32 * (2 + kGateWarps); // warp 0: chain walker; warps 1..kGateWarps: gates; last warp: tile loader
 constexpr size_t walk_smem_bytes(int stages) {
   return sizeof(double) * (size_t)walk_tile_doubles(stages) + sizeof(double2) * kStageBlocks * 32 * kStagePitch +
@@ -450,6 +461,359 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
       }
       bar_arrive(1 + kStageBlocks + slot, 64);  // slot may be overwritten
     }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) P.region_count[region] = *s_rcount;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Relay walker.  The only sequential thing in the statistics pass is the chain state (ex, ex2): loading
+// the samples, squaring them, gating the window sums and appending to the work list are not.  So the
+// CTA's 32 chains are walked by kRelayWarps warps taking turns: a turn is kRelayBlock window positions.
+// A warp's turn has three phases,
+//   prepare  wait for the tile, pull the turn's samples from shared memory into registers (incoming a[],
+//            outgoing o[]), mask them if the turn touches a chain end (and, for 16-position turns, square them);
+//   walk     receive (ex, ex2) from the previous turn's warp (shared-memory slot + named barrier), run the
+//            2 x 2 dependent DADDs per position with no memory instruction in the stream, hand the state on;
+//   gate     pre-gate the turn's post-add sums from registers and append the passing ones,
+// and only `walk` is on the critical path: the other warps prepare and gate while one walks.  Per
+// position the critical path is 2 dependent DADDs (16.1 cycles) plus 1/kRelayBlock of a hand-off
+// (measured ~230 cycles: STS -> BAR.ARV -> BAR.SYNC -> LDS; polling a shared-memory slot instead was
+// slower, ~540 cycles, and so was an mbarrier).
+// Tiles: incoming rows as in the walker above; outgoing rows carry one extra leading 16-byte pair
+// (34 samples, pitch 38) so that a turn never needs the previous tile when m is even (kDelta = 1: the
+// outgoing sample of tile column j is row element j + 1; kDelta = 0: element j + 2).
+#ifndef KVM_RELAY_WARPS
+#define KVM_RELAY_WARPS 4
+#endif
+#ifndef KVM_RELAY_BLOCK
+#define KVM_RELAY_BLOCK 16
+#endif
+constexpr int kRelayWarps = KVM_RELAY_WARPS;
+constexpr int kRelayThreads = 32 * (kRelayWarps + 1);  // warps 0..kRelayWarps-1 take turns, the last warp loads tiles
+constexpr int kRelayBlock = KVM_RELAY_BLOCK;           // window positions per turn: 16 or 32
+constexpr int kRelayTurnsPerTile = kWalkTile / kRelayBlock;
+constexpr bool kRelaySquareInWalk = kRelayBlock > 16;  // 32-position turns: no registers left for precomputed squares
+static_assert(kRelayBlock == 16 || kRelayBlock == 32, "a turn is half a tile or a tile");
+constexpr int kInPitch = 34;   // doubles; 16-byte aligned rows, conflict-free lane-private LDS.128
+constexpr int kOutPitch = 38;  // 34 samples + pad: lane stride 12 banks (mod 32) -> conflict-free LDS.128
+constexpr int kRelayStageDoubles = 32 * (kInPitch + kOutPitch);
+constexpr int kGatePitch = kRelayBlock + 1;  // double2 per lane row of a relay warp's flush staging (dense turns only)
+constexpr size_t relay_smem_bytes(int stages) {
+  return sizeof(double) * (size_t)stages * kRelayStageDoubles + sizeof(double2) * 2 * 32 +
+         sizeof(double2) * kRelayWarps * 32 * kGatePitch + sizeof(unsigned long long) * 2 * stages + 16;
+}
+
+#ifdef KVM_RELAY_PROF
+__device__ unsigned long long g_relay_prof[8 * 8];  // per relay warp: cycles in tile wait, prepare, state wait, walk, gate; turns
+__device__ __forceinline__ long long relay_clock() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
+#define RELAY_T(var) const long long var = relay_clock()
+#define RELAY_ACC(acc, expr) acc += (expr)
+#else
+#define RELAY_T(var)
+#define RELAY_ACC(acc, expr)
+#endif
+
+template <int STAGES, int kDelta, int kMode = 0>
+__global__ void __launch_bounds__(kRelayThreads, kRelayThreads <= 160 ? 2 : 1) cnsm_relay_kernel(WalkParams P) {
+  extern __shared__ __align__(16) unsigned char walk_smem_raw[];
+  double* tiles = reinterpret_cast<double*>(walk_smem_raw);  // [STAGES][ in 32 x kInPitch | out 32 x kOutPitch ]
+  double2* state = reinterpret_cast<double2*>(tiles + (size_t)STAGES * kRelayStageDoubles);  // [2][32]
+  double2* gate_stage = state + 2 * 32;                                                      // [kRelayWarps][32][kGatePitch]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(gate_stage + kRelayWarps * 32 * kGatePitch);
+  int* s_rcount = reinterpret_cast<int*>(bars + 2 * STAGES);
+
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  asm volatile("mov.u32 %0, %0;" : "+r"(lane));  // keep out of SR_TID.X re-reads in the loops
+  asm volatile("mov.u32 %0, %0;" : "+r"(warp));
+  const int region = blockIdx.x;
+  const int c = region * 32 + lane;
+  int pos = 0, len = 0;
+  if (c < P.K) {
+    pos = P.cbegin[c];
+    len = P.cnsamp[c];
+  }
+  const int m = P.m;
+  const int sha = pos & 1;  // column of sample 0 in the incoming tiles
+  const int ntl = (len > 0) ? (len + sha + kWalkTile - 1) / kWalkTile : 0;
+  const int ntiles = warp_max_i32(ntl);
+  const int k_w = (m - 1) / kWalkTile;  // first tile that can contain the end of a complete window
+  const uint32_t bar_ready = smem_u32(bars), bar_free = bar_ready + 8 * STAGES;
+  if (threadIdx.x == 0) {
+    *s_rcount = 0;
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(bar_ready + 8 * s, 32);
+      mbar_init(bar_free + 8 * s, kRelayTurnsPerTile);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kRelayWarps) {
+    // ------------------------------------------------------------------ tile loader
+    const int ab = pos - sha;                         // 16-byte aligned base of the incoming rows
+    const int ob = pos - (m - 1) - sha + kDelta - 2;  // aligned base of the outgoing rows (one pair early)
+    const double* __restrict__ T = P.T;
+    const int idx_lo = -kFrontPad, idx_hi = P.idx_hi;
+    int a_idx[16], o_idx[16];
+    {
+      const int half = lane >> 4, piece = (lane & 15) * 2;
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        a_idx[i] = __shfl_sync(kFullMask, ab, 2 * i + half) + piece;
+        o_idx[i] = __shfl_sync(kFullMask, ob, 2 * i + half) + piece + 2;
+      }
+    }
+    const unsigned long long pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+    const uint32_t t0 = smem_u32(tiles);
+    const uint32_t dst_in = t0 + (uint32_t)(((lane >> 4) * kInPitch + (lane & 15) * 2) * 8);
+    const uint32_t dst_out = t0 + (uint32_t)((32 * kInPitch + (lane >> 4) * kOutPitch + (lane & 15) * 2 + 2) * 8);
+    const uint32_t dst_lead = t0 + (uint32_t)((32 * kInPitch + lane * kOutPitch) * 8);
+    constexpr uint32_t kStageBytes = kRelayStageDoubles * 8;
+    for (int k = 0; k < ntiles; k++) {
+      const int stage = k % STAGES;
+      if (k >= STAGES) mbar_wait(bar_free + 8 * stage, (uint32_t)(((k / STAGES) - 1) & 1));
+      const uint32_t so = (uint32_t)stage * kStageBytes;
+      const int koff = k * kWalkTile;
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int ia = max(min(a_idx[i] + koff, idx_hi), idx_lo);
+        const int io = max(min(o_idx[i] + koff, idx_hi), idx_lo);
+        cp_async16_hint(dst_in + so + i * (2 * kInPitch * 8), T + ia, pol_keep);
+        cp_async16_hint(dst_out + so + i * (2 * kOutPitch * 8), T + io, pol_drop);
+      }
+      {
+        const int io = max(min(ob + koff, idx_hi), idx_lo);  // this lane's row, leading pair
+        cp_async16_hint(dst_lead + so, T + io, pol_drop);
+      }
+      mbar_arrive_on_cp_async(bar_ready + 8 * stage);
+    }
+  } else {
+    // ------------------------------------------------------------------ relay warps
+    const int nb = kRelayTurnsPerTile * ntiles;
+    const long long base = P.region_base[region];
+    const int mean_klo = P.mean_klo, var_klo = P.var_klo;
+    const unsigned mean_kspan = P.mean_kspan, var_kspan = P.var_kspan;
+    const double dm = P.dm;
+    const int32_t off0 = P.first_global + pos - (m - 1) - sha;  // + tile column = 1-based global window start
+#ifdef KVM_RELAY_PROF
+    long long pf_tile = 0, pf_prep = 0, pf_state = 0, pf_walk = 0, pf_gate = 0, pf_turns = 0;
+#endif
+    auto turn = [&](int b, auto steady_tag) {
+      constexpr bool kSteady = decltype(steady_tag)::value;
+      RELAY_T(t_a);
+      const int k = b / kRelayTurnsPerTile, h = b % kRelayTurnsPerTile;
+      const int col0 = b * kRelayBlock;  // tile column of the turn's first position
+      const int stage = k % STAGES;
+      // ---- prepare
+      const double* ra = tiles + (size_t)stage * kRelayStageDoubles + lane * kInPitch + h * kRelayBlock;
+      const double* ro = tiles + (size_t)stage * kRelayStageDoubles + 32 * kInPitch + lane * kOutPitch + h * kRelayBlock;
+      double a[kRelayBlock], o[kRelayBlock];
+#pragma unroll
+      for (int i = 0; i < kRelayBlock / 2; i++) {
+        const double2 v = *reinterpret_cast<const double2*>(ra + 2 * i);
+        a[2 * i] = v.x;
+        a[2 * i + 1] = v.y;
+      }
+      if (kDelta) {
+        double2 v = *reinterpret_cast<const double2*>(ro);
+        o[0] = v.y;
+#pragma unroll
+        for (int i = 1; i < kRelayBlock / 2; i++) {
+          v = *reinterpret_cast<const double2*>(ro + 2 * i);
+          o[2 * i - 1] = v.x;
+          o[2 * i] = v.y;
+        }
+        v = *reinterpret_cast<const double2*>(ro + kRelayBlock);
+        o[kRelayBlock - 1] = v.x;
+      } else {
+#pragma unroll
+        for (int i = 0; i < kRelayBlock / 2; i++) {
+          const double2 v = *reinterpret_cast<const double2*>(ro + 2 + 2 * i);
+          o[2 * i] = v.x;
+          o[2 * i + 1] = v.y;
+        }
+      }
+      const int s0 = col0 - sha;  // chain-relative index of the turn's first sample
+      if (!kSteady) {
+#pragma unroll
+        for (int j = 0; j < kRelayBlock; j++) {
+          const int s = s0 + j;
+          const bool act = (unsigned)s < (unsigned)len;
+          a[j] = act ? a[j] : 0.0;
+          o[j] = (act & (s >= m - 1)) ? o[j] : 0.0;
+        }
+      }
+      constexpr int kSq = kRelaySquareInWalk ? 1 : kRelayBlock;
+      double as[kSq], os[kSq];
+      if (!kRelaySquareInWalk) {
+#pragma unroll
+        for (int j = 0; j < kSq; j++) {
+          as[j] = xmul(a[j], a[j]);
+          os[j] = xmul(o[j], o[j]);
+        }
+        // pin the prepared operands in front of the hand-off (an empty volatile asm is not moved across bar.sync)
+#pragma unroll
+        for (int j = 0; j < kSq; j++) asm volatile("" : "+d"(as[j]), "+d"(os[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < kRelayBlock; j++) asm volatile("" : "+d"(a[j]), "+d"(o[j]));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_free + 8 * stage);  // this turn's reads of the tile are done
+      RELAY_T(t_b);
+      // ---- walk
+      double ex = 0.0, ex2 = 0.0;
+      if (b > 0) {
+        bar_sync(1 + ((b - 1) % kRelayWarps), 64);
+        const double2 st = state[((b - 1) & 1) * 32 + lane];
+        ex = st.x;
+        ex2 = st.y;
+      }
+#ifdef KVM_RELAY_PROF
+      asm volatile("" : "+d"(ex), "+d"(ex2));  // the state has arrived (BAR.SYNC blocks at its first consumer)
+#endif
+      RELAY_T(t_c);
+      double qx[kRelayBlock], q2[kRelayBlock];
+#pragma unroll
+      for (int j = 0; j < kRelayBlock; j++) {
+        const double aj2 = kRelaySquareInWalk ? xmul(a[j], a[j]) : as[j % kSq];
+        const double oj2 = kRelaySquareInWalk ? xmul(o[j], o[j]) : os[j % kSq];
+        ex = xadd(ex, a[j]);   // K/NormQueryEngine.java:498
+        ex2 = xadd(ex2, aj2);  // :499
+        qx[j] = ex;
+        q2[j] = ex2;
+        ex = xsub(ex, o[j]);   // :523
+        ex2 = xsub(ex2, oj2);  // :524
+      }
+      if (b + 1 < nb) {
+        state[(b & 1) * 32 + lane] = make_double2(ex, ex2);
+        bar_arrive(1 + (b % kRelayWarps), 64);
+      }
+      RELAY_T(t_d);
+      RELAY_ACC(pf_prep, t_b - t_a);
+      RELAY_ACC(pf_state, t_c - t_b);
+      RELAY_ACC(pf_walk, t_d - t_c);
+      RELAY_ACC(pf_turns, 1);
+      // ---- gate
+      if (k >= k_w) {  // (warm-up tiles: no complete window ends there)
+        if (kMode == 1) {
+          // IndexBuilder step 1 (K/IndexBuilder.java:251-265): key bucket of every window mean; b from one multiply
+          // when ex*(20/w) is clear of an integer by more than the rounding slack, else the reference's exact
+          // divide / multiply (MeanIntervalUtils.toRound, K/utils/MeanIntervalUtils.java:51-61).
+#pragma unroll
+          for (int j = 0; j < kRelayBlock; j++) {
+            const int s = s0 + j;
+            const bool win = kSteady || (((unsigned)s < (unsigned)len) & (s >= m - 1));
+            const double e = qx[j];
+            const double v2 = e * P.c20w;
+            double fl = floor(v2);
+            const double frac = v2 - fl;
+            const double gd = fabs(v2) * 4e-15 + 1e-290;
+            if (win && !(frac >= gd && frac <= 1.0 - gd)) {
+              const double v = xmul(xdiv(e, dm), 10.0);
+              fl = floor(xadd(v, v));  // 2v is exact
+            }
+            if (win) {
+              if (!(fabs(fl) < 2147483000.0)) *P.overflow = 1;
+              P.bucket_out[pos + s - (m - 1)] = (int)fl;
+            }
+          }
+        } else {
+          // mean gate first (integer pipe only); the variance keys are computed only if some window of the turn passed it
+          unsigned mask = 0;
+#pragma unroll
+          for (int j = 0; j < kRelayBlock; j++) {
+            const int s = s0 + j;
+            const bool win = kSteady || (((unsigned)s < (unsigned)len) & (s >= m - 1));
+            const bool pass = win & ((unsigned)(hi_key(qx[j]) - mean_klo) <= mean_kspan);
+            mask |= pass ? (1u << j) : 0u;
+          }
+          if (__any_sync(kFullMask, mask != 0)) {
+#pragma unroll
+            for (int j = 0; j < kRelayBlock; j++) {
+              const double v = __fma_rn(q2[j], dm, -(qx[j] * qx[j]));
+              const bool pass = (unsigned)(hi_key(v) - var_klo) <= var_kspan;
+              mask &= pass ? 0xffffffffu : ~(1u << j);
+            }
+            if (__any_sync(kFullMask, mask != 0)) {
+              const int cnt = __popc(mask);
+              const int incl = warp_incl_scan_i32(cnt, lane);
+              const int total = __shfl_sync(kFullMask, incl, 31);
+              int rbase = 0;
+              if (lane == 0) rbase = atomicAdd(s_rcount, total);
+              rbase = __shfl_sync(kFullMask, rbase, 0);
+              const int excl = incl - cnt;
+              if (kRelayBlock == 16 && total > 96) {
+                // dense turn (a matching region): transpose through this warp's staging rows so that every store
+                // instruction writes two runs of consecutive work-list slots — two chains per round, half a warp
+                // each, lane c of a half copies column c of its chain if it passed
+                double2* gs = gate_stage + (size_t)warp * 32 * kGatePitch;
+#pragma unroll
+                for (int j = 0; j < kRelayBlock; j++) gs[lane * kGatePitch + j] = make_double2(qx[j], q2[j]);
+                __syncwarp();
+                const unsigned nz = __ballot_sync(kFullMask, cnt > 0);
+                const int hl = lane & 15, hw = lane >> 4;
+                for (int pr = 0; pr < 16; pr++) {
+                  if (((nz >> (2 * pr)) & 3u) == 0) continue;
+                  const int owner = 2 * pr + hw;
+                  const unsigned omask = __shfl_sync(kFullMask, mask, owner);
+                  const int oexcl = __shfl_sync(kFullMask, excl, owner);
+                  const int32_t ooff = __shfl_sync(kFullMask, off0, owner);
+                  if ((omask >> hl) & 1u) {
+                    const double2 v2 = gs[owner * kGatePitch + hl];
+                    const long long gidx = base + rbase + oexcl + __popc(omask & ((1u << hl) - 1u));
+                    P.e_off[gidx] = ooff + col0 + hl;
+                    P.e_ex[gidx] = v2.x;
+                    P.e_ex2[gidx] = v2.y;
+                  }
+                }
+                __syncwarp();
+              } else {
+                long long gidx = base + rbase + excl;  // a chain's entries of the turn stay contiguous
+#pragma unroll
+                for (int j = 0; j < kRelayBlock; j++) {
+                  if ((mask >> j) & 1u) {
+                    P.e_off[gidx] = off0 + col0 + j;
+                    P.e_ex[gidx] = qx[j];
+                    P.e_ex2[gidx] = q2[j];
+                    gidx++;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      RELAY_T(t_e);
+      RELAY_ACC(pf_gate, t_e - t_d);
+    };
+    for (int b = warp; b < nb; b += kRelayWarps) {
+      const int k = b / kRelayTurnsPerTile;
+      RELAY_T(t_w0);
+      mbar_wait(bar_ready + 8 * (k % STAGES), (uint32_t)((k / STAGES) & 1));  // tile k has landed
+      RELAY_T(t_w1);
+      RELAY_ACC(pf_tile, t_w1 - t_w0);
+      const int sbase = b * kRelayBlock - sha;
+      const bool steady = __all_sync(kFullMask, (sbase >= m - 1) && (sbase + kRelayBlock <= len));
+      if (steady) turn(b, std::true_type{});
+      else turn(b, std::false_type{});
+    }
+#ifdef KVM_RELAY_PROF
+    if (lane == 0) {
+      atomicAdd(&g_relay_prof[warp * 8 + 0], (unsigned long long)pf_tile);
+      atomicAdd(&g_relay_prof[warp * 8 + 1], (unsigned long long)pf_prep);
+      atomicAdd(&g_relay_prof[warp * 8 + 2], (unsigned long long)pf_state);
+      atomicAdd(&g_relay_prof[warp * 8 + 3], (unsigned long long)pf_walk);
+      atomicAdd(&g_relay_prof[warp * 8 + 4], (unsigned long long)pf_gate);
+      atomicAdd(&g_relay_prof[warp * 8 + 5], (unsigned long long)pf_turns);
+    }
+#endif
   }
   __syncthreads();
   if (threadIdx.x == 0) P.region_count[region] = *s_rcount;
