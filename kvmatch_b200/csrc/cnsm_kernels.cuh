@@ -5,21 +5,21 @@
 // chain (ex += d; ...; ex -= T[j]) that restarts at every merged interval.  Its rounding errors
 // accumulate along the chain, so a prefix-sum or fresh-sum kernel cannot reproduce it to better than
 // ~1e-7 relative on long chains — not enough for bit-exact alpha/beta gates or 1e-9 distances.  The
-// chain is therefore emulated exactly: ONE THREAD PER CHAIN, the 32 lanes of a warp walking 32
-// different chains in lock-step.  Samples reach the lanes through a multi-stage ring of shared-memory
-// tiles filled asynchronously with 16-byte cp.async copies (two full 256-byte rows per instruction), preceded
-// by L2 line prefetches, so HBM sees only long sequential streams and the warp's issue slots go to the
-// two dependent FP64 chains.
+// chain is therefore emulated exactly: one lane per chain, 32 chains per CTA, and the only sequential
+// part — the (ex, ex2) recurrence — relayed between warps so that nothing else sits on its critical path.
+// Samples reach the lanes through a multi-stage ring of shared-memory tiles filled asynchronously with
+// 16-byte cp.async copies (two full 256-byte rows per instruction) carrying L2 eviction hints.
 //
-//   cnsm_walk_kernel   chain-exact ex/ex2 per window + a cheap conservative alpha/beta pre-gate;
-//                      windows that may pass are appended (offset, ex, ex2) to the warp's private
-//                      region of the work list (no global atomics in the streaming loop)
+//   cnsm_relay_kernel  chain-exact ex/ex2 per window + a cheap conservative alpha/beta pre-gate;
+//                      windows that may pass are appended (offset, ex, ex2) to the CTA's private
+//                      region of the work list (no global atomics in the streaming loop);
+//                      kMode 1: per-window key buckets for IndexBuilder's window-mean pass
 //   cnsm_plan_kernel   exclusive scan of per-region tile counts -> flat tile index for the evaluators
 //   cnsm_ed_eval_kernel  one thread per work-list entry: exact mean/std/gate (reference arithmetic),
-//                      then a fast FMA distance in |zQ|-descending order with early abandon against
+//                      then a fast 32-term FMA screen in |zQ|-descending order against
 //                      eps^2*(1+1e-9); survivors go to the exact list
-//   cnsm_ed_exact_kernel one thread per survivor: the reference's sequential, unfused sum -> the
-//                      accepted distances are bit-identical to the Java loop's
+//   cnsm_ed_exact_kernel one warp per survivor: warp-cooperative fast distance, then the reference's
+//                      sequential, unfused sum -> the accepted distances are bit-identical to the Java loop's
 #pragma once
 #include <type_traits>
 
@@ -28,15 +28,10 @@
 namespace kvm {
 
 constexpr int kWalkTile = 32;      // samples (columns) per shared-memory tile row
-constexpr int kWalkPitch = 34;     // row pitch in doubles: 16-byte aligned rows, conflict-free lane-private LDS.128
-constexpr int kFifoDepth = 16;     // per-lane staging of work-list entries between flushes
-constexpr int kFifoPitch = kFifoDepth + 1;
 constexpr int kFrontPad = 64;      // zero samples the ctx keeps in front of / behind the series so that
 constexpr int kTailPad = 192;      // whole-row bulk copies never leave the allocation
 constexpr int kFastTerms = 32;     // terms of the evaluator's fast screen
 constexpr int kEvalTile = 128;     // work-list entries per evaluator tile (= evaluator CTA size)
-
-constexpr int walk_tile_doubles(int stages) { return stages * 2 * 32 * kWalkPitch; }
 
 // ---- asynchronous global->shared copies (LDGSTS) ----------------------------------------------------
 // Per-lane 256-byte TMA row copies (cp.async.bulk) were measured first: the TMA unit serialises such small
@@ -129,343 +124,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-#ifndef KVM_STAGE_BLOCKS
-#define KVM_STAGE_BLOCKS 4
-#endif
-#ifndef KVM_WALK_STAGES
-#define KVM_WALK_STAGES 4
-#endif
-constexpr int kWalkStages = KVM_WALK_STAGES;  // tile ring depth
-constexpr int kStageBlocks = KVM_STAGE_BLOCKS;   // ring of staged (ex, ex2) blocks between the chain warp and the gate warps
-constexpr int kBlockCols = 16;    // window positions per staged block
-constexpr int kStagePitch = kBlockCols + 1;  // double2 per lane row: conflict-free lane-private 16-byte accesses
-#ifndef KVM_GATE_WARPS
-#define KVM_GATE_WARPS 3
-#endif
-constexpr int kGateWarps = KVM_GATE_WARPS;
-static_assert(kStageBlocks % kGateWarps != 0 ? kStageBlocks > kGateWarps : true, "a slot must not be awaited by two gate warps at once");
-constexpr int kWalkThreads = 32 * (2 + kGateWarps); // warp 0: chain walker; warps 1..kGateWarps: gates; last warp: tile loader
-constexpr size_t walk_smem_bytes(int stages) {
-  return sizeof(double) * (size_t)walk_tile_doubles(stages) + sizeof(double2) * kStageBlocks * 32 * kStagePitch +
-         sizeof(unsigned long long) * 2 * stages + 16;
-}
-
-// One CTA = 32 chains = one work-list region, five specialised warps:
-//   last warp (loader)     fills the tile ring: STAGES x (incoming, outgoing) tiles, row = 32 consecutive samples of
-//     one chain, by 16-byte cp.async copies (half a warp per row: every copy instruction moves two full 256-byte
-//     rows) with L2 eviction hints (incoming rows evict_last — they are re-read m-1 steps later as outgoing rows,
-//     which are read evict_first), and lets an mbarrier per stage track their completion.
-//   warp 0 (chain walker)  keeps only the two dependent FP64 recurrences (ex, ex2) in its instruction stream: per
-//     window position 1 LDS.128 per stream per sample pair (register double-buffered), 4 DADD, 2 DMUL and one
-//     STS.128 of the post-add (ex, ex2) into a staging block.  Its pace is the 2 x 8-cycle dependent-DADD latency.
-//   warps 1-3 (gates)      take staged blocks round-robin: conservative alpha/beta pre-gate on integer keys of the high
-//     words, then a warp-cooperative, coalesced append of the passing (offset, ex, ex2) to the region's slice of the
-//     work list.  Hand-off is by named barriers (bar.arrive / bar.sync), 4 blocks deep.
-// Rows are 16-byte aligned in global memory: the incoming row starts at pos & ~1; kDelta = 1 when m is even (the
-// outgoing row is then aligned one sample later, so its columns lag the incoming ones by one).
-template <int STAGES, int kDelta, int kMode = 0>
-__global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
-  extern __shared__ __align__(16) unsigned char walk_smem_raw[];
-  double* tiles = reinterpret_cast<double*>(walk_smem_raw);                      // [STAGES][2][32][pitch]
-  double2* stage_ring = reinterpret_cast<double2*>(tiles + walk_tile_doubles(STAGES));  // [blocks][32][kStagePitch]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(stage_ring + kStageBlocks * 32 * kStagePitch);
-  int* s_rcount = reinterpret_cast<int*>(bars + 2 * STAGES);
-
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // keep lane/warp in registers: ptxas otherwise re-reads SR_TID.X (a ~100-cycle S2R) inside the walker's hot loop
-  asm volatile("mov.u32 %0, %0;" : "+r"(lane));
-  asm volatile("mov.u32 %0, %0;" : "+r"(warp));
-  const int region = blockIdx.x;
-  const int c = region * 32 + lane;
-  int pos = 0, len = 0;
-  if (c < P.K) {
-    pos = P.cbegin[c];
-    len = P.cnsamp[c];
-  }
-  const int m = P.m;
-  const int sha = pos & 1;                 // column of sample 0 in the incoming tiles
-  const int ntl = (len > 0) ? (len + sha + kWalkTile - 1) / kWalkTile : 0;
-  const int ntiles = warp_max_i32(ntl);
-  const int k_w = (m - 1) / kWalkTile;     // first tile that can contain the end of a complete window
-  const int n_blocks = ntiles > k_w ? 2 * (ntiles - k_w) : 0;
-  const uint32_t bar_ready = smem_u32(bars), bar_free = bar_ready + 8 * STAGES;
-  if (threadIdx.x == 0) {
-    *s_rcount = 0;
-#pragma unroll
-    for (int s = 0; s < STAGES; s++) {
-      mbar_init(bar_ready + 8 * s, 32);
-      mbar_init(bar_free + 8 * s, 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (warp == 1 + kGateWarps) {
-    // ------------------------------------------------------------------ tile loader
-    const int ab = pos - sha;                     // 16-byte aligned base of the incoming rows
-    const int ob = pos - (m - 1) - sha + kDelta;  // aligned base of the outgoing rows
-    const double* __restrict__ T = P.T;
-    const int idx_lo = -kFrontPad, idx_hi = P.idx_hi;
-    // copy i of a tile: lanes 0-15 fill row 2i, lanes 16-31 row 2i+1, 16 bytes each
-    int a_idx[16], o_idx[16];
-    {
-      const int half = lane >> 4, piece = (lane & 15) * 2;
-#pragma unroll
-      for (int i = 0; i < 16; i++) {
-        a_idx[i] = __shfl_sync(kFullMask, ab, 2 * i + half) + piece;
-        o_idx[i] = __shfl_sync(kFullMask, ob, 2 * i + half) + piece;
-      }
-    }
-    const unsigned long long pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
-    const uint32_t dst0 = smem_u32(tiles) + (uint32_t)(((lane >> 4) * kWalkPitch + (lane & 15) * 2) * 8);
-    constexpr uint32_t kStageBytes = 2 * 32 * kWalkPitch * 8, kStreamBytes = 32 * kWalkPitch * 8;
-    constexpr uint32_t kPairBytes = 2 * kWalkPitch * 8;
-    for (int k = 0; k < ntiles; k++) {
-      const int stage = k % STAGES;
-      if (k >= STAGES) mbar_wait(bar_free + 8 * stage, (uint32_t)(((k / STAGES) - 1) & 1));  // chain warp left tile k-STAGES
-      const uint32_t dst = dst0 + (uint32_t)stage * kStageBytes;
-      const int koff = k * kWalkTile;
-#pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const int ia = max(min(a_idx[i] + koff, idx_hi), idx_lo);
-        const int io = max(min(o_idx[i] + koff, idx_hi), idx_lo);
-        cp_async16_hint(dst + i * kPairBytes, T + ia, pol_keep);
-        cp_async16_hint(dst + kStreamBytes + i * kPairBytes, T + io, pol_drop);
-      }
-      mbar_arrive_on_cp_async(bar_ready + 8 * stage);
-    }
-  } else if (warp == 0) {
-    // ------------------------------------------------------------------ chain walker (producer)
-    // One tile (16 sample pairs = 32 window positions = 2 staged blocks) per loop iteration, fully unrolled.
-    // Samples come through a 4-pair rolling register window: pair i+4 is loaded (one LDS.128 per stream) while
-    // pair i is consumed, across tile borders too (the next tile's mbarrier is polled at pair 12), so the
-    // shared-memory loads are spread along the dependent FP64 chain instead of bunching at block ends.
-    double ex = 0.0, ex2 = 0.0, carry = 0.0;
-    constexpr int kAhead = 4;
-    double2 RA[kAhead], RO[kAhead];
-    auto tile_rows = [&](int k, const double*& ra, const double*& ro) {
-      ra = tiles + (size_t)(k % STAGES) * (2 * 32 * kWalkPitch) + lane * kWalkPitch;
-      ro = ra + 32 * kWalkPitch;
-    };
-    int b = 0, pending_slot = -1;
-    // kStore: stage the post-add (ex, ex2) of every position; kSteady: every lane's columns are inside its chain
-    // and past the warm-up, so no per-column selects are needed.
-    auto walk_tile = [&](int k, auto store_tag, auto steady_tag) {
-      constexpr bool kStore = decltype(store_tag)::value, kSteady = decltype(steady_tag)::value;
-      const double* ra;
-      const double* ro;
-      tile_rows(k, ra, ro);
-      const double* na = nullptr;  // next tile's rows, valid once its copies have landed
-      const double* no = nullptr;
-      const int s0 = k * kWalkTile - sha;
-      double2* st = nullptr;
-      double2 p0 = make_double2(0.0, 0.0), p1 = p0;
-#pragma unroll
-      for (int i = 0; i < 16; i++) {
-        if (kStore && (i == 0 || i == 8)) {  // a new 16-position block starts: pick its staging slot
-          const int slot = b % kStageBlocks;
-          st = stage_ring + ((size_t)slot * 32 + lane) * kStagePitch;
-        }
-        const double2 A = RA[i % kAhead], O = RO[i % kAhead];
-        // refill this register slot with the pair 4 ahead
-        if (i + kAhead < 16) {
-          RA[i % kAhead] = *reinterpret_cast<const double2*>(ra + 2 * (i + kAhead));
-          RO[i % kAhead] = *reinterpret_cast<const double2*>(ro + 2 * (i + kAhead));
-        } else {
-          if (i + kAhead == 16 && k + 1 < ntiles) {
-            mbar_wait(bar_ready + 8 * ((k + 1) % STAGES), (uint32_t)(((k + 1) / STAGES) & 1));  // tile k+1 has landed
-            tile_rows(k + 1, na, no);
-          }
-          if (na != nullptr) {
-            RA[i % kAhead] = *reinterpret_cast<const double2*>(na + 2 * (i + kAhead - 16));
-            RO[i % kAhead] = *reinterpret_cast<const double2*>(no + 2 * (i + kAhead - 16));
-          }
-        }
-        double a0 = A.x, a1 = A.y;
-        double o0 = kDelta ? carry : O.x, o1 = kDelta ? O.x : O.y;
-        carry = O.y;
-        if (!kSteady) {
-          const int s = s0 + 2 * i;
-          const bool act0 = (unsigned)s < (unsigned)len, act1 = (unsigned)(s + 1) < (unsigned)len;
-          a0 = act0 ? a0 : 0.0;
-          a1 = act1 ? a1 : 0.0;
-          o0 = (act0 & (s >= m - 1)) ? o0 : 0.0;
-          o1 = (act1 & (s + 1 >= m - 1)) ? o1 : 0.0;
-        }
-        const double a0s = xmul(a0, a0), o0s = xmul(o0, o0), a1s = xmul(a1, a1), o1s = xmul(o1, o1);
-        ex = xadd(ex, a0);              // K/NormQueryEngine.java:498
-        ex2 = xadd(ex2, a0s);           // :499
-        const double2 q0 = make_double2(ex, ex2);
-        ex = xsub(ex, o0);              // :523
-        ex2 = xsub(ex2, o0s);           // :524
-        ex = xadd(ex, a1);
-        ex2 = xadd(ex2, a1s);
-        const double2 q1 = make_double2(ex, ex2);
-        ex = xsub(ex, o1);
-        ex2 = xsub(ex2, o1s);
-        if (kStore) {
-          if (i == 1 || i == 9) {
-            // block hand-off, placed after the block's first pair: the previous block's last stores were issued
-            // two pair-times ago, so the barrier instructions find nothing left to drain
-            if (pending_slot >= 0) bar_arrive(1 + pending_slot, 64);            // previous block is staged
-            if (b >= kStageBlocks) bar_sync(1 + kStageBlocks + (b % kStageBlocks), 64);  // this slot is drained
-          }
-          const int j = i & 7;  // pair index inside the block; its stores trail the arithmetic by one pair
-          if (j > 0) {
-            st[2 * j - 2] = p0;
-            st[2 * j - 1] = p1;
-          }
-          if (j == 7) {
-            st[14] = q0;
-            st[15] = q1;
-            pending_slot = b % kStageBlocks;
-            b++;
-          }
-        }
-        p0 = q0;
-        p1 = q1;
-      }
-    };
-    using T_ = std::true_type;
-    using F_ = std::false_type;
-    if (ntiles > 0) {
-      mbar_wait(bar_ready, 0);
-      const double* ra;
-      const double* ro;
-      tile_rows(0, ra, ro);
-#pragma unroll
-      for (int i = 0; i < kAhead; i++) {
-        RA[i] = *reinterpret_cast<const double2*>(ra + 2 * i);
-        RO[i] = *reinterpret_cast<const double2*>(ro + 2 * i);
-      }
-    }
-    for (int k = 0; k < ntiles; k++) {
-      const int sbase = k * kWalkTile - sha;
-      if (k < k_w) {  // warm-up: no complete window ends in this tile
-        walk_tile(k, F_{}, F_{});
-      } else {
-        const bool steady = __all_sync(kFullMask, (sbase >= m - 1) && (sbase + kWalkTile <= len));
-        if (steady) walk_tile(k, T_{}, T_{});
-        else walk_tile(k, T_{}, F_{});
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_free + 8 * (k % STAGES));  // every lane's reads of tile k have completed
-    }
-    if (pending_slot >= 0) bar_arrive(1 + pending_slot, 64);  // the last staged block
-  } else {
-    // ------------------------------------------------------------------ gate warps (consumers)
-    const int g = warp - 1;
-    const long long base = P.region_base[region];
-    const int mean_klo = P.mean_klo, var_klo = P.var_klo;
-    const unsigned mean_kspan = P.mean_kspan, var_kspan = P.var_kspan;
-    const double dm = P.dm;
-    const int32_t off0 = P.first_global + pos - (m - 1) - sha;  // + tile column = 1-based global window start
-    for (int b = g; b < n_blocks; b += kGateWarps) {
-      const int slot = b % kStageBlocks;
-      const int col0 = (k_w + (b >> 1)) * kWalkTile + (b & 1) * kBlockCols;  // tile column of the block's first entry
-      bar_sync(1 + slot, 64);  // wait for the chain warp to stage this block
-      const double2* st = stage_ring + ((size_t)slot * 32 + lane) * kStagePitch;
-      if (kMode == 1) {
-        // IndexBuilder step 1 (K/IndexBuilder.java:251-265): key bucket of every window mean.  b is taken from one
-        // multiply when ex*(20/w) is clear of an integer by more than the rounding slack, and from the reference's
-        // exact divide / multiply otherwise (MeanIntervalUtils.toRound, K/utils/MeanIntervalUtils.java:51-61).
-        double exv[kBlockCols];
-#pragma unroll
-        for (int cc = 0; cc < kBlockCols; cc++) exv[cc] = st[cc].x;
-        // release the slot before the global stores: a barrier arrive waits for this warp's pending stores, and
-        // 16 scattered global stores per block would otherwise throttle the chain warp through the ring
-        bar_arrive(1 + kStageBlocks + slot, 64);
-#pragma unroll
-        for (int cc = 0; cc < kBlockCols; cc++) {
-          const double ex = exv[cc];
-          const int s = col0 + cc - sha;
-          const bool win = ((unsigned)s < (unsigned)len) & (s >= m - 1);
-          double v2 = ex * P.c20w;
-          double fl = floor(v2);
-          const double frac = v2 - fl;
-          const double gd = fabs(v2) * 4e-15 + 1e-290;
-          if (win && !(frac >= gd && frac <= 1.0 - gd)) {  // (idle lanes hold ex == 0: keep them off the slow path)
-            const double v = xmul(xdiv(ex, dm), 10.0);
-            fl = floor(xadd(v, v));  // 2v is exact
-          }
-          if (win) {
-            if (!(fabs(fl) < 2147483000.0)) *P.overflow = 1;
-            P.bucket_out[pos + s - (m - 1)] = (int)fl;
-          }
-        }
-        continue;
-      }
-      unsigned mask = 0;
-#pragma unroll
-      for (int cc = 0; cc < kBlockCols; cc++) {
-        const double2 v2 = st[cc];
-        const int s = col0 + cc - sha;
-        const bool win = ((unsigned)s < (unsigned)len) & (s >= m - 1);
-        const double v = __fma_rn(v2.y, dm, -(v2.x * v2.x));
-        const bool pass = win & ((unsigned)(hi_key(v2.x) - mean_klo) <= mean_kspan) &
-                          ((unsigned)(hi_key(v) - var_klo) <= var_kspan);
-        mask |= pass ? (1u << cc) : 0u;
-      }
-      // warp-cooperative append: entry e of the block goes to lane e%32 -> coalesced stores, and every
-      // chain's entries stay contiguous (the evaluator's lanes then read neighbouring windows)
-      const int cnt = __popc(mask);
-      const int incl = warp_incl_scan_i32(cnt, lane);
-      const int total = __shfl_sync(kFullMask, incl, 31);
-      if (total > 0) {
-        const int excl = incl - cnt;
-        int rbase = 0;
-        if (lane == 0) rbase = atomicAdd(s_rcount, total);
-        rbase = __shfl_sync(kFullMask, rbase, 0);
-        if (total > 64) {
-          // dense block (a matching region: most lanes pass most columns): two chains per round, half a warp each;
-          // lane c of a half copies column c of its chain's staged row if it passed -> 16 consecutive work-list
-          // slots per half-warp (coalesced), no owner search
-          const unsigned nz = __ballot_sync(kFullMask, cnt > 0);
-          const int hl = lane & 15, hw = lane >> 4;
-          for (int pr = 0; pr < 16; pr++) {
-            if (((nz >> (2 * pr)) & 3u) == 0) continue;
-            const int owner = 2 * pr + hw;
-            const unsigned omask = __shfl_sync(kFullMask, mask, owner);
-            const int oexcl = __shfl_sync(kFullMask, excl, owner);
-            const int32_t ooff = __shfl_sync(kFullMask, off0, owner);
-            if ((omask >> hl) & 1u) {
-              const double2 v2 = stage_ring[((size_t)slot * 32 + owner) * kStagePitch + hl];
-              const long long gidx = base + rbase + oexcl + __popc(omask & ((1u << hl) - 1u));
-              P.e_off[gidx] = ooff + col0 + hl;
-              P.e_ex[gidx] = v2.x;
-              P.e_ex2[gidx] = v2.y;
-            }
-          }
-        } else {
-          for (int e0 = 0; e0 < total; e0 += 32) {
-            const int e = e0 + lane;
-            int owner = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-              const int t = __shfl_sync(kFullMask, excl, owner + step);
-              if (t <= e) owner += step;
-            }
-            const int j = e - __shfl_sync(kFullMask, excl, owner);
-            const unsigned omask = __shfl_sync(kFullMask, mask, owner);
-            const int32_t ooff = __shfl_sync(kFullMask, off0, owner);
-            if (e < total) {
-              const int cc = (int)__fns(omask, 0, j + 1);
-              const double2 v2 = stage_ring[((size_t)slot * 32 + owner) * kStagePitch + cc];
-              const long long gidx = base + rbase + e;
-              P.e_off[gidx] = ooff + col0 + cc;
-              P.e_ex[gidx] = v2.x;
-              P.e_ex2[gidx] = v2.y;
-            }
-          }
-        }
-      }
-      bar_arrive(1 + kStageBlocks + slot, 64);  // slot may be overwritten
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) P.region_count[region] = *s_rcount;
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Relay walker.  The only sequential thing in the statistics pass is the chain state (ex, ex2): loading
 // the samples, squaring them, gating the window sums and appending to the work list are not.  So the
@@ -484,7 +142,7 @@ __global__ void __launch_bounds__(kWalkThreads) cnsm_walk_kernel(WalkParams P) {
 // (34 samples, pitch 38) so that a turn never needs the previous tile when m is even (kDelta = 1: the
 // outgoing sample of tile column j is row element j + 1; kDelta = 0: element j + 2).
 #ifndef KVM_RELAY_WARPS
-#define KVM_RELAY_WARPS 4
+#define KVM_RELAY_WARPS 5
 #endif
 #ifndef KVM_RELAY_BLOCK
 #define KVM_RELAY_BLOCK 16
@@ -500,7 +158,7 @@ constexpr int kOutPitch = 38;  // 34 samples + pad: lane stride 12 banks (mod 32
 constexpr int kRelayStageDoubles = 32 * (kInPitch + kOutPitch);
 constexpr int kGatePitch = kRelayBlock + 1;  // double2 per lane row of a relay warp's flush staging (dense turns only)
 constexpr size_t relay_smem_bytes(int stages) {
-  return sizeof(double) * (size_t)stages * kRelayStageDoubles + sizeof(double2) * 2 * 32 +
+  return sizeof(double) * (size_t)stages * kRelayStageDoubles + sizeof(double2) * kRelayWarps * 32 +
          sizeof(double2) * kRelayWarps * 32 * kGatePitch + sizeof(unsigned long long) * 2 * stages + 16;
 }
 
@@ -519,11 +177,11 @@ __device__ __forceinline__ long long relay_clock() {
 #endif
 
 template <int STAGES, int kDelta, int kMode = 0>
-__global__ void __launch_bounds__(kRelayThreads, kRelayThreads <= 160 ? 2 : 1) cnsm_relay_kernel(WalkParams P) {
+__global__ void __launch_bounds__(kRelayThreads, kRelayThreads <= 224 ? 2 : 1) cnsm_relay_kernel(WalkParams P) {
   extern __shared__ __align__(16) unsigned char walk_smem_raw[];
   double* tiles = reinterpret_cast<double*>(walk_smem_raw);  // [STAGES][ in 32 x kInPitch | out 32 x kOutPitch ]
   double2* state = reinterpret_cast<double2*>(tiles + (size_t)STAGES * kRelayStageDoubles);  // [2][32]
-  double2* gate_stage = state + 2 * 32;                                                      // [kRelayWarps][32][kGatePitch]
+  double2* gate_stage = state + kRelayWarps * 32;                                                      // [kRelayWarps][32][kGatePitch]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(gate_stage + kRelayWarps * 32 * kGatePitch);
   int* s_rcount = reinterpret_cast<int*>(bars + 2 * STAGES);
 

@@ -362,17 +362,9 @@ struct NormSetup {
 };
 
 #ifndef KVM_RELAY_STAGES
-#define KVM_RELAY_STAGES 4
+#define KVM_RELAY_STAGES 3
 #endif
 constexpr int kRelayStages = KVM_RELAY_STAGES;
-// KVM_WALKER=lockstep selects the first-generation walker (kept for A/B measurements)
-bool use_relay() {
-  static const bool v = [] {
-    const char* e = std::getenv("KVM_WALKER");
-    return !(e && std::strcmp(e, "lockstep") == 0);
-  }();
-  return v;
-}
 
 int launch_walker(kvm_ctx* ctx, const Plan& P, int K, int m, double alpha, double beta, const NormSetup& S,
                   size_t off_cbegin, size_t off_nsamp, size_t off_region_base, int* launches) {
@@ -414,29 +406,26 @@ int launch_walker(kvm_ctx* ctx, const Plan& P, int K, int m, double alpha, doubl
   W.e_ex = ctx->wl_ex.as<double>();
   W.e_ex2 = ctx->wl_ex2.as<double>();
   W.region_count = ctx->region_count.as<int32_t>();
-  // 4-stage tile ring: 104 KB of shared memory per CTA, 2 CTAs (= 64 chains) per SM.  More resident chains
-  // would not help: ~6.5k chains x (m-1) x 8 B of lag windows is what stays L2-resident.
-  // (A 2-stage instantiation is deliberately not built: ptxas 12.9 emits its hinted LDGSTS with an
-  // uninitialised uniform descriptor register -> "illegal instruction"; the Makefile greps for that pattern.)
-  if (use_relay()) {
+  // Relay walker, 5 relay warps + loader, 3-stage tile ring: ~100 KB of shared memory per CTA, 2 CTAs (= 64 chains)
+  // per SM.  More resident chains would not help: ~8k chains x (m-1) x 8 B of lag windows is what stays
+  // L2-resident.  (A 2-stage instantiation is deliberately not built: ptxas 12.9 emits its hinted
+  // LDGSTS with an uninitialised uniform descriptor register -> "illegal instruction"; the Makefile greps for it.)
 #ifdef KVM_RELAY_PROF
-    unsigned long long z8[64] = {0};
-    cudaMemcpyToSymbolAsync(g_relay_prof, z8, sizeof(z8), 0, cudaMemcpyHostToDevice, ctx->stream);
+  unsigned long long z8[64] = {0};
+  cudaMemcpyToSymbolAsync(g_relay_prof, z8, sizeof(z8), 0, cudaMemcpyHostToDevice, ctx->stream);
 #endif
-    if ((m % 2) == 0) cnsm_relay_kernel<kRelayStages, 1><<<S.n_regions, kRelayThreads, relay_smem_bytes(kRelayStages), ctx->stream>>>(W);
-    else cnsm_relay_kernel<kRelayStages, 0><<<S.n_regions, kRelayThreads, relay_smem_bytes(kRelayStages), ctx->stream>>>(W);
+  if ((m % 2) == 0) cnsm_relay_kernel<kRelayStages, 1><<<S.n_regions, kRelayThreads, relay_smem_bytes(kRelayStages), ctx->stream>>>(W);
+  else cnsm_relay_kernel<kRelayStages, 0><<<S.n_regions, kRelayThreads, relay_smem_bytes(kRelayStages), ctx->stream>>>(W);
 #ifdef KVM_RELAY_PROF
-    cudaStreamSynchronize(ctx->stream);
-    cudaMemcpyFromSymbol(z8, g_relay_prof, sizeof(z8));
-    for (int w = 0; w < kRelayWarps; w++) {
-      const unsigned long long* z = z8 + 8 * w;
-      const double t = (double)std::max<unsigned long long>(z[5], 1);
-      std::fprintf(stderr, "[relay prof] warp %d cycles per turn: tile-wait %.0f prepare %.0f state-wait %.0f walk %.0f gate %.0f (turns %llu)\n",
-                   w, z[0] / t, z[1] / t, z[2] / t, z[3] / t, z[4] / t, z[5]);
-    }
+  cudaStreamSynchronize(ctx->stream);
+  cudaMemcpyFromSymbol(z8, g_relay_prof, sizeof(z8));
+  for (int w = 0; w < kRelayWarps; w++) {
+    const unsigned long long* z = z8 + 8 * w;
+    const double t = (double)std::max<unsigned long long>(z[5], 1);
+    std::fprintf(stderr, "[relay prof] warp %d cycles per turn: tile-wait %.0f prepare %.0f state-wait %.0f walk %.0f gate %.0f (turns %llu)\n",
+                 w, z[0] / t, z[1] / t, z[2] / t, z[3] / t, z[4] / t, z[5]);
+  }
 #endif
-  } else if ((m % 2) == 0) cnsm_walk_kernel<kWalkStages, 1><<<S.n_regions, kWalkThreads, walk_smem_bytes(kWalkStages), ctx->stream>>>(W);
-  else cnsm_walk_kernel<kWalkStages, 0><<<S.n_regions, kWalkThreads, walk_smem_bytes(kWalkStages), ctx->stream>>>(W);
   KVM_CUDA(ctx, cudaEventRecord(ctx->evs[0], ctx->stream));
   cnsm_plan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->region_count.as<int32_t>(), S.n_regions,
                                                 ctx->tile_prefix.as<int32_t>(),
@@ -712,12 +701,7 @@ int kvm_create(kvm_ctx** out, int device_id) {
     kvm_destroy(ctx);
     return fail(nullptr, KVM_E_CUDA, "cudaFuncSetAttribute(relay walker) failed: %s", msg);
   }
-  const int w4 = (int)walk_smem_bytes(kWalkStages);
-  if (cudaFuncSetAttribute(cnsm_walk_kernel<kWalkStages, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4) != cudaSuccess ||
-      cudaFuncSetAttribute(cnsm_walk_kernel<kWalkStages, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4) != cudaSuccess ||
-      cudaFuncSetAttribute(cnsm_ed_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kExactChunk * 4)) != cudaSuccess ||
-      cudaFuncSetAttribute(cnsm_walk_kernel<kWalkStages, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4) != cudaSuccess ||
-      cudaFuncSetAttribute(cnsm_walk_kernel<kWalkStages, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4) != cudaSuccess) {
+  if (cudaFuncSetAttribute(cnsm_ed_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kExactChunk * 4)) != cudaSuccess) {
     const char* msg = cudaGetErrorString(cudaGetLastError());
     kvm_destroy(ctx);
     return fail(nullptr, KVM_E_CUDA, "cudaFuncSetAttribute failed: %s", msg);
@@ -1022,11 +1006,8 @@ int kvm_window_mean_runs(kvm_ctx* ctx, int32_t w, kvm_runs* out) {
   W.c20w = 20.0 / (double)w;
   W.overflow = reinterpret_cast<int*>(ctx->counters.as<unsigned long long>() + kCntFlag);
   KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  if (use_relay()) {
-    if ((w % 2) == 0) cnsm_relay_kernel<kRelayStages, 1, 1><<<n_regions, kRelayThreads, relay_smem_bytes(kRelayStages), ctx->stream>>>(W);
-    else cnsm_relay_kernel<kRelayStages, 0, 1><<<n_regions, kRelayThreads, relay_smem_bytes(kRelayStages), ctx->stream>>>(W);
-  } else if ((w % 2) == 0) cnsm_walk_kernel<kWalkStages, 1, 1><<<n_regions, kWalkThreads, walk_smem_bytes(kWalkStages), ctx->stream>>>(W);
-  else cnsm_walk_kernel<kWalkStages, 0, 1><<<n_regions, kWalkThreads, walk_smem_bytes(kWalkStages), ctx->stream>>>(W);
+  if ((w % 2) == 0) cnsm_relay_kernel<kRelayStages, 1, 1><<<n_regions, kRelayThreads, relay_smem_bytes(kRelayStages), ctx->stream>>>(W);
+  else cnsm_relay_kernel<kRelayStages, 0, 1><<<n_regions, kRelayThreads, relay_smem_bytes(kRelayStages), ctx->stream>>>(W);
   rle_count_kernel<<<n_tiles, 256, 0, ctx->stream>>>(W.bucket_out, (long long)n_win, ctx->chain_count.as<int32_t>());
   rle_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->chain_count.as<int32_t>(), n_tiles, ctx->chain_prefix.as<long long>());
   KVM_CUDA(ctx, cudaGetLastError());
