@@ -296,7 +296,7 @@ def main():
                     "series_upload_s_once": t_load},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "cnsm_walk_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "cnsm_relay_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": walker_ms / k,
                          "whole_step_frac": (bytes_per_launch / ((dev_ms / k) * 1e-3) / 1e9) / peak},

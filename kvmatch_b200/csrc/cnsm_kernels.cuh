@@ -241,11 +241,14 @@ __global__ void __launch_bounds__(kRelayThreads, kRelayThreads <= 224 ? 2 : 1) c
 #pragma unroll
       for (int i = 0; i < 16; i++) {
         const int ia = max(min(a_idx[i] + koff, idx_hi), idx_lo);
-        const int io = max(min(o_idx[i] + koff, idx_hi), idx_lo);
         cp_async16_hint(dst_in + so + i * (2 * kInPitch * 8), T + ia, pol_keep);
-        cp_async16_hint(dst_out + so + i * (2 * kOutPitch * 8), T + io, pol_drop);
       }
-      {
+      if (k >= k_w) {  // warm-up tiles subtract nothing (their outgoing operands are masked): do not fetch them
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const int io = max(min(o_idx[i] + koff, idx_hi), idx_lo);
+          cp_async16_hint(dst_out + so + i * (2 * kOutPitch * 8), T + io, pol_drop);
+        }
         const int io = max(min(ob + koff, idx_hi), idx_lo);  // this lane's row, leading pair
         cp_async16_hint(dst_lead + so, T + io, pol_drop);
       }

@@ -24,7 +24,7 @@ walker_traffic = None
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1]["gpu__time_duration.sum"])):
     t = v["gpu__time_duration.sum"]
     rd, wr = sum(v["dram__bytes_read.sum"]) / len(t), sum(v["dram__bytes_write.sum"]) / len(t)
-    if "cnsm_walk" in k:
+    if "cnsm_relay" in k:
         walker_traffic = rd + wr
     lines.append(f"| {k} | {len(t)} | {sum(t) / len(t) / 1e3:.1f} | {sum(t) / tot:.3f} | {rd / 1e6:.1f} | {wr / 1e6:.1f} |")
 open(os.path.join(out_dir, f"launches_{tag}.md"), "w").write("\n".join(lines) + "\n")
@@ -39,14 +39,14 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]
 m = {hh: (u, v) for hh, u, v in zip(hdr, units, vals)}
-wl = [f"# ncu --set full: cnsm_walk_kernel — {tag}", "",
-      "One launch of the statistics walker inside `bench.py` (n=1e8, m=1024, chunk 12288, 8138 chains, 255 CTAs x 160 threads).", "",
+wl = [f"# ncu --set full: cnsm_relay_kernel — {tag}", "",
+      "One launch of the statistics walker inside `bench.py` (n=1e8, m=1024, chunk 6144, 16276 chains, 509 CTAs x 192 threads).", "",
       "| metric | value | unit |", "|---|---|---|"]
 for w in want:
     if w in m:
         wl.append(f"| {w} | {m[w][1]} | {m[w][0]} |")
 open(os.path.join(out_dir, f"walker_{tag}.md"), "w").write("\n".join(wl) + "\n")
-json.dump({"round": tag, "n_per_gpu": 100_000_000, "chain_chunk": 12288,
+json.dump({"round": tag, "n_per_gpu": 100_000_000, "chain_chunk": 6144,
            "walker_dram_bytes_per_launch": walker_traffic,
            "source": f"profiles/launches_{tag}.md (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over launches)"},
           open(os.path.join(out_dir, f"roofline_{tag}.json"), "w"), indent=1)
