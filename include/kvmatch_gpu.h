@@ -61,7 +61,8 @@ typedef struct kvm_result {
                               [1] planner + evaluator (exact gate, fast distance or lower bounds),
                               [2] exact stage (reference-order ED sum / banded DTW), [3] unused */
   int32_t n_launches;      /* kernels launched by this call */
-  int32_t reserved;
+  int32_t h2d_bytes;       /* bytes this call copied host->device (query, and the interval plan unless the previous
+                              call's plan was reused) */
 } kvm_result;
 
 /* IndexBuilder step-1 output for one window width w: the (key, first, last) intervals in the order

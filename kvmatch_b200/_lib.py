@@ -57,7 +57,7 @@ class KvmResult(C.Structure):
         ("kernel_ms", C.c_double),
         ("stage_ms", C.c_double * 4),
         ("n_launches", C.c_int32),
-        ("reserved", C.c_int32),
+        ("h2d_bytes", C.c_int32),
     ]
 
 

@@ -89,6 +89,10 @@ struct WalkParams {
   double* e_ex;
   double* e_ex2;
   int32_t* region_count;
+  // the last CTA to finish turns the region counts into the evaluators' tile index (null in kMode 1)
+  int32_t* tile_prefix;
+  unsigned long long* totals;
+  unsigned int* done;  // zeroed before the launch
   // kMode == 1 (IndexBuilder window means): per-window bucket ids instead of a work list
   int32_t* bucket_out;  // bucket_out[local window start] = floor(2 * fl(fl(ex/w) * 10))
   double c20w;          // 20 / w
@@ -160,6 +164,51 @@ constexpr int kGatePitch = kRelayBlock + 1;  // double2 per lane row of a relay 
 constexpr size_t relay_smem_bytes(int stages) {
   return sizeof(double) * (size_t)stages * kRelayStageDoubles + sizeof(double2) * kRelayWarps * 32 +
          sizeof(double2) * kRelayWarps * 32 * kGatePitch + sizeof(unsigned long long) * 2 * stages + 16;
+}
+
+// Exclusive scan over the walker regions by one CTA of NT threads: tile_prefix[r] = sum_{r'<r} ceil(count[r']/kEvalTile),
+// totals[0] = #tiles, totals[1] = #entries.  Run by the last walker CTA to finish (no separate launch); the counts
+// come from other CTAs, hence the L2 (cache-global) loads.
+template <int NT>
+__device__ __forceinline__ void plan_scan_cta(const int32_t* region_count, int n_regions, int32_t* __restrict__ tile_prefix,
+                                              unsigned long long* __restrict__ totals) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  __shared__ unsigned long long s_entries;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    s_carry = 0;
+    s_entries = 0ULL;
+  }
+  __syncthreads();
+  unsigned long long my_entries = 0;
+  for (int r0 = 0; r0 < n_regions; r0 += NT) {
+    const int r = r0 + tid;
+    const int cnt = (r < n_regions) ? __ldcg(region_count + r) : 0;
+    my_entries += (unsigned long long)cnt;
+    const int tiles = (cnt + kEvalTile - 1) / kEvalTile;
+    const int incl = warp_incl_scan_i32(tiles, lane);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = (lane < NT / 32) ? s_warp[lane] : 0;
+      const int wi = warp_incl_scan_i32(w, lane);
+      s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    const int excl = s_carry + s_warp[warp] + incl - tiles;
+    if (r < n_regions) tile_prefix[r] = excl;
+    __syncthreads();
+    if (tid == NT - 1) s_carry = excl + tiles;
+    __syncthreads();
+  }
+  atomicAdd(&s_entries, my_entries);
+  __syncthreads();
+  if (tid == 0) {
+    tile_prefix[n_regions] = s_carry;
+    totals[0] = (unsigned long long)s_carry;
+    totals[1] = s_entries;
+  }
 }
 
 #ifdef KVM_RELAY_PROF
@@ -477,50 +526,20 @@ __global__ void __launch_bounds__(kRelayThreads, kRelayThreads <= 224 ? 2 : 1) c
 #endif
   }
   __syncthreads();
-  if (threadIdx.x == 0) P.region_count[region] = *s_rcount;
-}
-
-// Single-CTA exclusive scan over regions: tile_prefix[r] = sum_{r'<r} ceil(count[r']/kEvalTile).
-// totals[0] = #tiles, totals[1] = #entries.
-__global__ void __launch_bounds__(1024) cnsm_plan_kernel(const int32_t* __restrict__ region_count, int n_regions,
-                                                         int32_t* __restrict__ tile_prefix,
-                                                         unsigned long long* __restrict__ totals) {
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
-  __shared__ unsigned long long s_entries;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
-    s_carry = 0;
-    s_entries = 0ULL;
-  }
-  __syncthreads();
-  unsigned long long my_entries = 0;
-  for (int r0 = 0; r0 < n_regions; r0 += 1024) {
-    const int r = r0 + tid;
-    const int cnt = (r < n_regions) ? region_count[r] : 0;
-    my_entries += (unsigned long long)cnt;
-    const int tiles = (cnt + kEvalTile - 1) / kEvalTile;
-    const int incl = warp_incl_scan_i32(tiles, lane);
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      const int w = s_warp[lane];
-      const int wi = warp_incl_scan_i32(w, lane);
-      s_warp[lane] = wi - w;
+  if (kMode == 0) {
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+      P.region_count[region] = *s_rcount;
+      __threadfence();
+      s_last = atomicAdd(P.done, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    const int excl = s_carry + s_warp[warp] + incl - tiles;
-    if (r < n_regions) tile_prefix[r] = excl;
-    __syncthreads();
-    if (tid == 1023) s_carry = excl + tiles;
-    __syncthreads();
-  }
-  atomicAdd(&s_entries, my_entries);
-  __syncthreads();
-  if (tid == 0) {
-    tile_prefix[n_regions] = s_carry;
-    totals[0] = (unsigned long long)s_carry;
-    totals[1] = s_entries;
+    if (s_last) {
+      __threadfence();
+      plan_scan_cta<kRelayThreads>(P.region_count, (int)gridDim.x, P.tile_prefix, P.totals);
+    }
+  } else if (threadIdx.x == 0) {
+    P.region_count[region] = *s_rcount;
   }
 }
 
@@ -633,6 +652,7 @@ struct ExactEdParams {
 };
 
 constexpr int kExactChunk = 1024;  // terms staged in shared memory per pass (8 KB per warp)
+constexpr int kExactWin = 2048;    // windows up to this length are staged in shared memory as a whole (16 KB per warp)
 
 // K/NormQueryEngine.java:513-520 verbatim arithmetic: x = (T[order[k]+j]-mean)/std; dist += (x-zQ[k])^2.
 // One warp per survivor: all lanes compute the per-term values (divisions in parallel, each term rounded
@@ -641,15 +661,25 @@ constexpr int kExactChunk = 1024;  // terms staged in shared memory per pass (8 
 __global__ void __launch_bounds__(128) cnsm_ed_exact_kernel(ExactEdParams P) {
   extern __shared__ double exact_terms[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  double* term = exact_terms + (size_t)warp * kExactChunk;
+  double* term = exact_terms + (size_t)warp * (kExactChunk + kExactWin);
+  double* win = term + kExactChunk;
   unsigned long long n = *P.in.count;
   if ((long long)n > P.in.cap) n = (unsigned long long)P.in.cap;
   const int m = P.m;
+  const bool staged = m <= kExactWin;
   for (unsigned long long e = (unsigned long long)blockIdx.x * n_warps + warp; e < n;
        e += (unsigned long long)gridDim.x * n_warps) {
     const int32_t off = P.in.off[e];
     const double mean = P.in.mean[e], stdv = P.in.stdv[e];
     const double* __restrict__ w = P.T + (off - P.first_global);
+    if (staged) {
+      // the window is contiguous: one coalesced pass brings it into shared memory (all loads in flight at once);
+      // the |zQ|-ordered accesses below then cost a shared-memory load instead of a dependent DRAM round trip
+      __syncwarp();
+      for (int k = lane; k < m; k += 32) win[k] = w[k];
+      __syncwarp();
+      w = win;
+    }
     // Tier 2: warp-cooperative fast distance (FMA, reciprocal) over all m terms, 128 terms per round in |zQ|
     // order, abandoned as soon as the partial sum exceeds eps^2*(1+1e-9).  Only windows that survive every
     // round reach the reference-order summation below.

@@ -39,6 +39,7 @@ class VerifyResult:
     kernel_ms: float
     n_launches: int
     stage_ms: tuple = (0.0, 0.0, 0.0, 0.0)
+    h2d_bytes: int = 0
 
     @property
     def count(self) -> int:
@@ -105,7 +106,7 @@ class GpuSeries:
         off = np.ctypeslib.as_array(r.offsets, shape=(c,)).copy() if c else np.zeros(0, np.int32)
         dist = np.ctypeslib.as_array(r.distances, shape=(c,)).copy() if c else np.zeros(0, np.float64)
         out = VerifyResult(off, dist, r.cnt_candidate, r.n_verified, r.s_total, r.n_gate_pass, r.n_lb_pass, r.n_exact,
-                           r.kernel_ms, r.n_launches, tuple(r.stage_ms))
+                           r.kernel_ms, r.n_launches, tuple(r.stage_ms), int(r.h2d_bytes))
         self._L.kvm_result_free(self._h, C.byref(r))
         return out
 

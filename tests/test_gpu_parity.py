@@ -280,3 +280,27 @@ def test_cnsm_ed_1e7_properties(gpu):
     # idempotent
     again = gpu.verify_cnsm_ed(q, 5.0, 1.5, 5.0, iv)
     assert again.offsets.tolist() == r5.offsets.tolist() and again.distances.tolist() == r5.distances.tolist()
+
+
+def test_cnsm_plan_reuse_across_calls(oracle):
+    """The cNSM engines keep the previous call's interval plan on the device: the same intervals under other
+    queries, other intervals, calls of the other engines in between and a series reload must all match the oracle."""
+    import kvmatch_b200
+    g = kvmatch_b200.GpuSeries(0)
+    n, m = 150_000, 256
+    s = datagen.generate(n, seed=77)
+    g.load(s)
+    iv_a = datagen.chain_intervals(n, m, 4096)
+    iv_b = datagen.chain_intervals(n, m, 3000, 2000, 140_000)
+    qs = [s[off:off + m].copy() for off in (5_000, 71_234, 120_001)]
+    plan = [(qs[0], iv_a), (qs[1], iv_a), (qs[2], iv_b), (qs[0], iv_b), ("ed", None), (qs[1], iv_b), (qs[2], iv_a)]
+    for q, iv in plan:
+        if isinstance(q, str):
+            assert_same(g.verify_ed(qs[0], 3.0, iv_a), oracle.verify_ed(s, qs[0], 3.0, iv_a))
+            continue
+        assert_same(g.verify_cnsm_ed(q, 4.0, 1.5, 3.0, iv), oracle.verify_cnsm_ed(s, q, 4.0, 1.5, 3.0, iv))
+    s2 = datagen.generate(n, seed=78)  # a new series invalidates the plan even for a byte-identical interval list
+    g.load(s2)
+    q = s2[9_000:9_000 + m].copy()
+    assert_same(g.verify_cnsm_ed(q, 4.0, 1.5, 3.0, iv_a), oracle.verify_cnsm_ed(s2, q, 4.0, 1.5, 3.0, iv_a))
+    g.close()
