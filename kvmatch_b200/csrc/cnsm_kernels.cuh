@@ -652,7 +652,6 @@ struct ExactEdParams {
 };
 
 constexpr int kExactChunk = 1024;  // terms staged in shared memory per pass (8 KB per warp)
-constexpr int kExactWin = 2048;    // windows up to this length are staged in shared memory as a whole (16 KB per warp)
 
 // K/NormQueryEngine.java:513-520 verbatim arithmetic: x = (T[order[k]+j]-mean)/std; dist += (x-zQ[k])^2.
 // One warp per survivor: all lanes compute the per-term values (divisions in parallel, each term rounded
@@ -661,25 +660,15 @@ constexpr int kExactWin = 2048;    // windows up to this length are staged in sh
 __global__ void __launch_bounds__(128) cnsm_ed_exact_kernel(ExactEdParams P) {
   extern __shared__ double exact_terms[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  double* term = exact_terms + (size_t)warp * (kExactChunk + kExactWin);
-  double* win = term + kExactChunk;
+  double* term = exact_terms + (size_t)warp * kExactChunk;
   unsigned long long n = *P.in.count;
   if ((long long)n > P.in.cap) n = (unsigned long long)P.in.cap;
   const int m = P.m;
-  const bool staged = m <= kExactWin;
   for (unsigned long long e = (unsigned long long)blockIdx.x * n_warps + warp; e < n;
        e += (unsigned long long)gridDim.x * n_warps) {
     const int32_t off = P.in.off[e];
     const double mean = P.in.mean[e], stdv = P.in.stdv[e];
     const double* __restrict__ w = P.T + (off - P.first_global);
-    if (staged) {
-      // the window is contiguous: one coalesced pass brings it into shared memory (all loads in flight at once);
-      // the |zQ|-ordered accesses below then cost a shared-memory load instead of a dependent DRAM round trip
-      __syncwarp();
-      for (int k = lane; k < m; k += 32) win[k] = w[k];
-      __syncwarp();
-      w = win;
-    }
     // Tier 2: warp-cooperative fast distance (FMA, reciprocal) over all m terms, 128 terms per round in |zQ|
     // order, abandoned as soon as the partial sum exceeds eps^2*(1+1e-9).  Only windows that survive every
     // round reach the reference-order summation below.

@@ -623,7 +623,7 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
       X.n_exact = ctx->counters.as<unsigned long long>() + kCntFlag;
       X.in = E.out;
       X.sink = sink_of(ctx);
-      cnsm_ed_exact_kernel<<<ctx->n_sms * 6, 128, sizeof(double) * (kExactChunk + kExactWin) * 4, ctx->stream>>>(X);
+      cnsm_ed_exact_kernel<<<ctx->n_sms * 6, 128, sizeof(double) * kExactChunk * 4, ctx->stream>>>(X);
       launches += 2;
     } else {
       LbNormParams L;
@@ -742,7 +742,7 @@ int kvm_create(kvm_ctx** out, int device_id) {
     kvm_destroy(ctx);
     return fail(nullptr, KVM_E_CUDA, "cudaFuncSetAttribute(relay walker) failed: %s", msg);
   }
-  if (cudaFuncSetAttribute(cnsm_ed_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (kExactChunk + kExactWin) * 4)) != cudaSuccess) {
+  if (cudaFuncSetAttribute(cnsm_ed_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kExactChunk * 4)) != cudaSuccess) {
     const char* msg = cudaGetErrorString(cudaGetLastError());
     kvm_destroy(ctx);
     return fail(nullptr, KVM_E_CUDA, "cudaFuncSetAttribute failed: %s", msg);
