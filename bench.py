@@ -279,7 +279,15 @@ def main():
         e2e_value = verified_all / wall_s_max
         # roofline of the dominant kernel (the statistics walker): algorithmic bytes = 8 B per touched sample
         # (bytes_alg = 8*S_total + 12*#answers), per launch, over its own CUDA-event duration
-        bytes_per_launch = (8.0 * s_total + 12.0 * answers) / k          # rank 0's shard
+        # S_total counts every touched sample once: the m-1 halo re-read between adjacent chains is NOT algorithmic
+        ivs = np.asarray(iv, dtype=np.int64).reshape(-1, 2)
+        lo_s, hi_s = ivs[:, 0], np.minimum(ivs[:, 1] + M - 1, n_total)
+        order = np.argsort(lo_s, kind="stable")
+        lo_s, hi_s = lo_s[order], hi_s[order]
+        reach = np.maximum.accumulate(hi_s)
+        prev_reach = np.concatenate(([lo_s[0] - 1], reach[:-1]))
+        unique_samples = int(np.sum(np.maximum(0, hi_s - np.maximum(lo_s - 1, prev_reach))))
+        bytes_per_launch = 8.0 * unique_samples + 12.0 * answers / k     # rank 0's shard
         walker_s = (walker_ms / k) * 1e-3
         achieved = bytes_per_launch / walker_s / 1e9
         traffic = None
@@ -304,6 +312,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "cnsm_relay_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": walker_ms / k,
+                         "samples_read_incl_chain_halos_per_launch": s_total / k,
                          "whole_step_frac": (bytes_per_launch / ((dev_ms / k) * 1e-3) / 1e9) / peak},
             "answers_per_step": answers_all / k, "gate_pass_per_step": gate_all / k,
             "wall_s_timed_region": t_wall_max, "datagen_s": t_gen,

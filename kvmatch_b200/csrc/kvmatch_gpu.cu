@@ -221,6 +221,7 @@ void envelope(const std::vector<double>& t, int r, std::vector<double>& lo, std:
 
 // One interval after the reference's shift / clamp (K/QueryEngine.java:345-349).
 int make_plan(kvm_ctx* ctx, const int32_t* lr, int K, int shift, int m, Plan* P) {
+  P->cnt_candidate = P->V = P->S = 0;
   P->cbegin.resize(K);
   P->nsamp.resize(K);
   P->ncand.resize(K);
@@ -490,8 +491,7 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
   const bool reuse = cache_on && C.valid && C.K == K && C.shift == shift && C.m == m &&
                      std::memcmp(C.lr.data(), lr, sizeof(int32_t) * 2 * (size_t)K) == 0;
   if (!reuse) {
-    C.valid = false;
-    C.plan = Plan();
+    C.valid = false;  // (the plan's vectors keep their capacity from call to call)
     if ((rc = make_plan(ctx, lr, K, shift, m, &C.plan))) return rc;
   }
   const Plan& P = C.plan;
@@ -510,28 +510,36 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
   S.n_regions = n_regions;
   double t_prep = 0, t_upload = 0;
   if (!reuse) {
-    std::vector<long long> region_base(n_regions + 1);
+    // built in place in the pinned staging block: [cbegin i32 x K | walker nsamp i32 x K | region_base i64 x (R+1)]
+    auto up256 = [](size_t x) { return (x + 255) & ~size_t(255); };
+    C.o_cbegin = 0;
+    C.o_nsamp = up256(sizeof(int32_t) * (size_t)K);
+    C.o_rbase = up256(C.o_nsamp + sizeof(int32_t) * (size_t)K);
+    const size_t bytes = C.o_rbase + sizeof(long long) * (size_t)(n_regions + 1);
+    KVM_CUDA(ctx, ctx->stage.ensure(bytes + 256));
+    KVM_CUDA(ctx, ctx->arena.ensure(bytes + 256));
+    unsigned char* st = static_cast<unsigned char*>(ctx->stage.p);
+    std::memcpy(st + C.o_cbegin, P.cbegin.data(), sizeof(int32_t) * (size_t)K);
+    int32_t* walk_nsamp = reinterpret_cast<int32_t*>(st + C.o_nsamp);
+    long long* region_base = reinterpret_cast<long long*>(st + C.o_rbase);
     long long acc = 0;
-    for (int r = 0; r < n_regions; r++) {
-      region_base[r] = acc;
-      for (int c = r * 32; c < std::min(K, r * 32 + 32); c++) acc += P.ncand[c];
+    for (int c = 0; c < K; c++) {
+      if ((c & 31) == 0) region_base[c >> 5] = acc;
+      acc += P.ncand[c];
+      walk_nsamp[c] = P.ncand[c] > 0 ? P.nsamp[c] : 0;
     }
     region_base[n_regions] = acc;
-    std::vector<int32_t> walk_nsamp(K);
-    for (int c = 0; c < K; c++) walk_nsamp[c] = P.ncand[c] > 0 ? P.nsamp[c] : 0;
-
-    Arena A;
-    C.o_cbegin = A.add(P.cbegin.data(), sizeof(int32_t) * K);
-    C.o_nsamp = A.add(walk_nsamp.data(), sizeof(int32_t) * K);
-    C.o_rbase = A.add(region_base.data(), sizeof(long long) * (n_regions + 1));
     t_prep = since(t_begin);
-    if ((rc = upload_arena(ctx, A))) return rc;
-    C.lr.assign(lr, lr + 2 * (size_t)K);
-    C.K = K;
-    C.shift = shift;
-    C.m = m;
-    C.n_regions = n_regions;
-    C.valid = true;  // (a failure below leaves the arena intact)
+    KVM_CUDA(ctx, cudaMemcpyAsync(ctx->arena.p, ctx->stage.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += (long long)bytes;
+    if (cache_on) {
+      C.lr.assign(lr, lr + 2 * (size_t)K);
+      C.K = K;
+      C.shift = shift;
+      C.m = m;
+      C.n_regions = n_regions;
+      C.valid = true;  // (a failure below leaves the arena intact)
+    }
   } else {
     t_prep = since(t_begin);
   }
