@@ -220,32 +220,59 @@ void envelope(const std::vector<double>& t, int r, std::vector<double>& lo, std:
 }
 
 // One interval after the reference's shift / clamp (K/QueryEngine.java:345-349).
+// The O(K) pass of make_plan on raw arrays; branch-free so that it vectorises (AVX2 clone picked at load time).
+__attribute__((target_clones("avx2", "default"))) int plan_pass(const int32_t* __restrict__ lr, int K, int64_t shift, int64_t m,
+                                                                   int64_t n, int64_t lo, int64_t hi, int32_t* __restrict__ cb,
+                                                                   int32_t* __restrict__ nsv, int32_t* __restrict__ ncv,
+                                                                   int64_t* totals) {
+  int64_t cnt = 0, S = 0, V = 0;
+  int bad = 0;
+  for (int p = 0; p < K; p++) {
+    const int64_t left = lr[2 * p], right = lr[2 * p + 1];
+    cnt += right - left + 1;
+    int64_t begin = left - shift, end = right - shift + m - 1;
+    begin = begin < 1 ? 1 : begin;
+    end = end > n ? n : end;
+    bad |= (end < begin) | (begin < lo) | (end > hi);
+    const int64_t ns = end - begin + 1;
+    const int64_t nc = ns >= m ? ns - m + 1 : 0;
+    cb[p] = (int32_t)(begin - lo);
+    nsv[p] = (int32_t)ns;
+    ncv[p] = (int32_t)nc;
+    S += ns;
+    V += nc;
+  }
+  totals[0] = cnt;
+  totals[1] = S;
+  totals[2] = V;
+  return bad;
+}
+
 int make_plan(kvm_ctx* ctx, const int32_t* lr, int K, int shift, int m, Plan* P) {
-  P->cnt_candidate = P->V = P->S = 0;
   P->cbegin.resize(K);
   P->nsamp.resize(K);
   P->ncand.resize(K);
-  const int64_t lo = ctx->first, hi = ctx->first + ctx->count - 1;
-  for (int p = 0; p < K; p++) {
-    const int64_t left = lr[2 * p], right = lr[2 * p + 1];
-    P->cnt_candidate += right - left + 1;
-    int64_t begin = left - shift, end = right - shift + (int64_t)m - 1;
-    if (begin < 1) begin = 1;
-    if (end > ctx->n) end = ctx->n;
-    if (end < begin)
-      return fail(ctx, KVM_E_RANGE, "interval %d [%lld,%lld] shift %d lies outside [1,%lld] (the reference throws)", p,
-                  (long long)left, (long long)right, shift, (long long)ctx->n);
-    if (begin < lo || end > hi)
-      return fail(ctx, KVM_E_RANGE, "interval %d needs samples [%lld,%lld]; this ctx holds [%lld,%lld]", p,
-                  (long long)begin, (long long)end, (long long)lo, (long long)hi);
-    const int64_t ns = end - begin + 1;
-    const int64_t nc = ns >= m ? ns - m + 1 : 0;
-    P->cbegin[p] = (int32_t)(begin - lo);
-    P->nsamp[p] = (int32_t)ns;
-    P->ncand[p] = (int32_t)nc;
-    P->S += ns;
-    P->V += nc;
+  const int64_t lo = ctx->first, hi = ctx->first + ctx->count - 1, n = ctx->n;
+  int64_t totals[3];
+  const int bad = plan_pass(lr, K, shift, m, n, lo, hi, P->cbegin.data(), P->nsamp.data(), P->ncand.data(), totals);
+  const int64_t cnt = totals[0], S = totals[1], V = totals[2];
+  if (bad) {
+    for (int p = 0; p < K; p++) {
+      const int64_t left = lr[2 * p], right = lr[2 * p + 1];
+      int64_t begin = left - shift, end = right - shift + (int64_t)m - 1;
+      if (begin < 1) begin = 1;
+      if (end > n) end = n;
+      if (end < begin)
+        return fail(ctx, KVM_E_RANGE, "interval %d [%lld,%lld] shift %d lies outside [1,%lld] (the reference throws)", p,
+                    (long long)left, (long long)right, shift, (long long)n);
+      if (begin < lo || end > hi)
+        return fail(ctx, KVM_E_RANGE, "interval %d needs samples [%lld,%lld]; this ctx holds [%lld,%lld]", p,
+                    (long long)begin, (long long)end, (long long)lo, (long long)hi);
+    }
   }
+  P->cnt_candidate = cnt;
+  P->S = S;
+  P->V = V;
   return KVM_OK;
 }
 
@@ -483,6 +510,7 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
   if (rc) return rc;
   if (mode == Mode::kDtw && (rho < 0 || m < 3)) return fail(ctx, KVM_E_ARG, "DTW needs rho >= 0 and m >= 3");
   if ((rc = begin_call(ctx))) return rc;
+  const double t_dbg0 = since(t_begin);
   NormPlanCache& C = ctx->norm_cache;
   static const bool cache_on = [] {  // KVM_PLAN_CACHE=0: plan and upload on every call (bench.py's e2e leg does this)
     const char* e = std::getenv("KVM_PLAN_CACHE");
@@ -494,6 +522,7 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
     C.valid = false;  // (the plan's vectors keep their capacity from call to call)
     if ((rc = make_plan(ctx, lr, K, shift, m, &C.plan))) return rc;
   }
+  const double t_dbg1 = since(t_begin);
   const Plan& P = C.plan;
   out->cnt_candidate = P.cnt_candidate;
   out->n_verified = P.V;
@@ -501,6 +530,7 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
 
   NormSetup S;
   query_stats(q, m, &S.meanQ, &S.stdQ);
+  const double t_dbg2 = since(t_begin);
   S.inv_alpha = 1.0 / alpha;
   S.degenerate = !(S.stdQ > 0.0) || !(S.stdQ < INFINITY);
   if (P.V == 0 || S.degenerate) return fetch_answers(ctx, 0, out);
@@ -522,11 +552,16 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
     std::memcpy(st + C.o_cbegin, P.cbegin.data(), sizeof(int32_t) * (size_t)K);
     int32_t* walk_nsamp = reinterpret_cast<int32_t*>(st + C.o_nsamp);
     long long* region_base = reinterpret_cast<long long*>(st + C.o_rbase);
+    const int32_t* __restrict__ ncv = P.ncand.data();
+    const int32_t* __restrict__ nsv = P.nsamp.data();
+    for (int c = 0; c < K; c++) walk_nsamp[c] = ncv[c] > 0 ? nsv[c] : 0;  // (vectorisable passes)
     long long acc = 0;
-    for (int c = 0; c < K; c++) {
-      if ((c & 31) == 0) region_base[c >> 5] = acc;
-      acc += P.ncand[c];
-      walk_nsamp[c] = P.ncand[c] > 0 ? P.nsamp[c] : 0;
+    for (int r = 0; r < n_regions; r++) {
+      region_base[r] = acc;
+      const int c_hi = std::min(K, r * 32 + 32);
+      long long sum = 0;
+      for (int c = r * 32; c < c_hi; c++) sum += ncv[c];
+      acc += sum;
     }
     region_base[n_regions] = acc;
     t_prep = since(t_begin);
@@ -662,7 +697,7 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
     const double t_launch = since(t_begin);
     if ((rc = read_counters(ctx, cnt))) return rc;
     if (env_int("KVM_TIMING", 0))
-      std::fprintf(stderr, "[kvm] prep %.0f us, upload %.0f, launched %.0f, synced %.0f\n", t_prep, t_upload, t_launch, since(t_begin));
+      std::fprintf(stderr, "[kvm] begin %.0f plan %.0f qstats %.0f prep %.0f us, upload %.0f, launched %.0f, synced %.0f\n", t_dbg0, t_dbg1, t_dbg2, t_prep, t_upload, t_launch, since(t_begin));
     total_ms += elapsed_ms(ctx);
     add_stage_ms(ctx, out);
     out->n_launches += launches;
