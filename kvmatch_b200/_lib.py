@@ -46,8 +46,8 @@ class KvmError(RuntimeError):
 class KvmResult(C.Structure):
     _fields_ = [
         ("count", C.c_int64),
-        ("offsets", C.POINTER(C.c_int32)),
-        ("distances", C.POINTER(C.c_double)),
+        ("offsets", C.c_void_p),     # const int32_t*
+        ("distances", C.c_void_p),   # const double*
         ("cnt_candidate", C.c_int64),
         ("n_verified", C.c_int64),
         ("s_total", C.c_int64),
@@ -74,8 +74,8 @@ class KvmRuns(C.Structure):
 
 
 _lib = None
-_dp = C.POINTER(C.c_double)
-_ip = C.POINTER(C.c_int32)
+_dp = C.c_void_p  # const double* / const int32_t* arguments are passed as plain addresses (cheapest ctypes path)
+_ip = C.c_void_p
 
 
 def load():
@@ -115,9 +115,16 @@ def load():
 
 def as_f64(a):
     a = np.ascontiguousarray(a, dtype=np.float64)
-    return a, a.ctypes.data_as(_dp)
+    return a, a.ctypes.data
 
 
 def as_intervals(intervals):
     lr = np.ascontiguousarray(np.asarray(intervals, dtype=np.int32).reshape(-1, 2))
-    return lr, lr.ctypes.data_as(_ip), int(lr.shape[0])
+    return lr, lr.ctypes.data, int(lr.shape[0])
+
+
+def copy_out(addr, count: int, dtype):
+    """A numpy copy of `count` elements at a library-owned host address."""
+    if not count:
+        return np.zeros(0, dtype)
+    return np.frombuffer(C.string_at(addr, count * np.dtype(dtype).itemsize), dtype=dtype)

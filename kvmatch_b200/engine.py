@@ -103,8 +103,8 @@ class GpuSeries:
 
     def _take(self, r: _lib.KvmResult) -> VerifyResult:
         c = r.count
-        off = np.ctypeslib.as_array(r.offsets, shape=(c,)).copy() if c else np.zeros(0, np.int32)
-        dist = np.ctypeslib.as_array(r.distances, shape=(c,)).copy() if c else np.zeros(0, np.float64)
+        off = _lib.copy_out(r.offsets, c, np.int32)
+        dist = _lib.copy_out(r.distances, c, np.float64)
         out = VerifyResult(off, dist, r.cnt_candidate, r.n_verified, r.s_total, r.n_gate_pass, r.n_lb_pass, r.n_exact,
                            r.kernel_ms, r.n_launches, tuple(r.stage_ms), int(r.h2d_bytes))
         self._L.kvm_result_free(self._h, C.byref(r))
