@@ -112,6 +112,16 @@ int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int
 int kvm_verify_cnsm_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int32_t rho, double alpha,
                         double beta, const int32_t* lr, int32_t K, int32_t shift, kvm_result* out);
 
+/* Index-free full scan with the semantics of the reference's UCR-DTW baseline executor
+ * (K/experiments/ucr/UcrDtwQueryExecutor.java:84-314): the series is streamed in EPOCH = 100000-sample buffers that
+ * overlap by m-1 (:97-131), the running statistics restart per buffer (:133-134), every window goes through the
+ * alpha/beta gate and the LB_Kim / LB_Keogh / DTW cascade, and answers carry 0-BASED offsets (:278).  Equivalent to
+ * kvm_verify_cnsm_dtw over the intervals [it*(EPOCH-m+1)+1, ...] with shift 0.  Needs the whole series on this ctx.
+ * (The ED baseline, UcrEdQueryExecutor.java:101-183, never restarts its statistics chain: one sequential chain over
+ * the whole series has no parallel bit-exact equivalent, so it is not offered; use kvm_verify_cnsm_ed on a chain grid.) */
+int kvm_scan_ucr_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int32_t rho, double alpha, double beta,
+                     kvm_result* out);
+
 /* IndexBuilder step 1 for window width w (K/IndexBuilder.java:194-301): sliding mean with the
  * reference's EPOCH=100000 restart structure, toRound key, run-length intervals split at 255.
  * Needs the whole series on this ctx (first == 1, count == n). */

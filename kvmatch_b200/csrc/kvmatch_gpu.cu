@@ -945,6 +945,30 @@ int kvm_verify_cnsm_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon
   return verify_norm(ctx, Mode::kDtw, q, m, epsilon, rho, alpha, beta, lr, K, shift, out);
 }
 
+int kvm_scan_ucr_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int32_t rho, double alpha, double beta,
+                     kvm_result* out) {
+  if (!ctx) return KVM_E_ARG;
+  if (!ctx->series) return fail(ctx, KVM_E_STATE, "no series loaded");
+  if (ctx->first != 1 || ctx->count != ctx->n) return fail(ctx, KVM_E_STATE, "the UCR scan needs the whole series on this ctx");
+  constexpr int64_t kEpoch = 100000;  // UcrDtwQueryExecutor.java:97
+  if (m < 3 || m > kEpoch) return fail(ctx, KVM_E_ARG, "UCR-DTW needs 3 <= m <= EPOCH");
+  const int64_t per = kEpoch - m + 1, last = ctx->n - m + 1;  // window starts per buffer; last 1-based start
+  std::vector<int32_t> lr;
+  for (int64_t left = 1; left <= last; left += per) {
+    lr.push_back((int32_t)left);
+    lr.push_back((int32_t)std::min(left + per - 1, last));
+  }
+  if (!out) return fail(ctx, KVM_E_ARG, "null/invalid argument");
+  if (lr.empty()) {  // series shorter than the query: nothing to scan
+    std::memset(out, 0, sizeof(*out));
+    return KVM_OK;
+  }
+  const int rc = verify_norm(ctx, Mode::kDtw, q, m, epsilon, rho, alpha, beta, lr.data(), (int)(lr.size() / 2), 0, out);
+  if (rc) return rc;
+  for (int32_t& o : ctx->res_off) o -= 1;  // 0-based offsets, :278
+  return KVM_OK;
+}
+
 int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int32_t rho, const int32_t* lr, int32_t K,
                    int32_t shift, kvm_result* out) {
   int rc = check_common(ctx, q, m, epsilon, lr, K, out);

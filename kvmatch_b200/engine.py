@@ -117,6 +117,13 @@ class GpuSeries:
         self._check(self._L.kvm_verify_ed(self._h, qp, len(q), epsilon, lp, K, shift, C.byref(r)))
         return self._take(r)
 
+    def scan_ucr_dtw(self, q, epsilon, rho, alpha, beta) -> VerifyResult:
+        """K/experiments/ucr/UcrDtwQueryExecutor.java:84-314: index-free cNSM-DTW scan, 0-based offsets."""
+        q, qp = _lib.as_f64(q)
+        r = _lib.KvmResult()
+        self._check(self._L.kvm_scan_ucr_dtw(self._h, qp, len(q), epsilon, rho, alpha, beta, C.byref(r)))
+        return self._take(r)
+
     def verify_cnsm_ed(self, q, epsilon, alpha, beta, intervals, shift=0) -> VerifyResult:
         q, qp = _lib.as_f64(q)
         lr, lp, K = _lib.as_intervals(intervals)

@@ -304,3 +304,28 @@ def test_cnsm_plan_reuse_across_calls(oracle):
     q = s2[9_000:9_000 + m].copy()
     assert_same(g.verify_cnsm_ed(q, 4.0, 1.5, 3.0, iv_a), oracle.verify_cnsm_ed(s2, q, 4.0, 1.5, 3.0, iv_a))
     g.close()
+
+
+@pytest.mark.parametrize("m,rho,eps", [(128, 6, 3.0), (1000, 50, 9.0)])
+def test_scan_ucr_dtw_matches_reference_executor(gpu, oracle, m, rho, eps):
+    """f4: kvm_scan_ucr_dtw against the oracle's restatement of UcrDtwQueryExecutor (EPOCH buffers with m-1 overlap,
+    statistics restart per buffer, 0-based offsets), three buffers long."""
+    n = 250_000  # multiple of 125: no phantom samples in the reference's block feed
+    s = datagen.generate(n, seed=4242)
+    gpu.load(s)
+    q = s[123_000:123_000 + m].copy() + 0.01 * np.cos(np.arange(m))
+    got = gpu.scan_ucr_dtw(q, eps, rho, 1.5, 5.0)
+    exp = oracle.ucr_dtw(s, q, eps, rho, 1.5, 5.0)
+    assert got.offsets.tolist() == exp.offsets.tolist()
+    assert got.distances.tolist() == exp.distances.tolist()
+    assert got.count > 0 and got.offsets.min() >= 0
+    assert got.n_verified == n - m + 1
+
+
+def test_scan_ucr_dtw_needs_whole_series(gpu):
+    import kvmatch_b200
+    s = datagen.generate(50_000, seed=5)
+    gpu.load(s[1000:], n=50_000, first=1001)
+    with pytest.raises(kvmatch_b200.KvmError) as e:
+        gpu.scan_ucr_dtw(s[:64].copy(), 1.0, 3, 1.5, 5.0)
+    assert e.value.code == kvmatch_b200._lib.KVM_E_STATE
