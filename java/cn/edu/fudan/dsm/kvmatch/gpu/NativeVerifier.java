@@ -67,6 +67,9 @@ public final class NativeVerifier implements AutoCloseable {
     private static final MethodHandle VERIFY_CNSM_DTW = fn("kvm_verify_cnsm_dtw",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_DOUBLE, JAVA_INT, JAVA_DOUBLE, JAVA_DOUBLE,
                     ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
+    private static final MethodHandle SCAN_UCR_DTW = fn("kvm_scan_ucr_dtw",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_DOUBLE, JAVA_INT, JAVA_DOUBLE, JAVA_DOUBLE,
+                    ADDRESS));
     private static final MethodHandle WINDOW_MEAN_RUNS = fn("kvm_window_mean_runs",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
 
@@ -141,6 +144,15 @@ public final class NativeVerifier implements AutoCloseable {
         try (Arena a = Arena.ofConfined()) {
             MemorySegment res = a.allocate(RESULT);
             check((int) VERIFY_DTW.invokeExact(ctx, doubles(a, q), q.size(), epsilon, rho, ints(a, lr), lr.length / 2, shift, res));
+            return take(res);
+        } catch (IOException e) { throw e; } catch (Throwable t) { throw new IOException(t); }
+    }
+
+    /** Index-free scan, UcrDtwQueryExecutor semantics (0-based offsets). */
+    public List<Answer> scanUcrDtw(List<Double> q, double epsilon, int rho, double alpha, double beta) throws IOException {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment res = a.allocate(RESULT);
+            check((int) SCAN_UCR_DTW.invokeExact(ctx, doubles(a, q), q.size(), epsilon, rho, alpha, beta, res));
             return take(res);
         } catch (IOException e) { throw e; } catch (Throwable t) { throw new IOException(t); }
     }
