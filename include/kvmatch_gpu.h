@@ -127,6 +127,28 @@ int kvm_scan_ucr_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, i
  * Needs the whole series on this ctx (first == 1, count == n). */
 int kvm_window_mean_runs(kvm_ctx* ctx, int32_t w, kvm_runs* out);
 
+/* The whole single-width index build: window-mean pass on the GPU, then IndexBuilder step 2 (adjacent-row merge,
+ * K/IndexBuilder.java:308-345, K/utils/IndexNodeUtils.java:30-90) and the file image IndexFileOperator.writeAll
+ * produces (K/operator/file/IndexFileOperator.java:127-164; row codec K/common/entity/IndexNode.java:51-96; statistic
+ * table K/utils/ByteUtils.java:84-100) on the host.  Writes `path` (the reference names it files/index-<N>-<w>);
+ * path == NULL only fills `info`.  Replaces SingleIndexBuilder.run() (K/IndexBuilder.java:186-347) for one w. */
+typedef struct kvm_index_info {
+  int64_t file_bytes;
+  int64_t n_runs;        /* step-1 (key, first, last) runs */
+  int64_t n_intervals;   /* intervals after the step-2 merge */
+  int64_t n_offsets;     /* window positions covered (= n - w + 1 on real data) */
+  int32_t n_rows_step1;  /* distinct keys */
+  int32_t n_rows;        /* rows after the merge */
+  double kernel_ms;      /* GPU time of the window-mean pass */
+  double host_ms;        /* step 2 + encoding + write */
+} kvm_index_info;
+int kvm_build_index_file(kvm_ctx* ctx, int32_t w, const char* path, kvm_index_info* info);
+/* Host-only half of the above (no GPU, no ctx): step 2 and the file image from runs the caller already holds, in the
+ * order IndexBuilder step 1 appends them.  *image is malloc'ed by the library; release it with kvm_image_free. */
+int kvm_index_image_from_runs(const double* keys, const int32_t* first, const int32_t* last, int64_t n_runs,
+                              unsigned char** image, kvm_index_info* info);
+void kvm_image_free(unsigned char* image);
+
 void kvm_result_free(kvm_ctx* ctx, kvm_result* r);
 void kvm_runs_free(kvm_ctx* ctx, kvm_runs* r);
 

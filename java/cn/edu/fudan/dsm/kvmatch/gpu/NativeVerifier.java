@@ -70,6 +70,13 @@ public final class NativeVerifier implements AutoCloseable {
     private static final MethodHandle SCAN_UCR_DTW = fn("kvm_scan_ucr_dtw",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_DOUBLE, JAVA_INT, JAVA_DOUBLE, JAVA_DOUBLE,
                     ADDRESS));
+    // struct kvm_index_info
+    private static final StructLayout INDEX_INFO = MemoryLayout.structLayout(
+            JAVA_LONG.withName("file_bytes"), JAVA_LONG.withName("n_runs"), JAVA_LONG.withName("n_intervals"),
+            JAVA_LONG.withName("n_offsets"), JAVA_INT.withName("n_rows_step1"), JAVA_INT.withName("n_rows"),
+            JAVA_DOUBLE.withName("kernel_ms"), JAVA_DOUBLE.withName("host_ms"));
+    private static final MethodHandle BUILD_INDEX_FILE = fn("kvm_build_index_file",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle WINDOW_MEAN_RUNS = fn("kvm_window_mean_runs",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
 
@@ -145,6 +152,15 @@ public final class NativeVerifier implements AutoCloseable {
             MemorySegment res = a.allocate(RESULT);
             check((int) VERIFY_DTW.invokeExact(ctx, doubles(a, q), q.size(), epsilon, rho, ints(a, lr), lr.length / 2, shift, res));
             return take(res);
+        } catch (IOException e) { throw e; } catch (Throwable t) { throw new IOException(t); }
+    }
+
+    /** SingleIndexBuilder.run() for one window width: writes the index file, returns the number of rows. */
+    public int buildIndexFile(int w, String path) throws IOException {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment info = a.allocate(INDEX_INFO);
+            check((int) BUILD_INDEX_FILE.invokeExact(ctx, w, a.allocateUtf8String(path), info));
+            return info.get(JAVA_INT, INDEX_INFO.byteOffset(MemoryLayout.PathElement.groupElement("n_rows")));
         } catch (IOException e) { throw e; } catch (Throwable t) { throw new IOException(t); }
     }
 

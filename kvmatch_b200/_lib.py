@@ -31,7 +31,7 @@ ERROR_NAMES = {
 EXPORTS = [
     "kvm_abi_version", "kvm_create", "kvm_destroy", "kvm_last_error", "kvm_load_series_host", "kvm_load_series_file",
     "kvm_verify_ed", "kvm_verify_cnsm_ed", "kvm_verify_dtw", "kvm_verify_cnsm_dtw", "kvm_scan_ucr_dtw",
-    "kvm_window_mean_runs",
+    "kvm_window_mean_runs", "kvm_build_index_file", "kvm_index_image_from_runs", "kvm_image_free",
     "kvm_result_free", "kvm_runs_free",
 ]
 
@@ -74,6 +74,13 @@ class KvmRuns(C.Structure):
     ]
 
 
+class KvmIndexInfo(C.Structure):
+    _fields_ = [
+        ("file_bytes", C.c_int64), ("n_runs", C.c_int64), ("n_intervals", C.c_int64), ("n_offsets", C.c_int64),
+        ("n_rows_step1", C.c_int32), ("n_rows", C.c_int32), ("kernel_ms", C.c_double), ("host_ms", C.c_double),
+    ]
+
+
 _lib = None
 _dp = C.c_void_p  # const double* / const int32_t* arguments are passed as plain addresses (cheapest ctypes path)
 _ip = C.c_void_p
@@ -107,6 +114,10 @@ def load():
                                       C.c_int32, C.c_int32, R]
     L.kvm_scan_ucr_dtw.argtypes = [vp, _dp, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_double, R]
     L.kvm_window_mean_runs.argtypes = [vp, C.c_int32, C.POINTER(KvmRuns)]
+    L.kvm_build_index_file.argtypes = [vp, C.c_int32, C.c_char_p, C.POINTER(KvmIndexInfo)]
+    L.kvm_index_image_from_runs.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(KvmIndexInfo)]
+    L.kvm_image_free.argtypes = [vp]
+    L.kvm_image_free.restype = None
     L.kvm_result_free.argtypes = [vp, R]
     L.kvm_result_free.restype = None
     L.kvm_runs_free.argtypes = [vp, C.POINTER(KvmRuns)]
@@ -130,3 +141,19 @@ def copy_out(addr, count: int, dtype):
     if not count:
         return np.zeros(0, dtype)
     return np.frombuffer(C.string_at(addr, count * np.dtype(dtype).itemsize), dtype=dtype)
+
+
+def index_image_from_runs(keys, first, last):
+    """kvm_index_image_from_runs: (file image bytes, KvmIndexInfo).  Host-only (no GPU needed)."""
+    L = load()
+    k = np.ascontiguousarray(keys, dtype=np.float64)
+    f = np.ascontiguousarray(first, dtype=np.int32)
+    l = np.ascontiguousarray(last, dtype=np.int32)
+    img = C.c_void_p()
+    info = KvmIndexInfo()
+    rc = L.kvm_index_image_from_runs(k.ctypes.data, f.ctypes.data, l.ctypes.data, len(k), C.byref(img), C.byref(info))
+    if rc != 0:
+        raise KvmError(rc, "kvm_index_image_from_runs failed")
+    data = C.string_at(img.value, info.file_bytes)
+    L.kvm_image_free(img)
+    return data, info

@@ -22,6 +22,7 @@
 
 #include "dtw_kernels.cuh"
 #include "index_kernels.cuh"
+#include "index_file.hpp"
 
 using namespace kvm;
 
@@ -1166,6 +1167,59 @@ int kvm_window_mean_runs(kvm_ctx* ctx, int32_t w, kvm_runs* out) {
   out->keys = ctx->run_key_v.data();
   out->first = ctx->run_first_v.data();
   out->last = ctx->run_last_v.data();
+  return KVM_OK;
+}
+
+int kvm_index_image_from_runs(const double* keys, const int32_t* first, const int32_t* last, int64_t n_runs,
+                              unsigned char** image, kvm_index_info* info) {
+  if (!keys || !first || !last || !image || !info || n_runs < 0) return KVM_E_ARG;
+  std::memset(info, 0, sizeof(*info));
+  *image = nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<unsigned char> file;
+  kvm_index::ImageInfo ii;
+  if (!kvm_index::build_image(keys, first, last, n_runs, file, &ii)) return KVM_E_RANGE;
+  *image = static_cast<unsigned char*>(std::malloc(file.size() ? file.size() : 1));
+  if (!*image) return KVM_E_OOM;
+  std::memcpy(*image, file.data(), file.size());
+  info->file_bytes = (int64_t)file.size();
+  info->n_runs = n_runs;
+  info->n_intervals = ii.intervals;
+  info->n_offsets = ii.offsets;
+  info->n_rows_step1 = ii.rows_step1;
+  info->n_rows = ii.rows;
+  info->host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return KVM_OK;
+}
+
+void kvm_image_free(unsigned char* image) { std::free(image); }
+
+int kvm_build_index_file(kvm_ctx* ctx, int32_t w, const char* path, kvm_index_info* info) {
+  if (!ctx) return KVM_E_ARG;
+  if (!info) return fail(ctx, KVM_E_ARG, "info is null");
+  std::memset(info, 0, sizeof(*info));
+  kvm_runs runs;
+  int rc = kvm_window_mean_runs(ctx, w, &runs);
+  if (rc) return rc;
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<unsigned char> file;
+  kvm_index::ImageInfo ii;
+  if (!kvm_index::build_image(runs.keys, runs.first, runs.last, runs.count, file, &ii))
+    return fail(ctx, KVM_E_RANGE, "no window of width %d in this series (the reference throws)", w);
+  if (path) {
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(ctx, KVM_E_IO, "cannot open %s for writing", path);
+    const size_t wrote = std::fwrite(file.data(), 1, file.size(), f);
+    if (std::fclose(f) != 0 || wrote != file.size()) return fail(ctx, KVM_E_IO, "short write to %s", path);
+  }
+  info->file_bytes = (int64_t)file.size();
+  info->n_runs = runs.count;
+  info->n_intervals = ii.intervals;
+  info->n_offsets = ii.offsets;
+  info->n_rows_step1 = ii.rows_step1;
+  info->n_rows = ii.rows;
+  info->kernel_ms = runs.kernel_ms;
+  info->host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return KVM_OK;
 }
 

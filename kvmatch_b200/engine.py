@@ -124,6 +124,12 @@ class GpuSeries:
         self._check(self._L.kvm_scan_ucr_dtw(self._h, qp, len(q), epsilon, rho, alpha, beta, C.byref(r)))
         return self._take(r)
 
+    def build_index_file(self, w: int, path: str | None):
+        """K/IndexBuilder.java:186-347 for one window width: returns the kvm_index_info fields."""
+        info = _lib.KvmIndexInfo()
+        self._check(self._L.kvm_build_index_file(self._h, w, path.encode() if path else None, C.byref(info)))
+        return info
+
     def verify_cnsm_ed(self, q, epsilon, alpha, beta, intervals, shift=0) -> VerifyResult:
         q, qp = _lib.as_f64(q)
         lr, lp, K = _lib.as_intervals(intervals)

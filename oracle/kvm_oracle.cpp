@@ -27,6 +27,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 namespace {
@@ -1004,6 +1005,217 @@ int kvo_read_series_be(const char* path, double* series, int64_t n) {
   }
   std::fclose(f);
   return KVO_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// IndexBuilder step 2 and the index file image.
+//   step 2            K/IndexBuilder.java:308-345 (row merge criterion :325-329)
+//   mergeIndexNode    K/utils/IndexNodeUtils.java:30-90 (incl. the copied, mutated `last` pairs)
+//   toBytesCompact    K/common/entity/IndexNode.java:51-96
+//   file layout       K/operator/file/IndexFileOperator.java:127-164, K/utils/ByteUtils.java:84-100
+// Returns the bytes IndexFileOperator.writeAll would put into files/index-N-w.
+// ---------------------------------------------------------------------------------------------
+namespace {
+typedef std::pair<int32_t, int32_t> IvPair;
+typedef std::vector<IvPair> IndexNodePositions;
+
+void add_interval(IndexNodePositions& node, IvPair position) {  // IndexNodeUtils.java:82-90
+  while (position.second - position.first >= kMaximumDiff) {
+    int32_t new_first = position.first + kMaximumDiff - 1;
+    node.push_back(IvPair(position.first, new_first));
+    position.first = new_first + 1;
+  }
+  node.push_back(position);
+}
+
+IndexNodePositions merge_index_node(const IndexNodePositions& node1, const IndexNodePositions& node2) {  // :30-80
+  IndexNodePositions ret;
+  size_t index1 = 0, index2 = 0;
+  bool has1 = false, has2 = false;  // `last1 == null` / `last2 == null`
+  IvPair last1, last2;
+  while (index1 < node1.size() && index2 < node2.size()) {
+    if (!has1) { last1 = node1[index1]; has1 = true; }
+    if (!has2) { last2 = node2[index2]; has2 = true; }
+    if (last1.second + 1 < last2.first) {
+      add_interval(ret, last1);
+      index1++;
+      has1 = false;
+    } else if (last2.second + 1 < last1.first) {
+      add_interval(ret, last2);
+      index2++;
+      has2 = false;
+    } else {
+      if (last1.second < last2.second) {
+        if (last1.first < last2.first) last2.first = last1.first;
+        index1++;
+        has1 = false;
+      } else {
+        if (last2.first < last1.first) last1.first = last2.first;
+        index2++;
+        has2 = false;
+      }
+    }
+  }
+  for (size_t i = index1; i < node1.size(); i++) {
+    if (!has1) { last1 = node1[i]; has1 = true; }
+    add_interval(ret, last1);
+    has1 = false;
+  }
+  for (size_t i = index2; i < node2.size(); i++) {
+    if (!has2) { last2 = node2[i]; has2 = true; }
+    add_interval(ret, last2);
+    has2 = false;
+  }
+  return ret;
+}
+
+void put_be32(std::vector<unsigned char>& b, size_t at, int32_t v) {  // hbase Bytes.toBytes(int): big-endian
+  for (int k = 0; k < 4; k++) b[at + k] = (unsigned char)(((uint32_t)v) >> (24 - 8 * k));
+}
+void push_be32(std::vector<unsigned char>& b, int32_t v) {
+  b.resize(b.size() + 4);
+  put_be32(b, b.size() - 4, v);
+}
+void push_be_double(std::vector<unsigned char>& b, double d) {  // Bytes.toBytes(double): big-endian raw long bits
+  uint64_t u;
+  std::memcpy(&u, &d, 8);
+  for (int k = 0; k < 8; k++) b.push_back((unsigned char)(u >> (56 - 8 * k)));
+}
+
+std::vector<unsigned char> to_bytes_compact(const IndexNodePositions& positions) {  // IndexNode.java:51-96
+  std::vector<unsigned char> result(4 * positions.size() * 2);
+  size_t index = 0, length = 0;
+  int count = 0;
+  bool is_packing = false;
+  while (index < positions.size()) {
+    if (!is_packing) {
+      put_be32(result, length, positions[index].first);
+      length += 4 + 1;  // first: 4 bytes, remain 1 byte for count
+      int diff = positions[index].second - positions[index].first;
+      result[length++] = (unsigned char)(signed char)(diff - 128);
+      is_packing = true;
+      count = 1;
+    } else {
+      int diff = positions[index].first - positions[index - 1].second;
+      if (diff < kMaximumDiff && (count - 1) / 2 + 2 < kMaximumDiff) {
+        result[length++] = (unsigned char)(signed char)(diff - 128);
+        diff = positions[index].second - positions[index].first;
+        result[length++] = (unsigned char)(signed char)(diff - 128);
+        count += 2;
+      } else {
+        result[length - count - 1] = (unsigned char)(signed char)((count - 1) / 2 - 128);
+        is_packing = false;
+        continue;
+      }
+    }
+    index++;
+  }
+  if (is_packing) result[length - count - 1] = (unsigned char)(signed char)((count - 1) / 2 - 128);
+  result.resize(length);
+  return result;
+}
+
+struct JavaDoubleLess {  // Double.compareTo: numeric, -0.0 < 0.0, NaN last
+  bool operator()(double a, double b) const { return java_double_compare(a, b) < 0; }
+};
+}  // namespace
+
+struct kvo_bytes {
+  int64_t count;
+  unsigned char* data;
+  int32_t n_rows_step1, n_rows;  // rows before / after the step-2 merge
+};
+
+int kvo_index_file_image(const double* series, int64_t n_file, int64_t n, int w, kvo_bytes* out) {
+  if (!out) return KVO_E_ARG;
+  std::memset(out, 0, sizeof(*out));
+  kvo_runs runs;
+  int rc = kvo_window_mean_runs(series, n_file, n, w, &runs);
+  if (rc) return rc;
+  // step 1's HashMap<Double, IndexNode> (K/IndexBuilder.java:268-306): positions appended per key in scan order
+  std::map<double, IndexNodePositions, JavaDoubleLess> index_node_map;
+  for (int64_t i = 0; i < runs.count; i++) index_node_map[runs.keys[i]].push_back(IvPair(runs.first[i], runs.last[i]));
+  kvo_runs_free(&runs);
+  out->n_rows_step1 = (int32_t)index_node_map.size();
+  if (index_node_map.empty()) return KVO_E_REF_THROWS;  // rawStatisticInfo.get(0) throws
+  // step 2 (:308-345)
+  std::vector<std::pair<double, int>> raw;  // (key, #intervals), sorted by key descending (:317)
+  double sum = 0;
+  for (auto& e : index_node_map) {
+    raw.push_back(std::make_pair(e.first, (int)e.second.size()));
+    sum += (double)e.second.size();
+  }
+  std::stable_sort(raw.begin(), raw.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) {
+    return java_double_compare(a.first, b.first) > 0;
+  });
+  const double average = sum / (double)raw.size();  // StatisticInfo.getAverage
+  std::map<double, IndexNodePositions, JavaDoubleLess> index_store;          // TreeMap
+  std::vector<std::pair<double, std::pair<int32_t, int32_t>>> statistic_info;  // (key, (#intervals, #offsets))
+  auto stat_pair = [](const IndexNodePositions& p) {
+    int32_t offs = 0;
+    for (auto& iv : p) offs += iv.second - iv.first + 1;
+    return std::make_pair((int32_t)p.size(), offs);
+  };
+  IndexNodePositions last = index_node_map[raw[0].first];
+  for (size_t i = 1; i < raw.size(); i++) {
+    const IndexNodePositions& current = index_node_map[raw[i].first];
+    bool is_merged = false;
+    if ((double)raw[i].second < average * 1.2) {
+      IndexNodePositions merged = merge_index_node(last, current);
+      if ((double)merged.size() < (double)(last.size() + current.size()) * 0.8) {
+        last = merged;
+        is_merged = true;
+      }
+    }
+    if (!is_merged) {
+      double key = raw[i - 1].first;
+      index_store[key] = last;
+      statistic_info.push_back(std::make_pair(key, stat_pair(last)));
+      last = current;
+    }
+  }
+  {
+    double key = raw[raw.size() - 1].first;
+    index_store[key] = last;
+    statistic_info.push_back(std::make_pair(key, stat_pair(last)));
+  }
+  out->n_rows = (int32_t)index_store.size();
+  // IndexFileOperator.writeAll (:127-164)
+  std::vector<unsigned char> file;
+  std::vector<int32_t> offsets;
+  for (auto& e : index_store) {
+    offsets.push_back((int32_t)file.size());
+    push_be_double(file, e.first);
+    std::vector<unsigned char> v = to_bytes_compact(e.second);
+    file.insert(file.end(), v.begin(), v.end());
+  }
+  offsets.push_back((int32_t)file.size());
+  std::stable_sort(statistic_info.begin(), statistic_info.end(),
+                   [](const std::pair<double, std::pair<int32_t, int32_t>>& a,
+                      const std::pair<double, std::pair<int32_t, int32_t>>& b) { return a.first < b.first; });  // comparingDouble
+  for (size_t i = 0; i < statistic_info.size(); i++) {  // ByteUtils.listTripleToByteArray: cumulative counts
+    if (i > 0) {
+      statistic_info[i].second.first += statistic_info[i - 1].second.first;
+      statistic_info[i].second.second += statistic_info[i - 1].second.second;
+    }
+    push_be_double(file, statistic_info[i].first);
+    push_be32(file, statistic_info[i].second.first);
+    push_be32(file, statistic_info[i].second.second);
+  }
+  offsets.push_back((int32_t)file.size());
+  for (int32_t o : offsets) push_be32(file, o);
+  out->count = (int64_t)file.size();
+  out->data = (unsigned char*)std::malloc(file.size() ? file.size() : 1);
+  std::memcpy(out->data, file.data(), file.size());
+  return KVO_OK;
+}
+
+void kvo_bytes_free(kvo_bytes* b) {
+  if (!b) return;
+  std::free(b->data);
+  b->data = nullptr;
+  b->count = 0;
 }
 
 }  // extern "C"

@@ -261,6 +261,25 @@ def window_mean_runs(series, w: int, n: int | None = None):
     return keys, first, last
 
 
+class _Bytes(C.Structure):
+    _fields_ = [("count", C.c_int64), ("data", C.POINTER(C.c_ubyte)), ("n_rows_step1", C.c_int32), ("n_rows", C.c_int32)]
+
+
+def index_file_image(series, w: int, n: int | None = None):
+    """IndexBuilder steps 1+2 and IndexFileOperator.writeAll for one window width: (file bytes, rows before the
+    step-2 merge, rows after)."""
+    s, sp = _d(series)
+    n = len(s) if n is None else n
+    b = _Bytes()
+    L = lib()
+    L.kvo_index_file_image.restype = C.c_int
+    _check(L.kvo_index_file_image(sp, C.c_int64(len(s)), C.c_int64(n), C.c_int(w), C.byref(b)))
+    data = C.string_at(b.data, b.count)
+    rows1, rows = b.n_rows_step1, b.n_rows
+    L.kvo_bytes_free(C.byref(b))
+    return data, rows1, rows
+
+
 def ucr_ed(series, q, epsilon, alpha, beta, N=None) -> OracleResult:
     s, sp = _d(series)
     q, qp = _d(q)

@@ -329,3 +329,16 @@ def test_scan_ucr_dtw_needs_whole_series(gpu):
     with pytest.raises(kvmatch_b200.KvmError) as e:
         gpu.scan_ucr_dtw(s[:64].copy(), 1.0, 3, 1.5, 5.0)
     assert e.value.code == kvmatch_b200._lib.KVM_E_STATE
+
+
+@pytest.mark.parametrize("w", [25, 400])
+def test_build_index_file_matches_oracle_image(gpu, oracle, series_1m, tmp_path, w):
+    """f2/f3: GPU window-mean pass + host step 2 + file codec against the oracle's image of files/index-N-w."""
+    s = series_1m[:300_000]
+    gpu.load(s)
+    path = tmp_path / f"index-{len(s)}-{w}"
+    info = gpu.build_index_file(w, str(path))
+    exp, rows1, rows = oracle.index_file_image(s, w)
+    assert path.read_bytes() == exp
+    assert (info.n_rows_step1, info.n_rows, info.file_bytes) == (rows1, rows, len(exp))
+    assert info.n_offsets == len(s) - w + 1
