@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstring>
 #include <numeric>
+#include <unordered_map>
 #include <vector>
 
 namespace kvm_index {
@@ -108,22 +109,44 @@ inline bool build_image(const double* keys, const int32_t* first, const int32_t*
                         std::vector<unsigned char>& file, ImageInfo* info) {
   file.clear();
   if (n_runs <= 0) return false;
-  // step-1 rows: runs grouped by key, inside a row in append order (the HashMap<Double, IndexNode> of :268-306)
-  std::vector<int64_t> order((size_t)n_runs);
-  std::iota(order.begin(), order.end(), (int64_t)0);
-  std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return java_cmp(keys[x], keys[y]) < 0; });
-  std::vector<Iv> flat((size_t)n_runs);
-  std::vector<double> row_key;
-  std::vector<int64_t> row_begin;
+  // step-1 rows: runs grouped by key, inside a row in append order (the HashMap<Double, IndexNode> of :268-306).
+  // Few distinct keys, many runs: hash the key bits to a dense id, counting-sort the runs by id (stable), and order
+  // only the distinct keys.
+  auto bits_of = [](double d) {
+    uint64_t u;
+    std::memcpy(&u, &d, 8);
+    return (d != d) ? 0x7ff8000000000000ULL : u;  // Double.equals: NaNs are one key
+  };
+  std::unordered_map<uint64_t, int32_t> id_of;
+  id_of.reserve(1 << 14);
+  std::vector<int32_t> run_id((size_t)n_runs);
+  std::vector<double> id_key;
+  std::vector<int64_t> id_count;
   for (int64_t r = 0; r < n_runs; r++) {
-    const int64_t s = order[(size_t)r];
-    if (r == 0 || java_cmp(keys[s], row_key.back()) != 0) {
-      row_key.push_back(keys[s]);
-      row_begin.push_back(r);
+    auto it = id_of.emplace(bits_of(keys[r]), (int32_t)id_key.size());
+    if (it.second) {
+      id_key.push_back(keys[r]);
+      id_count.push_back(0);
     }
-    flat[(size_t)r] = Iv{first[s], last[s]};
+    run_id[(size_t)r] = it.first->second;
+    id_count[(size_t)it.first->second]++;
   }
-  row_begin.push_back(n_runs);
+  const size_t n_ids = id_key.size();
+  std::vector<int32_t> by_key(n_ids);
+  std::iota(by_key.begin(), by_key.end(), 0);
+  std::sort(by_key.begin(), by_key.end(), [&](int32_t x, int32_t y) { return java_cmp(id_key[(size_t)x], id_key[(size_t)y]) < 0; });
+  std::vector<double> row_key(n_ids);
+  std::vector<int64_t> row_begin(n_ids + 1), cursor(n_ids);
+  int64_t acc = 0;
+  for (size_t k = 0; k < n_ids; k++) {
+    row_key[k] = id_key[(size_t)by_key[k]];
+    row_begin[k] = acc;
+    cursor[(size_t)by_key[k]] = acc;
+    acc += id_count[(size_t)by_key[k]];
+  }
+  row_begin[n_ids] = acc;
+  std::vector<Iv> flat((size_t)n_runs);
+  for (int64_t r = 0; r < n_runs; r++) flat[(size_t)cursor[(size_t)run_id[(size_t)r]]++] = Iv{first[r], last[r]};
   const int64_t R = (int64_t)row_key.size();
   info->rows_step1 = (int32_t)R;
   const double average = (double)n_runs / (double)R;  // mean #intervals per row (StatisticInfo.getAverage)

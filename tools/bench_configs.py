@@ -81,6 +81,20 @@ for w in (25, 50, 100, 200, 400):
     t = time.perf_counter(); ek, ef, el = kvm_oracle.window_mean_runs(s[:1_000_000], w); t_cpu += time.perf_counter() - t
     okr &= first.tolist() == ef.tolist() and last.tolist() == el.tolist() and keys.view(np.int64).tolist() == ek.view(np.int64).tolist()
 rows.append(("1 IndexBuilder step 1, n=1e6, 5 windows", 5_000_000, tot_ms, tot_ms, 0, 5e6 / t_cpu, "windows/s; unit = window means", okr))
+# whole single-width build (steps 1+2 + file image), 5 widths
+import tempfile
+tot_k = tot_wall = t_cpu = 0.0; okf = True; nbytes = 0
+with tempfile.TemporaryDirectory() as td:
+    for w in (25, 50, 100, 200, 400):
+        path = os.path.join(td, f"index-1000000-{w}")
+        g2.build_index_file(w, path)
+        t = time.perf_counter(); info = g2.build_index_file(w, path); tot_wall += (time.perf_counter() - t) * 1e3
+        tot_k += info.kernel_ms
+        t = time.perf_counter(); exp, _, _ = kvm_oracle.index_file_image(s[:1_000_000], w); t_cpu += time.perf_counter() - t
+        okf &= open(path, "rb").read() == exp
+        nbytes += len(exp)
+rows.append(("1 IndexBuilder steps 1+2 + index files, n=1e6, 5 windows", 5_000_000, tot_k, tot_wall, 0, 5e6 / t_cpu,
+             f"windows/s; kernel = window-mean pass, wall adds host step 2 + codec + write ({nbytes} file bytes, byte-identical)", okf))
 g2.close()
 
 print("| config | verified | kernel ms | wall ms | subseq/s (GPU kernel) | #answers | CPU oracle 1 core subseq/s | note | parity on CPU sample |")
