@@ -342,3 +342,47 @@ def test_build_index_file_matches_oracle_image(gpu, oracle, series_1m, tmp_path,
     assert path.read_bytes() == exp
     assert (info.n_rows_step1, info.n_rows, info.file_bytes) == (rows1, rows, len(exp))
     assert info.n_offsets == len(s) - w + 1
+
+
+def test_full_size_1e8_against_oracle_on_chain_subsets(oracle):
+    """BASELINE configs[1] at full size (n = 1e8, m = 1024): size-independent properties on the whole scan, and exact
+    parity with the oracle on every chain that holds an answer plus a random sample of other chains (a chain is an
+    independent unit of the path, so the oracle can be run on it alone)."""
+    import kvmatch_b200
+    n, m, chunk = 100_000_000, 1024, 6144
+    s = datagen.generate(n)
+    g = kvmatch_b200.GpuSeries(0)
+    g.load(s)
+    iv = np.asarray(datagen.chain_intervals(n, m, chunk), dtype=np.int64).reshape(-1, 2)
+    rng = np.random.default_rng(5)
+    for off in (3_941_174, 61_550_030):
+        q = s[off - 1:off - 1 + m].copy()
+        r5 = g.verify_cnsm_ed(q, 5.0, 1.5, 5.0, iv)
+        r1 = g.verify_cnsm_ed(q, 1.0, 1.5, 5.0, iv)
+        assert r5.n_verified == n - m + 1 and r5.cnt_candidate == n - m + 1
+        assert np.all(np.diff(r5.offsets) > 0) and np.all(r5.distances <= 5.0)
+        i = r5.offsets.tolist().index(off)
+        assert r5.distances[i] < 1e-9   # the planted self-match (not exactly 0: chain sums vs the query's fresh sums)
+        assert set(r1.offsets.tolist()) <= set(r5.offsets.tolist())      # monotone in epsilon
+        hit = np.unique(np.searchsorted(iv[:, 0], r5.offsets, side="right") - 1)
+        others = rng.choice(len(iv), size=24, replace=False)
+        sub = iv[np.unique(np.concatenate([hit, others]))]
+        exp = oracle.verify_cnsm_ed(s, q, 5.0, 1.5, 5.0, sub)
+        got = g.verify_cnsm_ed(q, 5.0, 1.5, 5.0, sub)
+        assert_same(got, exp)
+        assert got.n_gate_pass == exp.n_gate_pass
+        assert got.offsets.tolist() == [o for o in r5.offsets.tolist() if np.any((sub[:, 0] <= o) & (o <= sub[:, 1]))]
+    # RSM-ED and cNSM-DTW on the same series, same scheme
+    q = s[off - 1:off - 1 + m].copy()
+    full = g.verify_ed(q, 10.0, [(1, n - m + 1)])
+    assert off in full.offsets.tolist()
+    sub = iv[np.unique(np.concatenate([np.searchsorted(iv[:, 0], full.offsets, side="right") - 1, rng.choice(len(iv), 16)]))]
+    assert_same(g.verify_ed(q, 10.0, sub), oracle.verify_ed(s, q, 10.0, sub))
+    m2, rho = 512, 25
+    q2 = s[off - 1:off - 1 + m2].copy()
+    iv2 = np.asarray(datagen.chain_intervals(n, m2, 100_000 - m2 + 1), dtype=np.int64).reshape(-1, 2)
+    d = g.verify_cnsm_dtw(q2, 1.0, rho, 1.5, 5.0, iv2)
+    assert off in d.offsets.tolist() and d.n_verified == n - m2 + 1
+    sub2 = iv2[np.unique(np.concatenate([np.searchsorted(iv2[:, 0], d.offsets, side="right") - 1, rng.choice(len(iv2), 3)]))]
+    assert_same(g.verify_cnsm_dtw(q2, 1.0, rho, 1.5, 5.0, sub2), oracle.verify_cnsm_dtw(s, q2, 1.0, rho, 1.5, 5.0, sub2))
+    g.close()
