@@ -130,6 +130,9 @@ struct kvm_ctx {
   DevBuf seg_b, seg_first, seg_last, chain_count, chain_prefix, run_key, run_b, run_first, run_last;
   long long cand_cap = 0, ans_cap = 0;
   NormPlanCache norm_cache;
+  Plan plan_scratch;                 // RSM engines: host planning buffers kept across calls (no fresh pages per call)
+  std::vector<int32_t> tp_scratch;
+  Arena arena_scratch;
   long long h2d_bytes = 0;  // host->device bytes of the current call
   bool eager_valid = false;  // h_off/h_dist hold the first kEagerAnswers answers of the last read_counters
   PinBuf stage, stage2, h_counters, h_off, h_dist, h_key, h_first, h_last, h_b;
@@ -388,8 +391,8 @@ int zero_counters(kvm_ctx* ctx) {
 }
 
 // Tile prefix for kernels that enumerate candidates straight from the intervals.
-std::vector<int32_t> tile_prefix_of(const Plan& P, int tile, int64_t* n_tiles) {
-  std::vector<int32_t> tp(P.ncand.size() + 1);
+void tile_prefix_of(const Plan& P, int tile, int64_t* n_tiles, std::vector<int32_t>& tp) {
+  tp.resize(P.ncand.size() + 1);
   int64_t acc = 0;
   for (size_t p = 0; p < P.ncand.size(); p++) {
     tp[p] = (int32_t)acc;
@@ -397,7 +400,6 @@ std::vector<int32_t> tile_prefix_of(const Plan& P, int tile, int64_t* n_tiles) {
   }
   tp[P.ncand.size()] = (int32_t)acc;
   *n_tiles = acc;
-  return tp;
 }
 
 // Everything the cNSM engines share: query statistics, pre-gate constants, walker + planner launch.
@@ -890,20 +892,42 @@ int kvm_verify_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, cons
   int rc = check_common(ctx, q, m, epsilon, lr, K, out);
   if (rc) return rc;
   if ((rc = begin_call(ctx))) return rc;
-  Plan P;
-  if ((rc = make_plan(ctx, lr, K, shift, m, &P))) return rc;
+  // The plan is built in place in the pinned staging block ([q | cbegin | ncand | tile prefix]): with 1e5 short
+  // intervals (the index-pruned shape) the host side otherwise costs more than the kernel.
+  auto up256 = [](size_t x) { return (x + 255) & ~size_t(255); };
+  const size_t o_q = 0;
+  const size_t o_cbegin = up256(sizeof(double) * (size_t)m);
+  const size_t o_ncand = up256(o_cbegin + sizeof(int32_t) * (size_t)K);
+  const size_t o_tp = up256(o_ncand + sizeof(int32_t) * (size_t)K);
+  const size_t bytes = o_tp + sizeof(int32_t) * ((size_t)K + 1);
+  ctx->norm_cache.valid = false;  // the arena is about to be overwritten
+  KVM_CUDA(ctx, ctx->stage.ensure(bytes + 256));
+  KVM_CUDA(ctx, ctx->arena.ensure(bytes + 256));
+  unsigned char* st = static_cast<unsigned char*>(ctx->stage.p);
+  int32_t* cb = reinterpret_cast<int32_t*>(st + o_cbegin);
+  int32_t* nc = reinterpret_cast<int32_t*>(st + o_ncand);
+  int32_t* tp = reinterpret_cast<int32_t*>(st + o_tp);
+  Plan& P = ctx->plan_scratch;
+  P.nsamp.resize(K);
+  int64_t totals[3];
+  if (plan_pass(lr, K, shift, m, ctx->n, ctx->first, ctx->first + ctx->count - 1, cb, P.nsamp.data(), nc, totals))
+    return make_plan(ctx, lr, K, shift, m, &P);  // locates the offending interval and sets the error
+  P.cnt_candidate = totals[0];
+  P.S = totals[1];
+  P.V = totals[2];
   out->cnt_candidate = P.cnt_candidate;
   out->n_verified = P.V;
   out->s_total = P.S;
   if (P.V == 0) return fetch_answers(ctx, 0, out);
   int64_t n_tiles = 0;
-  std::vector<int32_t> tp = tile_prefix_of(P, kEdTile, &n_tiles);
-  Arena A;
-  const size_t o_q = A.add(q, sizeof(double) * m);
-  const size_t o_cbegin = A.add(P.cbegin.data(), sizeof(int32_t) * K);
-  const size_t o_ncand = A.add(P.ncand.data(), sizeof(int32_t) * K);
-  const size_t o_tp = A.add(tp.data(), sizeof(int32_t) * (K + 1));
-  if ((rc = upload_arena(ctx, A))) return rc;
+  for (int p = 0; p < K; p++) {
+    tp[p] = (int32_t)n_tiles;
+    n_tiles += (nc[p] + kEdTile - 1) / kEdTile;
+  }
+  tp[K] = (int32_t)n_tiles;
+  std::memcpy(st + o_q, q, sizeof(double) * (size_t)m);
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->arena.p, ctx->stage.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->h2d_bytes += (long long)bytes;
   if ((rc = ensure_answers(ctx, std::max<long long>(ctx->ans_cap, 1 << 16)))) return rc;
   const unsigned char* base = ctx->arena.as<unsigned char>();
   unsigned long long cnt[kNumCounters];
@@ -976,7 +1000,7 @@ int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int
   if (rc) return rc;
   if (rho < 0 || m < 3) return fail(ctx, KVM_E_ARG, "DTW needs rho >= 0 and m >= 3");
   if ((rc = begin_call(ctx))) return rc;
-  Plan P;
+  Plan& P = ctx->plan_scratch;
   if ((rc = make_plan(ctx, lr, K, shift, m, &P))) return rc;
   out->cnt_candidate = P.cnt_candidate;
   out->n_verified = P.V;
@@ -985,8 +1009,10 @@ int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int
   std::vector<double> qv(q, q + m), uq, lq;
   envelope(qv, rho, lq, uq);  // K/QueryEngineDtw.java:362
   int64_t n_tiles = 0;
-  std::vector<int32_t> tp = tile_prefix_of(P, kEdTile, &n_tiles);
-  Arena A;
+  std::vector<int32_t>& tp = ctx->tp_scratch;
+  tile_prefix_of(P, kEdTile, &n_tiles, tp);
+  Arena& A = ctx->arena_scratch;
+  A.host.clear();
   const size_t o_q = A.add(q, sizeof(double) * m);
   const size_t o_uq = A.add(uq.data(), sizeof(double) * m);
   const size_t o_lq = A.add(lq.data(), sizeof(double) * m);
