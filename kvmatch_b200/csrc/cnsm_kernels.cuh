@@ -575,7 +575,7 @@ __device__ __forceinline__ bool cnsm_exact_gate(double ex, double ex2, int m, do
   return (fabs(xsub(mean, meanQ)) <= beta) && (ratio <= alpha) && (ratio >= inv_alpha);  // :511
 }
 
-__global__ void __launch_bounds__(kEvalTile) cnsm_ed_eval_kernel(EvalParams P) {
+__global__ void __launch_bounds__(kEvalTile, 16) cnsm_ed_eval_kernel(EvalParams P) {
   __shared__ int s_r;
   __shared__ unsigned int s_gate;
   if (threadIdx.x == 0) s_gate = 0;
