@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-query-set", action="store_true", help="skip the query-set side measurement")
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("KVM_BENCH_CHUNK", DEFAULT_CHUNK)))
     ap.add_argument("--ref-sample", type=float, default=N_PER_GPU)   # samples scanned per reference step
     ap.add_argument("--cpu-queries", type=int, default=10)          # queries the 1-core CPU baseline times
@@ -318,6 +319,26 @@ def main():
             "wall_s_timed_region": t_wall_max, "datagen_s": t_gen,
             "best_of_last_query": best,
         }
+        # Beside the headline (not part of it): the same 10 queries as ONE query-set call (kvm_verify_cnsm_ed_batch, an
+        # addition to the reference's per-query engines: one statistics pass serves the set), host buffers in, answers out
+        if world == 1 and not args.no_query_set:
+            qs = np.stack(queries[:N_QUERIES])
+            res = g.verify_cnsm_ed_batch(qs, EPSILON, ALPHA, BETA, iv)
+            reps = 5
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                res = g.verify_cnsm_ed_batch(qs, EPSILON, ALPHA, BETA, iv)
+            per_call = (time.perf_counter() - t0) / reps
+            single = [g.verify_cnsm_ed(q, EPSILON, ALPHA, BETA, iv) for q in qs]
+            line["query_set"] = {
+                "queries_per_call": int(len(qs)), "ms_per_call": 1e3 * per_call,
+                "value": float(sum(r.n_verified for r in res)) / per_call, "unit": "subsequences/s",
+                "kernel_ms_per_call": float(sum(r.kernel_ms for r in res)),
+                "statistics_pass_ms": float(res[0].stage_ms[0] * len(qs)),
+                "identical_to_single_calls": bool(all(a.offsets.tolist() == b.offsets.tolist() and
+                                                      a.distances.tolist() == b.distances.tolist()
+                                                      for a, b in zip(res, single))),
+                "note": "through the ABI with host buffers (compare with e2e, not with value)"}
         # CPU baseline beside it (N=1 only): the oracle port on 1 core (the reference is single-threaded), the same
         # series, chains and queries; bounded to --cpu-queries whole-series queries (~0.7 s each)
         if world == 1:

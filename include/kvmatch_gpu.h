@@ -112,6 +112,15 @@ int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int
 int kvm_verify_cnsm_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int32_t rho, double alpha,
                         double beta, const int32_t* lr, int32_t K, int32_t shift, kvm_result* out);
 
+/* Query set (an addition to the reference's per-query engines): n_queries (<= 16) raw queries of one length m, stored
+ * back to back, verified over ONE interval list with the cNSM-ED semantics of kvm_verify_cnsm_ed.  The window
+ * statistics (K/NormQueryEngine.java:498-499,523-524) do not depend on the query, so one statistics pass serves the
+ * whole set; outs[q] is what kvm_verify_cnsm_ed(queries + q*m, ...) returns.  outs[q].offsets / distances stay valid
+ * until the next query-set call on this ctx (kvm_result_free is not needed for them).  What the reference's experiment
+ * drivers do query by query (K/experiments/NormQueryTestGroupBySelectivity.java:110-127). */
+int kvm_verify_cnsm_ed_batch(kvm_ctx* ctx, const double* queries, int32_t n_queries, int32_t m, double epsilon,
+                             double alpha, double beta, const int32_t* lr, int32_t K, int32_t shift, kvm_result* outs);
+
 /* Index-free full scan with the semantics of the reference's UCR-DTW baseline executor
  * (K/experiments/ucr/UcrDtwQueryExecutor.java:84-314): the series is streamed in EPOCH = 100000-sample buffers that
  * overlap by m-1 (:97-131), the running statistics restart per buffer (:133-134), every window goes through the

@@ -30,7 +30,7 @@ ERROR_NAMES = {
 # every symbol include/kvmatch_gpu.h declares
 EXPORTS = [
     "kvm_abi_version", "kvm_create", "kvm_destroy", "kvm_last_error", "kvm_load_series_host", "kvm_load_series_file",
-    "kvm_verify_ed", "kvm_verify_cnsm_ed", "kvm_verify_dtw", "kvm_verify_cnsm_dtw", "kvm_scan_ucr_dtw",
+    "kvm_verify_ed", "kvm_verify_cnsm_ed", "kvm_verify_dtw", "kvm_verify_cnsm_dtw", "kvm_verify_cnsm_ed_batch", "kvm_scan_ucr_dtw",
     "kvm_window_mean_runs", "kvm_build_index_file", "kvm_index_image_from_runs", "kvm_image_free",
     "kvm_result_free", "kvm_runs_free",
 ]
@@ -112,6 +112,8 @@ def load():
     L.kvm_verify_dtw.argtypes = [vp, _dp, C.c_int32, C.c_double, C.c_int32, _ip, C.c_int32, C.c_int32, R]
     L.kvm_verify_cnsm_dtw.argtypes = [vp, _dp, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_double, _ip,
                                       C.c_int32, C.c_int32, R]
+    L.kvm_verify_cnsm_ed_batch.argtypes = [vp, _dp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, _ip, C.c_int32,
+                                           C.c_int32, R]
     L.kvm_scan_ucr_dtw.argtypes = [vp, _dp, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_double, R]
     L.kvm_window_mean_runs.argtypes = [vp, C.c_int32, C.POINTER(KvmRuns)]
     L.kvm_build_index_file.argtypes = [vp, C.c_int32, C.c_char_p, C.POINTER(KvmIndexInfo)]

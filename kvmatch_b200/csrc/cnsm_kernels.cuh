@@ -70,6 +70,21 @@ __device__ __forceinline__ int hi_key(double x) {
   return h ^ ((h >> 31) & 0x7fffffff);
 }
 
+// kMode 2 (query sets): the chain sums do not depend on the query, only the gate's key ranges do, so one statistics
+// pass can gate a whole set of queries of one length over one interval list and feed one work list per query.
+constexpr int kMaxBatch = 16;
+struct BatchGate {
+  int n_q;
+  int mean_klo[kMaxBatch], var_klo[kMaxBatch];
+  unsigned mean_kspan[kMaxBatch], var_kspan[kMaxBatch];
+  int32_t* e_off[kMaxBatch];
+  double* e_ex[kMaxBatch];
+  double* e_ex2[kMaxBatch];
+  int32_t* region_count[kMaxBatch];
+  int32_t* tile_prefix[kMaxBatch];
+  unsigned long long* totals[kMaxBatch];
+};
+
 struct WalkParams {
   const double* __restrict__ T;         // sample 0 of this shard; kFrontPad/kTailPad zero samples surround it
   const int32_t* __restrict__ cbegin;   // per chain: local 0-based index of its first sample
@@ -97,6 +112,7 @@ struct WalkParams {
   int32_t* bucket_out;  // bucket_out[local window start] = floor(2 * fl(fl(ex/w) * 10))
   double c20w;          // 20 / w
   int* overflow;        // set when a bucket does not fit int32
+  const BatchGate* batch;  // kMode == 2 only (device memory)
 };
 
 // ---- named barriers (producer/consumer hand-off inside a CTA) --------------------------------------
@@ -234,6 +250,8 @@ __global__ void __launch_bounds__(kRelayThreads, kRelayThreads <= 224 ? 2 : 1) c
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(gate_stage + kRelayWarps * 32 * kGatePitch);
   int* s_rcount = reinterpret_cast<int*>(bars + 2 * STAGES);
 
+  __shared__ int s_rcount_q[kMode == 2 ? kMaxBatch : 1];
+
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   asm volatile("mov.u32 %0, %0;" : "+r"(lane));  // keep out of SR_TID.X re-reads in the loops
   asm volatile("mov.u32 %0, %0;" : "+r"(warp));
@@ -250,6 +268,7 @@ __global__ void __launch_bounds__(kRelayThreads, kRelayThreads <= 224 ? 2 : 1) c
   const int ntiles = warp_max_i32(ntl);
   const int k_w = (m - 1) / kWalkTile;  // first tile that can contain the end of a complete window
   const uint32_t bar_ready = smem_u32(bars), bar_free = bar_ready + 8 * STAGES;
+  if (kMode == 2 && threadIdx.x < kMaxBatch) s_rcount_q[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     *s_rcount = 0;
 #pragma unroll
@@ -434,6 +453,90 @@ __global__ void __launch_bounds__(kRelayThreads, kRelayThreads <= 224 ? 2 : 1) c
               P.bucket_out[pos + s - (m - 1)] = (int)fl;
             }
           }
+        } else if (kMode == 2) {
+          // query set: the window keys once, then one (mean, variance) range test per query and position
+          const BatchGate* __restrict__ G = P.batch;
+          const int n_q = __ldg(&G->n_q);
+          int km[kRelayBlock], kv[kRelayBlock];
+          unsigned wmask = 0;
+#pragma unroll
+          for (int j = 0; j < kRelayBlock; j++) {
+            const int s = s0 + j;
+            const bool win = kSteady || (((unsigned)s < (unsigned)len) & (s >= m - 1));
+            wmask |= win ? (1u << j) : 0u;
+            km[j] = hi_key(qx[j]);
+            kv[j] = hi_key(__fma_rn(q2[j], dm, -(qx[j] * qx[j])));
+          }
+          // the turn's range of mean keys per lane: most queries are rejected by two compares and a vote
+          int km_lo = INT32_MAX, km_hi = INT32_MIN;
+#pragma unroll
+          for (int j = 0; j < kRelayBlock; j++) {
+            if ((wmask >> j) & 1u) {
+              km_lo = min(km_lo, km[j]);
+              km_hi = max(km_hi, km[j]);
+            }
+          }
+          bool staged = false;  // this turn's sums are in the warp's staging rows (dense flushes)
+          for (int q = 0; q < n_q; q++) {
+            const int mklo = __ldg(&G->mean_klo[q]), vklo = __ldg(&G->var_klo[q]);
+            const unsigned mspan = __ldg(&G->mean_kspan[q]), vspan = __ldg(&G->var_kspan[q]);
+            // [km_lo, km_hi] misses [mklo, mklo + mspan] for every lane -> nothing of this turn can pass
+            if (!__any_sync(kFullMask, (long long)km_hi >= (long long)mklo && (long long)km_lo <= (long long)mklo + (long long)mspan))
+              continue;
+            unsigned mask = 0;
+#pragma unroll
+            for (int j = 0; j < kRelayBlock; j++)
+              mask |= (((unsigned)(km[j] - mklo) <= mspan) & ((unsigned)(kv[j] - vklo) <= vspan)) ? (1u << j) : 0u;
+            mask &= wmask;
+            if (!__any_sync(kFullMask, mask != 0)) continue;
+            int32_t* __restrict__ qe_off = G->e_off[q];
+            double* __restrict__ qe_ex = G->e_ex[q];
+            double* __restrict__ qe_ex2 = G->e_ex2[q];
+            const int cnt = __popc(mask);
+            const int incl = warp_incl_scan_i32(cnt, lane);
+            const int total = __shfl_sync(kFullMask, incl, 31);
+            int rbase = 0;
+            if (lane == 0) rbase = atomicAdd(&s_rcount_q[q], total);
+            rbase = __shfl_sync(kFullMask, rbase, 0);
+            const int excl = incl - cnt;
+            if (kRelayBlock == 16 && total > 96) {
+              double2* gs = gate_stage + (size_t)warp * 32 * kGatePitch;
+              if (!staged) {
+#pragma unroll
+                for (int j = 0; j < kRelayBlock; j++) gs[lane * kGatePitch + j] = make_double2(qx[j], q2[j]);
+                __syncwarp();
+                staged = true;
+              }
+              const unsigned nz = __ballot_sync(kFullMask, cnt > 0);
+              const int hl = lane & 15, hw = lane >> 4;
+              for (int pr = 0; pr < 16; pr++) {
+                if (((nz >> (2 * pr)) & 3u) == 0) continue;
+                const int owner = 2 * pr + hw;
+                const unsigned omask = __shfl_sync(kFullMask, mask, owner);
+                const int oexcl = __shfl_sync(kFullMask, excl, owner);
+                const int32_t ooff = __shfl_sync(kFullMask, off0, owner);
+                if ((omask >> hl) & 1u) {
+                  const double2 v2 = gs[owner * kGatePitch + hl];
+                  const long long gidx = base + rbase + oexcl + __popc(omask & ((1u << hl) - 1u));
+                  qe_off[gidx] = ooff + col0 + hl;
+                  qe_ex[gidx] = v2.x;
+                  qe_ex2[gidx] = v2.y;
+                }
+              }
+            } else {
+              long long gidx = base + rbase + excl;
+#pragma unroll
+              for (int j = 0; j < kRelayBlock; j++) {
+                if ((mask >> j) & 1u) {
+                  qe_off[gidx] = off0 + col0 + j;
+                  qe_ex[gidx] = qx[j];
+                  qe_ex2[gidx] = q2[j];
+                  gidx++;
+                }
+              }
+            }
+          }
+          if (staged) __syncwarp();
         } else {
           // mean gate first (integer pipe only); the variance keys are computed only if some window of the turn passed it
           unsigned mask = 0;
@@ -537,6 +640,24 @@ __global__ void __launch_bounds__(kRelayThreads, kRelayThreads <= 224 ? 2 : 1) c
     if (s_last) {
       __threadfence();
       plan_scan_cta<kRelayThreads>(P.region_count, (int)gridDim.x, P.tile_prefix, P.totals);
+    }
+  } else if (kMode == 2) {
+    __shared__ bool s_last2;
+    const BatchGate* __restrict__ G = P.batch;
+    const int n_q = G->n_q;
+    if ((int)threadIdx.x < n_q) {
+      G->region_count[threadIdx.x][region] = s_rcount_q[threadIdx.x];
+      __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_last2 = atomicAdd(P.done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last2) {
+      __threadfence();
+      for (int q = 0; q < n_q; q++) {
+        plan_scan_cta<kRelayThreads>(G->region_count[q], (int)gridDim.x, G->tile_prefix[q], G->totals[q]);
+        __syncthreads();
+      }
     }
   } else if (threadIdx.x == 0) {
     P.region_count[region] = *s_rcount;

@@ -111,6 +111,20 @@ struct NormPlanCache {
   size_t o_cbegin = 0, o_nsamp = 0, o_rbase = 0;
 };
 
+// Per-query device buffers of a query set (kvm_verify_cnsm_ed_batch): swapped into the ctx's single-query slots while
+// that query's evaluator / exact stages run, so those stages are the single-query code.
+struct BatchSlot {
+  DevBuf wl_off, wl_ex, wl_ex2, region_count, tile_prefix, counters, qarena, cand_off, cand_mean, cand_std, ans_off, ans_dist;
+  long long cand_cap = 0, ans_cap = 0;
+  std::vector<int32_t> off;
+  std::vector<double> dist;
+  void release() {
+    DevBuf* all[] = {&wl_off, &wl_ex, &wl_ex2, &region_count, &tile_prefix, &counters, &qarena, &cand_off, &cand_mean,
+                     &cand_std, &ans_off, &ans_dist};
+    for (DevBuf* b : all) b->release();
+    cand_cap = ans_cap = 0;
+  }
+};
 }  // namespace
 
 struct kvm_ctx {
@@ -118,7 +132,7 @@ struct kvm_ctx {
   int n_sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t evs[2] = {nullptr, nullptr};  // stage boundaries inside a call
+  cudaEvent_t evs[4] = {nullptr, nullptr, nullptr, nullptr};  // stage boundaries inside a call ([2],[3]: query sets)
   std::string err;
 
   DevBuf series_buf;  // [kFrontPad zeros | samples | kTailPad zeros]
@@ -130,6 +144,8 @@ struct kvm_ctx {
   DevBuf seg_b, seg_first, seg_last, chain_count, chain_prefix, run_key, run_b, run_first, run_last;
   long long cand_cap = 0, ans_cap = 0;
   NormPlanCache norm_cache;
+  std::vector<BatchSlot> slots;      // query sets
+  DevBuf batch_gate;
   Plan plan_scratch;                 // RSM engines: host planning buffers kept across calls (no fresh pages per call)
   std::vector<int32_t> tp_scratch;
   Arena arena_scratch;
@@ -409,6 +425,29 @@ struct NormSetup {
   bool degenerate = false;  // stdQ is 0/NaN: no window can pass the gate
 };
 
+// Conservative pre-gate key ranges of one query (see launch_walker).
+void gate_keys(int m, const NormSetup& S, double alpha, double beta, int* mean_klo, unsigned* mean_kspan, int* var_klo,
+               unsigned* var_kspan) {
+  const double dm = (double)m;
+  const double amq = std::fabs(S.meanQ) + std::fabs(beta);
+  const double beta_hi = beta + 1e-14 * amq + 1e-290;
+  const double hi2 = (alpha * S.stdQ) * (alpha * S.stdQ), lo2 = (S.stdQ * S.inv_alpha) * (S.stdQ * S.inv_alpha);
+  const double d2 = 1e-13 * (hi2 + 2.0 * amq * amq) + 1e-290;
+  const double var_hi = hi2 * (1.0 + 1e-12) + d2, var_lo = lo2 * (1.0 - 1e-12) - d2;
+  double e_lo = dm * (S.meanQ - beta_hi), e_hi = dm * (S.meanQ + beta_hi);
+  e_lo -= std::fabs(e_lo) * 1e-12;
+  e_hi += std::fabs(e_hi) * 1e-12;
+  double v_lo = dm * dm * var_lo, v_hi = dm * dm * var_hi;
+  v_lo -= std::fabs(v_lo) * 1e-12;
+  v_hi += std::fabs(v_hi) * 1e-12;
+  const long long mk_lo = (long long)host_hi_key(e_lo) - 1, mk_hi = (long long)host_hi_key(e_hi) + 1;
+  const long long vk_lo = (long long)host_hi_key(v_lo) - 1, vk_hi = (long long)host_hi_key(v_hi) + 1;
+  *mean_klo = (int)std::max<long long>(mk_lo, INT32_MIN);
+  *var_klo = (int)std::max<long long>(vk_lo, INT32_MIN);
+  *mean_kspan = (unsigned)(std::min<long long>(mk_hi, INT32_MAX) - *mean_klo);
+  *var_kspan = (unsigned)(std::min<long long>(vk_hi, INT32_MAX) - *var_klo);
+}
+
 #ifndef KVM_RELAY_STAGES
 #define KVM_RELAY_STAGES 3
 #endif
@@ -430,26 +469,7 @@ int launch_walker(kvm_ctx* ctx, const Plan& P, int K, int m, double alpha, doubl
   // Conservative pre-gate: a superset of the exact gate (rounding of the chain sums' products is far below
   // these slacks, and the integer keys widen each bound by one high-word unit); the exact gate is
   // re-evaluated with the reference's arithmetic by the evaluators.
-  {
-    const double dm = (double)m;
-    const double amq = std::fabs(S.meanQ) + std::fabs(beta);
-    const double beta_hi = beta + 1e-14 * amq + 1e-290;
-    const double hi2 = (alpha * S.stdQ) * (alpha * S.stdQ), lo2 = (S.stdQ * S.inv_alpha) * (S.stdQ * S.inv_alpha);
-    const double d2 = 1e-13 * (hi2 + 2.0 * amq * amq) + 1e-290;
-    const double var_hi = hi2 * (1.0 + 1e-12) + d2, var_lo = lo2 * (1.0 - 1e-12) - d2;
-    double e_lo = dm * (S.meanQ - beta_hi), e_hi = dm * (S.meanQ + beta_hi);
-    e_lo -= std::fabs(e_lo) * 1e-12;
-    e_hi += std::fabs(e_hi) * 1e-12;
-    double v_lo = dm * dm * var_lo, v_hi = dm * dm * var_hi;
-    v_lo -= std::fabs(v_lo) * 1e-12;
-    v_hi += std::fabs(v_hi) * 1e-12;
-    const long long mk_lo = (long long)host_hi_key(e_lo) - 1, mk_hi = (long long)host_hi_key(e_hi) + 1;
-    const long long vk_lo = (long long)host_hi_key(v_lo) - 1, vk_hi = (long long)host_hi_key(v_hi) + 1;
-    W.mean_klo = (int)std::max<long long>(mk_lo, INT32_MIN);
-    W.var_klo = (int)std::max<long long>(vk_lo, INT32_MIN);
-    W.mean_kspan = (unsigned)(std::min<long long>(mk_hi, INT32_MAX) - W.mean_klo);
-    W.var_kspan = (unsigned)(std::min<long long>(vk_hi, INT32_MAX) - W.var_klo);
-  }
+  gate_keys(m, S, alpha, beta, &W.mean_klo, &W.mean_kspan, &W.var_klo, &W.var_kspan);
   W.e_off = ctx->wl_off.as<int32_t>();
   W.e_ex = ctx->wl_ex.as<double>();
   W.e_ex2 = ctx->wl_ex2.as<double>();
@@ -457,6 +477,7 @@ int launch_walker(kvm_ctx* ctx, const Plan& P, int K, int m, double alpha, doubl
   W.tile_prefix = ctx->tile_prefix.as<int32_t>();
   W.totals = ctx->counters.as<unsigned long long>() + kCntTiles;
   W.done = reinterpret_cast<unsigned int*>(ctx->counters.as<unsigned long long>() + kCntDone);
+  W.batch = nullptr;
   // Relay walker, 5 relay warps + loader, 3-stage tile ring: ~100 KB of shared memory per CTA, 2 CTAs (= 64 chains)
   // per SM.  More resident chains would not help: ~8k chains x (m-1) x 8 B of lag windows is what stays
   // L2-resident.  (A 2-stage instantiation is deliberately not built: ptxas 12.9 emits its hinted
@@ -774,7 +795,8 @@ int kvm_create(kvm_ctx** out, int device_id) {
   ctx->n_sms = prop.multiProcessorCount;
   if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-      cudaEventCreate(&ctx->evs[0]) != cudaSuccess || cudaEventCreate(&ctx->evs[1]) != cudaSuccess) {
+      cudaEventCreate(&ctx->evs[0]) != cudaSuccess || cudaEventCreate(&ctx->evs[1]) != cudaSuccess ||
+      cudaEventCreate(&ctx->evs[2]) != cudaSuccess || cudaEventCreate(&ctx->evs[3]) != cudaSuccess) {
     const char* msg = cudaGetErrorString(cudaGetLastError());
     delete ctx;
     return fail(nullptr, KVM_E_CUDA, "stream/event creation failed: %s", msg);
@@ -783,6 +805,8 @@ int kvm_create(kvm_ctx** out, int device_id) {
   if (cudaFuncSetAttribute(cnsm_relay_kernel<kRelayStages, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4) != cudaSuccess ||
       cudaFuncSetAttribute(cnsm_relay_kernel<kRelayStages, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4) != cudaSuccess ||
       cudaFuncSetAttribute(cnsm_relay_kernel<kRelayStages, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4) != cudaSuccess ||
+      cudaFuncSetAttribute(cnsm_relay_kernel<kRelayStages, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4) != cudaSuccess ||
+      cudaFuncSetAttribute(cnsm_relay_kernel<kRelayStages, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4) != cudaSuccess ||
       cudaFuncSetAttribute(cnsm_relay_kernel<kRelayStages, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4) != cudaSuccess) {
     const char* msg = cudaGetErrorString(cudaGetLastError());
     kvm_destroy(ctx);
@@ -806,6 +830,8 @@ void kvm_destroy(kvm_ctx* ctx) {
                    &ctx->ans_off, &ctx->ans_dist, &ctx->seg_b, &ctx->seg_first, &ctx->seg_last, &ctx->chain_count,
                    &ctx->chain_prefix, &ctx->run_key, &ctx->run_b, &ctx->run_first, &ctx->run_last};
   for (DevBuf* b : dev) b->release();
+  for (BatchSlot& sl : ctx->slots) sl.release();
+  ctx->batch_gate.release();
   PinBuf* pin[] = {&ctx->stage, &ctx->stage2, &ctx->h_counters, &ctx->h_off, &ctx->h_dist, &ctx->h_key, &ctx->h_first, &ctx->h_last,
                    &ctx->h_b};
   for (PinBuf* b : pin) b->release();
@@ -963,6 +989,258 @@ int kvm_verify_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, cons
 int kvm_verify_cnsm_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, double alpha, double beta,
                        const int32_t* lr, int32_t K, int32_t shift, kvm_result* out) {
   return verify_norm(ctx, Mode::kEd, q, m, epsilon, 0, alpha, beta, lr, K, shift, out);
+}
+
+namespace {
+void swap_slot(kvm_ctx* c, BatchSlot& s) {
+  std::swap(c->wl_off, s.wl_off);
+  std::swap(c->wl_ex, s.wl_ex);
+  std::swap(c->wl_ex2, s.wl_ex2);
+  std::swap(c->region_count, s.region_count);
+  std::swap(c->tile_prefix, s.tile_prefix);
+  std::swap(c->counters, s.counters);
+  std::swap(c->qarena, s.qarena);
+  std::swap(c->cand_off, s.cand_off);
+  std::swap(c->cand_mean, s.cand_mean);
+  std::swap(c->cand_std, s.cand_std);
+  std::swap(c->ans_off, s.ans_off);
+  std::swap(c->ans_dist, s.ans_dist);
+  std::swap(c->cand_cap, s.cand_cap);
+  std::swap(c->ans_cap, s.ans_cap);
+}
+}  // namespace
+
+// Query set: Q queries of one length over one interval list.  One statistics pass (cnsm_relay_kernel, kMode 2) gates all
+// of them; the evaluator / exact stages then run per query on that query's work list.  Results are what Q calls of
+// kvm_verify_cnsm_ed would return (same kernels, same arithmetic); outs[q].offsets / distances stay valid until the next
+// batch call on this ctx.
+int kvm_verify_cnsm_ed_batch(kvm_ctx* ctx, const double* queries, int32_t n_queries, int32_t m, double epsilon, double alpha,
+                             double beta, const int32_t* lr, int32_t K, int32_t shift, kvm_result* outs) {
+  if (!ctx) return KVM_E_ARG;
+  if (!queries || !outs || n_queries < 1 || n_queries > kMaxBatch)
+    return fail(ctx, KVM_E_ARG, "a query set holds 1..%d queries", kMaxBatch);
+  const int Q = n_queries;
+  int rc = check_common(ctx, queries, m, epsilon, lr, K, &outs[0]);
+  if (rc) return rc;
+  for (int q = 0; q < Q; q++) std::memset(&outs[q], 0, sizeof(kvm_result));
+  if ((rc = begin_call(ctx))) return rc;
+  // ---- plan (shared): the single-query engine's plan, built in place in pinned staging
+  ctx->norm_cache.valid = false;
+  Plan& P = ctx->plan_scratch;
+  if ((rc = make_plan(ctx, lr, K, shift, m, &P))) return rc;
+  const int n_regions = (K + 31) / 32;
+  auto up256 = [](size_t x) { return (x + 255) & ~size_t(255); };
+  const size_t o_cbegin = 0, o_nsamp = up256(sizeof(int32_t) * (size_t)K);
+  const size_t o_rbase = up256(o_nsamp + sizeof(int32_t) * (size_t)K);
+  const size_t o_gate = up256(o_rbase + sizeof(long long) * (size_t)(n_regions + 1));
+  const size_t bytes = o_gate + sizeof(BatchGate);
+  KVM_CUDA(ctx, ctx->stage.ensure(bytes + 256));
+  KVM_CUDA(ctx, ctx->arena.ensure(bytes + 256));
+  unsigned char* st = static_cast<unsigned char*>(ctx->stage.p);
+  std::memcpy(st + o_cbegin, P.cbegin.data(), sizeof(int32_t) * (size_t)K);
+  {
+    int32_t* walk_nsamp = reinterpret_cast<int32_t*>(st + o_nsamp);
+    long long* region_base = reinterpret_cast<long long*>(st + o_rbase);
+    long long acc = 0;
+    for (int c = 0; c < K; c++) {
+      if ((c & 31) == 0) region_base[c >> 5] = acc;
+      acc += P.ncand[c];
+      walk_nsamp[c] = P.ncand[c] > 0 ? P.nsamp[c] : 0;
+    }
+    region_base[n_regions] = acc;
+  }
+  // ---- per query: statistics, gate keys, buffers
+  if (ctx->slots.size() < (size_t)Q) ctx->slots.resize(Q);
+  std::vector<NormSetup> S(Q);
+  BatchGate* G = reinterpret_cast<BatchGate*>(st + o_gate);
+  std::memset(G, 0, sizeof(BatchGate));
+  G->n_q = Q;
+  const bool nothing = P.V == 0;
+  for (int q = 0; q < Q; q++) {
+    outs[q].cnt_candidate = P.cnt_candidate;
+    outs[q].n_verified = P.V;
+    outs[q].s_total = P.S;
+    query_stats(queries + (size_t)q * m, m, &S[q].meanQ, &S[q].stdQ);
+    S[q].inv_alpha = 1.0 / alpha;
+    S[q].n_regions = n_regions;
+    S[q].degenerate = !(S[q].stdQ > 0.0) || !(S[q].stdQ < INFINITY);
+    BatchSlot& sl = ctx->slots[q];
+    if (nothing) continue;
+    KVM_CUDA(ctx, sl.wl_off.ensure(sizeof(int32_t) * (size_t)P.V));
+    KVM_CUDA(ctx, sl.wl_ex.ensure(sizeof(double) * (size_t)P.V));
+    KVM_CUDA(ctx, sl.wl_ex2.ensure(sizeof(double) * (size_t)P.V));
+    KVM_CUDA(ctx, sl.region_count.ensure(sizeof(int32_t) * (n_regions + 1)));
+    KVM_CUDA(ctx, sl.tile_prefix.ensure(sizeof(int32_t) * (n_regions + 2)));
+    KVM_CUDA(ctx, sl.counters.ensure(sizeof(unsigned long long) * kNumCounters));
+    KVM_CUDA(ctx, cudaMemsetAsync(sl.counters.p, 0, sizeof(unsigned long long) * kNumCounters, ctx->stream));
+    if (S[q].degenerate) {  // no window can pass: an empty key range
+      G->mean_klo[q] = G->var_klo[q] = INT32_MAX;
+      G->mean_kspan[q] = G->var_kspan[q] = 0;
+    } else {
+      gate_keys(m, S[q], alpha, beta, &G->mean_klo[q], &G->mean_kspan[q], &G->var_klo[q], &G->var_kspan[q]);
+    }
+    G->e_off[q] = sl.wl_off.as<int32_t>();
+    G->e_ex[q] = sl.wl_ex.as<double>();
+    G->e_ex2[q] = sl.wl_ex2.as<double>();
+    G->region_count[q] = sl.region_count.as<int32_t>();
+    G->tile_prefix[q] = sl.tile_prefix.as<int32_t>();
+    G->totals[q] = sl.counters.as<unsigned long long>() + kCntTiles;
+  }
+  if (nothing) {
+    for (int q = 0; q < Q; q++)
+      if ((rc = fetch_answers(ctx, 0, &outs[q]))) return rc;
+    return KVM_OK;
+  }
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->arena.p, ctx->stage.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->h2d_bytes += (long long)bytes;
+  const unsigned char* base = ctx->arena.as<unsigned char>();
+  // ---- one statistics pass for the set
+  if ((rc = zero_counters(ctx))) return rc;
+  WalkParams W;
+  std::memset(&W, 0, sizeof(W));
+  W.T = ctx->series;
+  W.cbegin = reinterpret_cast<const int32_t*>(base + o_cbegin);
+  W.cnsamp = reinterpret_cast<const int32_t*>(base + o_nsamp);
+  W.region_base = reinterpret_cast<const long long*>(base + o_rbase);
+  W.K = K;
+  W.m = m;
+  W.first_global = (int32_t)ctx->first;
+  W.dm = (double)m;
+  W.idx_hi = (int)((ctx->count + kTailPad - 2) & ~int64_t(1));
+  W.done = reinterpret_cast<unsigned int*>(ctx->counters.as<unsigned long long>() + kCntDone);
+  W.batch = reinterpret_cast<const BatchGate*>(base + o_gate);
+  KVM_CUDA(ctx, cudaEventRecord(ctx->evs[2], ctx->stream));
+  if ((m % 2) == 0) cnsm_relay_kernel<kRelayStages, 1, 2><<<n_regions, kRelayThreads, relay_smem_bytes(kRelayStages), ctx->stream>>>(W);
+  else cnsm_relay_kernel<kRelayStages, 0, 2><<<n_regions, kRelayThreads, relay_smem_bytes(kRelayStages), ctx->stream>>>(W);
+  KVM_CUDA(ctx, cudaEventRecord(ctx->evs[3], ctx->stream));
+  KVM_CUDA(ctx, cudaGetLastError());
+  float walk_ms = 0.f;
+  // ---- while the statistics pass runs: every query's z-normalisation and |z| ordering (K/NormQueryEngine.java:438-448)
+  // into one pinned block [q][zq f64 x m | order i32 x m], one copy per query into its own device buffer
+  const size_t q_zq = 0, q_order = up256(sizeof(double) * (size_t)m), q_bytes = up256(q_order + sizeof(int32_t) * (size_t)m);
+  const size_t o_zq = q_zq, o_order = q_order;
+  KVM_CUDA(ctx, ctx->stage2.ensure(q_bytes * (size_t)Q + 256));
+  {
+    std::vector<double> z(m);
+    for (int q = 0; q < Q; q++) {
+      if (S[q].degenerate) continue;
+      BatchSlot& sl = ctx->slots[q];
+      KVM_CUDA(ctx, sl.qarena.ensure(q_bytes + 256));
+      unsigned char* dst = static_cast<unsigned char*>(ctx->stage2.p) + q_bytes * (size_t)q;
+      double* zq = reinterpret_cast<double*>(dst + q_zq);
+      int32_t* order = reinterpret_cast<int32_t*>(dst + q_order);
+      const double* qq = queries + (size_t)q * m;
+      for (int i = 0; i < m; i++) z[i] = (qq[i] - S[q].meanQ) / S[q].stdQ;
+      for (int i = 0; i < m; i++) order[i] = i;
+      std::stable_sort(order, order + m, [&](int32_t a, int32_t b) {
+        return java_double_compare(std::fabs(z[b]), std::fabs(z[a])) < 0;
+      });
+      for (int i = 0; i < m; i++) zq[i] = z[order[i]];
+      KVM_CUDA(ctx, cudaMemcpyAsync(sl.qarena.p, dst, q_bytes, cudaMemcpyHostToDevice, ctx->stream));
+      ctx->h2d_bytes += (long long)q_bytes;
+    }
+  }
+  // ---- per query: the single-query evaluator + exact stages on that query's buffers
+  const double eps2 = epsilon * epsilon;
+  for (int q = 0; q < Q; q++) {
+    BatchSlot& sl = ctx->slots[q];
+    kvm_result* out = &outs[q];
+    out->n_launches = (q == 0) ? 1 : 0;
+    if (S[q].degenerate) {
+      sl.off.clear();
+      sl.dist.clear();
+      continue;
+    }
+    swap_slot(ctx, sl);
+    rc = KVM_OK;
+    cudaError_t ce = cudaSuccess;
+    if (ce == cudaSuccess) rc = ensure_answers(ctx, std::max<long long>(ctx->ans_cap, 1 << 16));
+    if (ce == cudaSuccess && rc == KVM_OK) rc = ensure_cands(ctx, std::max<long long>(ctx->cand_cap, 1 << 18));
+    unsigned long long cnt[kNumCounters] = {0};
+    for (int attempt = 0; ce == cudaSuccess && rc == KVM_OK && attempt < 8; attempt++) {
+      if (attempt > 0) {  // re-run this query's tail only: keep the walker's totals, clear the tail's counters
+        unsigned long long* c = ctx->counters.as<unsigned long long>();
+        cudaMemsetAsync(c + kCntAnswers, 0, sizeof(unsigned long long) * 3, ctx->stream);  // answers, cand, gate
+        cudaMemsetAsync(c + kCntFlag, 0, sizeof(unsigned long long), ctx->stream);
+      }
+      const unsigned char* qbase = ctx->qarena.as<unsigned char>();
+      EvalParams E;
+      E.T = ctx->series;
+      E.first_global = (int32_t)ctx->first;
+      E.m = m;
+      E.e_off = ctx->wl_off.as<int32_t>();
+      E.e_ex = ctx->wl_ex.as<double>();
+      E.e_ex2 = ctx->wl_ex2.as<double>();
+      E.region_base = reinterpret_cast<const long long*>(base + o_rbase);
+      E.region_count = ctx->region_count.as<int32_t>();
+      E.tile_prefix = ctx->tile_prefix.as<int32_t>();
+      E.totals = ctx->counters.as<unsigned long long>() + kCntTiles;
+      E.n_regions = n_regions;
+      E.zq = reinterpret_cast<const double*>(qbase + o_zq);
+      E.order = reinterpret_cast<const int32_t*>(qbase + o_order);
+      E.meanQ = S[q].meanQ;
+      E.stdQ = S[q].stdQ;
+      E.alpha = alpha;
+      E.inv_alpha = S[q].inv_alpha;
+      E.beta = beta;
+      E.eps2 = eps2;
+      E.eps2_hi = eps2 * (1.0 + 1e-9) + 1e-18;
+      E.out = cands_of(ctx);
+      E.gate_pass = ctx->counters.as<unsigned long long>() + kCntGate;
+      cudaEventRecord(ctx->evs[0], ctx->stream);
+      cnsm_ed_eval_kernel<<<ctx->n_sms * 16, kEvalTile, 0, ctx->stream>>>(E);
+      cudaEventRecord(ctx->evs[1], ctx->stream);
+      ExactEdParams X;
+      X.T = E.T;
+      X.first_global = E.first_global;
+      X.m = m;
+      X.zq = E.zq;
+      X.order = E.order;
+      X.eps2 = eps2;
+      X.eps2_hi = E.eps2_hi;
+      X.n_exact = ctx->counters.as<unsigned long long>() + kCntFlag;
+      X.in = E.out;
+      X.sink = sink_of(ctx);
+      cnsm_ed_exact_kernel<<<ctx->n_sms * 6, 128, sizeof(double) * kExactChunk * 4, ctx->stream>>>(X);
+      cudaEventRecord(ctx->ev1, ctx->stream);
+      out->n_launches += 2;
+      if ((rc = read_counters(ctx, cnt))) break;
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, ctx->evs[0], ctx->evs[1]);
+      cudaEventElapsedTime(&b, ctx->evs[1], ctx->ev1);
+      out->stage_ms[1] += a;
+      out->stage_ms[2] += b;
+      const bool cand_over = (long long)cnt[kCntCand] > ctx->cand_cap, ans_over = (long long)cnt[kCntAnswers] > ctx->ans_cap;
+      if (!cand_over && !ans_over) break;
+      if (attempt == 7) rc = fail(ctx, KVM_E_OOM, "candidate/answer buffers kept overflowing");
+      if (rc == KVM_OK && cand_over) rc = ensure_cands(ctx, (long long)cnt[kCntCand] + 1024);
+      if (rc == KVM_OK && ans_over) rc = ensure_answers(ctx, (long long)cnt[kCntAnswers] + 1024);
+    }
+    if (ce != cudaSuccess) rc = fail(ctx, KVM_E_CUDA, "CUDA error in the query set: %s", cudaGetErrorString(ce));
+    if (rc == KVM_OK) {
+      out->n_gate_pass = (int64_t)cnt[kCntGate];
+      out->n_exact = (int64_t)cnt[kCntFlag];
+      rc = fetch_answers(ctx, (long long)cnt[kCntAnswers], out);
+    }
+    if (rc == KVM_OK) {  // fetch_answers points into ctx-owned vectors that the next query overwrites
+      sl.off.assign(out->offsets, out->offsets + out->count);
+      sl.dist.assign(out->distances, out->distances + out->count);
+    }
+    swap_slot(ctx, sl);
+    if (rc) return rc;
+  }
+  KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaEventElapsedTime(&walk_ms, ctx->evs[2], ctx->evs[3]);
+  for (int q = 0; q < Q; q++) {
+    BatchSlot& sl = ctx->slots[q];
+    outs[q].offsets = sl.off.data();
+    outs[q].distances = sl.dist.data();
+    outs[q].count = (int64_t)sl.off.size();
+    outs[q].h2d_bytes = (int32_t)std::min<long long>(ctx->h2d_bytes, INT32_MAX);
+    outs[q].stage_ms[0] = (double)walk_ms / Q;  // the set's one statistics pass, shared
+    outs[q].kernel_ms = outs[q].stage_ms[0] + outs[q].stage_ms[1] + outs[q].stage_ms[2];
+  }
+  return KVM_OK;
 }
 
 int kvm_verify_cnsm_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int32_t rho, double alpha, double beta,
@@ -1141,6 +1419,7 @@ int kvm_window_mean_runs(kvm_ctx* ctx, int32_t w, kvm_runs* out) {
   W.tile_prefix = nullptr;
   W.totals = nullptr;
   W.done = nullptr;
+  W.batch = nullptr;
   W.bucket_out = ctx->seg_b.as<int32_t>();
   W.c20w = 20.0 / (double)w;
   W.overflow = reinterpret_cast<int*>(ctx->counters.as<unsigned long long>() + kCntFlag);

@@ -117,6 +117,24 @@ class GpuSeries:
         self._check(self._L.kvm_verify_ed(self._h, qp, len(q), epsilon, lp, K, shift, C.byref(r)))
         return self._take(r)
 
+    def verify_cnsm_ed_batch(self, queries, epsilon, alpha, beta, intervals, shift=0) -> list:
+        """A set of equal-length queries over one interval list: one statistics pass, per-query results
+        (kvm_verify_cnsm_ed_batch).  `queries`: 2-D array (Q, m)."""
+        qs = np.ascontiguousarray(queries, dtype=np.float64)
+        if qs.ndim != 2:
+            raise ValueError("queries must be a (Q, m) array")
+        lr, lp, K = _lib.as_intervals(intervals)
+        res = (_lib.KvmResult * qs.shape[0])()
+        self._check(self._L.kvm_verify_cnsm_ed_batch(self._h, qs.ctypes.data, qs.shape[0], qs.shape[1], epsilon, alpha, beta,
+                                                     lp, K, shift, res))
+        out = []
+        for r in res:
+            c = r.count
+            out.append(VerifyResult(_lib.copy_out(r.offsets, c, np.int32), _lib.copy_out(r.distances, c, np.float64),
+                                    r.cnt_candidate, r.n_verified, r.s_total, r.n_gate_pass, r.n_lb_pass, r.n_exact,
+                                    r.kernel_ms, r.n_launches, tuple(r.stage_ms), int(r.h2d_bytes)))
+        return out
+
     def scan_ucr_dtw(self, q, epsilon, rho, alpha, beta) -> VerifyResult:
         """K/experiments/ucr/UcrDtwQueryExecutor.java:84-314: index-free cNSM-DTW scan, 0-based offsets."""
         q, qp = _lib.as_f64(q)

@@ -386,3 +386,25 @@ def test_full_size_1e8_against_oracle_on_chain_subsets(oracle):
     sub2 = iv2[np.unique(np.concatenate([np.searchsorted(iv2[:, 0], d.offsets, side="right") - 1, rng.choice(len(iv2), 3)]))]
     assert_same(g.verify_cnsm_dtw(q2, 1.0, rho, 1.5, 5.0, sub2), oracle.verify_cnsm_dtw(s, q2, 1.0, rho, 1.5, 5.0, sub2))
     g.close()
+
+
+@pytest.mark.parametrize("m,chunk", [(128, 4096), (1024, 6144), (257, 5000)])
+def test_cnsm_ed_query_set_equals_single_queries(gpu, oracle, series_1m, m, chunk):
+    """kvm_verify_cnsm_ed_batch: one statistics pass for a set of queries must return, per query, exactly what the
+    single-query entry (itself checked against the oracle) returns — sparse, dense and degenerate queries mixed."""
+    s = series_1m
+    n = len(s)
+    gpu.load(s)
+    iv = datagen.chain_intervals(n, m, chunk)
+    offs = [1234, 250_000, 500_017, 777_777, 999_000 - m]
+    qs = np.stack([s[o:o + m] for o in offs] + [np.full(m, 3.25)])      # the last one is degenerate (std = 0)
+    qs[1] = qs[1] + 0.01 * np.sin(np.arange(m))                          # a near match instead of an exact one
+    got = gpu.verify_cnsm_ed_batch(qs, 5.0, 1.5, 5.0, iv)
+    assert len(got) == len(qs)
+    for q, r in zip(qs, got):
+        one = gpu.verify_cnsm_ed(q, 5.0, 1.5, 5.0, iv)
+        assert_same(r, one)
+        assert r.n_gate_pass == one.n_gate_pass and r.n_exact == one.n_exact
+    exp = oracle.verify_cnsm_ed(s, qs[0], 5.0, 1.5, 5.0, iv)
+    assert_same(got[0], exp)
+    assert got[-1].count == 0
