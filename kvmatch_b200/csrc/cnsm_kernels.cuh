@@ -14,7 +14,8 @@
 //                      windows that may pass are appended (offset, ex, ex2) to the CTA's private
 //                      region of the work list (no global atomics in the streaming loop);
 //                      kMode 1: per-window key buckets for IndexBuilder's window-mean pass
-//   cnsm_plan_kernel   exclusive scan of per-region tile counts -> flat tile index for the evaluators
+//   plan_scan_cta      exclusive scan of per-region tile counts -> flat tile index for the evaluators, run by the
+//                      last walker CTA to finish; kMode 2: one statistics pass gating a set of queries
 //   cnsm_ed_eval_kernel  one thread per work-list entry: exact mean/std/gate (reference arithmetic),
 //                      then a fast 32-term FMA screen in |zQ|-descending order against
 //                      eps^2*(1+1e-9); survivors go to the exact list

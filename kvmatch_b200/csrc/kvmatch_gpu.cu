@@ -418,7 +418,7 @@ void tile_prefix_of(const Plan& P, int tile, int64_t* n_tiles, std::vector<int32
   *n_tiles = acc;
 }
 
-// Everything the cNSM engines share: query statistics, pre-gate constants, walker + planner launch.
+// Everything the cNSM engines share: query statistics, pre-gate constants, walker launch.
 struct NormSetup {
   double meanQ = 0, stdQ = 0, inv_alpha = 0;
   int n_regions = 0;
