@@ -115,10 +115,15 @@ struct NormPlanCache {
 // that query's evaluator / exact stages run, so those stages are the single-query code.
 struct BatchSlot {
   DevBuf wl_off, wl_ex, wl_ex2, region_count, tile_prefix, counters, qarena, cand_off, cand_mean, cand_std, ans_off, ans_dist;
+  PinBuf h_counters, h_off, h_dist;
+  bool eager_valid = false;
   long long cand_cap = 0, ans_cap = 0;
   std::vector<int32_t> off;
   std::vector<double> dist;
   void release() {
+    h_counters.release();
+    h_off.release();
+    h_dist.release();
     DevBuf* all[] = {&wl_off, &wl_ex, &wl_ex2, &region_count, &tile_prefix, &counters, &qarena, &cand_off, &cand_mean,
                      &cand_std, &ans_off, &ans_dist};
     for (DevBuf* b : all) b->release();
@@ -145,6 +150,8 @@ struct kvm_ctx {
   long long cand_cap = 0, ans_cap = 0;
   NormPlanCache norm_cache;
   std::vector<BatchSlot> slots;      // query sets
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // query sets: per-query evaluator / exact stages run concurrently
+  cudaEvent_t ev_set = nullptr;
   DevBuf batch_gate;
   Plan plan_scratch;                 // RSM engines: host planning buffers kept across calls (no fresh pages per call)
   std::vector<int32_t> tp_scratch;
@@ -342,6 +349,24 @@ int upload_arena(kvm_ctx* ctx, const Arena& A) {
 }
 
 constexpr long long kEagerAnswers = 1024;  // answers fetched together with the counters (one sync for typical queries)
+
+// Enqueue the device->host copies of the counters and of the first kEagerAnswers answers (no synchronisation).
+int enqueue_counter_read(kvm_ctx* ctx) {
+  KVM_CUDA(ctx, ctx->h_counters.ensure(sizeof(unsigned long long) * kNumCounters));
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters.p, ctx->counters.p, sizeof(unsigned long long) * kNumCounters,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->eager_valid = false;
+  if (ctx->ans_cap >= kEagerAnswers) {
+    KVM_CUDA(ctx, ctx->h_off.ensure(sizeof(int32_t) * kEagerAnswers));
+    KVM_CUDA(ctx, ctx->h_dist.ensure(sizeof(double) * kEagerAnswers));
+    KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_off.p, ctx->ans_off.p, sizeof(int32_t) * kEagerAnswers, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_dist.p, ctx->ans_dist.p, sizeof(double) * kEagerAnswers, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    ctx->eager_valid = true;
+  }
+  return KVM_OK;
+}
 
 int read_counters(kvm_ctx* ctx, unsigned long long* out) {
   KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters.p, ctx->counters.p, sizeof(unsigned long long) * kNumCounters,
@@ -831,6 +856,9 @@ void kvm_destroy(kvm_ctx* ctx) {
                    &ctx->chain_prefix, &ctx->run_key, &ctx->run_b, &ctx->run_first, &ctx->run_last};
   for (DevBuf* b : dev) b->release();
   for (BatchSlot& sl : ctx->slots) sl.release();
+  for (cudaStream_t st : ctx->aux)
+    if (st) cudaStreamDestroy(st);
+  if (ctx->ev_set) cudaEventDestroy(ctx->ev_set);
   ctx->batch_gate.release();
   PinBuf* pin[] = {&ctx->stage, &ctx->stage2, &ctx->h_counters, &ctx->h_off, &ctx->h_dist, &ctx->h_key, &ctx->h_first, &ctx->h_last,
                    &ctx->h_b};
@@ -1007,6 +1035,10 @@ void swap_slot(kvm_ctx* c, BatchSlot& s) {
   std::swap(c->ans_dist, s.ans_dist);
   std::swap(c->cand_cap, s.cand_cap);
   std::swap(c->ans_cap, s.ans_cap);
+  std::swap(c->h_counters, s.h_counters);
+  std::swap(c->h_off, s.h_off);
+  std::swap(c->h_dist, s.h_dist);
+  std::swap(c->eager_valid, s.eager_valid);
 }
 }  // namespace
 
@@ -1140,86 +1172,113 @@ int kvm_verify_cnsm_ed_batch(kvm_ctx* ctx, const double* queries, int32_t n_quer
       ctx->h2d_bytes += (long long)q_bytes;
     }
   }
-  // ---- per query: the single-query evaluator + exact stages on that query's buffers
+  // ---- per query: the single-query evaluator + exact stages on that query's buffers.  All launches and result
+  // copies are enqueued first, then ONE synchronisation; a query whose candidate / answer buffers overflowed is re-run.
   const double eps2 = epsilon * epsilon;
+  auto launch_tail = [&](int q) -> int {  // ctx holds slot q's buffers
+    const unsigned char* qbase = ctx->qarena.as<unsigned char>();
+    EvalParams E;
+    E.T = ctx->series;
+    E.first_global = (int32_t)ctx->first;
+    E.m = m;
+    E.e_off = ctx->wl_off.as<int32_t>();
+    E.e_ex = ctx->wl_ex.as<double>();
+    E.e_ex2 = ctx->wl_ex2.as<double>();
+    E.region_base = reinterpret_cast<const long long*>(base + o_rbase);
+    E.region_count = ctx->region_count.as<int32_t>();
+    E.tile_prefix = ctx->tile_prefix.as<int32_t>();
+    E.totals = ctx->counters.as<unsigned long long>() + kCntTiles;
+    E.n_regions = n_regions;
+    E.zq = reinterpret_cast<const double*>(qbase + o_zq);
+    E.order = reinterpret_cast<const int32_t*>(qbase + o_order);
+    E.meanQ = S[q].meanQ;
+    E.stdQ = S[q].stdQ;
+    E.alpha = alpha;
+    E.inv_alpha = S[q].inv_alpha;
+    E.beta = beta;
+    E.eps2 = eps2;
+    E.eps2_hi = eps2 * (1.0 + 1e-9) + 1e-18;
+    E.out = cands_of(ctx);
+    E.gate_pass = ctx->counters.as<unsigned long long>() + kCntGate;
+    cnsm_ed_eval_kernel<<<ctx->n_sms * 16, kEvalTile, 0, ctx->stream>>>(E);
+    ExactEdParams X;
+    X.T = E.T;
+    X.first_global = E.first_global;
+    X.m = m;
+    X.zq = E.zq;
+    X.order = E.order;
+    X.eps2 = eps2;
+    X.eps2_hi = E.eps2_hi;
+    X.n_exact = ctx->counters.as<unsigned long long>() + kCntFlag;
+    X.in = E.out;
+    X.sink = sink_of(ctx);
+    cnsm_ed_exact_kernel<<<ctx->n_sms * 6, 128, sizeof(double) * kExactChunk * 4, ctx->stream>>>(X);
+    KVM_CUDA(ctx, cudaGetLastError());
+    outs[q].n_launches += 2;
+    return enqueue_counter_read(ctx);
+  };
+  // the per-query stages are latency-bound kernels that leave the GPU half empty: spread them over a few streams
+  constexpr int kAux = 3;
+  for (int i = 0; i < kAux; i++)
+    if (!ctx->aux[i]) KVM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+  if (!ctx->ev_set) KVM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_set, cudaEventDisableTiming));
+  KVM_CUDA(ctx, cudaEventRecord(ctx->ev_set, ctx->stream));  // statistics pass + every query's upload
+  for (int i = 0; i < kAux; i++) KVM_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[i], ctx->ev_set, 0));
+  cudaStream_t main_stream = ctx->stream;
   for (int q = 0; q < Q; q++) {
     BatchSlot& sl = ctx->slots[q];
-    kvm_result* out = &outs[q];
-    out->n_launches = (q == 0) ? 1 : 0;
+    outs[q].n_launches = (q == 0) ? 1 : 0;
     if (S[q].degenerate) {
       sl.off.clear();
       sl.dist.clear();
       continue;
     }
     swap_slot(ctx, sl);
+    rc = ensure_answers(ctx, std::max<long long>(ctx->ans_cap, 1 << 16));
+    if (rc == KVM_OK) rc = ensure_cands(ctx, std::max<long long>(ctx->cand_cap, 1 << 18));
+    ctx->stream = ctx->aux[q % kAux];
+    if (rc == KVM_OK) rc = launch_tail(q);
+    ctx->stream = main_stream;
+    swap_slot(ctx, sl);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < kAux; i++) {  // join
+    KVM_CUDA(ctx, cudaEventRecord(ctx->ev_set, ctx->aux[i]));
+    KVM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_set, 0));
+  }
+  KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float tail_ms = 0.f;
+  cudaEventElapsedTime(&tail_ms, ctx->evs[3], ctx->ev1);
+  int n_live = 0;
+  for (int q = 0; q < Q; q++) n_live += S[q].degenerate ? 0 : 1;
+  for (int q = 0; q < Q; q++) {
+    if (S[q].degenerate) continue;
+    BatchSlot& sl = ctx->slots[q];
+    kvm_result* out = &outs[q];
+    swap_slot(ctx, sl);
+    unsigned long long cnt[kNumCounters];
+    std::memcpy(cnt, ctx->h_counters.p, sizeof(cnt));
     rc = KVM_OK;
-    cudaError_t ce = cudaSuccess;
-    if (ce == cudaSuccess) rc = ensure_answers(ctx, std::max<long long>(ctx->ans_cap, 1 << 16));
-    if (ce == cudaSuccess && rc == KVM_OK) rc = ensure_cands(ctx, std::max<long long>(ctx->cand_cap, 1 << 18));
-    unsigned long long cnt[kNumCounters] = {0};
-    for (int attempt = 0; ce == cudaSuccess && rc == KVM_OK && attempt < 8; attempt++) {
-      if (attempt > 0) {  // re-run this query's tail only: keep the walker's totals, clear the tail's counters
-        unsigned long long* c = ctx->counters.as<unsigned long long>();
-        cudaMemsetAsync(c + kCntAnswers, 0, sizeof(unsigned long long) * 3, ctx->stream);  // answers, cand, gate
-        cudaMemsetAsync(c + kCntFlag, 0, sizeof(unsigned long long), ctx->stream);
-      }
-      const unsigned char* qbase = ctx->qarena.as<unsigned char>();
-      EvalParams E;
-      E.T = ctx->series;
-      E.first_global = (int32_t)ctx->first;
-      E.m = m;
-      E.e_off = ctx->wl_off.as<int32_t>();
-      E.e_ex = ctx->wl_ex.as<double>();
-      E.e_ex2 = ctx->wl_ex2.as<double>();
-      E.region_base = reinterpret_cast<const long long*>(base + o_rbase);
-      E.region_count = ctx->region_count.as<int32_t>();
-      E.tile_prefix = ctx->tile_prefix.as<int32_t>();
-      E.totals = ctx->counters.as<unsigned long long>() + kCntTiles;
-      E.n_regions = n_regions;
-      E.zq = reinterpret_cast<const double*>(qbase + o_zq);
-      E.order = reinterpret_cast<const int32_t*>(qbase + o_order);
-      E.meanQ = S[q].meanQ;
-      E.stdQ = S[q].stdQ;
-      E.alpha = alpha;
-      E.inv_alpha = S[q].inv_alpha;
-      E.beta = beta;
-      E.eps2 = eps2;
-      E.eps2_hi = eps2 * (1.0 + 1e-9) + 1e-18;
-      E.out = cands_of(ctx);
-      E.gate_pass = ctx->counters.as<unsigned long long>() + kCntGate;
-      cudaEventRecord(ctx->evs[0], ctx->stream);
-      cnsm_ed_eval_kernel<<<ctx->n_sms * 16, kEvalTile, 0, ctx->stream>>>(E);
-      cudaEventRecord(ctx->evs[1], ctx->stream);
-      ExactEdParams X;
-      X.T = E.T;
-      X.first_global = E.first_global;
-      X.m = m;
-      X.zq = E.zq;
-      X.order = E.order;
-      X.eps2 = eps2;
-      X.eps2_hi = E.eps2_hi;
-      X.n_exact = ctx->counters.as<unsigned long long>() + kCntFlag;
-      X.in = E.out;
-      X.sink = sink_of(ctx);
-      cnsm_ed_exact_kernel<<<ctx->n_sms * 6, 128, sizeof(double) * kExactChunk * 4, ctx->stream>>>(X);
-      cudaEventRecord(ctx->ev1, ctx->stream);
-      out->n_launches += 2;
-      if ((rc = read_counters(ctx, cnt))) break;
-      float a = 0.f, b = 0.f;
-      cudaEventElapsedTime(&a, ctx->evs[0], ctx->evs[1]);
-      cudaEventElapsedTime(&b, ctx->evs[1], ctx->ev1);
-      out->stage_ms[1] += a;
-      out->stage_ms[2] += b;
+    for (int attempt = 1; attempt < 8; attempt++) {
       const bool cand_over = (long long)cnt[kCntCand] > ctx->cand_cap, ans_over = (long long)cnt[kCntAnswers] > ctx->ans_cap;
       if (!cand_over && !ans_over) break;
-      if (attempt == 7) rc = fail(ctx, KVM_E_OOM, "candidate/answer buffers kept overflowing");
-      if (rc == KVM_OK && cand_over) rc = ensure_cands(ctx, (long long)cnt[kCntCand] + 1024);
+      if (cand_over) rc = ensure_cands(ctx, (long long)cnt[kCntCand] + 1024);
       if (rc == KVM_OK && ans_over) rc = ensure_answers(ctx, (long long)cnt[kCntAnswers] + 1024);
+      if (rc) break;
+      // re-run this query's tail only: keep the walker's totals, clear the tail's counters
+      unsigned long long* c = ctx->counters.as<unsigned long long>();
+      cudaMemsetAsync(c + kCntAnswers, 0, sizeof(unsigned long long) * 3, ctx->stream);  // answers, cand, gate
+      cudaMemsetAsync(c + kCntFlag, 0, sizeof(unsigned long long), ctx->stream);
+      if ((rc = launch_tail(q))) break;
+      cudaStreamSynchronize(ctx->stream);
+      std::memcpy(cnt, ctx->h_counters.p, sizeof(cnt));
+      if (attempt == 7) rc = fail(ctx, KVM_E_OOM, "candidate/answer buffers kept overflowing");
     }
-    if (ce != cudaSuccess) rc = fail(ctx, KVM_E_CUDA, "CUDA error in the query set: %s", cudaGetErrorString(ce));
     if (rc == KVM_OK) {
       out->n_gate_pass = (int64_t)cnt[kCntGate];
       out->n_exact = (int64_t)cnt[kCntFlag];
+      out->stage_ms[1] = n_live ? (double)tail_ms / n_live : 0.0;  // evaluator + exact, averaged over the set
       rc = fetch_answers(ctx, (long long)cnt[kCntAnswers], out);
     }
     if (rc == KVM_OK) {  // fetch_answers points into ctx-owned vectors that the next query overwrites

@@ -16,4 +16,9 @@ r = g.verify_ed(q, 30.0, [(1, n - m + 1)]); e = o.verify_ed(s, q, 30.0, [(1, n -
 assert r.offsets.tolist() == e.offsets.tolist(), "ed"
 k, f, l, ms, nl = g.window_mean_runs(50); ek, ef, el = o.window_mean_runs(s, 50)
 assert f.tolist() == ef.tolist() and l.tolist() == el.tolist(), "runs"
+qs = np.stack([s[o:o + m] for o in (100, 20_000, 40_000)])
+rb = g.verify_cnsm_ed_batch(qs, 4.0, 1.5, 5.0, iv)
+for qq, r1 in zip(qs, rb):
+    one = g.verify_cnsm_ed(qq, 4.0, 1.5, 5.0, iv)
+    assert r1.offsets.tolist() == one.offsets.tolist() and r1.distances.tolist() == one.distances.tolist(), "query set"
 print("sanitizer workload ok")
