@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kRelayThreads, kRelayThreads <= 224 ? 2 : 1) c
 #pragma unroll
     for (int s = 0; s < STAGES; s++) {
       mbar_init(bar_ready + 8 * s, 32);
-      mbar_init(bar_free + 8 * s, kRelayTurnsPerTile);
+      mbar_init(bar_free + 8 * s, 32 * kRelayTurnsPerTile);  // every lane of the tile's turns arrives for itself
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -394,8 +394,7 @@ __global__ void __launch_bounds__(kRelayThreads, kRelayThreads <= 224 ? 2 : 1) c
 #pragma unroll
         for (int j = 0; j < kRelayBlock; j++) asm volatile("" : "+d"(a[j]), "+d"(o[j]));
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_free + 8 * stage);  // this turn's reads of the tile are done
+      mbar_arrive(bar_free + 8 * stage);  // this lane's reads of the tile are done (its loaded values have been consumed)
       RELAY_T(t_b);
       // ---- walk
       double ex = 0.0, ex2 = 0.0;
