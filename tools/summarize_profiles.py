@@ -18,7 +18,7 @@ for r in data:
 tot = sum(sum(v["gpu__time_duration.sum"]) for v in agg.values())
 lines = [f"# ncu launch list — {tag}", "",
          "Command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
-         "--csv python bench.py --steps 10 --warmup 3 --cpu-queries 0` (cold-cache, serialised: compare SHARES).", "",
+         "--csv python bench.py --steps 10 --warmup 3 --cpu-queries 0 --no-query-set` (cold-cache, serialised: compare SHARES).", "",
          "| kernel | launches | avg µs | share of step | avg DRAM read MB | avg DRAM write MB |", "|---|---|---|---|---|---|"]
 walker_traffic = None
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1]["gpu__time_duration.sum"])):
