@@ -702,9 +702,25 @@ __global__ void __launch_bounds__(kEvalTile, 16) cnsm_ed_eval_kernel(EvalParams 
   if (threadIdx.x == 0) s_gate = 0;
   const int n_tiles = (int)P.totals[0];
   const int m = P.m;
+  int r_prev = 0;  // thread 0: region of this CTA's previous tile (tiles are visited in ascending order)
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     __syncthreads();
-    if (threadIdx.x == 0) s_r = find_segment<int32_t>(P.tile_prefix, P.n_regions + 1, t);
+    if (threadIdx.x == 0) {
+      // tile -> region: gallop forward from the previous tile's region, then bisect.  In a matching region the next
+      // tile of this CTA lies a region or two ahead: 2-3 dependent loads instead of log2(n_regions).
+      int lo = r_prev, hi = r_prev + 1, step = 1;
+      while (hi <= P.n_regions && __ldg(P.tile_prefix + hi) <= t) {
+        lo = hi;
+        step *= 2;
+        hi = min(P.n_regions + 1, hi + step);
+      }
+      while (hi - lo > 1) {  // tile_prefix[lo] <= t < tile_prefix[hi] (tile_prefix[n_regions + 1] = +inf)
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(P.tile_prefix + mid) <= t) lo = mid; else hi = mid;
+      }
+      r_prev = lo;
+      s_r = lo;
+    }
     __syncthreads();
     const int r = s_r;
     const int i = (t - P.tile_prefix[r]) * kEvalTile + (int)threadIdx.x;
