@@ -88,6 +88,13 @@ def run(iters=40, seed=2026, verbose=True):
             if not (f.tolist() == ef.tolist() and l.tolist() == el.tolist() and k.view(np.int64).tolist() == ek.view(np.int64).tolist()):
                 bad += 1
                 print("MISMATCH runs", ctx, w, flush=True)
+            import tempfile
+            with tempfile.TemporaryDirectory() as td:
+                path = os.path.join(td, "index")
+                g.build_index_file(w, path)
+                if open(path, "rb").read() != o.index_file_image(s, w)[0]:
+                    bad += 1
+                    print("MISMATCH index file", ctx, w, flush=True)
         if verbose and it % 10 == 9:
             print(f"{it + 1} iterations, {bad} mismatches, {time.time() - t0:.0f}s", flush=True)
     g.close()
