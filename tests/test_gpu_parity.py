@@ -408,3 +408,30 @@ def test_cnsm_ed_query_set_equals_single_queries(gpu, oracle, series_1m, m, chun
     exp = oracle.verify_cnsm_ed(s, qs[0], 5.0, 1.5, 5.0, iv)
     assert_same(got[0], exp)
     assert got[-1].count == 0
+
+
+def test_every_window_is_an_answer_buffers_regrow(oracle):
+    """Periodic data, generous thresholds: all 3e5 windows are answers, so the candidate and answer buffers overflow
+    their first allocation and every engine (and the query-set entry) must re-run and still match the oracle."""
+    import kvmatch_b200
+    n, m = 300_000, 64
+    t = np.arange(n)
+    s = np.sin(2 * np.pi * t / 64.0) * 3 + 0.001 * np.cos(t * 0.37)
+    g = kvmatch_b200.GpuSeries(0)
+    g.load(s)
+    iv = datagen.chain_intervals(n, m, 5000)
+    q = s[1000:1000 + m].copy()
+    for got, exp in [
+        (g.verify_cnsm_ed(q, 50.0, 2.0, 100.0, iv), oracle.verify_cnsm_ed(s, q, 50.0, 2.0, 100.0, iv)),
+        (g.verify_ed(q, 500.0, iv), oracle.verify_ed(s, q, 500.0, iv)),
+        (g.verify_cnsm_dtw(q, 50.0, 3, 2.0, 100.0, iv), oracle.verify_cnsm_dtw(s, q, 50.0, 3, 2.0, 100.0, iv)),
+        (g.verify_dtw(q, 500.0, 3, iv), oracle.verify_dtw(s, q, 500.0, 3, iv)),
+    ]:
+        assert got.count == n - m + 1
+        assert_same(got, exp)
+    qs = np.stack([q, s[5:5 + m], s[77:77 + m]])
+    for r, qq in zip(g.verify_cnsm_ed_batch(qs, 50.0, 2.0, 100.0, iv), qs):
+        assert_same(r, oracle.verify_cnsm_ed(s, qq, 50.0, 2.0, 100.0, iv))
+    small = g.verify_cnsm_ed(q, 0.01, 1.1, 0.1, iv)                     # and a selective call on the grown buffers
+    assert_same(small, oracle.verify_cnsm_ed(s, q, 0.01, 1.1, 0.1, iv))
+    g.close()
