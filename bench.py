@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-query-set", action="store_true", help="skip the query-set side measurement")
+    ap.add_argument("--no-dtw", action="store_true", help="skip the cNSM-DTW side measurement")
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("KVM_BENCH_CHUNK", DEFAULT_CHUNK)))
     ap.add_argument("--ref-sample", type=float, default=N_PER_GPU)   # samples scanned per reference step
     ap.add_argument("--cpu-queries", type=int, default=10)          # queries the 1-core CPU baseline times
@@ -339,6 +340,23 @@ def main():
                                                       a.distances.tolist() == b.distances.tolist()
                                                       for a, b in zip(res, single))),
                 "note": "through the ABI with host buffers (compare with e2e, not with value)"}
+        # Also beside the headline: the metric's other half, cNSM-DTW (BASELINE configs[3] shape on this GPU's shard:
+        # m = 2048, rho = 5 % = 102, the headline's chain grid), two of the seeded offsets, kernel time from CUDA events
+        if world == 1 and not args.no_dtw:
+            m2, rho2, eps2 = 2048, 102, 1.0
+            iv2 = datagen.chain_intervals(n_total, m2, chunk)
+            rows = []
+            for o2 in offs[:2]:
+                q2 = query_of(n_total, o2, m2)
+                g.verify_cnsm_dtw(q2, eps2, rho2, ALPHA, BETA, iv2)
+                t0 = time.perf_counter()
+                r2 = g.verify_cnsm_dtw(q2, eps2, rho2, ALPHA, BETA, iv2)
+                rows.append({"offset": int(o2), "kernel_ms": r2.kernel_ms, "wall_ms": 1e3 * (time.perf_counter() - t0),
+                             "verified": int(r2.n_verified), "gate_pass": int(r2.n_gate_pass), "dtws": int(r2.n_lb_pass),
+                             "answers": int(r2.count), "stage_ms": [float(x) for x in r2.stage_ms[:3]]})
+            line["cnsm_dtw"] = {"config": f"m={m2} rho={rho2} eps={eps2} alpha={ALPHA} beta={BETA}, n={n_total}, chain_chunk={chunk}",
+                                "value": float(sum(r["verified"] for r in rows) / sum(r["kernel_ms"] * 1e-3 for r in rows)),
+                                "unit": "subsequences/s", "queries": rows}
         # CPU baseline beside it (N=1 only): the oracle port on 1 core (the reference is single-threaded), the same
         # series, chains and queries; bounded to --cpu-queries whole-series queries (~0.7 s each)
         if world == 1:
