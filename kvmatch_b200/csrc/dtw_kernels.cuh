@@ -252,6 +252,12 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
         bv[r] = ld(B, j0 - r);
       }
     }
+    unsigned band_even = 0, band_odd = 0;  // this lane's cells that lie inside the band
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      band_even |= (u0 + 2 * r <= 2 * rho) ? (1u << r) : 0u;
+      band_odd |= (u0 + 2 * r + 1 <= 2 * rho) ? (1u << r) : 0u;
+    }
     bool abandoned = false;
     for (int d = 0; d <= last; d++) {
       // Early abandon (the reference abandons per row with min_cost + cb[i+r+1], DtwUtils.java:324-326).  On the
@@ -271,6 +277,9 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
           break;
         }
       }
+      // In the interior (rho <= d <= 2m-2-rho) every band cell lies inside the matrix, so validity is the lane-constant
+      // band bit and the per-cell index arithmetic drops out of the dependent chain; edges use the general form.
+      const bool interior = (d > rho) && (d < last - rho);
       if (((d + rho) & 1) == 0) {
         double left = __shfl_up_sync(kFullMask, Od[R - 1], 1);
         if (lane == 0) left = kDtwInf;
@@ -282,19 +291,29 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
           for (int r = R - 1; r > 0; r--) bv[r] = bv[r - 1];
           bv[0] = ld(B, d - i0);
         }
+        if (interior) {
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          const int i = i0 + r, j = d - i;
-          const bool valid = (u0 + 2 * r <= 2 * rho) && i >= 0 && j >= 0 && i < m && j < m;
-          double v = kDtwInf;
-          if (valid) {
+          for (int r = 0; r < R; r++) {
             const double c = xsqdist(av[r], bv[r]);
             const double x = (r == 0) ? left : Od[r - 1];
-            const double y = Od[r];
-            const double z = Ev[r];
-            v = (d == 0) ? c : xadd(umin_pos(umin_pos(x, y), z), c);
+            const double v = xadd(umin_pos(umin_pos(x, Od[r]), Ev[r]), c);
+            Ev[r] = ((band_even >> r) & 1u) ? v : kDtwInf;
           }
-          Ev[r] = v;
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const int i = i0 + r, j = d - i;
+            const bool valid = (u0 + 2 * r <= 2 * rho) && i >= 0 && j >= 0 && i < m && j < m;
+            double v = kDtwInf;
+            if (valid) {
+              const double c = xsqdist(av[r], bv[r]);
+              const double x = (r == 0) ? left : Od[r - 1];
+              const double y = Od[r];
+              const double z = Ev[r];
+              v = (d == 0) ? c : xadd(umin_pos(umin_pos(x, y), z), c);
+            }
+            Ev[r] = v;
+          }
         }
       } else {
         double right = __shfl_down_sync(kFullMask, Ev[0], 1);
@@ -306,19 +325,29 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
           for (int r = 0; r < R - 1; r++) av[r] = av[r + 1];
           av[R - 1] = ld(A, i0 + R - 1);
         }
+        if (interior) {
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          const int i = i0 + r, j = d - i;
-          const bool valid = (u0 + 2 * r + 1 <= 2 * rho) && i >= 0 && j >= 0 && i < m && j < m;
-          double v = kDtwInf;
-          if (valid) {
+          for (int r = 0; r < R; r++) {
             const double c = xsqdist(av[r], bv[r]);
-            const double x = Ev[r];
             const double y = (r == R - 1) ? right : Ev[r + 1];
-            const double z = Od[r];
-            v = (d == 0) ? c : xadd(umin_pos(umin_pos(x, y), z), c);
+            const double v = xadd(umin_pos(umin_pos(Ev[r], y), Od[r]), c);
+            Od[r] = ((band_odd >> r) & 1u) ? v : kDtwInf;
           }
-          Od[r] = v;
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const int i = i0 + r, j = d - i;
+            const bool valid = (u0 + 2 * r + 1 <= 2 * rho) && i >= 0 && j >= 0 && i < m && j < m;
+            double v = kDtwInf;
+            if (valid) {
+              const double c = xsqdist(av[r], bv[r]);
+              const double x = Ev[r];
+              const double y = (r == R - 1) ? right : Ev[r + 1];
+              const double z = Od[r];
+              v = (d == 0) ? c : xadd(umin_pos(umin_pos(x, y), z), c);
+            }
+            Od[r] = v;
+          }
         }
       }
     }
