@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KVM_ABI_VERSION 1
+#define KVM_ABI_VERSION 2
 
 enum {
   KVM_OK = 0,
@@ -57,12 +57,16 @@ typedef struct kvm_result {
   int64_t n_lb_pass;       /* DTW: windows surviving the GPU lower bounds, i.e. full DTWs computed */
   int64_t n_exact;         /* ED: windows re-evaluated by the sequential reference-order path */
   double kernel_ms;        /* device time of this call's kernels (CUDA events on the ctx stream) */
-  double stage_ms[4];      /* the same, per stage: [0] streaming kernel (ED scan / statistics walker / raw LB scan),
-                              [1] planner + evaluator (exact gate, fast distance or lower bounds),
-                              [2] exact stage (reference-order ED sum / banded DTW), [3] unused */
+  double stage_ms[4];      /* the same, per stage.  cNSM engines: [0] streaming statistics pass (gate + in-stream lower
+                              bound), [1] exact re-walk of the flagged chains, [2] exact stage (cNSM-ED: exact gate +
+                              reference-order sum; cNSM-DTW: exact gate + lower bounds), [3] cNSM-DTW: banded DTW.
+                              RSM engines: [0] ED scan / raw LB scan, [2] banded DTW. */
   int32_t n_launches;      /* kernels launched by this call */
   int32_t h2d_bytes;       /* bytes this call copied host->device (query, and the interval plan unless the previous
                               call's plan was reused) */
+  int64_t n_rewalked;        /* cNSM: windows whose chain sums were recomputed exactly (ambiguous gate or surviving the
+                                in-stream lower bound) */
+  int64_t n_chains_rewalked; /* cNSM: statistic chains (merged intervals) walked exactly for them */
 } kvm_result;
 
 /* IndexBuilder step-1 output for one window width w: the (key, first, last) intervals in the order
@@ -84,6 +88,18 @@ int kvm_abi_version(void);
 int kvm_create(kvm_ctx** out, int device_id);
 void kvm_destroy(kvm_ctx* ctx);
 const char* kvm_last_error(const kvm_ctx* ctx); /* ctx may be NULL: last kvm_create error */
+
+/* Per-ctx options (defaults in parentheses; the environment variables KVM_CNSM_PATH=relay, KVM_STREAM_FORCE_ALL=1,
+ * KVM_PLAN_CACHE=0 set the defaults of new contexts).  None of them changes a result.
+ *   KVM_OPT_CNSM_PATH        KVM_CNSM_STREAM (default): the cNSM statistics run as an HBM stream with guard bands and an
+ *                            exact re-walk of the ambiguous / surviving windows; KVM_CNSM_RELAY: every chain is walked
+ *                            exactly (the round-1 kernel; also what queries too long for the stream's tile use)
+ *   KVM_OPT_STREAM_FLAG_ALL  1: the stream flags every window inside its outer gate band, so the exact stages decide
+ *                            everything (a self-check of the guard bands; default 0)
+ *   KVM_OPT_PLAN_CACHE       1 (default): an interval list identical to the previous call's reuses its device plan */
+enum { KVM_OPT_CNSM_PATH = 1, KVM_OPT_STREAM_FLAG_ALL = 2, KVM_OPT_PLAN_CACHE = 3 };
+enum { KVM_CNSM_STREAM = 0, KVM_CNSM_RELAY = 1 };
+int kvm_set_option(kvm_ctx* ctx, int32_t option, int64_t value);
 
 /* Load samples [first, first+count-1] (1-based) of a series whose total length is n.
  * first=1,count=n loads everything (single GPU).  Replaces TimeSeriesOperator.readTimeSeries

@@ -21,6 +21,8 @@ KVM_E_CUDA = -4
 KVM_E_IO = -5
 KVM_E_STATE = -6
 KVM_E_RANGE = -7
+KVM_OPT_CNSM_PATH, KVM_OPT_STREAM_FLAG_ALL, KVM_OPT_PLAN_CACHE = 1, 2, 3
+KVM_CNSM_STREAM, KVM_CNSM_RELAY = 0, 1
 
 ERROR_NAMES = {
     KVM_E_NODEVICE: "KVM_E_NODEVICE", KVM_E_ARG: "KVM_E_ARG", KVM_E_OOM: "KVM_E_OOM", KVM_E_CUDA: "KVM_E_CUDA",
@@ -29,7 +31,8 @@ ERROR_NAMES = {
 
 # every symbol include/kvmatch_gpu.h declares
 EXPORTS = [
-    "kvm_abi_version", "kvm_create", "kvm_destroy", "kvm_last_error", "kvm_load_series_host", "kvm_load_series_file",
+    "kvm_abi_version", "kvm_create", "kvm_destroy", "kvm_last_error", "kvm_set_option", "kvm_load_series_host",
+    "kvm_load_series_file",
     "kvm_verify_ed", "kvm_verify_cnsm_ed", "kvm_verify_dtw", "kvm_verify_cnsm_dtw", "kvm_verify_cnsm_ed_batch", "kvm_scan_ucr_dtw",
     "kvm_window_mean_runs", "kvm_build_index_file", "kvm_index_image_from_runs", "kvm_image_free",
     "kvm_result_free", "kvm_runs_free",
@@ -59,6 +62,8 @@ class KvmResult(C.Structure):
         ("stage_ms", C.c_double * 4),
         ("n_launches", C.c_int32),
         ("h2d_bytes", C.c_int32),
+        ("n_rewalked", C.c_int64),
+        ("n_chains_rewalked", C.c_int64),
     ]
 
 
@@ -104,6 +109,7 @@ def load():
     L.kvm_destroy.restype = None
     L.kvm_last_error.argtypes = [vp]
     L.kvm_last_error.restype = C.c_char_p
+    L.kvm_set_option.argtypes = [vp, C.c_int32, C.c_int64]
     L.kvm_load_series_host.argtypes = [vp, _dp, C.c_int64, C.c_int64, C.c_int64]
     L.kvm_load_series_file.argtypes = [vp, C.c_char_p, C.c_int64, C.c_int64, C.c_int64]
     L.kvm_verify_ed.argtypes = [vp, _dp, C.c_int32, C.c_double, _ip, C.c_int32, C.c_int32, R]

@@ -736,8 +736,7 @@ __global__ void __launch_bounds__(kEvalTile, 16) cnsm_ed_eval_kernel(EvalParams 
     if ((threadIdx.x & 31) == 0 && gmask) atomicAdd(&s_gate, (unsigned)__popc(gmask));
     if (!live) continue;
     // fast distance: x = T*rstd - mean*rstd, FMA allowed (approximate; the guard band absorbs it)
-    const double rstd = 1.0 / stdv;
-    const double nmr = -mean * rstd;
+    const double rstd = 1.0 / stdv;  // x = (w - mean) * rstd: the error does not grow with |mean| / std
     const double* __restrict__ w = P.T + (off - P.first_global);
     // Fast screen: the kFastTerms largest-|zQ| terms (a lower bound of the full distance).  Windows still under
     // eps^2 after them are rare (near matches); they go to the warp-cooperative exact stage instead of having
@@ -752,14 +751,14 @@ __global__ void __launch_bounds__(kEvalTile, 16) cnsm_ed_eval_kernel(EvalParams 
       for (int u = 0; u < 4; u++) wv[u] = w[__ldg(P.order + k + u)];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const double df = __fma_rn(wv[u], rstd, nmr) - __ldg(P.zq + k + u);
+        const double df = (wv[u] - mean) * rstd - __ldg(P.zq + k + u);
         dist = __fma_rn(df, df, dist);
       }
       alive = dist <= P.eps2_hi;
     }
     if (alive) {
       for (; k < kmax; k++) {
-        const double df = __fma_rn(w[__ldg(P.order + k)], rstd, nmr) - __ldg(P.zq + k);
+        const double df = (w[__ldg(P.order + k)] - mean) * rstd - __ldg(P.zq + k);
         dist = __fma_rn(df, df, dist);
       }
     }
@@ -776,6 +775,14 @@ __global__ void __launch_bounds__(kEvalTile, 16) cnsm_ed_eval_kernel(EvalParams 
   if (threadIdx.x == 0 && s_gate) atomicAdd(P.gate_pass, (unsigned long long)s_gate);
 }
 
+struct XList {  // windows whose exact chain sums were recomputed by chain_rewalk_kernel (stream_kernels.cuh)
+  int32_t* off;
+  double* ex;
+  double* ex2;
+  unsigned long long* count;
+  long long cap;
+};
+
 struct ExactEdParams {
   const double* __restrict__ T;
   int32_t first_global;
@@ -786,6 +793,11 @@ struct ExactEdParams {
   CandList in;
   AnswerSink sink;
   unsigned long long* n_exact;  // windows that reached the reference-order summation
+  // kFromSums: entries are (offset, ex, ex2); the exact gate runs here
+  XList xin;
+  double meanQ, stdQ, alpha, inv_alpha, beta;
+  unsigned long long* gate_pass;
+  int win_cap;  // doubles of per-warp window staging behind the term buffer (0 = none)
 };
 
 constexpr int kExactChunk = 1024;  // terms staged in shared memory per pass (8 KB per warp)
@@ -794,23 +806,45 @@ constexpr int kExactChunk = 1024;  // terms staged in shared memory per pass (8 
 // One warp per survivor: all lanes compute the per-term values (divisions in parallel, each term rounded
 // exactly as the reference's), lane 0 then adds them in the reference's order — the sum is bit-identical,
 // and the critical path is one dependent DADD per term instead of one scattered DRAM load per term.
+template <bool kFromSums>
 __global__ void __launch_bounds__(128) cnsm_ed_exact_kernel(ExactEdParams P) {
   extern __shared__ double exact_terms[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  double* term = exact_terms + (size_t)warp * kExactChunk;
-  unsigned long long n = *P.in.count;
-  if ((long long)n > P.in.cap) n = (unsigned long long)P.in.cap;
+  // per warp: kExactChunk per-term values, then (win_cap >= m) the window itself, staged with coalesced loads so that
+  // the |zQ|-ordered gathers below hit shared memory instead of paying a DRAM round trip per dependent batch
+  double* term = exact_terms + (size_t)warp * (kExactChunk + P.win_cap);
+  double* win = term + kExactChunk;
+  const bool staged = P.win_cap >= P.m;
+  unsigned long long n = kFromSums ? *P.xin.count : *P.in.count;
+  const long long cap = kFromSums ? P.xin.cap : P.in.cap;
+  if ((long long)n > cap) n = (unsigned long long)cap;
   const int m = P.m;
   for (unsigned long long e = (unsigned long long)blockIdx.x * n_warps + warp; e < n;
        e += (unsigned long long)gridDim.x * n_warps) {
-    const int32_t off = P.in.off[e];
-    const double mean = P.in.mean[e], stdv = P.in.stdv[e];
-    const double* __restrict__ w = P.T + (off - P.first_global);
+    int32_t off;
+    double mean, stdv;
+    if (kFromSums) {  // exact statistics and gate from the re-walked chain sums (K/NormQueryEngine.java:508-511)
+      off = P.xin.off[e];
+      const bool pass = cnsm_exact_gate(P.xin.ex[e], P.xin.ex2[e], m, P.meanQ, P.stdQ, P.alpha, P.inv_alpha, P.beta, mean, stdv);
+      if (!pass) continue;
+      if (lane == 0) atomicAdd(P.gate_pass, 1ULL);
+    } else {
+      off = P.in.off[e];
+      mean = P.in.mean[e];
+      stdv = P.in.stdv[e];
+    }
+    const double* __restrict__ wg = P.T + (off - P.first_global);
+    if (staged) {
+      __syncwarp();
+      for (int k = lane; k < m; k += 32) win[k] = wg[k];
+      __syncwarp();
+    }
+    const double* w = staged ? win : wg;
     // Tier 2: warp-cooperative fast distance (FMA, reciprocal) over all m terms, 128 terms per round in |zQ|
     // order, abandoned as soon as the partial sum exceeds eps^2*(1+1e-9).  Only windows that survive every
     // round reach the reference-order summation below.
     {
-      const double rstd = 1.0 / stdv, nmr = -mean * rstd;
+      const double rstd = 1.0 / stdv;  // x = (w - mean) * rstd: the error does not grow with |mean| / std
       double part = 0.0;
       bool over = false;
       for (int k0 = 0; k0 < m && !over; k0 += 128) {
@@ -824,7 +858,7 @@ __global__ void __launch_bounds__(128) cnsm_ed_exact_kernel(ExactEdParams P) {
         for (int u = 0; u < 4; u++) {
           const int k = k0 + u * 32 + lane;
           if (k < m) {
-            const double df = __fma_rn(wv[u], rstd, nmr) - __ldg(P.zq + k);
+            const double df = (wv[u] - mean) * rstd - __ldg(P.zq + k);
             part = __fma_rn(df, df, part);
           }
         }

@@ -33,14 +33,15 @@ __device__ __forceinline__ double fsq(double a, double b) {
 }
 
 // true = the candidate may still be an answer
-__device__ __forceinline__ bool lb_cascade(const double* __restrict__ w, const LbQuery& Q, double rstd, double nmr) {
+// x = (w - mean) * rstd (well conditioned for any |mean| / std; exact for the raw engines' mean = 0, rstd = 1)
+__device__ __forceinline__ bool lb_cascade(const double* __restrict__ w, const LbQuery& Q, double rstd, double mean) {
   const int m = Q.m;
   const double* __restrict__ q = Q.q;
   double lb = 0.0;
   if (m >= 6) {  // LB_KimFL, K/utils/DtwUtils.java:149-189 (all five stages, no early return)
-    const double x0 = __fma_rn(w[0], rstd, nmr), x1 = __fma_rn(w[1], rstd, nmr), x2 = __fma_rn(w[2], rstd, nmr);
-    const double y0 = __fma_rn(w[m - 1], rstd, nmr), y1 = __fma_rn(w[m - 2], rstd, nmr),
-                 y2 = __fma_rn(w[m - 3], rstd, nmr);
+    const double x0 = ((w[0] - mean) * rstd), x1 = ((w[1] - mean) * rstd), x2 = ((w[2] - mean) * rstd);
+    const double y0 = ((w[m - 1] - mean) * rstd), y1 = ((w[m - 2] - mean) * rstd),
+                 y2 = ((w[m - 3] - mean) * rstd);
     const double q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
     const double p0 = __ldg(q + m - 1), p1 = __ldg(q + m - 2), p2 = __ldg(q + m - 3);
     lb = fsq(x0, q0) + fsq(y0, p0);
@@ -57,7 +58,7 @@ __device__ __forceinline__ bool lb_cascade(const double* __restrict__ w, const L
   for (; k + 4 <= m && alive; k += 4) {
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const double x = __fma_rn(w[k + u], rstd, nmr);
+      const double x = ((w[k + u] - mean) * rstd);
       const double up = __ldg(Q.uq + k + u), lo = __ldg(Q.lq + k + u);
       const double d = (x > up) ? (x - up) : ((x < lo) ? (x - lo) : 0.0);
       lb = __fma_rn(d, d, lb);
@@ -66,7 +67,7 @@ __device__ __forceinline__ bool lb_cascade(const double* __restrict__ w, const L
   }
   if (alive) {
     for (; k < m; k++) {
-      const double x = __fma_rn(w[k], rstd, nmr);
+      const double x = ((w[k] - mean) * rstd);
       const double up = __ldg(Q.uq + k), lo = __ldg(Q.lq + k);
       const double d = (x > up) ? (x - up) : ((x < lo) ? (x - lo) : 0.0);
       lb = __fma_rn(d, d, lb);
@@ -139,10 +140,38 @@ __global__ void __launch_bounds__(kEvalTile) cnsm_dtw_lb_kernel(LbNormParams P) 
     if ((threadIdx.x & 31) == 0 && gmask) atomicAdd(&s_gate, (unsigned)__popc(gmask));
     if (!live) continue;
     const double rstd = 1.0 / stdv;
-    if (lb_cascade(E.T + (off - E.first_global), P.Q, rstd, -mean * rstd)) cand_append(E.out, off, mean, stdv);
+    if (lb_cascade(E.T + (off - E.first_global), P.Q, rstd, mean)) cand_append(E.out, off, mean, stdv);
   }
   __syncthreads();
   if (threadIdx.x == 0 && s_gate) atomicAdd(E.gate_pass, (unsigned long long)s_gate);
+}
+
+// cNSM-DTW stage 1 behind the streaming statistics pass (stream_kernels.cuh): entries are the flagged windows with
+// their exact chain sums -> exact gate (counted) -> lower bounds -> candidate list.
+struct LbListParams {
+  const double* __restrict__ T;
+  int32_t first_global;
+  int m;
+  XList in;
+  double meanQ, stdQ, alpha, inv_alpha, beta;
+  LbQuery Q;
+  CandList out;
+  unsigned long long* gate_pass;
+};
+
+__global__ void __launch_bounds__(128) cnsm_dtw_lb_list_kernel(LbListParams P) {
+  unsigned long long n = *P.in.count;
+  if ((long long)n > P.in.cap) n = (unsigned long long)P.in.cap;
+  unsigned my_gate = 0;
+  for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (unsigned long long)gridDim.x * blockDim.x) {
+    double mean, stdv;
+    const int32_t off = P.in.off[e];
+    if (!cnsm_exact_gate(P.in.ex[e], P.in.ex2[e], P.m, P.meanQ, P.stdQ, P.alpha, P.inv_alpha, P.beta, mean, stdv)) continue;
+    my_gate++;
+    if (lb_cascade(P.T + (off - P.first_global), P.Q, 1.0 / stdv, mean)) cand_append(P.out, off, mean, stdv);
+  }
+  if (my_gate) atomicAdd(P.gate_pass, (unsigned long long)my_gate);
 }
 
 // min of two non-negative doubles through their bit patterns (for x, y >= +0 the IEEE order is the unsigned integer

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "dtw_kernels.cuh"
+#include "stream_kernels.cuh"
 #include "index_kernels.cuh"
 #include "index_file.hpp"
 
@@ -111,6 +112,17 @@ struct NormPlanCache {
   size_t o_cbegin = 0, o_nsamp = 0, o_rbase = 0;
 };
 
+// Host plan of the streaming statistics pass (stream_kernels.cuh): live chains, segments of adjacent chains cut into
+// tiles.  Cached like NormPlanCache (same key) while it stays resident in ctx->sarena.
+struct StreamPlan {
+  bool valid = false;
+  std::vector<int32_t> lr;
+  int K = 0, shift = 0, m = 0, nt = 0;
+  int n_chains = 0, n_tiles = 0;
+  int64_t V = 0, S = 0, cnt_candidate = 0, l_max = 0;
+  size_t o_tiles = 0, o_cb = 0, o_nc = 0, o_vb = 0, bytes = 0;
+};
+
 // Per-query device buffers of a query set (kvm_verify_cnsm_ed_batch): swapped into the ctx's single-query slots while
 // that query's evaluator / exact stages run, so those stages are the single-query code.
 struct BatchSlot {
@@ -149,6 +161,16 @@ struct kvm_ctx {
   DevBuf seg_b, seg_first, seg_last, chain_count, chain_prefix, run_key, run_b, run_first, run_last;
   long long cand_cap = 0, ans_cap = 0;
   NormPlanCache norm_cache;
+  // streaming cNSM path
+  double absmax = 0.0;               // max |sample| of the loaded shard (guard band of the stream, stream_guard())
+  StreamPlan splan;
+  DevBuf sarena, need_bits, chain_last, flagged, x_off, x_ex, x_ex2, bmax;
+  long long n_bmax = 0;
+  long long x_cap = 0;
+  size_t need_words = 0, chain_last_n = 0;
+  bool stream_dirty = true;          // need_bits / chain_last may hold leftovers (first use, or a call that failed)
+  int opt_relay = 0, opt_force_all = 0, opt_plan_cache = 1;  // kvm_set_option (defaults from the environment)
+  PinBuf sstage;
   std::vector<BatchSlot> slots;      // query sets
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // query sets: per-query evaluator / exact stages run concurrently
   cudaEvent_t ev_set = nullptr;
@@ -547,6 +569,9 @@ double elapsed_ms(kvm_ctx* ctx) {
 }
 
 enum class Mode { kEd, kDtw };
+int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon, int rho, double alpha, double beta,
+                       const int32_t* lr, int K, int shift, int nt, kvm_result* out);
+int stream_nt_for(int m);
 
 // cNSM-ED and cNSM-DTW share everything up to the evaluator.
 int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon, int rho, double alpha, double beta,
@@ -559,12 +584,15 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
   if (rc) return rc;
   if (mode == Mode::kDtw && (rho < 0 || m < 3)) return fail(ctx, KVM_E_ARG, "DTW needs rho >= 0 and m >= 3");
   if ((rc = begin_call(ctx))) return rc;
+  {
+    // default: the streaming statistics pass; KVM_CNSM_PATH=relay (or a query too long for its shared-memory tile, or a
+    // series with non-finite samples) selects the round-1 relay walker, which walks every chain exactly
+    const int nt = stream_nt_for(m);
+    if (!ctx->opt_relay && nt > 0 && std::isfinite(ctx->absmax)) return verify_norm_stream(ctx, mode, q, m, epsilon, rho, alpha, beta, lr, K, shift, nt, out);
+  }
   const double t_dbg0 = since(t_begin);
   NormPlanCache& C = ctx->norm_cache;
-  static const bool cache_on = [] {  // KVM_PLAN_CACHE=0: plan and upload on every call (bench.py's e2e leg does this)
-    const char* e = std::getenv("KVM_PLAN_CACHE");
-    return !(e && e[0] == '0');
-  }();
+  const bool cache_on = ctx->opt_plan_cache != 0;  // off: plan and upload on every call (bench.py's e2e leg)
   const bool reuse = cache_on && C.valid && C.K == K && C.shift == shift && C.m == m &&
                      std::memcmp(C.lr.data(), lr, sizeof(int32_t) * 2 * (size_t)K) == 0;
   if (!reuse) {
@@ -715,7 +743,9 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
       X.n_exact = ctx->counters.as<unsigned long long>() + kCntFlag;
       X.in = E.out;
       X.sink = sink_of(ctx);
-      cnsm_ed_exact_kernel<<<ctx->n_sms * 6, 128, sizeof(double) * kExactChunk * 4, ctx->stream>>>(X);
+      X.win_cap = 0;
+      X.win_cap = 0;
+    cnsm_ed_exact_kernel<false><<<ctx->n_sms * 6, 128, sizeof(double) * kExactChunk * 4, ctx->stream>>>(X);
       launches += 2;
     } else {
       LbNormParams L;
@@ -759,6 +789,458 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
   out->kernel_ms = total_ms;
   out->n_gate_pass = (int64_t)cnt[kCntGate];
   if (mode == Mode::kEd) out->n_exact = (int64_t)cnt[kCntFlag]; else out->n_lb_pass = (int64_t)cnt[kCntCand];
+  return fetch_answers(ctx, (long long)cnt[kCntAnswers], out);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming cNSM path (stream_kernels.cuh): stream + guard band, exact re-walk of the flagged chains, exact stages.
+
+constexpr double kUlpHalf = 1.1102230246251565e-16;  // 2^-53
+
+// Guard bands of the stream's gate and of its in-stream lower bound.  Every term is a worst-case bound, in units of
+// A = max |sample| over everything a chain has summed when it reaches a window (evaluated per tile on the device from
+// the block-maximum table, kvm::stream_guard_eval):
+//  * the reference chain (K/NormQueryEngine.java:498-499,523-524) has performed at most 2*l_max roundings when it
+//    reaches a window, each at most u*|partial sum| <= u*m*A (ex) or u*m*A^2 (ex2); fl(d*d) itself is off by at most
+//    u*d^2 and a window holds m of them;
+//  * the stream's own sums go through fewer than 320 roundings (11-term group sums, block scan, remainder, 11 slides)
+//    on values bounded by (samples of a tile)*A resp. *A^2;
+//  * the reference's divide / multiply / subtract / sqrt at :508-511 and our threshold arithmetic add a few u
+//    relative to the quantities near the thresholds (inside stream_guard_eval).
+// The sum is doubled.  A window whose stream sums lie outside the *_out band certainly fails the reference's gate,
+// inside the *_in band it certainly passes; in between it is re-walked exactly.
+// In-stream lower bound: an answer has passed the exact gate (std >= stdQ/alpha) and |x_k| <= max|zQ| + eps in every
+// term, so |x_stream - x_ref| <= dx and sqrt(partial sum) moves by at most sqrt(n_terms)*dx.
+kvm::GuardCoef stream_guard(int m, int nt, int64_t l_max, const NormSetup& S, double alpha, double beta, double eps,
+                            double zq_absmax, int n_terms) {
+  const double u = kUlpHalf;
+  const double dm = (double)m;
+  const double nt_s = (double)kvm::kGroup * nt + dm;
+  const double E1 = 2.0 * (double)l_max * u * dm * 1.01;
+  const double E2 = (2.0 * (double)l_max * 1.01 + dm) * u * dm;
+  const double e1 = 320.0 * u * nt_s;
+  const double e2 = (320.0 * nt_s + 33.0 * 8.0) * u;
+  kvm::GuardCoef C;
+  C.cd1 = 2.0 * (E1 + e1) * 1.000001;
+  C.cd2 = 2.0 * (E2 + e2) * 1.000002;
+  C.dm = dm;
+  C.abs_mean_beta = std::fabs(S.meanQ) + std::fabs(beta);
+  C.c_lo = dm * (S.meanQ - beta);
+  C.c_hi = dm * (S.meanQ + beta);
+  C.hi = (alpha * S.stdQ) * (alpha * S.stdQ);
+  C.lo = (S.stdQ * S.inv_alpha) * (S.stdQ * S.inv_alpha);
+  C.std_lo = S.stdQ * S.inv_alpha * (1.0 - 1e-9);
+  C.xm = zq_absmax + std::fabs(eps) + 1.0;
+  C.sqrt_terms = std::sqrt((double)std::max(n_terms, 8));
+  C.eps_abs = std::fabs(eps);
+  return C;
+}
+
+// threads per CTA of the stream kernel for this query length: the variant that keeps the most threads resident per
+// SM (shared memory is the limit; ties go to the larger tile = fewer halo re-reads).  0 = the tile does not fit: the
+// relay walker takes the call.
+int stream_nt_for(int m) {
+  static const int forced = env_int("KVM_STREAM_NT", 0);  // developer knob
+  constexpr size_t kSmemSm = 227 * 1024, kSmemCta = 227 * 1024 - 512;
+  const int cand[] = {256, 224, 192, 160, 128};
+  int best = 0, best_threads = 0;
+  for (int nt : cand) {
+    const size_t sm = kvm::stream_smem_bytes(nt, m);
+    if (sm > kSmemCta) continue;
+    if (forced == nt) return nt;
+    int ctas = (int)(kSmemSm / (sm + 1024));
+    ctas = std::min(ctas, nt <= 192 ? 3 : (nt <= 256 ? 2 : 1));  // the kernels' __launch_bounds__
+    if (nt * ctas > best_threads) {
+      best_threads = nt * ctas;
+      best = nt;
+    }
+  }
+  return best;
+}
+
+template <int kMode>
+cudaError_t launch_stream(int nt, int grid, size_t smem, cudaStream_t st, const kvm::StreamParams& P) {
+  switch (nt) {
+    case 256: kvm::cnsm_stream_kernel<256, kMode><<<grid, 256, smem, st>>>(P); break;
+    case 224: kvm::cnsm_stream_kernel<224, kMode><<<grid, 224, smem, st>>>(P); break;
+    case 192: kvm::cnsm_stream_kernel<192, kMode><<<grid, 192, smem, st>>>(P); break;
+    case 160: kvm::cnsm_stream_kernel<160, kMode><<<grid, 160, smem, st>>>(P); break;
+    default: kvm::cnsm_stream_kernel<128, kMode><<<grid, 128, smem, st>>>(P); break;
+  }
+  return cudaGetLastError();
+}
+
+int set_stream_attrs() {
+  const int big = 227 * 1024 - 512;  // the opt-in maximum minus the kernel's static shared memory
+  cudaError_t e = cudaSuccess;
+#define KVM_ATTR(NT, MODE) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(kvm::cnsm_stream_kernel<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  KVM_ATTR(256, 0) KVM_ATTR(224, 0) KVM_ATTR(192, 0) KVM_ATTR(160, 0) KVM_ATTR(128, 0)
+  KVM_ATTR(256, 1) KVM_ATTR(224, 1) KVM_ATTR(192, 1) KVM_ATTR(160, 1) KVM_ATTR(128, 1)
+#undef KVM_ATTR
+  return e == cudaSuccess ? 0 : 1;
+}
+
+// Build (or reuse) the stream plan for this interval list: [tiles | cbegin | ncand | vbase] in ctx->sarena.
+int stream_plan(kvm_ctx* ctx, const int32_t* lr, int K, int shift, int m, int nt, bool cache_on) {
+  StreamPlan& SP = ctx->splan;
+  if (cache_on && SP.valid && SP.K == K && SP.shift == shift && SP.m == m && SP.nt == nt &&
+      std::memcmp(SP.lr.data(), lr, sizeof(int32_t) * 2 * (size_t)K) == 0)
+    return KVM_OK;
+  SP.valid = false;
+  Plan& P = ctx->plan_scratch;
+  int rc = make_plan(ctx, lr, K, shift, m, &P);
+  if (rc) return rc;
+  SP.cnt_candidate = P.cnt_candidate;
+  SP.V = P.V;
+  SP.S = P.S;
+  const int W = kvm::kGroup * nt;
+  // upper bounds for the staging layout: every live chain opens at most one extra tile
+  const size_t max_tiles = (size_t)(P.V / W) + (size_t)K + 2;
+  auto up256 = [](size_t x) { return (x + 255) & ~size_t(255); };
+  SP.o_tiles = 0;
+  SP.o_cb = up256(sizeof(kvm::StreamTile) * max_tiles);
+  SP.o_nc = up256(SP.o_cb + sizeof(int32_t) * ((size_t)K + 1));
+  SP.o_vb = up256(SP.o_nc + sizeof(int32_t) * ((size_t)K + 1));
+  const size_t cap_bytes = up256(SP.o_vb + sizeof(int32_t) * ((size_t)K + 1));
+  KVM_CUDA(ctx, ctx->sstage.ensure(cap_bytes + 256));
+  unsigned char* st = static_cast<unsigned char*>(ctx->sstage.p);
+  kvm::StreamTile* tiles = reinterpret_cast<kvm::StreamTile*>(st + SP.o_tiles);
+  int32_t* cb = reinterpret_cast<int32_t*>(st + SP.o_cb);
+  int32_t* nc = reinterpret_cast<int32_t*>(st + SP.o_nc);
+  int32_t* vb = reinterpret_cast<int32_t*>(st + SP.o_vb);
+  int n_live = 0, n_tiles = 0;
+  int64_t v = 0, l_max = 0;
+  int open = -1;  // index of the tile still being filled
+  int64_t prev_end = INT64_MIN;
+  for (int p = 0; p < K; p++) {
+    const int32_t c = P.ncand[p];
+    if (c <= 0) continue;
+    const int32_t b = P.cbegin[p];
+    cb[n_live] = b;
+    nc[n_live] = c;
+    vb[n_live] = (int32_t)v;
+    l_max = std::max<int64_t>(l_max, P.nsamp[p]);
+    if ((int64_t)b != prev_end) open = -1;  // not adjacent to the previous chain: a new segment
+    int32_t pos = b, rem = c;
+    while (rem > 0) {
+      if (open < 0) {
+        open = n_tiles++;
+        tiles[open] = kvm::StreamTile{pos, 0, n_live, (int32_t)(v + (pos - b))};
+      }
+      const int32_t take = std::min<int32_t>(rem, W - tiles[open].nwin);
+      tiles[open].nwin += take;
+      pos += take;
+      rem -= take;
+      if (tiles[open].nwin == W) open = -1;
+    }
+    prev_end = (int64_t)b + c;
+    v += c;
+    n_live++;
+  }
+  SP.n_chains = n_live;
+  SP.n_tiles = n_tiles;
+  SP.l_max = l_max;
+  SP.bytes = cap_bytes;
+  if (n_tiles > 0) {
+    KVM_CUDA(ctx, ctx->sarena.ensure(cap_bytes + 256));
+    // (tiles, cbegin, ncand, vbase live in separate 256-byte aligned blocks of one staging buffer: one copy)
+    KVM_CUDA(ctx, cudaMemcpyAsync(ctx->sarena.p, ctx->sstage.p, cap_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += (long long)(sizeof(kvm::StreamTile) * (size_t)n_tiles + 3 * sizeof(int32_t) * (size_t)n_live);
+  }
+  SP.K = K;
+  SP.shift = shift;
+  SP.m = m;
+  SP.nt = nt;
+  if (cache_on) {
+    SP.lr.assign(lr, lr + 2 * (size_t)K);
+    SP.valid = true;
+  }
+  return KVM_OK;
+}
+
+// Launch shape of cnsm_ed_exact_kernel: warps per CTA and the per-warp window staging that fits shared memory.
+template <bool kFromSums>
+void launch_exact(kvm_ctx* ctx, ExactEdParams& X) {
+  const size_t budget = 200 * 1024;
+  int warps = 4;
+  X.win_cap = (X.m + 1) & ~1;
+  while (warps > 1 && sizeof(double) * (size_t)warps * (kExactChunk + X.win_cap) > budget) warps >>= 1;
+  if (sizeof(double) * (size_t)warps * (kExactChunk + X.win_cap) > budget) {
+    warps = 4;
+    X.win_cap = 0;
+  }
+  const size_t smem = sizeof(double) * (size_t)warps * (kExactChunk + X.win_cap);
+  cnsm_ed_exact_kernel<kFromSums><<<ctx->n_sms * 6, warps * 32, smem, ctx->stream>>>(X);
+}
+
+int ensure_xlist(kvm_ctx* ctx, long long cap) {
+  if (cap <= ctx->x_cap) return KVM_OK;
+  ctx->x_cap = 0;
+  KVM_CUDA(ctx, ctx->x_off.ensure(sizeof(int32_t) * cap));
+  KVM_CUDA(ctx, ctx->x_ex.ensure(sizeof(double) * cap));
+  KVM_CUDA(ctx, ctx->x_ex2.ensure(sizeof(double) * cap));
+  ctx->x_cap = cap;
+  return KVM_OK;
+}
+
+int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon, int rho, double alpha, double beta,
+                       const int32_t* lr, int K, int shift, int nt, kvm_result* out) {
+  const bool cache_on = ctx->opt_plan_cache != 0;
+  int rc = stream_plan(ctx, lr, K, shift, m, nt, cache_on);
+  if (rc) return rc;
+  const StreamPlan& SP = ctx->splan;
+  out->cnt_candidate = SP.cnt_candidate;
+  out->n_verified = SP.V;
+  out->s_total = SP.S;
+  NormSetup S;
+  query_stats(q, m, &S.meanQ, &S.stdQ);
+  S.inv_alpha = 1.0 / alpha;
+  S.degenerate = !(S.stdQ > 0.0) || !(S.stdQ < INFINITY);
+  if (SP.V == 0 || S.degenerate) return fetch_answers(ctx, 0, out);
+
+  // ---- query: z-normalisation (K/NormQueryEngine.java:438-441); the stream needs only the screen table, the full
+  // |z| ordering (:448) is prepared while it runs
+  std::vector<double> z(m);
+  double zmax = 0.0;
+  for (int i = 0; i < m; i++) {
+    z[i] = (q[i] - S.meanQ) / S.stdQ;
+    zmax = std::max(zmax, std::fabs(z[i]));
+  }
+  const int n_screen = std::min(m, kvm::kScreenTerms);
+  std::vector<int32_t> order(m);
+  for (int i = 0; i < m; i++) order[i] = i;
+  std::vector<double> uq, lq;
+  int32_t scr_i[kvm::kScreenTerms] = {0};
+  double scr_a[kvm::kScreenTerms] = {0}, scr_b[kvm::kScreenTerms] = {0};
+  if (mode == Mode::kEd) {
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+      return java_double_compare(std::fabs(z[b]), std::fabs(z[a])) < 0;  // K/NormQueryEngine.java:448
+    });
+    for (int k = 0; k < n_screen; k++) {
+      scr_i[k] = order[k];
+      scr_a[k] = scr_b[k] = z[order[k]];
+    }
+  } else {
+    envelope(z, rho, lq, uq);  // K/NormQueryEngineDtw.java:469
+    for (int k = 0; k < n_screen; k++) {
+      const int i = (int)(((int64_t)(2 * k + 1) * m) / (2 * n_screen));  // evenly spread positions
+      scr_i[k] = i;
+      scr_a[k] = uq[i];
+      scr_b[k] = lq[i];
+    }
+  }
+  const kvm::GuardCoef GC = stream_guard(m, nt, SP.l_max, S, alpha, beta, epsilon, zmax, m);
+
+  // ---- buffers
+  const size_t words = (size_t)(SP.V + 63) / 32 + 4;
+  if (words > ctx->need_words) {
+    KVM_CUDA(ctx, ctx->need_bits.ensure(sizeof(unsigned) * words));
+    ctx->need_words = ctx->need_bits.cap / sizeof(unsigned);
+    ctx->stream_dirty = true;
+  }
+  if ((size_t)SP.n_chains > ctx->chain_last_n) {
+    KVM_CUDA(ctx, ctx->chain_last.ensure(sizeof(int32_t) * (size_t)SP.n_chains));
+    KVM_CUDA(ctx, ctx->flagged.ensure(sizeof(int32_t) * (size_t)SP.n_chains));
+    ctx->chain_last_n = std::min(ctx->chain_last.cap, ctx->flagged.cap) / sizeof(int32_t);
+    ctx->stream_dirty = true;
+  }
+  if (ctx->stream_dirty) {
+    KVM_CUDA(ctx, cudaMemsetAsync(ctx->need_bits.p, 0, ctx->need_bits.cap, ctx->stream));
+    KVM_CUDA(ctx, cudaMemsetAsync(ctx->chain_last.p, 0xff, ctx->chain_last.cap, ctx->stream));
+  }
+  ctx->stream_dirty = true;  // until this call has completed
+  if ((rc = ensure_xlist(ctx, std::max<long long>(ctx->x_cap, 1 << 18)))) return rc;
+  if ((rc = ensure_answers(ctx, std::max<long long>(ctx->ans_cap, 1 << 16)))) return rc;
+  if (mode == Mode::kDtw && (rc = ensure_cands(ctx, std::max<long long>(ctx->cand_cap, 1 << 18)))) return rc;
+
+  // ---- query block: [scr_idx | scr_a | scr_b | zq | order | uq | lq]; the screen part goes up before the stream
+  auto up256 = [](size_t x) { return (x + 255) & ~size_t(255); };
+  const size_t o_si = 0, o_sa = 256, o_sb = 512, o_zq = 768;
+  const size_t o_order = up256(o_zq + sizeof(double) * (size_t)m);
+  const size_t o_uq = up256(o_order + sizeof(int32_t) * (size_t)m);
+  const size_t o_lq = up256(o_uq + sizeof(double) * (size_t)m);
+  const size_t q_bytes = up256(o_lq + sizeof(double) * (size_t)m);
+  KVM_CUDA(ctx, ctx->stage2.ensure(q_bytes + 256));
+  KVM_CUDA(ctx, ctx->qarena.ensure(q_bytes + 256));
+  unsigned char* qs = static_cast<unsigned char*>(ctx->stage2.p);
+  std::memcpy(qs + o_si, scr_i, sizeof(scr_i));
+  std::memcpy(qs + o_sa, scr_a, sizeof(scr_a));
+  std::memcpy(qs + o_sb, scr_b, sizeof(scr_b));
+  const bool dtw = mode == Mode::kDtw;
+  if (dtw) {
+    std::memcpy(qs + o_zq, z.data(), sizeof(double) * (size_t)m);
+    std::memcpy(qs + o_uq, uq.data(), sizeof(double) * (size_t)m);
+    std::memcpy(qs + o_lq, lq.data(), sizeof(double) * (size_t)m);
+  } else {
+    double* zq = reinterpret_cast<double*>(qs + o_zq);
+    for (int i = 0; i < m; i++) zq[i] = z[order[i]];
+    std::memcpy(qs + o_order, order.data(), sizeof(int32_t) * (size_t)m);
+  }
+  const size_t q_used = dtw ? q_bytes : o_uq;
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->qarena.p, ctx->stage2.p, q_used, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->h2d_bytes += (long long)q_used;
+  const unsigned char* qbase = ctx->qarena.as<unsigned char>();
+  const unsigned char* sbase = ctx->sarena.as<unsigned char>();
+  unsigned long long* counters = ctx->counters.as<unsigned long long>();
+
+  const double eps2 = epsilon * epsilon;
+  const double eps2_hi = eps2 * (1.0 + 1e-9) + 1e-18;
+  const int force_all = ctx->opt_force_all;
+  unsigned long long cnt[kNumCounters];
+  double total_ms = 0;
+  for (int attempt = 0; attempt < 8; attempt++) {
+    int launches = 0;
+    if ((rc = zero_counters(ctx))) return rc;
+    KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    kvm::StreamParams W{};
+    W.T = ctx->series;
+    W.tiles = reinterpret_cast<const kvm::StreamTile*>(sbase + SP.o_tiles);
+    W.cbegin = reinterpret_cast<const int32_t*>(sbase + SP.o_cb);
+    W.ncand = reinterpret_cast<const int32_t*>(sbase + SP.o_nc);
+    W.n_chains = SP.n_chains;
+    W.m = m;
+    W.dm = (double)m;
+    W.inv_m = 1.0 / (double)m;
+    W.inv_m2 = W.inv_m * W.inv_m;
+    W.C = GC;
+    W.bmax = ctx->bmax.as<double>();
+    W.n_bmax = (int)ctx->n_bmax;
+    W.l_max = (int)SP.l_max;
+    W.scr_idx = reinterpret_cast<const int32_t*>(qbase + o_si);
+    W.scr_a = reinterpret_cast<const double*>(qbase + o_sa);
+    W.scr_b = reinterpret_cast<const double*>(qbase + o_sb);
+    W.q_full = reinterpret_cast<const double*>(qbase + o_zq);
+    W.order_full = reinterpret_cast<const int32_t*>(qbase + o_order);
+    W.uq_full = reinterpret_cast<const double*>(qbase + o_uq);
+    W.lq_full = reinterpret_cast<const double*>(qbase + o_lq);
+    W.n_screen = n_screen;
+    W.force_all = force_all;
+    W.need_bits = ctx->need_bits.as<unsigned>();
+    W.chain_last = ctx->chain_last.as<int32_t>();
+    W.flagged = ctx->flagged.as<int32_t>();
+    W.n_flagged = counters + kCntTiles;
+    W.gate_pass = counters + kCntGate;
+    W.n_need = counters + kCntDone;
+    const size_t smem = kvm::stream_smem_bytes(nt, m);
+#ifdef KVM_STREAM_PROF
+    unsigned long long z16[16] = {0};
+    cudaMemcpyToSymbolAsync(kvm::g_stream_prof, z16, sizeof(z16), 0, cudaMemcpyHostToDevice, ctx->stream);
+#endif
+    KVM_CUDA(ctx, dtw ? launch_stream<1>(nt, SP.n_tiles, smem, ctx->stream, W) : launch_stream<0>(nt, SP.n_tiles, smem, ctx->stream, W));
+#ifdef KVM_STREAM_PROF
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpyFromSymbol(z16, kvm::g_stream_prof, sizeof(z16));
+    {
+      const double c = (double)std::max<unsigned long long>(z16[8], 1);
+      std::fprintf(stderr, "[stream prof] nt %d tiles %llu cycles/CTA: setup %.0f tma-wait %.0f group-sums %.0f scan %.0f init %.0f slide %.0f "
+                   "sync %.0f tier2+end %.0f\n", nt, z16[8], z16[0] / c, z16[1] / c, z16[2] / c, z16[3] / c, z16[4] / c, z16[5] / c, z16[6] / c, z16[7] / c);
+    }
+#endif
+    KVM_CUDA(ctx, cudaEventRecord(ctx->evs[0], ctx->stream));
+    kvm::RewalkParams R{};
+    R.T = ctx->series;
+    R.cbegin = W.cbegin;
+    R.vbase = reinterpret_cast<const int32_t*>(sbase + SP.o_vb);
+    R.m = m;
+    R.first_global = (int32_t)ctx->first;
+    R.need_bits = W.need_bits;
+    R.chain_last = W.chain_last;
+    R.flagged = W.flagged;
+    R.n_flagged = W.n_flagged;
+    R.out = kvm::XList{ctx->x_off.as<int32_t>(), ctx->x_ex.as<double>(), ctx->x_ex2.as<double>(), counters + kCntEntries, ctx->x_cap};
+    kvm::chain_rewalk_kernel<<<std::min(SP.n_chains, ctx->n_sms * 16), 32, 0, ctx->stream>>>(R);
+    KVM_CUDA(ctx, cudaGetLastError());
+    KVM_CUDA(ctx, cudaEventRecord(ctx->evs[1], ctx->stream));
+    launches += 2;
+    if (!dtw) {
+      ExactEdParams X{};
+      X.T = ctx->series;
+      X.first_global = (int32_t)ctx->first;
+      X.m = m;
+      X.zq = reinterpret_cast<const double*>(qbase + o_zq);
+      X.order = reinterpret_cast<const int32_t*>(qbase + o_order);
+      X.eps2 = eps2;
+      X.eps2_hi = eps2_hi;
+      X.n_exact = counters + kCntFlag;
+      X.sink = sink_of(ctx);
+      X.xin = R.out;
+      X.meanQ = S.meanQ;
+      X.stdQ = S.stdQ;
+      X.alpha = alpha;
+      X.inv_alpha = S.inv_alpha;
+      X.beta = beta;
+      X.gate_pass = counters + kCntGate;
+      launch_exact<true>(ctx, X);
+      launches += 1;
+    } else {
+      LbListParams L{};
+      L.T = ctx->series;
+      L.first_global = (int32_t)ctx->first;
+      L.m = m;
+      L.in = R.out;
+      L.meanQ = S.meanQ;
+      L.stdQ = S.stdQ;
+      L.alpha = alpha;
+      L.inv_alpha = S.inv_alpha;
+      L.beta = beta;
+      L.Q = LbQuery{reinterpret_cast<const double*>(qbase + o_zq), reinterpret_cast<const double*>(qbase + o_uq),
+                    reinterpret_cast<const double*>(qbase + o_lq), m, eps2_hi};
+      L.out = cands_of(ctx);
+      L.gate_pass = counters + kCntGate;
+      cnsm_dtw_lb_list_kernel<<<ctx->n_sms * 8, 128, 0, ctx->stream>>>(L);
+      KVM_CUDA(ctx, cudaEventRecord(ctx->evs[2], ctx->stream));
+      DtwParams D{};
+      D.T = ctx->series;
+      D.first_global = (int32_t)ctx->first;
+      D.m = m;
+      D.rho = rho;
+      D.q = L.Q.q;
+      D.uq = L.Q.uq;
+      D.lq = L.Q.lq;
+      D.eps2 = eps2;
+      D.eps2_hi = eps2_hi;
+      D.n_abandoned = counters + kCntFlag;
+      D.in = L.out;
+      D.sink = sink_of(ctx);
+      if ((rc = launch_dtw(ctx, D))) return rc;
+      launches += 2;
+    }
+    KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    KVM_CUDA(ctx, cudaGetLastError());
+    if ((rc = read_counters(ctx, cnt))) return rc;
+    total_ms += elapsed_ms(ctx);
+    {
+      float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
+      cudaEventElapsedTime(&a, ctx->ev0, ctx->evs[0]);
+      cudaEventElapsedTime(&b, ctx->evs[0], ctx->evs[1]);
+      if (dtw) {
+        cudaEventElapsedTime(&c, ctx->evs[1], ctx->evs[2]);
+        cudaEventElapsedTime(&d, ctx->evs[2], ctx->ev1);
+      } else {
+        cudaEventElapsedTime(&c, ctx->evs[1], ctx->ev1);
+      }
+      out->stage_ms[0] += a;
+      out->stage_ms[1] += b;
+      out->stage_ms[2] += c;
+      out->stage_ms[3] += d;
+    }
+    out->n_launches += launches;
+    const bool x_over = (long long)cnt[kCntEntries] > ctx->x_cap;
+    const bool cand_over = dtw && (long long)cnt[kCntCand] > ctx->cand_cap, ans_over = (long long)cnt[kCntAnswers] > ctx->ans_cap;
+    if (!x_over && !cand_over && !ans_over) break;
+    if (attempt == 7) return fail(ctx, KVM_E_OOM, "result buffers kept overflowing");
+    if (x_over && (rc = ensure_xlist(ctx, (long long)cnt[kCntEntries] + 1024))) return rc;
+    if (cand_over && (rc = ensure_cands(ctx, (long long)cnt[kCntCand] + 1024))) return rc;
+    if (ans_over && (rc = ensure_answers(ctx, (long long)cnt[kCntAnswers] + 1024))) return rc;
+  }
+  ctx->stream_dirty = false;  // the re-walk consumed every flag it was given
+  out->kernel_ms = total_ms;
+  out->n_gate_pass = (int64_t)cnt[kCntGate];
+  out->n_rewalked = (int64_t)cnt[kCntEntries];
+  out->n_chains_rewalked = (int64_t)cnt[kCntTiles];
+  if (!dtw) out->n_exact = (int64_t)cnt[kCntFlag]; else out->n_lb_pass = (int64_t)cnt[kCntCand];
   return fetch_answers(ctx, (long long)cnt[kCntAnswers], out);
 }
 
@@ -818,6 +1300,12 @@ int kvm_create(kvm_ctx** out, int device_id) {
   kvm_ctx* ctx = new kvm_ctx();
   ctx->device = device_id;
   ctx->n_sms = prop.multiProcessorCount;
+  {
+    const char* e = std::getenv("KVM_CNSM_PATH");
+    ctx->opt_relay = (e && std::strcmp(e, "relay") == 0) ? 1 : 0;
+    ctx->opt_force_all = env_int("KVM_STREAM_FORCE_ALL", 0);
+    ctx->opt_plan_cache = env_int("KVM_PLAN_CACHE", 1);
+  }
   if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreate(&ctx->evs[0]) != cudaSuccess || cudaEventCreate(&ctx->evs[1]) != cudaSuccess ||
@@ -837,13 +1325,35 @@ int kvm_create(kvm_ctx** out, int device_id) {
     kvm_destroy(ctx);
     return fail(nullptr, KVM_E_CUDA, "cudaFuncSetAttribute(relay walker) failed: %s", msg);
   }
-  if (cudaFuncSetAttribute(cnsm_ed_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kExactChunk * 4)) != cudaSuccess) {
+  if (cudaFuncSetAttribute(cnsm_ed_exact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(cnsm_ed_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+      set_stream_attrs() != 0) {
     const char* msg = cudaGetErrorString(cudaGetLastError());
     kvm_destroy(ctx);
     return fail(nullptr, KVM_E_CUDA, "cudaFuncSetAttribute failed: %s", msg);
   }
   *out = ctx;
   return KVM_OK;
+}
+
+int kvm_set_option(kvm_ctx* ctx, int32_t option, int64_t value) {
+  if (!ctx) return KVM_E_ARG;
+  switch (option) {
+    case KVM_OPT_CNSM_PATH:
+      if (value != KVM_CNSM_STREAM && value != KVM_CNSM_RELAY) return fail(ctx, KVM_E_ARG, "cnsm path %lld", (long long)value);
+      ctx->opt_relay = value == KVM_CNSM_RELAY;
+      return KVM_OK;
+    case KVM_OPT_STREAM_FLAG_ALL:
+      ctx->opt_force_all = value != 0;
+      return KVM_OK;
+    case KVM_OPT_PLAN_CACHE:
+      ctx->opt_plan_cache = value != 0;
+      ctx->norm_cache.valid = false;
+      ctx->splan.valid = false;
+      return KVM_OK;
+    default:
+      return fail(ctx, KVM_E_ARG, "unknown option %d", (int)option);
+  }
 }
 
 void kvm_destroy(kvm_ctx* ctx) {
@@ -853,7 +1363,8 @@ void kvm_destroy(kvm_ctx* ctx) {
   DevBuf* dev[] = {&ctx->series_buf, &ctx->arena, &ctx->qarena, &ctx->counters, &ctx->wl_off, &ctx->wl_ex, &ctx->wl_ex2,
                    &ctx->region_count, &ctx->tile_prefix, &ctx->cand_off, &ctx->cand_mean, &ctx->cand_std,
                    &ctx->ans_off, &ctx->ans_dist, &ctx->seg_b, &ctx->seg_first, &ctx->seg_last, &ctx->chain_count,
-                   &ctx->chain_prefix, &ctx->run_key, &ctx->run_b, &ctx->run_first, &ctx->run_last};
+                   &ctx->chain_prefix, &ctx->run_key, &ctx->run_b, &ctx->run_first, &ctx->run_last, &ctx->sarena,
+                   &ctx->need_bits, &ctx->chain_last, &ctx->flagged, &ctx->x_off, &ctx->x_ex, &ctx->x_ex2, &ctx->bmax};
   for (DevBuf* b : dev) b->release();
   for (BatchSlot& sl : ctx->slots) sl.release();
   for (cudaStream_t st : ctx->aux)
@@ -861,7 +1372,7 @@ void kvm_destroy(kvm_ctx* ctx) {
   if (ctx->ev_set) cudaEventDestroy(ctx->ev_set);
   ctx->batch_gate.release();
   PinBuf* pin[] = {&ctx->stage, &ctx->stage2, &ctx->h_counters, &ctx->h_off, &ctx->h_dist, &ctx->h_key, &ctx->h_first, &ctx->h_last,
-                   &ctx->h_b};
+                   &ctx->h_b, &ctx->sstage};
   for (PinBuf* b : pin) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -892,6 +1403,24 @@ static int alloc_series(kvm_ctx* ctx, int64_t n, int64_t first, int64_t count) {
   return KVM_OK;
 }
 
+// Block-maximum table of |sample| (and the global maximum): scales the guard bands of the streaming statistics pass
+static int measure_absmax(kvm_ctx* ctx) {
+  ctx->absmax = NAN;
+  ctx->splan.valid = false;
+  ctx->n_bmax = (ctx->count + kvm::kBmaxBlock - 1) / kvm::kBmaxBlock;
+  KVM_CUDA(ctx, ctx->bmax.ensure(sizeof(double) * (size_t)ctx->n_bmax));
+  KVM_CUDA(ctx, ctx->counters.ensure(sizeof(unsigned long long) * kNumCounters));
+  KVM_CUDA(ctx, ctx->h_counters.ensure(sizeof(unsigned long long) * kNumCounters));
+  KVM_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long), ctx->stream));
+  blockmax_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(ctx->series, (long long)ctx->count, ctx->bmax.as<double>(),
+                                                          ctx->n_bmax, ctx->counters.as<unsigned long long>());
+  KVM_CUDA(ctx, cudaGetLastError());
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters.p, ctx->counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::memcpy(&ctx->absmax, ctx->h_counters.p, sizeof(double));
+  return KVM_OK;
+}
+
 int kvm_load_series_host(kvm_ctx* ctx, const double* samples, int64_t n, int64_t first, int64_t count) {
   if (!ctx) return KVM_E_ARG;
   if (!samples) return fail(ctx, KVM_E_ARG, "samples is null");
@@ -900,7 +1429,7 @@ int kvm_load_series_host(kvm_ctx* ctx, const double* samples, int64_t n, int64_t
   KVM_CUDA(ctx, cudaMemcpyAsync(ctx->series, samples, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice,
                                 ctx->stream));
   KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return KVM_OK;
+  return measure_absmax(ctx);
 }
 
 int kvm_load_series_file(kvm_ctx* ctx, const char* path, int64_t n, int64_t first, int64_t count) {
@@ -938,7 +1467,7 @@ int kvm_load_series_file(kvm_ctx* ctx, const char* path, int64_t n, int64_t firs
   bswap64_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(reinterpret_cast<unsigned long long*>(ctx->series), (long long)count);
   KVM_CUDA(ctx, cudaGetLastError());
   KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return KVM_OK;
+  return measure_absmax(ctx);
 }
 
 int kvm_verify_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, const int32_t* lr, int32_t K, int32_t shift,
@@ -1212,7 +1741,8 @@ int kvm_verify_cnsm_ed_batch(kvm_ctx* ctx, const double* queries, int32_t n_quer
     X.n_exact = ctx->counters.as<unsigned long long>() + kCntFlag;
     X.in = E.out;
     X.sink = sink_of(ctx);
-    cnsm_ed_exact_kernel<<<ctx->n_sms * 6, 128, sizeof(double) * kExactChunk * 4, ctx->stream>>>(X);
+    X.win_cap = 0;
+    cnsm_ed_exact_kernel<false><<<ctx->n_sms * 6, 128, sizeof(double) * kExactChunk * 4, ctx->stream>>>(X);
     KVM_CUDA(ctx, cudaGetLastError());
     outs[q].n_launches += 2;
     return enqueue_counter_read(ctx);

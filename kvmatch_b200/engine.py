@@ -40,6 +40,8 @@ class VerifyResult:
     n_launches: int
     stage_ms: tuple = (0.0, 0.0, 0.0, 0.0)
     h2d_bytes: int = 0
+    n_rewalked: int = 0
+    n_chains_rewalked: int = 0
 
     @property
     def count(self) -> int:
@@ -88,6 +90,11 @@ class GpuSeries:
         if rc != 0:
             raise _lib.KvmError(rc, self._L.kvm_last_error(self._h).decode())
 
+    def set_option(self, option: int, value: int):
+        """kvm_set_option: _lib.KVM_OPT_* (cNSM path, flag-all self-check, plan cache).  Never changes a result."""
+        self._check(self._L.kvm_set_option(self._h, option, value))
+        return self
+
     def load(self, samples, n: int | None = None, first: int = 1):
         a, p = _lib.as_f64(samples)
         n = len(a) if n is None else n
@@ -106,7 +113,8 @@ class GpuSeries:
         off = _lib.copy_out(r.offsets, c, np.int32)
         dist = _lib.copy_out(r.distances, c, np.float64)
         out = VerifyResult(off, dist, r.cnt_candidate, r.n_verified, r.s_total, r.n_gate_pass, r.n_lb_pass, r.n_exact,
-                           r.kernel_ms, r.n_launches, tuple(r.stage_ms), int(r.h2d_bytes))
+                           r.kernel_ms, r.n_launches, tuple(r.stage_ms), int(r.h2d_bytes), int(r.n_rewalked),
+                           int(r.n_chains_rewalked))
         self._L.kvm_result_free(self._h, C.byref(r))
         return out
 
@@ -132,7 +140,8 @@ class GpuSeries:
             c = r.count
             out.append(VerifyResult(_lib.copy_out(r.offsets, c, np.int32), _lib.copy_out(r.distances, c, np.float64),
                                     r.cnt_candidate, r.n_verified, r.s_total, r.n_gate_pass, r.n_lb_pass, r.n_exact,
-                                    r.kernel_ms, r.n_launches, tuple(r.stage_ms), int(r.h2d_bytes)))
+                                    r.kernel_ms, r.n_launches, tuple(r.stage_ms), int(r.h2d_bytes), int(r.n_rewalked),
+                           int(r.n_chains_rewalked)))
         return out
 
     def scan_ucr_dtw(self, q, epsilon, rho, alpha, beta) -> VerifyResult:

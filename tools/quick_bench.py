@@ -26,7 +26,8 @@ for chunk in chunks:
             best = min(best, r.kernel_ms)
         print(f"chunk {chunk:6d} K {len(iv):6d} off {off:9d} kernel {best:8.3f} ms wall {wall:8.3f} ms  "
               f"{r.n_verified / best / 1e6:9.1f} Gsubseq/s  frac {8 * n / (best * 1e-3) / 6553e9:5.3f}  "
-              f"gate {r.n_gate_pass} exact {r.n_exact} answers {r.count} stages {r.stage_ms[0]:.3f}/{r.stage_ms[1]:.3f}/{r.stage_ms[2]:.3f}", flush=True)
+              f"gate {r.n_gate_pass} exact {r.n_exact} answers {r.count} stages {r.stage_ms[0]:.3f}/{r.stage_ms[1]:.3f}/{r.stage_ms[2]:.3f} "
+              f"rewalked {r.n_rewalked} in {r.n_chains_rewalked} chains", flush=True)
 iv = datagen.chain_intervals(n, m, 100000 - m + 1)
 q = s[offs[0] - 1:offs[0] - 1 + m].copy()
 r = g.verify_ed(q, 10.0, iv); r = g.verify_ed(q, 10.0, iv)
