@@ -119,6 +119,7 @@ struct StreamPlan {
   std::vector<int32_t> lr;
   int K = 0, shift = 0, m = 0, nt = 0;
   int n_chains = 0, n_tiles = 0;
+  int n_segments = 0, s_base = 0;
   int64_t V = 0, S = 0, cnt_candidate = 0, l_max = 0;
   size_t o_tiles = 0, o_cb = 0, o_nc = 0, o_vb = 0, bytes = 0;
 };
@@ -825,12 +826,14 @@ kvm::GuardCoef stream_guard(int m, int nt, int64_t l_max, const NormSetup& S, do
   C.cd1 = 2.0 * (E1 + e1) * 1.000001;
   C.cd2 = 2.0 * (E2 + e2) * 1.000002;
   C.dm = dm;
+  C.inv_dm = 1.0 / dm;
   C.abs_mean_beta = std::fabs(S.meanQ) + std::fabs(beta);
   C.c_lo = dm * (S.meanQ - beta);
   C.c_hi = dm * (S.meanQ + beta);
   C.hi = (alpha * S.stdQ) * (alpha * S.stdQ);
   C.lo = (S.stdQ * S.inv_alpha) * (S.stdQ * S.inv_alpha);
   C.std_lo = S.stdQ * S.inv_alpha * (1.0 - 1e-9);
+  C.inv_std_lo = C.std_lo > 0.0 ? 1.02 / C.std_lo : 0.0;
   C.xm = zq_absmax + std::fabs(eps) + 1.0;
   C.sqrt_terms = std::sqrt((double)std::max(n_terms, 8));
   C.eps_abs = std::fabs(eps);
@@ -910,7 +913,7 @@ int stream_plan(kvm_ctx* ctx, const int32_t* lr, int K, int shift, int m, int nt
   int32_t* cb = reinterpret_cast<int32_t*>(st + SP.o_cb);
   int32_t* nc = reinterpret_cast<int32_t*>(st + SP.o_nc);
   int32_t* vb = reinterpret_cast<int32_t*>(st + SP.o_vb);
-  int n_live = 0, n_tiles = 0;
+  int n_live = 0, n_tiles = 0, n_segments = 0;
   int64_t v = 0, l_max = 0;
   int open = -1;  // index of the tile still being filled
   int64_t prev_end = INT64_MIN;
@@ -922,7 +925,10 @@ int stream_plan(kvm_ctx* ctx, const int32_t* lr, int K, int shift, int m, int nt
     nc[n_live] = c;
     vb[n_live] = (int32_t)v;
     l_max = std::max<int64_t>(l_max, P.nsamp[p]);
-    if ((int64_t)b != prev_end) open = -1;  // not adjacent to the previous chain: a new segment
+    if ((int64_t)b != prev_end) {  // not adjacent to the previous chain: a new segment
+      open = -1;
+      if (n_segments++ == 0) SP.s_base = b;
+    }
     int32_t pos = b, rem = c;
     while (rem > 0) {
       if (open < 0) {
@@ -940,6 +946,7 @@ int stream_plan(kvm_ctx* ctx, const int32_t* lr, int K, int shift, int m, int nt
     n_live++;
   }
   SP.n_chains = n_live;
+  SP.n_segments = n_segments;
   SP.n_tiles = n_tiles;
   SP.l_max = l_max;
   SP.bytes = cap_bytes;
@@ -1108,9 +1115,13 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
     W.bmax = ctx->bmax.as<double>();
     W.n_bmax = (int)ctx->n_bmax;
     W.l_max = (int)SP.l_max;
-    W.scr_idx = reinterpret_cast<const int32_t*>(qbase + o_si);
-    W.scr_a = reinterpret_cast<const double*>(qbase + o_sa);
-    W.scr_b = reinterpret_cast<const double*>(qbase + o_sb);
+    W.vbase = reinterpret_cast<const int32_t*>(sbase + SP.o_vb);
+    W.uniform = SP.n_segments == 1 ? 1 : 0;  // one run of adjacent window starts: tiles follow from the CTA index
+    W.s_base = SP.s_base;
+    W.total_win = (int32_t)SP.V;
+    std::memcpy(W.scr_idx, scr_i, sizeof(scr_i));
+    std::memcpy(W.scr_a, scr_a, sizeof(scr_a));
+    std::memcpy(W.scr_b, scr_b, sizeof(scr_b));
     W.q_full = reinterpret_cast<const double*>(qbase + o_zq);
     W.order_full = reinterpret_cast<const int32_t*>(qbase + o_order);
     W.uq_full = reinterpret_cast<const double*>(qbase + o_uq);
@@ -1134,8 +1145,9 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
     cudaMemcpyFromSymbol(z16, kvm::g_stream_prof, sizeof(z16));
     {
       const double c = (double)std::max<unsigned long long>(z16[8], 1);
-      std::fprintf(stderr, "[stream prof] nt %d tiles %llu cycles/CTA: setup %.0f tma-wait %.0f group-sums %.0f scan %.0f init %.0f slide %.0f "
-                   "sync %.0f tier2+end %.0f\n", nt, z16[8], z16[0] / c, z16[1] / c, z16[2] / c, z16[3] / c, z16[4] / c, z16[5] / c, z16[6] / c, z16[7] / c);
+      std::fprintf(stderr, "[stream prof] nt %d tiles %llu cycles/CTA (thread 0): setup %.0f guard+tma-wait %.0f group-sums %.0f warp-local %.0f "
+                   "end %.0f | chains needed %llu, warps slid %llu of %llu, candidates %llu\n", nt, z16[8], z16[0] / c, z16[1] / c, z16[2] / c,
+                   z16[5] / c, z16[6] / c, z16[10], z16[9], (unsigned long long)SP.n_tiles * (nt / 32), z16[11]);
     }
 #endif
     KVM_CUDA(ctx, cudaEventRecord(ctx->evs[0], ctx->stream));

@@ -53,17 +53,19 @@ struct StreamGate {  // on ex (= m * mean) and t2 = m*ex2 - ex^2 (= m^2 * varian
 // amplitude varies by orders of magnitude (random walks) keeps tight bands where the values are small.
 struct GuardCoef {
   double cd1, cd2;          // |ex_stream - ex_chain| <= cd1*A, |ex2_stream - ex2_chain| <= cd2*A^2
-  double dm, abs_mean_beta; // m, |meanQ| + |beta|
+  double dm, inv_dm;        // m, 1/m (the guard keeps 4u of slack for the rounded reciprocals)
+  double abs_mean_beta;     // |meanQ| + |beta|
   double c_lo, c_hi;        // m*(meanQ -+ beta)
   double lo, hi;            // variance band (stdQ/alpha)^2, (stdQ*alpha)^2
-  double std_lo, xm, sqrt_terms, eps_abs;
+  double std_lo, inv_std_lo;  // lowest std of a gate pass, and 1.02 / it
+  double xm, sqrt_terms, eps_abs;
 };
 
 __host__ __device__ inline void stream_guard_eval(const GuardCoef& C, double A, StreamGate* G, double* thr) {
   const double u = 1.1102230246251565e-16;  // 2^-53
   const double dm = C.dm;
   const double d1 = C.cd1 * A, d2 = C.cd2 * A * A;
-  const double Mb = C.abs_mean_beta + 2.0 * d1 / dm + 1e-300;  // |mean| of a window in the outer mean band
+  const double Mb = C.abs_mean_beta + 2.0 * d1 * C.inv_dm * (1.0 + 8.0 * u) + 1e-300;  // |mean| of a window in the outer band
   const double g1 = d1 + dm * 16.0 * u * Mb;
   G->e_lo_out = C.c_lo - g1;
   G->e_lo_in = C.c_lo + g1;
@@ -76,12 +78,12 @@ __host__ __device__ inline void stream_guard_eval(const GuardCoef& C, double A, 
   G->v_lo_in = lo2 + g2;
   G->v_hi_in = hi2 - g2;
   G->v_hi_out = hi2 + g2;
-  const double g_mean = g1 / dm + 4.0 * u * Mb;
-  const double g_var = g2 / (dm * dm);
+  const double g_mean = g1 * C.inv_dm * (1.0 + 8.0 * u) + 4.0 * u * Mb;
+  const double g_var = g2 * C.inv_dm * C.inv_dm * (1.0 + 8.0 * u);
   double t = 1.0 / 0.0;
   if (C.std_lo > 0.0 && g_var < 0.01 * C.std_lo * C.std_lo) {
-    const double g_std = g_var / C.std_lo;
-    const double dx = (g_mean + C.xm * g_std) / (0.99 * C.std_lo) + 16.0 * u * C.xm;
+    const double g_std = g_var * C.inv_std_lo;                        // >= g_var / std_lo
+    const double dx = (g_mean + C.xm * g_std) * C.inv_std_lo + 16.0 * u * C.xm;  // >= (...) / (0.99 std_lo)
     const double D = C.sqrt_terms * dx;
     t = (C.eps_abs + D) * (C.eps_abs + D) * (1.0 + 1e-12) + 1e-300;
   }
@@ -95,6 +97,7 @@ struct StreamParams {
   const StreamTile* __restrict__ tiles;
   const int32_t* __restrict__ cbegin;  // live chains: local index of the first sample
   const int32_t* __restrict__ ncand;   //              window starts
+  const int32_t* __restrict__ vbase;   //              ordinal of the first window
   int n_chains;
   int m;
   double dm, inv_m, inv_m2;
@@ -102,10 +105,16 @@ struct StreamParams {
   const double* __restrict__ bmax;  // max |sample| per kBmaxBlock samples of the shard
   int n_bmax;
   int l_max;                        // samples of the longest chain
-  // in-stream lower bound: ED: idx = order[k], a = zq (sorted order); DTW: idx = sampled positions, a = upper, b = lower envelope
-  const int32_t* __restrict__ scr_idx;
-  const double* __restrict__ scr_a;
-  const double* __restrict__ scr_b;
+  // uniform tiling (one segment of total_win adjacent window starts cut every 33*NT): the tile is computed from the
+  // CTA index instead of being loaded (no dependent global load in front of the TMA issue)
+  int uniform;
+  int32_t s_base;
+  int32_t total_win;
+  // in-stream lower bound table (in the parameter block = constant memory).  ED: idx = order[k], a = zQ (sorted
+  // order); DTW: idx = evenly spread positions, a = upper, b = lower envelope
+  int32_t scr_idx[kScreenTerms];
+  double scr_a[kScreenTerms];
+  double scr_b[kScreenTerms];
   // the rest of the bound, for table survivors.  ED: q_full = zQ in |z|-descending order, order_full = its
   // permutation; DTW: q_full = zQ in natural order, uq_full / lq_full = its envelope
   const double* __restrict__ q_full;
@@ -157,19 +166,32 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+constexpr int kQ1Cap = 40, kQ1Drain = 8;  // candidate queue per warp: drained (32 at a time) once it holds 8
+
+constexpr size_t stream_xs_doubles(int nt, int m) { return ((size_t)kGroup * nt + m + 42) & ~size_t(1); }
+constexpr size_t stream_gs_doubles(int nt, int m) { return ((size_t)nt + (m + kGroup - 1) / kGroup + 8) & ~size_t(1); }
 constexpr size_t stream_smem_bytes(int nt, int m) {
-  const size_t n_xs = ((size_t)kGroup * nt + m + 42) & ~size_t(1);
-  const size_t ng = ((size_t)kGroup * nt + m + kGroup) / 11 + 4;
-  return 16 + sizeof(double) * (n_xs + 2 * ng + 2 * kScreenTerms) + sizeof(int32_t) * kScreenTerms + 16;
+  return 16 + sizeof(double) * (stream_xs_doubles(nt, m) + 2 * stream_gs_doubles(nt, m)) +
+         (size_t)(nt / 32) * kQ1Cap * (2 * sizeof(double) + sizeof(int32_t)) + 16;
 }
 
-// Flag the window that starts at local sample s (ordinal v); p = a live chain at or before its chain (rare path;
+// Flag the window that starts at local sample s (ordinal v).  p = a live chain at or before its chain, or -1 when the
+// tile was computed arithmetically: then the chain is found by bisection over the chains' first ordinals (rare path;
 // arguments by value so that the kernel's parameter block never needs an address).
 __device__ __noinline__ void stream_flag(const int32_t* __restrict__ cbegin, const int32_t* __restrict__ ncand,
-                                         unsigned* need_bits, int32_t* chain_last, int32_t* flagged,
-                                         unsigned long long* n_flagged, unsigned long long* n_need, int s, int p,
-                                         unsigned v) {
-  while (s >= __ldg(cbegin + p) + __ldg(ncand + p)) p++;  // chains of one segment are consecutive
+                                         const int32_t* __restrict__ vbase, int n_chains, unsigned* need_bits,
+                                         int32_t* chain_last, int32_t* flagged, unsigned long long* n_flagged,
+                                         unsigned long long* n_need, int s, int p, unsigned v) {
+  if (p < 0) {
+    int lo = 0, hi = n_chains;  // largest p with vbase[p] <= v
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((unsigned)__ldg(vbase + mid) <= v) lo = mid; else hi = mid;
+    }
+    p = lo;
+  } else {
+    while (s >= __ldg(cbegin + p) + __ldg(ncand + p)) p++;  // chains of one segment are consecutive
+  }
   atomicOr(need_bits + (v >> 5), 1u << (v & 31));
   const int old = atomicMax(chain_last + p, s - __ldg(cbegin + p));
   if (old < 0) {
@@ -179,26 +201,40 @@ __device__ __noinline__ void stream_flag(const int32_t* __restrict__ cbegin, con
   atomicAdd(n_need, 1ULL);
 }
 
-// Shared-memory queue of the windows that survived the table tier of the in-stream lower bound; the CTA's warps finish
-// their bound cooperatively after the slide phase.  It reuses the group-prefix arrays (dead by then).
-struct StreamQueue {
-  int* count;
-  int cap;
-  int* w;       // window index in the tile; bit 30 = certainly inside the gate
+#ifdef KVM_STREAM_PROF
+__device__ unsigned long long g_stream_prof[16];  // thread 0 of every CTA: cycles per phase, CTA count
+__device__ __forceinline__ long long stream_clock() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
+#define STREAM_T(var) const long long var = stream_clock()
+#define STREAM_SET(var) var = stream_clock()
+#define STREAM_COUNT(i, n) do { if ((n) != 0) atomicAdd(&g_stream_prof[i], (unsigned long long)(n)); } while (0)
+#else
+#define STREAM_COUNT(i, n)
+#define STREAM_T(var)
+#define STREAM_SET(var)
+#endif
+
+// Warp-private shared-memory queue of the windows the hot loop found inside the outer variance band: (window, ex, ex2).
+// Drained 32 at a time with one window per lane (stream_candidate).
+struct WarpQueue {
+  int* w;
   double* ex;
   double* ex2;
 };
 
-// The rare path of the stream: a window inside the outer mean band.  Returns 1 when the window certainly passes the
-// gate and certainly is no answer (it is only counted).  Otherwise the window is either flagged for the exact re-walk
-// (ambiguous gate and already pruned) or queued for the second tier of the bound.
-// Table tier: ED: the 32 largest-|zQ| terms of the distance; DTW: LB_KimFL (K/utils/DtwUtils.java:149-189) and 32
-// evenly spread terms of LB_Keogh on the query envelope.  `wv` = the window's first sample in shared memory.
+// One queued candidate per lane: the exact outer-band tests, then the table tier of the lower bound — ED: the 32
+// largest-|zQ| terms of the distance; DTW: LB_KimFL (K/utils/DtwUtils.java:149-189) and 32 evenly spread terms of
+// LB_Keogh on the query envelope.  Returns 1 when the window certainly passes the gate and certainly is no answer (it
+// is only counted).  A window that is ambiguous or survives the table is flagged: its chain is re-walked exactly and
+// the exact stage (cnsm_ed_exact_kernel / cnsm_dtw_lb_list_kernel, a warp resp. a thread per window over the whole
+// GPU) finishes the bound.  (A second in-stream tier over all m terms was measured: clusters of near matches made
+// single CTAs run for 0.3 ms.)  `wv` = the window's first sample in shared memory.
 template <int kMode>
-__device__ __forceinline__ unsigned stream_window(const StreamParams& P, const StreamTile& tile, const double* __restrict__ wv,
-                                                  int w, double ex, double ex2, const int32_t* __restrict__ scr_i,
-                                                  const double* __restrict__ scr_a, const double* __restrict__ scr_b,
-                                                  const StreamQueue& Q, const StreamGate& G, const double thr) {
+__device__ __forceinline__ unsigned stream_candidate(const StreamParams& P, const StreamTile& tile, const double* __restrict__ wv,
+                                                     int w, double ex, double ex2, const StreamGate& G, const double thr) {
   if (!(ex >= G.e_lo_out && ex <= G.e_hi_out)) return 0u;
   const double t2 = __fma_rn(P.dm, ex2, -__dmul_rn(ex, ex));
   if (!(t2 >= G.v_lo_out && t2 <= G.v_hi_out)) return 0u;
@@ -228,12 +264,12 @@ __device__ __forceinline__ unsigned stream_window(const StreamParams& P, const S
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         if (kk + u < n_scr) {
-          const double x = (wv[scr_i[kk + u]] - mean) * rstd;
+          const double x = (wv[P.scr_idx[kk + u]] - mean) * rstd;
           double d;
           if (kMode == 0) {
-            d = x - scr_a[kk + u];
+            d = x - P.scr_a[kk + u];
           } else {
-            const double up = scr_a[kk + u], lo = scr_b[kk + u];
+            const double up = P.scr_a[kk + u], lo = P.scr_b[kk + u];
             d = (x > up) ? (x - up) : ((x < lo) ? (x - lo) : 0.0);
           }
           dist = __fma_rn(d, d, dist);
@@ -241,132 +277,126 @@ __device__ __forceinline__ unsigned stream_window(const StreamParams& P, const S
       }
       survive = dist <= thr;
     }
-    if (survive && n_scr < m) {  // second tier: queue for the warps (a full queue falls through to the flag)
-      const int slot = atomicAdd(Q.count, 1);
-      if (slot < Q.cap) {
-        Q.w[slot] = w | (sure ? (1 << 30) : 0);
-        Q.ex[slot] = ex;
-        Q.ex2[slot] = ex2;
-        return 0u;
-      }
-    }
   }
   if (!survive && sure) return 1u;
-  stream_flag(P.cbegin, P.ncand, P.need_bits, P.chain_last, P.flagged, P.n_flagged, P.n_need, tile.s0 + w, tile.chain,
-              (unsigned)(tile.v0 + w));
+  stream_flag(P.cbegin, P.ncand, P.vbase, P.n_chains, P.need_bits, P.chain_last, P.flagged, P.n_flagged, P.n_need, tile.s0 + w,
+              tile.chain, (unsigned)(tile.v0 + w));
   return 0u;
 }
 
-// Second tier, one warp per queued window: the whole bound with the lanes striding over its terms — ED: the full
-// |zQ|-ordered sum (a permutation of the distance's terms); DTW: LB_Keogh on the query envelope over all m positions.
-// Returns (lane 0) 1 when the window is certainly a gate pass and certainly no answer.
+// Drain up to 32 entries from the front of the queue (one per lane); the rest moves to the front.  n = entries
+// (warp-uniform); returns the new count.
 template <int kMode>
-__device__ __forceinline__ unsigned stream_tier2(const StreamParams& P, const StreamTile& tile, const double* __restrict__ xs,
-                                                 int wq, double ex, double ex2, int lane, const double thr) {
-  const int w = wq & ((1 << 30) - 1);
-  const bool sure = (wq >> 30) & 1;
-  const int m = P.m;
-  const double t2 = __fma_rn(P.dm, ex2, -__dmul_rn(ex, ex));
-  const double mean = ex * P.inv_m;
-  const double rstd = rsqrt(t2 * P.inv_m2);
-  const double* __restrict__ wv = xs + w;
-  double part = 0.0;
-  bool survive = true;
-  for (int k0 = 0; k0 < m && survive; k0 += 128) {
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int k = k0 + u * 32 + lane;
-      if (k < m) {
-        double d;
-        if (kMode == 0) {
-          d = (wv[__ldg(P.order_full + k)] - mean) * rstd - __ldg(P.q_full + k);
-        } else {
-          const double x = (wv[k] - mean) * rstd;
-          const double up = __ldg(P.uq_full + k), lo = __ldg(P.lq_full + k);
-          d = (x > up) ? (x - up) : ((x < lo) ? (x - lo) : 0.0);
-        }
-        part = __fma_rn(d, d, part);
-      }
-    }
-    double tot = part;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFullMask, tot, o);
-    survive = tot <= thr;
+__device__ __forceinline__ int stream_drain(const StreamParams& P, const StreamTile& tile, const double* __restrict__ xs,
+                                            const WarpQueue& Q, int n, int lane, const StreamGate& G, const double thr,
+                                            unsigned& my_gate) {
+  const int nb = min(n, 32), rest = n - nb;
+  int mw = 0;
+  double mex = 0.0, mex2 = 0.0;
+  if (lane < rest) {
+    mw = Q.w[nb + lane];
+    mex = Q.ex[nb + lane];
+    mex2 = Q.ex2[nb + lane];
   }
-  if (lane != 0) return 0u;
-  if (!survive && sure) return 1u;
-  stream_flag(P.cbegin, P.ncand, P.need_bits, P.chain_last, P.flagged, P.n_flagged, P.n_need, tile.s0 + w, tile.chain,
-              (unsigned)(tile.v0 + w));
-  return 0u;
+  if (lane < nb) {
+    const int w = Q.w[lane];
+    my_gate += stream_candidate<kMode>(P, tile, xs + w, w, Q.ex[lane], Q.ex2[lane], G, thr);
+  }
+  __syncwarp();
+  if (lane < rest) {
+    Q.w[lane] = mw;
+    Q.ex[lane] = mex;
+    Q.ex2[lane] = mex2;
+  }
+  __syncwarp();
+  return rest;
 }
 
-#ifdef KVM_STREAM_PROF
-__device__ unsigned long long g_stream_prof[16];  // thread 0 of every CTA: cycles per phase, CTA count
-__device__ __forceinline__ long long stream_clock() {
-  long long t;
-  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
-  return t;
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
-#define STREAM_T(var) const long long var = stream_clock()
-#else
-#define STREAM_T(var)
-#endif
 
-constexpr int kSub = 11;            // a thread's 33 windows are three independent chains of 11 (instruction-level parallelism)
-constexpr int kSubs = kGroup / kSub;
-
-// kMode 0: cNSM-ED, 1: cNSM-DTW (they differ in the in-stream lower bound only)
+// kMode 0: cNSM-ED, 1: cNSM-DTW (they differ in the table tier of the in-stream lower bound only)
+//
+// One CTA per tile of up to 33*NT adjacent window starts; thread t owns the chain of 33 windows starting at 33t.
+//   1. One elected lane issues the TMA bulk copies of the tile's nwin + m - 1 samples (one mbarrier); meanwhile the last
+//      warp evaluates the tile's guard bands from the block-maximum table.
+//   2. Thread t sums the 33 samples (and their squares) of group t, t + NT, ...   — barrier —
+//   3. Warp-local: the window sums of the warp's first chain are a direct sum of group sums, the other 31 chains follow
+//      from a shuffle scan of gs[g + m/33] - gs[g] (+ m % 33 samples each).
+//   4. Chain-level skip from the group sums (see below); only warps with an unskippable chain slide, branch-free,
+//      recording the windows inside the outer variance band; those are replayed into the warp's queue and finished
+//      one per lane.
 template <int NT, int kMode>
 __global__ void __launch_bounds__(NT, NT <= 192 ? 3 : (NT <= 256 ? 2 : 1)) cnsm_stream_kernel(StreamParams P) {
   extern __shared__ __align__(16) unsigned char stream_smem[];
-  __shared__ double s_w1[NT / 32], s_w2[NT / 32];
-  __shared__ int s_qcount;
   __shared__ StreamGate s_gate;
   __shared__ double s_thr;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(kFullMask, tid >> 5, 0);  // (tells the compiler it is warp-uniform)
   STREAM_T(c0);
-  const StreamTile tile = P.tiles[blockIdx.x];
+  StreamTile tile;
+  if (P.uniform) {
+    const int i0 = (int)blockIdx.x * (kGroup * NT);
+    tile.s0 = P.s_base + i0;
+    tile.nwin = min(kGroup * NT, P.total_win - i0);
+    tile.chain = -1;
+    tile.v0 = i0;
+  } else {
+    tile = P.tiles[blockIdx.x];
+  }
   const int m = P.m;
   const int nwin = tile.nwin;
   const int ns = nwin + m - 1;                 // samples the tile's windows cover
   const int s0a = tile.s0 & ~1;                // 16-byte aligned copy start
   const int lead = tile.s0 - s0a;
   const int nload = (lead + ns + 1) & ~1;      // even number of doubles
-  const int ng = (ns + kSub - 1) / kSub;       // 11-sample groups
-  const size_t n_xs = ((size_t)kGroup * NT + m + 42) & ~size_t(1);
-  const size_t ng_cap = ((size_t)kGroup * NT + m + kGroup) / kSub + 4;
+  const int ng = (ns + kGroup - 1) / kGroup;   // 33-sample groups holding samples
+  const size_t n_xs = stream_xs_doubles(NT, m);
+  const int gs_cap = (int)stream_gs_doubles(NT, m);
   double* xs_raw = reinterpret_cast<double*>(stream_smem + 16);
   double* xs = xs_raw + lead;
-  double* gp1 = xs_raw + n_xs;
-  double* gp2 = gp1 + ng_cap;
-  double* scr_a = gp2 + ng_cap;
-  double* scr_b = scr_a + kScreenTerms;
-  int32_t* scr_i = reinterpret_cast<int32_t*>(scr_b + kScreenTerms);
+  double* gs1 = xs_raw + n_xs;
+  double* gs2 = gs1 + gs_cap;
+  double* q_ex = gs2 + gs_cap;
+  double* q_ex2 = q_ex + (NT / 32) * kQ1Cap;
+  int* q_w = reinterpret_cast<int*>(q_ex2 + (NT / 32) * kQ1Cap);
   const uint32_t bar = smem_u32(stream_smem);
 
-  if (tid == 0) {
-    s_qcount = 0;
-    mbar_init(bar, 1);
-    fence_mbar_init();
-    const uint32_t bytes = (uint32_t)nload * 8u;
-    mbar_expect_tx(bar, bytes);
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(P.T + s0a);
-    const uint32_t dst = smem_u32(xs_raw);
-    constexpr uint32_t kChunk = 16384;
-    for (uint32_t o = 0; o < bytes; o += kChunk) tma_bulk_g2s(dst + o, src + o, min(kChunk, bytes - o), bar);
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+      const uint32_t bytes = (uint32_t)nload * 8u;
+      mbar_expect_tx(bar, bytes);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(P.T + s0a);
+      const uint32_t dst = smem_u32(xs_raw);
+      constexpr uint32_t kChunk = 32768;
+      for (uint32_t o = 0; o < bytes; o += kChunk) tma_bulk_g2s(dst + o, src + o, min(kChunk, bytes - o), bar);
+    }
   }
-  if (tid < P.n_screen) {
-    scr_i[tid] = __ldg(P.scr_idx + tid);
-    scr_a[tid] = __ldg(P.scr_a + tid);
-    scr_b[tid] = __ldg(P.scr_b + tid);
-  }
+  // Guard bands of this tile (last warp; finished after barrier (1), while the samples are in flight): A = max |sample|
+  // over every sample a chain can have summed before or inside one of the tile's windows, i.e. from l_max samples
+  // before the tile to its end (block-maximum table, kBmaxBlock granularity).  The table load is issued first.
+  const int bm_lo = max(0, tile.s0 - P.l_max) / kBmaxBlock;
+  const int bm_hi = min(P.n_bmax - 1, (tile.s0 + ns) / kBmaxBlock);
+  double amax_first = 0.0;  // (not consumed before the barrier: the load stays in flight)
+  if (warp == NT / 32 - 1 && bm_lo + lane <= bm_hi) amax_first = __ldg(P.bmax + bm_lo + lane);
+  // zero what follows the copied samples (never part of a valid window; keeps the group sums finite)
+  for (int i = nload + tid; i < lead + ns + kGroup + 2; i += NT) xs_raw[i] = 0.0;
+  __syncthreads();  // (1) mbarrier initialised; zero tail staged
+  STREAM_T(c1);
   if (warp == NT / 32 - 1) {
-    // guard bands of this tile: A = max |sample| over every sample a chain can have summed before or inside one of the
-    // tile's windows, i.e. from l_max samples before the tile to its end (block-maximum table, kBmaxBlock granularity)
-    const int b_lo = max(0, tile.s0 - P.l_max) / kBmaxBlock;
-    const int b_hi = min(P.n_bmax - 1, (tile.s0 + ns) / kBmaxBlock);
-    unsigned long long mx = 0ULL;
-    for (int b = b_lo + lane; b <= b_hi; b += 32) mx = max(mx, (unsigned long long)__double_as_longlong(__ldg(P.bmax + b)));
+    unsigned long long mx = (unsigned long long)__double_as_longlong(amax_first);
+    for (int b = bm_lo + 32 + lane; b <= bm_hi; b += 32) mx = max(mx, (unsigned long long)__double_as_longlong(__ldg(P.bmax + b)));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(kFullMask, mx, o));
     if (lane == 0) {
@@ -377,51 +407,59 @@ __global__ void __launch_bounds__(NT, NT <= 192 ? 3 : (NT <= 256 ? 2 : 1)) cnsm_
       s_thr = t;
     }
   }
-  // zero what follows the copied samples (never part of a valid window; keeps the group prefix finite)
-  for (int i = nload + tid; i < lead + ns + kGroup + 2; i += NT) xs_raw[i] = 0.0;
-  __syncthreads();  // barrier initialised; screen table, guard bands and zero tail staged
-  STREAM_T(c1);
   mbar_wait(bar, 0);
   STREAM_T(c2);
+#ifdef KVM_STREAM_PROF
+  if (P.force_all == 99) return;  // experiment: the copy alone
+  if (P.force_all == 98 && blockIdx.x > 1000000) return;
+#endif
 
-  // ---- sums of 11-sample groups (lane stride 11 doubles: conflict-free), three independent groups at a time
-  for (int g0 = tid; g0 <= ng; g0 += kSubs * NT) {
-    double a1[kSubs], a2[kSubs];
+  // ---- sums of 33-sample groups (lane stride 33 doubles: conflict-free); three partial sums per group for ILP;
+  // groups past the last sample are written as zeros up to the arrays' capacity
+  for (int g = tid; g < gs_cap; g += NT) {
+    double a1[3] = {0.0, 0.0, 0.0}, a2[3] = {0.0, 0.0, 0.0};
+    if (g < ng) {
+      const double* __restrict__ x = xs + g * kGroup;
 #pragma unroll
-    for (int b = 0; b < kSubs; b++) a1[b] = a2[b] = 0.0;
+      for (int j = 0; j < kGroup / 3; j++) {
 #pragma unroll
-    for (int j = 0; j < kSub; j++) {
-#pragma unroll
-      for (int b = 0; b < kSubs; b++) {
-        const int g = g0 + b * NT;
-        if (g < ng) {
-          const double v = xs[g * kSub + j];
-          a1[b] += v;
-          a2[b] = __fma_rn(v, v, a2[b]);
+        for (int u = 0; u < 3; u++) {
+          const double v = x[3 * j + u];
+          a1[u] += v;
+          a2[u] = __fma_rn(v, v, a2[u]);
         }
       }
     }
-#pragma unroll
-    for (int b = 0; b < kSubs; b++) {
-      const int g = g0 + b * NT;
-      if (g <= ng) {
-        gp1[g] = a1[b];
-        gp2[g] = a2[b];
-      }
-    }
+    gs1[g] = (a1[0] + a1[1]) + a1[2];
+    gs2[g] = (a2[0] + a2[1]) + a2[2];
   }
-  __syncthreads();
+  __syncthreads();  // (2) group sums and guard bands ready
   STREAM_T(c3);
-  // ---- exclusive prefix over the groups, in place (blocked: thread t owns elements [t*E, (t+1)*E))
-  {
-    const int E = (ng + 1 + NT - 1) / NT;
-    const int e0 = min(tid * E, ng + 1), e1 = min(e0 + E, ng + 1);
-    double t1 = 0.0, t2 = 0.0;
-    for (int e = e0; e < e1; e++) {
-      t1 += gp1[e];
-      t2 += gp2[e];
+
+  // ---- warp-local from here on
+  const int w0 = tid * kGroup;
+  unsigned my_gate = 0;
+  if (warp * 32 * kGroup < nwin) {  // (warp-uniform) the warp holds at least one window
+    const int qa = m / kGroup, qb = m - qa * kGroup;
+    const int gw = 32 * warp;  // the warp's first chain = group index
+    // window sums of the warp's first chain: W(gw) = sum_{k < qa} gs[gw + k]
+    double W1 = 0.0, W2 = 0.0;
+    for (int k = lane; k < qa; k += 32) {
+      W1 += gs1[gw + k];
+      W2 += gs2[gw + k];
     }
-    double i1 = t1, i2 = t2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      W1 += __shfl_xor_sync(kFullMask, W1, o);
+      W2 += __shfl_xor_sync(kFullMask, W2, o);
+    }
+    // chain g = tid: W(g) - W(gw) = sum_{gw <= k < g} (gs[k + qa] - gs[k])
+    const int g = tid;
+    const double so = gs1[g], go = gs2[g];               // sum / sum of squares of the chain's outgoing samples
+    const double r1a = gs1[g + qa], r2a = gs2[g + qa];
+    const double r1b = qb ? gs1[g + qa + 1] : 0.0, r2b = qb ? gs2[g + qa + 1] : 0.0;
+    const double d1 = r1a - so, d2 = r2a - go;
+    double i1 = d1, i2 = d2;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const double u1 = __shfl_up_sync(kFullMask, i1, o), u2 = __shfl_up_sync(kFullMask, i2, o);
@@ -430,118 +468,104 @@ __global__ void __launch_bounds__(NT, NT <= 192 ? 3 : (NT <= 256 ? 2 : 1)) cnsm_
         i2 += u2;
       }
     }
-    if (lane == 31) {
-      s_w1[warp] = i1;
-      s_w2[warp] = i2;
-    }
-    __syncthreads();
-    double b1 = i1 - t1, b2 = i2 - t2;  // exclusive within the warp
-    for (int w = 0; w < warp; w++) {
-      b1 += s_w1[w];
-      b2 += s_w2[w];
-    }
-    for (int e = e0; e < e1; e++) {
-      const double v1 = gp1[e], v2 = gp2[e];
-      gp1[e] = b1;
-      gp2[e] = b2;
-      b1 += v1;
-      b2 += v2;
-    }
-  }
-  __syncthreads();
-  STREAM_T(c4);
-
-  // ---- this thread's 33 consecutive windows = three chains of 11.  A chain's first window takes its sums from two
-  // prefix entries (+ m % 11 samples); the sums then slide branch-free (one dependent DADD / DFMA per window and chain)
-  // while a bit records the windows inside the outer mean band; the rare chains with a bit set are replayed (same
-  // operations, same values) window by window through stream_window().
-  const int w0 = tid * kGroup;
-  unsigned my_gate = 0;
-  const int qa = m / kSub, qb = m - qa * kSub;
-  double ex[kSubs], ex2[kSubs];
-#pragma unroll
-  for (int b = 0; b < kSubs; b++) ex[b] = ex2[b] = 0.0;
-  const bool active = w0 < nwin;
-  if (active) {
-#pragma unroll
-    for (int b = 0; b < kSubs; b++) {
-      const int g = kSubs * tid + b;
-      ex[b] = gp1[g + qa] - gp1[g];
-      ex2[b] = gp2[g + qa] - gp2[g];
-    }
-    for (int j = 0; j < qb; j++) {
-#pragma unroll
-      for (int b = 0; b < kSubs; b++) {
-        const double v = xs[(kSubs * tid + b + qa) * kSub + j];
-        ex[b] += v;
-        ex2[b] = __fma_rn(v, v, ex2[b]);
+    double ex = W1 + (i1 - d1), ex2 = W2 + (i2 - d2);
+    {
+      const double* __restrict__ x = xs + (g + qa) * kGroup;
+      for (int j = 0; j < qb; j++) {
+        const double v = x[j];
+        ex += v;
+        ex2 = __fma_rn(v, v, ex2);
       }
     }
-  }
-  __syncthreads();  // every thread has read its prefix entries: the arrays now hold the second-tier queue
-  STREAM_T(c5);
-  StreamQueue Q;
-  Q.count = &s_qcount;
-  Q.ex = gp1;
-  Q.ex2 = gp2;
-  Q.cap = (int)((ng_cap * 2) / 3);
-  Q.w = reinterpret_cast<int*>(gp2 + Q.cap);  // the last third of gp2 holds the 4-byte indices
-  if (active) {
-    const int nw = min(kGroup, nwin - w0);
-    const double* __restrict__ xo = xs + w0;
-    const double* __restrict__ xi = xs + w0 + m;
-    // Outer mean band as an integer test (DSETP issues at a fraction of the DADD rate on sm_100): |ex - mid| <= rad,
-    // compared on the high words — monotone, so it can only admit more windows than the exact test, which
-    // stream_window() repeats in double precision.
-    const double e_mid = 0.5 * (s_gate.e_lo_out + s_gate.e_hi_out);
-    const double e_rad = 0.5 * (s_gate.e_hi_out - s_gate.e_lo_out) * (1.0 + 1e-15) + 1e-300;
-    const int r_hi = (e_rad >= 0.0) ? __double2hiint(e_rad) : -1;
-    double ex_s[kSubs], ex2_s[kSubs];
-    unsigned mask[kSubs];
-#pragma unroll
-    for (int b = 0; b < kSubs; b++) {
-      ex_s[b] = ex[b];
-      ex2_s[b] = ex2[b];
-      mask[b] = 0u;
+    const int nw = max(0, min(kGroup, nwin - w0));
+    const StreamGate& G = s_gate;
+    // Chain-level skip.  Along the chain's 32 slide steps, with y = x - c centred on the first window's own mean
+    // c = ex/m (t2 = m*ex2 - ex^2 does not depend on c, and ex_y starts at 0):
+    //   ex2_y moves within [-Gout, +Gin]   (Gout / Gin = sum of y^2 over the outgoing / incoming samples, from the
+    //                                        group sums: G - c*(2S - n*c), n = 33 outgoing, 33 or 66 incoming)
+    //   |ex_y| <= sum|y_in| + sum|y_out| <= T, T^2 <= 2*(n_in*Gin + 33*Gout)         (Cauchy-Schwarz)
+    // so t2 stays within [t2 - m*Gout - T^2, t2 + m*Gin] and ex within ex -+ T.  If those ranges miss the outer
+    // variance band or the outer mean band, none of the chain's windows can be inside both: the chain is not slid.
+    // (errG covers the cancellation in G - c*(2S - n*c): 2|c S| <= n c^2 + G.)
+    bool need;
+    {
+      const double e_mid = 0.5 * (G.e_lo_out + G.e_hi_out), e_rad = 0.5 * (G.e_hi_out - G.e_lo_out);
+      const double n_in = qb ? 66.0 : 33.0;
+      const double si = r1a + r1b, gi = r2a + r2b;
+      const double c = ex * P.inv_m;
+      const double errG = 64.0 * 1.1102230246251565e-16 * (gi + go + 99.0 * c * c);
+      const double Gin = fmax(gi - c * (2.0 * si - n_in * c), 0.0) + errG;
+      const double Gout = fmax(go - c * (2.0 * so - 33.0 * c), 0.0) + errG;
+      const double T2 = 2.0 * (n_in * Gin + 33.0 * Gout) * (1.0 + 1e-12);
+      const double t2v = __fma_rn(P.dm, ex2, -__dmul_rn(ex, ex));
+      const double dmean = fabs(ex - e_mid) - e_rad;
+      const bool skip_mean = dmean > 0.0 && dmean * dmean > T2;
+      const bool skip_var = (t2v + P.dm * Gin * (1.0 + 1e-12) < G.v_lo_out) || (t2v - (P.dm * Gout + T2) * (1.0 + 1e-12) > G.v_hi_out);
+      need = !(skip_mean || skip_var) && nw > 0;
     }
+    STREAM_T(c4);
+    STREAM_COUNT(10, need ? 1 : 0);  // chains that could not be skipped
+    if (__any_sync(kFullMask, need)) {
+      STREAM_COUNT(9, lane == 0 ? 1 : 0);  // warps that slide
+      WarpQueue Q;
+      Q.ex = q_ex + warp * kQ1Cap;
+      Q.ex2 = q_ex2 + warp * kQ1Cap;
+      Q.w = q_w + warp * kQ1Cap;
+      const double* __restrict__ xo = xs + w0;
+      const double* __restrict__ xi = xs + w0 + m;
+      // Hot-loop test: the outer variance band only, on the high word of t2 = m*ex2 - ex^2 as a signed integer range
+      // (for t2 >= 0 the high words order like the values; a band that reaches down to 0 or below admits every
+      // negative t2).  DSETP issues at a fraction of the DADD rate on sm_100, and the mean band is already enforced
+      // per chain by the skip test; stream_candidate() repeats both tests exactly.
+      int kv_lo = (G.v_lo_out > 0.0) ? __double2hiint(G.v_lo_out) : (int)0x80000000;
+      const int kv_hi = (G.v_hi_out >= 0.0) ? __double2hiint(G.v_hi_out) : -1;
+      if (!(G.v_hi_out >= 0.0)) kv_lo = 0x7fffffff;  // empty band
+      const double dmv = P.dm;
+      // slide: branch-free, one dependent DADD / DFMA per window; bit j = window j inside the band
+      unsigned long long mk = 0ULL;
+      {
+        double e1 = ex, e2 = ex2;
 #pragma unroll
-    for (int j = 0; j < kSub; j++) {
-#pragma unroll
-      for (int b = 0; b < kSubs; b++) {
-        const double a = xi[b * kSub + j], o = xo[b * kSub + j];
-        mask[b] |= ((__double2hiint(ex[b] - e_mid) & 0x7fffffff) <= r_hi) ? (1u << j) : 0u;
-        const double dl = a - o, sm = a + o;
-        ex[b] += dl;
-        ex2[b] = __fma_rn(dl, sm, ex2[b]);
+        for (int j = 0; j < kGroup; j++) {
+          const double a = xi[j], o = xo[j];
+          const int h = __double2hiint(__fma_rn(dmv, e2, -__dmul_rn(e1, e1)));
+          mk |= (h >= kv_lo && h <= kv_hi) ? (1ULL << j) : 0ULL;
+          const double dl = a - o, sm = a + o;
+          e1 += dl;
+          e2 = __fma_rn(dl, sm, e2);
+        }
       }
-    }
-#pragma unroll
-    for (int b = 0; b < kSubs; b++) {
-      const int left = nw - b * kSub;  // valid windows of this chain
-      unsigned mk = mask[b];
-      if (left < kSub) mk &= (left > 0) ? ((1u << left) - 1u) : 0u;
-      if (mk) {
-        double rex = ex_s[b], rex2 = ex2_s[b];
-        const int kb = b * kSub;
-        for (int j = 0; (mk >> j) != 0u; j++) {
-          if ((mk >> j) & 1u)
-            my_gate += stream_window<kMode>(P, tile, xo + kb + j, w0 + kb + j, rex, rex2, scr_i, scr_a, scr_b, Q, s_gate, s_thr);
-          const double av = xi[kb + j], ov = xo[kb + j];
+      if (!need) mk = 0ULL;
+      if (nw < kGroup) mk &= (1ULL << nw) - 1ULL;
+      STREAM_COUNT(11, __popcll(mk));  // candidates (hot-loop bits)
+      const unsigned any_lo = __reduce_or_sync(kFullMask, (unsigned)mk), any_hi = __reduce_or_sync(kFullMask, (unsigned)(mk >> 32));
+      const unsigned long long all = ((unsigned long long)any_hi << 32) | any_lo;
+      if (all != 0ULL) {
+        // replay (same operations, same values) step by step, each step pushing its candidates into the queue
+        int n1 = 0;
+        double rex = ex, rex2 = ex2;
+        for (int j = 0; (all >> j) != 0ULL; j++) {
+          const bool hit = (mk >> j) & 1ULL;
+          const unsigned bal = __ballot_sync(kFullMask, hit);
+          if (hit) {
+            const int slot = n1 + __popc(bal & ((1u << lane) - 1u));
+            Q.w[slot] = w0 + j;
+            Q.ex[slot] = rex;
+            Q.ex2[slot] = rex2;
+          }
+          n1 += __popc(bal);
+          const double av = xi[j], ov = xo[j];
           const double dl = av - ov, sm = av + ov;
           rex += dl;
           rex2 = __fma_rn(dl, sm, rex2);
+          __syncwarp();
+          if (n1 >= kQ1Drain) n1 = stream_drain<kMode>(P, tile, xs, Q, n1, lane, G, s_thr, my_gate);
         }
+        while (n1 > 0) n1 = stream_drain<kMode>(P, tile, xs, Q, n1, lane, G, s_thr, my_gate);
       }
     }
   }
-  // ---- second tier of the bound for the queued windows, one warp each
-  STREAM_T(c6);
-  __syncthreads();
-  STREAM_T(c7);
-  {
-    const int nq = min(s_qcount, Q.cap);
-    for (int e = warp; e < nq; e += NT / 32) my_gate += stream_tier2<kMode>(P, tile, xs, Q.w[e], Q.ex[e], Q.ex2[e], lane, s_thr);
-  }
+  STREAM_T(c5);
   // ---- certain gate passes
   unsigned tot = my_gate;
 #pragma unroll
@@ -549,8 +573,8 @@ __global__ void __launch_bounds__(NT, NT <= 192 ? 3 : (NT <= 256 ? 2 : 1)) cnsm_
   if (lane == 0 && tot) atomicAdd(P.gate_pass, (unsigned long long)tot);
 #ifdef KVM_STREAM_PROF
   if (tid == 0) {
-    const long long c8 = stream_clock();
-    const long long d[9] = {c1 - c0, c2 - c1, c3 - c2, c4 - c3, c5 - c4, c6 - c5, c7 - c6, c8 - c7, 1};
+    const long long c6 = stream_clock();
+    const long long d[9] = {c1 - c0, c2 - c1, c3 - c2, 0, 0, c5 - c3, c6 - c5, 0, 1};
     for (int i = 0; i < 9; i++) atomicAdd(&g_stream_prof[i], (unsigned long long)d[i]);
   }
 #endif
