@@ -42,7 +42,7 @@ EPSILON = 5.0            # middle of the reference's cNSM grid {1,5,10} (NormQue
 N_PER_GPU = 100_000_000
 N_QUERIES = 10           # seeded query offsets, cycled over the steps
 SEED = datagen.DEFAULT_SEED
-DEFAULT_CHUNK = 6144     # candidates per statistic chain (see DESIGN.md 4.2 "chain chunking")
+DEFAULT_CHUNK = 1024     # candidates per statistic chain (see DESIGN.md "chain chunking")
 
 
 def load_peaks():

@@ -798,6 +798,7 @@ struct ExactEdParams {
   double meanQ, stdQ, alpha, inv_alpha, beta;
   unsigned long long* gate_pass;
   int win_cap;  // doubles of per-warp window staging behind the term buffer (0 = none)
+  int q_cap;    // doubles (and ints) of the per-CTA staging of zQ / order (0 = none)
 };
 
 constexpr int kExactChunk = 1024;  // terms staged in shared memory per pass (8 KB per warp)
@@ -810,15 +811,30 @@ template <bool kFromSums>
 __global__ void __launch_bounds__(128) cnsm_ed_exact_kernel(ExactEdParams P) {
   extern __shared__ double exact_terms[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  // per warp: kExactChunk per-term values, then (win_cap >= m) the window itself, staged with coalesced loads so that
-  // the |zQ|-ordered gathers below hit shared memory instead of paying a DRAM round trip per dependent batch
-  double* term = exact_terms + (size_t)warp * (kExactChunk + P.win_cap);
-  double* win = term + kExactChunk;
-  const bool staged = P.win_cap >= P.m;
   unsigned long long n = kFromSums ? *P.xin.count : *P.in.count;
   const long long cap = kFromSums ? P.xin.cap : P.in.cap;
   if ((long long)n > cap) n = (unsigned long long)cap;
+  if ((unsigned long long)blockIdx.x * n_warps >= n) return;  // (CTA-uniform) nothing for this CTA
   const int m = P.m;
+  // Shared memory: [q_cap doubles zQ | q_cap ints order] once per CTA (q_cap >= m: the |zQ|-ordered query, staged so
+  // that the dependent order -> sample gathers never leave the SM), then per warp kExactChunk per-term values and
+  // (win_cap >= m) the window itself, staged with coalesced loads.
+  double* zq_s = exact_terms;
+  int32_t* ord_s = reinterpret_cast<int32_t*>(exact_terms + P.q_cap);
+  double* warp_base = exact_terms + P.q_cap + (P.q_cap + 1) / 2;
+  double* term = warp_base + (size_t)warp * (kExactChunk + P.win_cap);
+  double* win = term + kExactChunk;
+  const bool staged = P.win_cap >= m;
+  const bool q_staged = P.q_cap >= m;
+  if (q_staged) {
+    for (int k = threadIdx.x; k < m; k += blockDim.x) {
+      zq_s[k] = __ldg(P.zq + k);
+      ord_s[k] = __ldg(P.order + k);
+    }
+    __syncthreads();
+  }
+  const double* __restrict__ zq = q_staged ? zq_s : P.zq;
+  const int32_t* __restrict__ order = q_staged ? ord_s : P.order;
   for (unsigned long long e = (unsigned long long)blockIdx.x * n_warps + warp; e < n;
        e += (unsigned long long)gridDim.x * n_warps) {
     int32_t off;
@@ -834,31 +850,48 @@ __global__ void __launch_bounds__(128) cnsm_ed_exact_kernel(ExactEdParams P) {
       stdv = P.in.stdv[e];
     }
     const double* __restrict__ wg = P.T + (off - P.first_global);
+    const double rstd = 1.0 / stdv;  // x = (w - mean) * rstd: the error does not grow with |mean| / std
+    // Tier 2a: the 128 largest-|zQ| terms straight from global memory (fast FMA arithmetic): most entries end here,
+    // before their window is staged.
+    {
+      double part = 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int k = u * 32 + lane;
+        if (k < m) {
+          const double df = (wg[order[k]] - mean) * rstd - zq[k];
+          part = __fma_rn(df, df, part);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFullMask, part, o);
+      if (!(part <= P.eps2_hi)) continue;
+    }
     if (staged) {
       __syncwarp();
-      for (int k = lane; k < m; k += 32) win[k] = wg[k];
+      for (int k0 = 0; k0 < m; k0 += 256) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = (k0 + u * 32 + lane < m) ? wg[k0 + u * 32 + lane] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          if (k0 + u * 32 + lane < m) win[k0 + u * 32 + lane] = v[u];
+      }
       __syncwarp();
     }
     const double* w = staged ? win : wg;
-    // Tier 2: warp-cooperative fast distance (FMA, reciprocal) over all m terms, 128 terms per round in |zQ|
-    // order, abandoned as soon as the partial sum exceeds eps^2*(1+1e-9).  Only windows that survive every
-    // round reach the reference-order summation below.
+    // Tier 2b: warp-cooperative fast distance over all m terms, 256 terms per round in |zQ| order, abandoned as soon
+    // as the partial sum exceeds eps^2*(1+1e-9).  Only windows that survive every round reach the reference-order
+    // summation below.
     {
-      const double rstd = 1.0 / stdv;  // x = (w - mean) * rstd: the error does not grow with |mean| / std
       double part = 0.0;
       bool over = false;
-      for (int k0 = 0; k0 < m && !over; k0 += 128) {
-        double wv[4];
+      for (int k0 = 0; k0 < m && !over; k0 += 256) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int k = k0 + u * 32 + lane;
-          wv[u] = (k < m) ? w[__ldg(P.order + k)] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 8; u++) {
           const int k = k0 + u * 32 + lane;
           if (k < m) {
-            const double df = (wv[u] - mean) * rstd - __ldg(P.zq + k);
+            const double df = (w[order[k]] - mean) * rstd - zq[k];
             part = __fma_rn(df, df, part);
           }
         }
@@ -870,37 +903,39 @@ __global__ void __launch_bounds__(128) cnsm_ed_exact_kernel(ExactEdParams P) {
       if (over) continue;
     }
     if (lane == 0) atomicAdd(P.n_exact, 1ULL);
+    // Tier 3: K/NormQueryEngine.java:513-520 verbatim arithmetic, x = (T[order[k]+j]-mean)/std; dist += (x-zQ[k])^2:
+    // all lanes compute the per-term values (each rounded exactly as the reference's), lane 0 adds them in the
+    // reference's order.
     double dist = 0.0;
     bool alive = true;
     for (int k0 = 0; k0 < m && alive; k0 += kExactChunk) {
       const int kc = min(kExactChunk, m - k0);
       __syncwarp();
-      // independent scattered loads, 8 in flight per lane
       for (int kb = 0; kb < kc; kb += 256) {
         double wv[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
           const int k = kb + u * 32 + lane;
-          wv[u] = (k < kc) ? w[__ldg(P.order + k0 + k)] : 0.0;
+          wv[u] = (k < kc) ? w[order[k0 + k]] : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
           const int k = kb + u * 32 + lane;
-          if (k < kc) term[k] = xsqdist(xdiv(xsub(wv[u], mean), stdv), __ldg(P.zq + k0 + k));
+          if (k < kc) term[k] = xsqdist(xdiv(xsub(wv[u], mean), stdv), zq[k0 + k]);
         }
       }
       __syncwarp();
       if (lane == 0) {
+        // The reference leaves its loop at the first partial sum above eps^2 (:516); the terms are non-negative, so
+        // testing once per chunk accepts the same windows with the same sums, and the additions form one dependent
+        // chain with every load hoisted out of it.
         int k = 0;
-        for (; k + 8 <= kc && alive; k += 8) {
+        for (; k + 32 <= kc; k += 32) {
 #pragma unroll
-          for (int u = 0; u < 8; u++) dist = xadd(dist, term[k + u]);
-          alive = dist <= P.eps2;
+          for (int u = 0; u < 32; u++) dist = xadd(dist, term[k + u]);
         }
-        if (alive) {
-          for (; k < kc; k++) dist = xadd(dist, term[k]);
-          alive = dist <= P.eps2;
-        }
+        for (; k < kc; k++) dist = xadd(dist, term[k]);
+        alive = dist <= P.eps2;
       }
       alive = __shfl_sync(kFullMask, alive, 0);
     }

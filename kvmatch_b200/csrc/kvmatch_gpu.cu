@@ -120,6 +120,7 @@ struct StreamPlan {
   int K = 0, shift = 0, m = 0, nt = 0;
   int n_chains = 0, n_tiles = 0;
   int n_segments = 0, s_base = 0;
+  int regular = 0, chunk = 0;  // one segment cut into chains of `chunk` windows (the last one may be shorter)
   int64_t V = 0, S = 0, cnt_candidate = 0, l_max = 0;
   size_t o_tiles = 0, o_cb = 0, o_nc = 0, o_vb = 0, bytes = 0;
 };
@@ -746,6 +747,7 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
       X.sink = sink_of(ctx);
       X.win_cap = 0;
       X.win_cap = 0;
+    X.q_cap = 0;
     cnsm_ed_exact_kernel<false><<<ctx->n_sms * 6, 128, sizeof(double) * kExactChunk * 4, ctx->stream>>>(X);
       launches += 2;
     } else {
@@ -885,6 +887,22 @@ int set_stream_attrs() {
   return e == cudaSuccess ? 0 : 1;
 }
 
+// 0 when intervals 1..K-1 each start right after their predecessor and hold c0 window starts (the last one: 1..c0).
+// Written on the (left, right) pairs as 64-bit words so that the loop vectorises.
+__attribute__((target_clones("avx2", "default"))) int regular_grid_pass(const int32_t* __restrict__ lr, int K, int32_t c0) {
+  unsigned bad = 0;
+  for (int p = 1; p < K - 1; p++) {
+    const uint32_t left = (uint32_t)lr[2 * p], right = (uint32_t)lr[2 * p + 1], prev = (uint32_t)lr[2 * p - 1];
+    bad |= (left - prev - 1u) | (right - left - (uint32_t)(c0 - 1));
+  }
+  if (K > 1) {
+    const int64_t left = lr[2 * K - 2], right = lr[2 * K - 1], prev = lr[2 * K - 3];
+    const int64_t c = right - left + 1;
+    bad |= (unsigned)((left != prev + 1) | (c < 1) | (c > c0));
+  }
+  return bad != 0;
+}
+
 // Build (or reuse) the stream plan for this interval list: [tiles | cbegin | ncand | vbase] in ctx->sarena.
 int stream_plan(kvm_ctx* ctx, const int32_t* lr, int K, int shift, int m, int nt, bool cache_on) {
   StreamPlan& SP = ctx->splan;
@@ -892,13 +910,47 @@ int stream_plan(kvm_ctx* ctx, const int32_t* lr, int K, int shift, int m, int nt
       std::memcmp(SP.lr.data(), lr, sizeof(int32_t) * 2 * (size_t)K) == 0)
     return KVM_OK;
   SP.valid = false;
+  const int W = kvm::kGroup * nt;
+  // Regular grid (an index-free scan: adjacent intervals of one length, the last one possibly shorter, nothing clamped):
+  // recognised in one vectorisable pass over the caller's list; needs no per-chain tables on either side.
+  if (K >= 1) {
+    const int64_t c0 = (int64_t)lr[1] - lr[0] + 1;
+    int bad = (c0 < 1) | (c0 > INT32_MAX / 2);
+    if (!bad) bad = regular_grid_pass(lr, K, (int32_t)c0);
+    const int64_t first_begin = (int64_t)lr[0] - shift, last_end = (int64_t)lr[2 * K - 1] - shift + m - 1;
+    const int64_t lo = ctx->first, hi = ctx->first + ctx->count - 1;
+    if (!bad && first_begin >= 1 && first_begin >= lo && last_end <= ctx->n && last_end <= hi) {
+      const int64_t V = (int64_t)lr[2 * K - 1] - lr[0] + 1;
+      SP.cnt_candidate = V;
+      SP.V = V;
+      SP.S = V + (int64_t)K * (m - 1);
+      SP.regular = 1;
+      SP.chunk = (int)c0;
+      SP.s_base = (int)(first_begin - lo);
+      SP.n_chains = K;
+      SP.n_segments = 1;
+      SP.n_tiles = (int)((V + W - 1) / W);
+      SP.l_max = c0 + m - 1;
+      SP.bytes = 0;
+      SP.K = K;
+      SP.shift = shift;
+      SP.m = m;
+      SP.nt = nt;
+      if (cache_on) {
+        SP.lr.assign(lr, lr + 2 * (size_t)K);
+        SP.valid = true;
+      }
+      return KVM_OK;
+    }
+  }
   Plan& P = ctx->plan_scratch;
   int rc = make_plan(ctx, lr, K, shift, m, &P);
   if (rc) return rc;
   SP.cnt_candidate = P.cnt_candidate;
   SP.V = P.V;
   SP.S = P.S;
-  const int W = kvm::kGroup * nt;
+  SP.regular = 0;
+  SP.chunk = 0;
   // upper bounds for the staging layout: every live chain opens at most one extra tile
   const size_t max_tiles = (size_t)(P.V / W) + (size_t)K + 2;
   auto up256 = [](size_t x) { return (x + 255) & ~size_t(255); };
@@ -967,19 +1019,28 @@ int stream_plan(kvm_ctx* ctx, const int32_t* lr, int K, int shift, int m, int nt
   return KVM_OK;
 }
 
-// Launch shape of cnsm_ed_exact_kernel: warps per CTA and the per-warp window staging that fits shared memory.
+// Launch shape of cnsm_ed_exact_kernel: warps per CTA, the per-CTA query staging and the per-warp window staging that
+// fit shared memory.
 template <bool kFromSums>
 void launch_exact(kvm_ctx* ctx, ExactEdParams& X) {
   const size_t budget = 200 * 1024;
+  auto bytes = [&](int warps) {
+    return sizeof(double) * ((size_t)X.q_cap + (X.q_cap + 1) / 2 + (size_t)warps * (kExactChunk + X.win_cap));
+  };
   int warps = 4;
   X.win_cap = (X.m + 1) & ~1;
-  while (warps > 1 && sizeof(double) * (size_t)warps * (kExactChunk + X.win_cap) > budget) warps >>= 1;
-  if (sizeof(double) * (size_t)warps * (kExactChunk + X.win_cap) > budget) {
+  X.q_cap = (X.m + 1) & ~1;
+  while (warps > 1 && bytes(warps) > budget) warps >>= 1;
+  if (bytes(warps) > budget) {
+    X.q_cap = 0;
+    warps = 4;
+    while (warps > 1 && bytes(warps) > budget) warps >>= 1;
+  }
+  if (bytes(warps) > budget) {
     warps = 4;
     X.win_cap = 0;
   }
-  const size_t smem = sizeof(double) * (size_t)warps * (kExactChunk + X.win_cap);
-  cnsm_ed_exact_kernel<kFromSums><<<ctx->n_sms * 6, warps * 32, smem, ctx->stream>>>(X);
+  cnsm_ed_exact_kernel<kFromSums><<<ctx->n_sms * 6, warps * 32, bytes(warps), ctx->stream>>>(X);
 }
 
 int ensure_xlist(kvm_ctx* ctx, long long cap) {
@@ -994,9 +1055,13 @@ int ensure_xlist(kvm_ctx* ctx, long long cap) {
 
 int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon, int rho, double alpha, double beta,
                        const int32_t* lr, int K, int shift, int nt, kvm_result* out) {
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
+  static const int timing = env_int("KVM_TIMING", 0);
   const bool cache_on = ctx->opt_plan_cache != 0;
   int rc = stream_plan(ctx, lr, K, shift, m, nt, cache_on);
   if (rc) return rc;
+  const double t_plan = since();
   const StreamPlan& SP = ctx->splan;
   out->cnt_candidate = SP.cnt_candidate;
   out->n_verified = SP.V;
@@ -1022,12 +1087,16 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
   int32_t scr_i[kvm::kScreenTerms] = {0};
   double scr_a[kvm::kScreenTerms] = {0}, scr_b[kvm::kScreenTerms] = {0};
   if (mode == Mode::kEd) {
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-      return java_double_compare(std::fabs(z[b]), std::fabs(z[a])) < 0;  // K/NormQueryEngine.java:448
+    // the first n_screen entries of the stable sort by |z| descending (ties: lower index first); the full sort (:448),
+    // which only the exact stage needs, runs on the host while the stream runs on the device
+    std::vector<int32_t> top(order);
+    std::partial_sort(top.begin(), top.begin() + n_screen, top.end(), [&](int32_t a, int32_t b) {
+      const int c = java_double_compare(std::fabs(z[b]), std::fabs(z[a]));
+      return c < 0 || (c == 0 && a < b);
     });
     for (int k = 0; k < n_screen; k++) {
-      scr_i[k] = order[k];
-      scr_a[k] = scr_b[k] = z[order[k]];
+      scr_i[k] = top[k];
+      scr_a[k] = scr_b[k] = z[top[k]];
     }
   } else {
     envelope(z, rho, lq, uq);  // K/NormQueryEngineDtw.java:469
@@ -1072,22 +1141,15 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
   KVM_CUDA(ctx, ctx->stage2.ensure(q_bytes + 256));
   KVM_CUDA(ctx, ctx->qarena.ensure(q_bytes + 256));
   unsigned char* qs = static_cast<unsigned char*>(ctx->stage2.p);
-  std::memcpy(qs + o_si, scr_i, sizeof(scr_i));
-  std::memcpy(qs + o_sa, scr_a, sizeof(scr_a));
-  std::memcpy(qs + o_sb, scr_b, sizeof(scr_b));
   const bool dtw = mode == Mode::kDtw;
-  if (dtw) {
+  if (dtw) {  // the stream's LB_KimFL reads the natural-order query: everything goes up before it
     std::memcpy(qs + o_zq, z.data(), sizeof(double) * (size_t)m);
     std::memcpy(qs + o_uq, uq.data(), sizeof(double) * (size_t)m);
     std::memcpy(qs + o_lq, lq.data(), sizeof(double) * (size_t)m);
-  } else {
-    double* zq = reinterpret_cast<double*>(qs + o_zq);
-    for (int i = 0; i < m; i++) zq[i] = z[order[i]];
-    std::memcpy(qs + o_order, order.data(), sizeof(int32_t) * (size_t)m);
+    KVM_CUDA(ctx, cudaMemcpyAsync(ctx->qarena.as<unsigned char>() + o_zq, qs + o_zq, q_bytes - o_zq, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += (long long)(q_bytes - o_zq);
   }
-  const size_t q_used = dtw ? q_bytes : o_uq;
-  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->qarena.p, ctx->stage2.p, q_used, cudaMemcpyHostToDevice, ctx->stream));
-  ctx->h2d_bytes += (long long)q_used;
+  bool sorted_up = dtw;
   const unsigned char* qbase = ctx->qarena.as<unsigned char>();
   const unsigned char* sbase = ctx->sarena.as<unsigned char>();
   unsigned long long* counters = ctx->counters.as<unsigned long long>();
@@ -1104,9 +1166,14 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
     kvm::StreamParams W{};
     W.T = ctx->series;
     W.tiles = reinterpret_cast<const kvm::StreamTile*>(sbase + SP.o_tiles);
-    W.cbegin = reinterpret_cast<const int32_t*>(sbase + SP.o_cb);
-    W.ncand = reinterpret_cast<const int32_t*>(sbase + SP.o_nc);
-    W.n_chains = SP.n_chains;
+    W.chains.cbegin = reinterpret_cast<const int32_t*>(sbase + SP.o_cb);
+    W.chains.ncand = reinterpret_cast<const int32_t*>(sbase + SP.o_nc);
+    W.chains.vbase = reinterpret_cast<const int32_t*>(sbase + SP.o_vb);
+    W.chains.n_chains = SP.n_chains;
+    W.chains.regular = SP.regular;
+    W.chains.s_base = SP.s_base;
+    W.chains.chunk = SP.chunk;
+    W.chains.total_win = (int32_t)SP.V;
     W.m = m;
     W.dm = (double)m;
     W.inv_m = 1.0 / (double)m;
@@ -1115,7 +1182,6 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
     W.bmax = ctx->bmax.as<double>();
     W.n_bmax = (int)ctx->n_bmax;
     W.l_max = (int)SP.l_max;
-    W.vbase = reinterpret_cast<const int32_t*>(sbase + SP.o_vb);
     W.uniform = SP.n_segments == 1 ? 1 : 0;  // one run of adjacent window starts: tiles follow from the CTA index
     W.s_base = SP.s_base;
     W.total_win = (int32_t)SP.V;
@@ -1153,8 +1219,7 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
     KVM_CUDA(ctx, cudaEventRecord(ctx->evs[0], ctx->stream));
     kvm::RewalkParams R{};
     R.T = ctx->series;
-    R.cbegin = W.cbegin;
-    R.vbase = reinterpret_cast<const int32_t*>(sbase + SP.o_vb);
+    R.chains = W.chains;
     R.m = m;
     R.first_global = (int32_t)ctx->first;
     R.need_bits = W.need_bits;
@@ -1166,6 +1231,17 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
     KVM_CUDA(ctx, cudaGetLastError());
     KVM_CUDA(ctx, cudaEventRecord(ctx->evs[1], ctx->stream));
     launches += 2;
+    if (!sorted_up) {  // cNSM-ED: the full |z| ordering for the exact stage, while the stream and the re-walk run
+      std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        return java_double_compare(std::fabs(z[b]), std::fabs(z[a])) < 0;  // K/NormQueryEngine.java:448
+      });
+      double* zq = reinterpret_cast<double*>(qs + o_zq);
+      for (int i = 0; i < m; i++) zq[i] = z[order[i]];
+      std::memcpy(qs + o_order, order.data(), sizeof(int32_t) * (size_t)m);
+      KVM_CUDA(ctx, cudaMemcpyAsync(ctx->qarena.as<unsigned char>() + o_zq, qs + o_zq, o_uq - o_zq, cudaMemcpyHostToDevice, ctx->stream));
+      ctx->h2d_bytes += (long long)(o_uq - o_zq);
+      sorted_up = true;
+    }
     if (!dtw) {
       ExactEdParams X{};
       X.T = ctx->series;
@@ -1221,7 +1297,9 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
     }
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     KVM_CUDA(ctx, cudaGetLastError());
+    const double t_launched = since();
     if ((rc = read_counters(ctx, cnt))) return rc;
+    if (timing) std::fprintf(stderr, "[kvm stream] plan %.0f us, launched %.0f, synced %.0f (K %d, regular %d)\n", t_plan, t_launched, since(), K, SP.regular);
     total_ms += elapsed_ms(ctx);
     {
       float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
@@ -1754,6 +1832,7 @@ int kvm_verify_cnsm_ed_batch(kvm_ctx* ctx, const double* queries, int32_t n_quer
     X.in = E.out;
     X.sink = sink_of(ctx);
     X.win_cap = 0;
+    X.q_cap = 0;
     cnsm_ed_exact_kernel<false><<<ctx->n_sms * 6, 128, sizeof(double) * kExactChunk * 4, ctx->stream>>>(X);
     KVM_CUDA(ctx, cudaGetLastError());
     outs[q].n_launches += 2;

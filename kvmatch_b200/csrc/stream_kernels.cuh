@@ -92,13 +92,33 @@ __host__ __device__ inline void stream_guard_eval(const GuardCoef& C, double A, 
 
 constexpr int kBmaxBlock = 1024;  // samples per entry of the block-maximum table
 
+// Geometry of the live chains (merged intervals with at least one window).  A regular grid — one run of adjacent
+// window starts cut every `chunk` (an index-free scan) — needs no tables: everything follows from the chain index.
+struct ChainTable {
+  const int32_t* __restrict__ cbegin;  // local index of the chain's first sample
+  const int32_t* __restrict__ ncand;   // window starts
+  const int32_t* __restrict__ vbase;   // ordinal of the chain's first window over all live chains (list order)
+  int n_chains;
+  int regular;
+  int32_t s_base, chunk, total_win;    // regular grids only
+  __device__ __forceinline__ int begin(int p) const { return regular ? s_base + p * chunk : __ldg(cbegin + p); }
+  __device__ __forceinline__ int count(int p) const { return regular ? min(chunk, total_win - p * chunk) : __ldg(ncand + p); }
+  __device__ __forceinline__ int ordinal(int p) const { return regular ? p * chunk : __ldg(vbase + p); }
+  __device__ __forceinline__ int chain_of(unsigned v) const {  // largest p with ordinal(p) <= v
+    if (regular) return (int)(v / (unsigned)chunk);
+    int lo = 0, hi = n_chains;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((unsigned)__ldg(vbase + mid) <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+  }
+};
+
 struct StreamParams {
   const double* __restrict__ T;
   const StreamTile* __restrict__ tiles;
-  const int32_t* __restrict__ cbegin;  // live chains: local index of the first sample
-  const int32_t* __restrict__ ncand;   //              window starts
-  const int32_t* __restrict__ vbase;   //              ordinal of the first window
-  int n_chains;
+  ChainTable chains;
   int m;
   double dm, inv_m, inv_m2;
   GuardCoef C;
@@ -166,7 +186,7 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-constexpr int kQ1Cap = 40, kQ1Drain = 8;  // candidate queue per warp: drained (32 at a time) once it holds 8
+constexpr int kQ1Cap = 64, kQ1Drain = 32;  // candidate queue per warp: drained 32 at a time (full lanes) as soon as it holds 32
 
 constexpr size_t stream_xs_doubles(int nt, int m) { return ((size_t)kGroup * nt + m + 42) & ~size_t(1); }
 constexpr size_t stream_gs_doubles(int nt, int m) { return ((size_t)nt + (m + kGroup - 1) / kGroup + 8) & ~size_t(1); }
@@ -176,24 +196,16 @@ constexpr size_t stream_smem_bytes(int nt, int m) {
 }
 
 // Flag the window that starts at local sample s (ordinal v).  p = a live chain at or before its chain, or -1 when the
-// tile was computed arithmetically: then the chain is found by bisection over the chains' first ordinals (rare path;
-// arguments by value so that the kernel's parameter block never needs an address).
-__device__ __noinline__ void stream_flag(const int32_t* __restrict__ cbegin, const int32_t* __restrict__ ncand,
-                                         const int32_t* __restrict__ vbase, int n_chains, unsigned* need_bits,
-                                         int32_t* chain_last, int32_t* flagged, unsigned long long* n_flagged,
-                                         unsigned long long* n_need, int s, int p, unsigned v) {
+// tile was computed arithmetically (then the chain follows from the ordinal).  Rare path.
+__device__ __noinline__ void stream_flag(const ChainTable C, unsigned* need_bits, int32_t* chain_last, int32_t* flagged,
+                                         unsigned long long* n_flagged, unsigned long long* n_need, int s, int p, unsigned v) {
   if (p < 0) {
-    int lo = 0, hi = n_chains;  // largest p with vbase[p] <= v
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if ((unsigned)__ldg(vbase + mid) <= v) lo = mid; else hi = mid;
-    }
-    p = lo;
+    p = C.chain_of(v);
   } else {
-    while (s >= __ldg(cbegin + p) + __ldg(ncand + p)) p++;  // chains of one segment are consecutive
+    while (s >= C.begin(p) + C.count(p)) p++;  // chains of one segment are consecutive
   }
   atomicOr(need_bits + (v >> 5), 1u << (v & 31));
-  const int old = atomicMax(chain_last + p, s - __ldg(cbegin + p));
+  const int old = atomicMax(chain_last + p, s - C.begin(p));
   if (old < 0) {
     const unsigned long long slot = atomicAdd(n_flagged, 1ULL);
     flagged[slot] = p;
@@ -279,8 +291,8 @@ __device__ __forceinline__ unsigned stream_candidate(const StreamParams& P, cons
     }
   }
   if (!survive && sure) return 1u;
-  stream_flag(P.cbegin, P.ncand, P.vbase, P.n_chains, P.need_bits, P.chain_last, P.flagged, P.n_flagged, P.n_need, tile.s0 + w,
-              tile.chain, (unsigned)(tile.v0 + w));
+  stream_flag(P.chains, P.need_bits, P.chain_last, P.flagged, P.n_flagged, P.n_need, tile.s0 + w, tile.chain,
+              (unsigned)(tile.v0 + w));
   return 0u;
 }
 
@@ -583,8 +595,7 @@ __global__ void __launch_bounds__(NT, NT <= 192 ? 3 : (NT <= 256 ? 2 : 1)) cnsm_
 // ---------------------------------------------------------------------------------------------------------------
 struct RewalkParams {
   const double* __restrict__ T;
-  const int32_t* __restrict__ cbegin;
-  const int32_t* __restrict__ vbase;  // live chains: ordinal of the chain's first window
+  ChainTable chains;
   int m;
   int32_t first_global;
   unsigned* need_bits;
@@ -616,9 +627,9 @@ __global__ void __launch_bounds__(32) chain_rewalk_kernel(RewalkParams P) {
   const unsigned long long n = *P.n_flagged;
   for (unsigned long long ci = blockIdx.x; ci < n; ci += gridDim.x) {
     const int p = P.flagged[ci];
-    const int cb = P.cbegin[p];
+    const int cb = P.chains.begin(p);
     const int last = P.chain_last[p];
-    const int vb = P.vbase[p];
+    const int vb = P.chains.ordinal(p);
     __syncwarp();
     if (lane == 0) P.chain_last[p] = -1;  // ready for the next call
     const int qend = (m - 1) + last;       // last sample position (0-based within the chain) the walk consumes
