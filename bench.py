@@ -1,19 +1,22 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native KV-match phase-2 path.
 
-A "step" is one cNSM-ED verification pass (BASELINE.json configs[1]: NormQueryEngine, query length 1024,
-alpha=1.5, beta=5) of one query over every window start of a DataGenerator-style synthetic series, index-free:
-the merged-interval list handed to the C ABI is [1, n-m+1] cut into statistic chains of --chunk candidates
-(<= 100000-m+1, the reference's own epoch chunking, K/experiments/ucr/UcrDtwQueryExecutor.java:97).
+A "step" is one cNSM-ED verification query (BASELINE.json: NormQueryEngine, query length 1024, alpha=1.5, beta=5,
+epsilon=5) over EVERY window start of ONE DataGenerator-style synthetic series of n = 1e9 samples (the size
+BASELINE.json's metric quotes its latency on; 8 GB, fits one B200), index-free: the merged-interval list handed to
+the C ABI is [1, n-m+1] cut into statistic chains of --chunk candidates (<= 100000-m+1, the reference's own epoch
+chunking, K/experiments/ucr/UcrDtwQueryExecutor.java:97).
 
   python bench.py --gpus N --steps K --warmup W              # ours (one process per GPU under torchrun for N>1)
   python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU loops (oracle port), rank 0 only
 
-N GPUs: weak scaling — every rank holds its own n_per_gpu samples (+ m-1 halo) of one global series of length
-N*n_per_gpu and verifies its own window starts; the only exchange is the tail (counts, sparse answers, best
-match) over torch.distributed/NCCL.  `value` = window starts verified by all ranks / max-over-ranks device time
-of the K timed steps (CUDA events on the library's stream, series resident in HBM).  `e2e` = the same through
-the C ABI call with host buffers (query + interval list copied in, answers copied out, every step).
+N GPUs: STRONG scaling — the same series sharded by offset range (rank r holds its 1/N of the window starts plus an
+m-1 halo; chains are never split); every step ends with the multi-GPU tail inside the timed region: ONE packed
+all_gather (count, counters, best match, the first 512 answers of every rank; kvmatch_b200/sharding.PackedMerger).
+`value` = window starts verified by all ranks / max-over-ranks device time of the K timed steps (the library's CUDA
+events per kernel stage + CUDA events around the exchange; series resident in HBM).  `e2e` = the same through the C
+ABI with host buffers (query + interval list in, answers out, exchange included), from the barrier-bracketed wall
+clock of the K steps.  At N=1 the line also carries BASELINE.json configs[1] itself (n = 1e8) as `cfg2_n1e8`.
 """
 from __future__ import annotations
 
@@ -39,10 +42,11 @@ from kvmatch_b200 import datagen, sharding  # noqa: E402
 M = 1024
 ALPHA, BETA = 1.5, 5.0
 EPSILON = 5.0            # middle of the reference's cNSM grid {1,5,10} (NormQueryDtwSelectivityGenerate.java:72-86)
-N_PER_GPU = 100_000_000
+N_TOTAL = 1_000_000_000  # one series for every N (strong scaling); KVM_BENCH_N overrides (developer runs)
+N_CFG2 = 100_000_000     # BASELINE.json configs[1]
 N_QUERIES = 10           # seeded query offsets, cycled over the steps
 SEED = datagen.DEFAULT_SEED
-DEFAULT_CHUNK = 1024     # candidates per statistic chain (see DESIGN.md "chain chunking")
+DEFAULT_CHUNK = 2048     # candidates per statistic chain (see DESIGN.md "chain chunking")
 
 
 def load_peaks():
@@ -136,11 +140,11 @@ def run_reference(args, rank, world):
     this times the C++ restatement in oracle/ on the host cores, rank 0 only; other ranks exit without work."""
     if rank != 0:
         return
-    n = N_PER_GPU * world
+    n = args.n
     cores = os.cpu_count() or 1
     chunk = min(args.chunk, 100000 - M + 1)
     # bounded sample: the first `sample_n` samples of the same series, same chains, same queries
-    sample_n = int(args.ref_sample)
+    sample_n = int(min(args.ref_sample, n))
     series = datagen.generate_range(n, 0, sample_n, SEED)
     iv = datagen.chain_intervals(sample_n, M, chunk)
     offs = query_offsets(n, M, N_QUERIES)
@@ -156,7 +160,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "verified subsequences/sec (cNSM-ED)", "value": value, "unit": "subsequences/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(n, chunk, world),
         "cpu_baseline": {"value": value, "unit": "subsequences/s", "cores": cores, "kind": "port",
                          "sample": f"first {sample_n} samples ({len(iv)} chains of <= {chunk} candidates) of the same "
@@ -170,25 +174,75 @@ def run_reference(args, rank, world):
 
 
 def workload_config(n_total, chunk, world):
-    return {"workload": "cNSM-ED NormQueryEngine phase-2 verification, index-free scan of every window start "
-                        "(BASELINE.json configs[1])",
-            "n_per_gpu": N_PER_GPU, "n_total": n_total, "query_length": M, "alpha": ALPHA, "beta": BETA,
-            "epsilon": EPSILON, "chain_chunk": chunk, "queries": N_QUERIES, "parallelism": f"offset-shard x{world}",
-            "l2": "inputs (800 MB per GPU) exceed the 126 MB L2; no explicit flush between steps"}
+    return {"workload": "cNSM-ED NormQueryEngine phase-2 verification, index-free scan of every window start of one "
+                        "series of n samples (BASELINE.json metric: n = 1e9; configs[1] = the same at n = 1e8, reported "
+                        "as cfg2_n1e8 at N=1)",
+            "n_total": n_total, "query_length": M, "alpha": ALPHA, "beta": BETA, "epsilon": EPSILON,
+            "chain_chunk": chunk, "queries": N_QUERIES, "parallelism": f"offset-shard x{world} (strong scaling)",
+            "tail": "one packed all_gather per query, inside the timed step",
+            "l2": "inputs (8 GB / N per GPU) exceed the 126 MB L2; no explicit flush between steps"}
+
+
+def unique_samples_of(iv, n_total):
+    """every touched series sample counted once (the m-1 halo between adjacent chains is not
+    algorithmic)."""
+    ivs = np.asarray(iv, dtype=np.int64).reshape(-1, 2)
+    lo_s, hi_s = ivs[:, 0], np.minimum(ivs[:, 1] + M - 1, n_total)
+    order = np.argsort(lo_s, kind="stable")
+    lo_s, hi_s = lo_s[order], hi_s[order]
+    reach = np.maximum.accumulate(hi_s)
+    prev_reach = np.concatenate(([lo_s[0] - 1], reach[:-1]))
+    return int(np.sum(np.maximum(0, hi_s - np.maximum(lo_s - 1, prev_reach))))
+
+
+def offline_traffic(n, chunk):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this configuration (a constant
+    measured offline, labelled as such), or None."""
+    prof = os.path.join(ROOT, "profiles", "roofline_r02.json")
+    if os.path.exists(prof):
+        pj = json.load(open(prof))
+        for row in pj.get("captures", []):
+            if row.get("n") == n and row.get("chain_chunk") == chunk:
+                return row.get("dram_bytes_per_launch"), row.get("source")
+    return None, None
+
+
+def timed_queries(g, queries, iv, steps, warmup, merger=None, barrier=None):
+    """warmup untimed + `steps` timed cNSM-ED queries through the C ABI (host buffers in, answers out), each followed
+    by the multi-GPU exchange when a merger is given.  Returns per-step lists and the barrier-bracketed wall time."""
+    def one(i):
+        t = time.perf_counter()
+        r = g.verify_cnsm_ed(queries[i % len(queries)], EPSILON, ALPHA, BETA, iv)
+        merged = None
+        tail_ms = 0.0
+        if merger is not None:
+            merged = merger.merge(r.offsets, r.distances, {"n_verified": r.n_verified, "gate": r.n_gate_pass})
+            tail_ms = merger.last_device_ms
+        return r, merged, tail_ms, time.perf_counter() - t
+    for i in range(warmup):
+        one(i)
+    if barrier:
+        barrier()
+    t0 = time.perf_counter()
+    rows = [one(warmup + i) for i in range(steps)]
+    if barrier:
+        barrier()
+    return rows, time.perf_counter() - t0
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-query-set", action="store_true", help="skip the query-set side measurement")
-    ap.add_argument("--no-dtw", action="store_true", help="skip the cNSM-DTW side measurement")
+    ap.add_argument("--n", type=float, default=float(os.environ.get("KVM_BENCH_N", N_TOTAL)))
+    ap.add_argument("--no-side", action="store_true", help="skip the side measurements (cfg2_n1e8, cNSM-DTW, window means)")
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("KVM_BENCH_CHUNK", DEFAULT_CHUNK)))
-    ap.add_argument("--ref-sample", type=float, default=N_PER_GPU)   # samples scanned per reference step
-    ap.add_argument("--cpu-queries", type=int, default=10)          # queries the 1-core CPU baseline times
+    ap.add_argument("--ref-sample", type=float, default=1e8)   # samples scanned per reference step
+    ap.add_argument("--cpu-queries", type=int, default=10)     # queries the 1-core CPU baseline times
     args = ap.parse_args()
+    args.n = int(args.n)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -210,7 +264,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n_total = N_PER_GPU * world
+    n_total = args.n
     chunk = min(args.chunk, 100000 - M + 1)
     shard = sharding.make_shard(n_total, M, rank, world, grid=chunk)
     t0 = time.perf_counter()
@@ -224,164 +278,234 @@ def main():
     iv = sharding.assign_intervals(all_iv, 0, M, shard)
     offs = query_offsets(n_total, M, N_QUERIES)
     queries = [query_of(n_total, o, M) for o in offs]
+    merger = sharding.PackedMerger(["n_verified", "gate"], device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(i):
-        t = time.perf_counter()
-        r = g.verify_cnsm_ed(queries[i % N_QUERIES], EPSILON, ALPHA, BETA, iv)  # host buffers in, host answers out
-        return r, time.perf_counter() - t
-
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for i in range(args.warmup):
-        one_step(i)
-    sampler.lines.clear()  # keep only samples taken from here on (the timed region)
-    barrier()
-    t_wall0 = time.perf_counter()
-    dev_ms = walker_ms = wall_s = 0.0
-    verified = launches = answers = s_total = gate = h2d = 0
-    lat = []
-    for i in range(args.steps):
-        r, dt = one_step(args.warmup + i)
-        dev_ms += r.kernel_ms
-        walker_ms += r.stage_ms[0]
-        wall_s += dt
-        lat.append(dt)
-        verified += r.n_verified
-        launches += r.n_launches
-        answers += r.count
-        s_total += r.s_total
-        gate += r.n_gate_pass
-        h2d += r.h2d_bytes
-        last = r
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
+    # the clock samples of the warm-up are dropped at the first barrier: only the timed region counts
+    first_barrier = [True]
+
+    def barrier_hook():
+        barrier()
+        if first_barrier[0]:
+            sampler.lines.clear()
+            first_barrier[0] = False
+    rows, t_wall = timed_queries(g, queries, iv, args.steps, args.warmup, merger, barrier=barrier_hook)
     clocks = sampler.stop()
 
-    # the multi-GPU tail of one query (not inside the timed kernels): counts, answers, best match
-    offs_m, dists_m, totals, best = sharding.merge_answers(last.offsets, last.distances,
-                                                           {"n_verified": last.n_verified}, device=dev)
+    k = args.steps
+    dev_ms = sum(r.kernel_ms + tail for r, _, tail, _ in rows)
+    kern_ms = sum(r.kernel_ms for r, _, _, _ in rows)
+    stream_ms = sum(r.stage_ms[0] for r, _, _, _ in rows)
+    tail_ms = sum(tail for _, _, tail, _ in rows)
+    lat = [dt for _, _, _, dt in rows]
+    verified = sum(r.n_verified for r, _, _, _ in rows)
+    launches = sum(r.n_launches for r, _, _, _ in rows)
+    answers = sum(r.count for r, _, _, _ in rows)
+    gate = sum(r.n_gate_pass for r, _, _, _ in rows)
+    h2d = sum(r.h2d_bytes for r, _, _, _ in rows)
+    rewalked = sum(r.n_rewalked for r, _, _, _ in rows)
+    last, last_merged = rows[-1][0], rows[-1][1]
 
-    stats = torch.tensor([dev_ms, t_wall, wall_s, walker_ms], dtype=torch.float64, device=dev)
-    sums = torch.tensor([verified, launches, answers, s_total, gate], dtype=torch.float64, device=dev)
+    stats = torch.tensor([dev_ms, t_wall, kern_ms, stream_ms, tail_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([verified, launches, answers, gate, rewalked], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    dev_ms_max, t_wall_max, wall_s_max, walker_ms_max = [float(x) for x in stats.tolist()]
-    verified_all, launches_all, answers_all, s_total_all, gate_all = [float(x) for x in sums.tolist()]
+    dev_ms_max, t_wall_max, kern_ms_max, stream_ms_max, tail_ms_max = [float(x) for x in stats.tolist()]
+    verified_all, launches_all, answers_all, gate_all, rewalked_all = [float(x) for x in sums.tolist()]
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        k = args.steps
         value = verified_all / (dev_ms_max * 1e-3)
-        e2e_value = verified_all / wall_s_max
-        # roofline of the dominant kernel (the statistics walker): algorithmic bytes = 8 B per touched sample
-        # (bytes_alg = 8*S_total + 12*#answers), per launch, over its own CUDA-event duration
-        # S_total counts every touched sample once: the m-1 halo re-read between adjacent chains is NOT algorithmic
-        ivs = np.asarray(iv, dtype=np.int64).reshape(-1, 2)
-        lo_s, hi_s = ivs[:, 0], np.minimum(ivs[:, 1] + M - 1, n_total)
-        order = np.argsort(lo_s, kind="stable")
-        lo_s, hi_s = lo_s[order], hi_s[order]
-        reach = np.maximum.accumulate(hi_s)
-        prev_reach = np.concatenate(([lo_s[0] - 1], reach[:-1]))
-        unique_samples = int(np.sum(np.maximum(0, hi_s - np.maximum(lo_s - 1, prev_reach))))
-        bytes_per_launch = 8.0 * unique_samples + 12.0 * answers / k     # rank 0's shard
-        walker_s = (walker_ms / k) * 1e-3
-        achieved = bytes_per_launch / walker_s / 1e9
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "roofline_r01.json")
-        if os.path.exists(prof):
-            pj = json.load(open(prof))
-            if pj.get("chain_chunk") == chunk and pj.get("n_per_gpu") == N_PER_GPU:
-                traffic = pj.get("walker_dram_bytes_per_launch")
+        e2e_value = verified_all / t_wall_max
+        # roofline of the dominant kernel (the streaming statistics pass): algorithmic bytes = 8 B per touched sample
+        # (bytes_alg = 8*S_total + 12*#answers), rank 0's shard, per launch, over its own CUDA-event time
+        unique_samples = unique_samples_of(iv, n_total)
+        bytes_per_launch = 8.0 * unique_samples + 12.0 * answers / k
+        stream_s = (stream_ms / k) * 1e-3
+        achieved = bytes_per_launch / stream_s / 1e9
+        traffic, traffic_src = offline_traffic(int(n_total // world), chunk)
         line = {
             "metric": "verified subsequences/sec (cNSM-ED)", "value": value, "unit": "subsequences/s",
             "n_gpus": world, "steps": k, "warmup": args.warmup, "ms_per_step": dev_ms_max / k,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(n_total, chunk, world),
             "e2e": {"value": e2e_value, "unit": "subsequences/s",
                     "h2d_bytes_per_step": int(h2d / k),
                     "d2h_bytes_per_step": int(12 * answers / k + 64),
-                    "ms_per_step": 1e3 * wall_s_max / k,
+                    "ms_per_step": 1e3 * t_wall_max / k,
                     "latency_ms_p50": 1e3 * float(np.median(lat)), "latency_ms_p95": 1e3 * float(np.percentile(lat, 95)),
                     "series_upload_s_once": t_load},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "cnsm_relay_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": walker_ms / k,
-                         "samples_read_incl_chain_halos_per_launch": s_total / k,
-                         "whole_step_frac": (bytes_per_launch / ((dev_ms / k) * 1e-3) / 1e9) / peak},
-            "answers_per_step": answers_all / k, "gate_pass_per_step": gate_all / k,
+            "roofline": {"bound": "hbm", "kernel": "cnsm_stream_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_offline_ncu": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": stream_ms / k,
+                         "whole_step_frac": (bytes_per_launch / ((kern_ms / k) * 1e-3) / 1e9) / peak,
+                         "stage_ms_per_step": {"stream": stream_ms / k,
+                                               "rewalk": sum(r.stage_ms[1] for r, _, _, _ in rows) / k,
+                                               "exact": sum(r.stage_ms[2] for r, _, _, _ in rows) / k}},
+            "tail": {"ms_per_step_device_max_over_ranks": tail_ms_max / k, "collectives_per_step": 1 if world > 1 else 0,
+                     "overflow_rounds": merger.overflows, "packed_bytes_per_rank": 8 * merger.len},
+            "parity": "oracle-only (reference unpinned: Java 8, no JVM in this image)",
+            "answers_per_step": answers_all / k, "gate_pass_per_step": gate_all / k, "rewalked_windows_per_step": rewalked_all / k,
             "wall_s_timed_region": t_wall_max, "datagen_s": t_gen,
-            "best_of_last_query": best,
+            "best_of_last_query": last_merged[3] if last_merged else None,
         }
-        # Beside the headline (not part of it): the same 10 queries as ONE query-set call (kvm_verify_cnsm_ed_batch, an
-        # addition to the reference's per-query engines: one statistics pass serves the set), host buffers in, answers out
-        if world == 1 and not args.no_query_set:
-            qs = np.stack(queries[:N_QUERIES])
-            res = g.verify_cnsm_ed_batch(qs, EPSILON, ALPHA, BETA, iv)
-            reps = 5
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                res = g.verify_cnsm_ed_batch(qs, EPSILON, ALPHA, BETA, iv)
-            per_call = (time.perf_counter() - t0) / reps
-            single = [g.verify_cnsm_ed(q, EPSILON, ALPHA, BETA, iv) for q in qs]
-            line["query_set"] = {
-                "queries_per_call": int(len(qs)), "ms_per_call": 1e3 * per_call,
-                "value": float(sum(r.n_verified for r in res)) / per_call, "unit": "subsequences/s",
-                "kernel_ms_per_call": float(sum(r.kernel_ms for r in res)),
-                "statistics_pass_ms": float(res[0].stage_ms[0] * len(qs)),
-                "identical_to_single_calls": bool(all(a.offsets.tolist() == b.offsets.tolist() and
-                                                      a.distances.tolist() == b.distances.tolist()
-                                                      for a, b in zip(res, single))),
-                "note": "through the ABI with host buffers (compare with e2e, not with value)"}
-        # Also beside the headline: the metric's other half, cNSM-DTW (BASELINE configs[3] shape on this GPU's shard:
-        # m = 2048, rho = 5 % = 102, the headline's chain grid), two of the seeded offsets, kernel time from CUDA events
-        if world == 1 and not args.no_dtw:
-            m2, rho2, eps2 = 2048, 102, 1.0
-            iv2 = datagen.chain_intervals(n_total, m2, chunk)
-            rows = []
-            for o2 in offs[:2]:
-                q2 = query_of(n_total, o2, m2)
-                g.verify_cnsm_dtw(q2, eps2, rho2, ALPHA, BETA, iv2)
-                t0 = time.perf_counter()
-                r2 = g.verify_cnsm_dtw(q2, eps2, rho2, ALPHA, BETA, iv2)
-                rows.append({"offset": int(o2), "kernel_ms": r2.kernel_ms, "wall_ms": 1e3 * (time.perf_counter() - t0),
-                             "verified": int(r2.n_verified), "gate_pass": int(r2.n_gate_pass), "dtws": int(r2.n_lb_pass),
-                             "answers": int(r2.count), "stage_ms": [float(x) for x in r2.stage_ms[:3]]})
-            line["cnsm_dtw"] = {"config": f"m={m2} rho={rho2} eps={eps2} alpha={ALPHA} beta={BETA}, n={n_total}, chain_chunk={chunk}",
-                                "value": float(sum(r["verified"] for r in rows) / sum(r["kernel_ms"] * 1e-3 for r in rows)),
-                                "unit": "subsequences/s", "queries": rows}
-        # CPU baseline beside it (N=1 only): the oracle port on 1 core (the reference is single-threaded), the same
-        # series, chains and queries; bounded to --cpu-queries whole-series queries (~0.7 s each)
-        if world == 1:
-            nq = max(1, min(args.cpu_queries, k))
-            cpu_v = cpu_t = 0.0
-            ok = True
-            for j in range(nq):
-                qi = (args.warmup + k - 1 - j) % N_QUERIES
-                v, dt, outs = oracle_sample(local, queries[qi], iv, 1)
-                cpu_v += v
-                cpu_t += dt
-                if j == 0:  # parity spot check on the last timed query (the oracle as checker, never as the thing measured)
-                    ok = bool(last.offsets.tolist() == outs[0].offsets.tolist() and
-                              last.distances.tolist() == outs[0].distances.tolist() and
-                              last.n_gate_pass == outs[0].n_gate_pass)
-            line["cpu_baseline"] = {"value": cpu_v / cpu_t, "unit": "subsequences/s", "cores": 1, "kind": "port",
-                                    "sample": f"{nq} of the timed queries over the whole series ({len(iv)} chains), "
-                                              f"{cpu_t:.1f} s on 1 core ({os.cpu_count()} cores on the box); series "
-                                              f"resident in RAM (kinder than the reference, which re-reads its file)"}
-            line["parity_vs_oracle_last_query"] = ok
+        if world == 1 and not args.no_side:
+            side_measurements(line, g, kvmatch_b200, local, n_total, chunk, queries, offs, iv, last, args, peak)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     g.close()
+
+
+def side_measurements(line, g, kvmatch_b200, local, n_total, chunk, queries, offs, iv, last, args, peak):
+    """N=1 only, beside the headline: BASELINE configs[1] at n = 1e8, the CPU baseline with a parity spot check, the
+    metric's other half (cNSM-DTW), the query set and the fused window-mean pass."""
+    k = args.steps
+    # ---- CPU baseline: the oracle port on 1 core (the reference is single-threaded), first 1e8 samples of the same
+    # series and chains; the oracle also checks the last timed query on that prefix
+    sample_n = int(min(1e8, n_total))
+    iv_s = datagen.chain_intervals(sample_n, M, chunk)
+    prefix = local[:sample_n]
+    nq = max(1, min(args.cpu_queries, N_QUERIES))
+    cpu_v = cpu_t = 0.0
+    ok = True
+    for j in range(nq):
+        qi = (args.warmup + k - 1 - j) % N_QUERIES
+        v, dt, outs = oracle_sample(prefix, queries[qi], iv_s, 1)
+        cpu_v += v
+        cpu_t += dt
+        if j == 0:  # parity spot check (the oracle as checker, never as the thing measured)
+            hi = sample_n - M + 1
+            keep = last.offsets <= hi
+            ok = bool(last.offsets[keep].tolist() == outs[0].offsets.tolist() and
+                      last.distances[keep].tolist() == outs[0].distances.tolist())
+    line["cpu_baseline"] = {"value": cpu_v / cpu_t, "unit": "subsequences/s", "cores": 1, "kind": "port",
+                            "sample": f"{nq} of the timed queries over the first {sample_n} samples ({len(iv_s)} chains), "
+                                      f"{cpu_t:.1f} s on 1 core ({os.cpu_count()} cores on the box); series resident in "
+                                      f"RAM (kinder than the reference, which re-reads its file)"}
+    line["parity_vs_oracle_last_query"] = ok
+    # ---- BASELINE configs[1]: the same engine on an n = 1e8 series (the series BENCH_r01 used)
+    s8 = datagen.generate(N_CFG2, SEED)
+    g8 = kvmatch_b200.GpuSeries(0)
+    g8.load(s8)
+    iv8 = datagen.chain_intervals(N_CFG2, M, chunk)
+    q8 = [query_of(N_CFG2, o, M) for o in query_offsets(N_CFG2, M, N_QUERIES)]
+    rows8, wall8 = timed_queries(g8, q8, iv8, max(20, k), 3)
+    k8 = len(rows8)
+    kern8 = sum(r.kernel_ms for r, _, _, _ in rows8)
+    stream8 = sum(r.stage_ms[0] for r, _, _, _ in rows8)
+    b8 = 8.0 * unique_samples_of(iv8, N_CFG2) + 12.0 * sum(r.count for r, _, _, _ in rows8) / k8
+    tr8, tr8_src = offline_traffic(N_CFG2, chunk)
+    exp8 = oracle_sample(s8, q8[(3 + k8 - 1) % N_QUERIES], iv8, os.cpu_count() or 1)[2]
+    got8 = rows8[-1][0]
+    exp_off = np.concatenate([o.offsets for o in exp8])
+    exp_dist = np.concatenate([o.distances for o in exp8])
+    line["cfg2_n1e8"] = {
+        "value": sum(r.n_verified for r, _, _, _ in rows8) / (kern8 * 1e-3), "unit": "subsequences/s",
+        "ms_per_step": kern8 / k8, "e2e_value": sum(r.n_verified for r, _, _, _ in rows8) / wall8,
+        "e2e_ms_per_step": 1e3 * wall8 / k8, "steps": k8,
+        "roofline": {"bound": "hbm", "kernel": "cnsm_stream_kernel", "achieved": b8 / (stream8 / k8 * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": b8 / (stream8 / k8 * 1e-3) / 1e9 / peak,
+                     "whole_step_frac": b8 / (kern8 / k8 * 1e-3) / 1e9 / peak, "traffic_offline_ncu": tr8,
+                     "traffic_source": tr8_src, "kernel_ms_per_launch": stream8 / k8},
+        "parity_vs_oracle_whole_series": bool(got8.offsets.tolist() == exp_off.tolist() and
+                                              got8.distances.tolist() == exp_dist.tolist() and
+                                              got8.n_gate_pass == sum(o.n_gate_pass for o in exp8))}
+    # ---- the same 10 queries as ONE query-set call (an addition to the reference's per-query engines; n = 1e8)
+    try:
+        qs = np.stack(q8[:N_QUERIES])
+        res = g8.verify_cnsm_ed_batch(qs, EPSILON, ALPHA, BETA, iv8)
+        t0 = time.perf_counter()
+        res = g8.verify_cnsm_ed_batch(qs, EPSILON, ALPHA, BETA, iv8)
+        per_call = time.perf_counter() - t0
+        line["query_set"] = {"n": N_CFG2, "queries_per_call": int(len(qs)), "ms_per_call": 1e3 * per_call,
+                             "value": float(sum(r.n_verified for r in res)) / per_call, "unit": "subsequences/s",
+                             "note": "relay walker, through the ABI with host buffers (compare with cfg2_n1e8.e2e_value)"}
+    except Exception as e:
+        line["query_set"] = {"error": repr(e)}
+    g8.close()
+    del s8
+    # ---- the metric's other half: cNSM-DTW, BASELINE configs[3] (n = 1e9, m = 2048, rho = 5 % = 102), the seeded
+    # queries at eps in {1, 5, 10} within a time budget; DTW roofline = 5 flops per executed band cell / FP64 peak
+    try:
+        line["cnsm_dtw"] = dtw_block(g, n_total, chunk, offs)
+    except Exception as e:
+        line["cnsm_dtw"] = {"error": repr(e)}
+    # ---- IndexBuilder's window-mean pass, all five windows of Sigma
+    try:
+        line["window_mean"] = window_mean_block(kvmatch_b200, peak)
+    except Exception as e:  # keep the headline even if a side block fails
+        line["window_mean"] = {"error": repr(e)}
+
+
+FP64_PEAK_FLOPS = 36.5e12  # measured on this pool's B200 with tools/fp64_peak.cu (18.27e12 DFMA/s), DESIGN.md
+
+
+def dtw_block(g, n_total, chunk, offs, budget_s=25.0):
+    m2, rho2 = 2048, 102
+    iv2 = datagen.chain_intervals(n_total, m2, chunk)
+    cells_full = m2 * (2 * rho2 + 1) - rho2 * (rho2 + 1)
+    out = {"config": f"m={m2} rho={rho2} alpha={ALPHA} beta={BETA}, n={n_total}, chain_chunk={chunk}", "eps": {}}
+    t_start = time.perf_counter()
+    for eps in (1.0, 5.0, 10.0):
+        rows = []
+        for o2 in offs:
+            if time.perf_counter() - t_start > budget_s and rows:
+                break
+            q2 = query_of(n_total, o2, m2)
+            t0 = time.perf_counter()
+            r2 = g.verify_cnsm_dtw(q2, eps, rho2, ALPHA, BETA, iv2)
+            rows.append({"offset": int(o2), "kernel_ms": r2.kernel_ms, "wall_ms": 1e3 * (time.perf_counter() - t0),
+                         "verified": int(r2.n_verified), "gate_pass": int(r2.n_gate_pass), "dtws": int(r2.n_lb_pass),
+                         "cells": int(getattr(r2, "n_dtw_cells", 0)), "answers": int(r2.count),
+                         "stage_ms": [float(x) for x in r2.stage_ms]})
+        kt = sum(r["kernel_ms"] for r in rows) * 1e-3
+        dtw_t = sum(r["stage_ms"][3] for r in rows) * 1e-3
+        cells = sum(r["cells"] for r in rows)
+        out["eps"][str(eps)] = {
+            "queries": len(rows), "value": sum(r["verified"] for r in rows) / kt if kt else None, "unit": "subsequences/s",
+            "kernel_ms_p50": float(np.median([r["kernel_ms"] for r in rows])),
+            "dtws": sum(r["dtws"] for r in rows), "cells_executed": cells,
+            "roofline": {"bound": "fp64", "kernel": "dtw_band_kernel", "unit": "TFLOP/s", "peak": FP64_PEAK_FLOPS / 1e12,
+                         "achieved": 5.0 * cells / dtw_t / 1e12 if dtw_t and cells else None,
+                         "frac": 5.0 * cells / dtw_t / FP64_PEAK_FLOPS if dtw_t and cells else None,
+                         "cells_if_no_abandon": sum(r["dtws"] for r in rows) * cells_full},
+            "rows": rows}
+        if time.perf_counter() - t_start > budget_s:
+            break
+    return out
+
+
+def window_mean_block(kvmatch_b200, peak):
+    out = {}
+    for n in (1_000_000, N_CFG2):
+        s = datagen.generate(n, SEED)
+        g = kvmatch_b200.GpuSeries(0)
+        g.load(s)
+        if not hasattr(g, "window_mean_runs_all"):
+            g.close()
+            return {"error": "fused pass not built"}
+        g.window_mean_runs_all(kvmatch_b200.WU_LIST)
+        res = g.window_mean_runs_all(kvmatch_b200.WU_LIST)
+        ms = res.kernel_ms
+        out[f"n={n}"] = {"windows": list(kvmatch_b200.WU_LIST), "kernel_ms_all_windows": ms, "runs": int(res.n_runs),
+                        "rewalked_chains": int(res.n_chains_rewalked),
+                        "roofline": {"bound": "hbm", "kernel": "window_mean_stream_kernel", "unit": "GB/s", "peak": peak,
+                                     "achieved": (8.0 * n + 16.0 * res.n_runs) / (ms * 1e-3) / 1e9,
+                                     "frac": (8.0 * n + 16.0 * res.n_runs) / (ms * 1e-3) / 1e9 / peak}}
+        g.close()
+    return out
 
 
 if __name__ == "__main__":

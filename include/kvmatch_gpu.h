@@ -152,6 +152,12 @@ int kvm_scan_ucr_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, i
  * Needs the whole series on this ctx (first == 1, count == n). */
 int kvm_window_mean_runs(kvm_ctx* ctx, int32_t w, kvm_runs* out);
 
+/* The same for all window widths of an index build at once (the reference's Sigma = {25,50,100,200,400},
+ * K/IndexBuilder.java:98-120 runs one SingleIndexBuilder pass per width: its own "TODO: naive"): ONE pass over the
+ * series serves up to 5 widths.  outs[q] is what kvm_window_mean_runs(ctx, widths[q], ...) returns; its arrays stay
+ * valid until the next window-mean call on this ctx; outs[q].reserved = epochs of that width re-walked exactly. */
+int kvm_window_mean_runs_all(kvm_ctx* ctx, const int32_t* widths, int32_t n_widths, kvm_runs* outs);
+
 /* The whole single-width index build: window-mean pass on the GPU, then IndexBuilder step 2 (adjacent-row merge,
  * K/IndexBuilder.java:308-345, K/utils/IndexNodeUtils.java:30-90) and the file image IndexFileOperator.writeAll
  * produces (K/operator/file/IndexFileOperator.java:127-164; row codec K/common/entity/IndexNode.java:51-96; statistic

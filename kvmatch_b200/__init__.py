@@ -6,4 +6,4 @@ and the multi-GPU offset sharding.  There is no CPU fallback.
 """
 from ._lib import KvmError, LIB_PATH  # noqa: F401
 from .engine import (GpuSeries, IndexBuilder, NormQueryEngine, NormQueryEngineDtw, QueryEngine,  # noqa: F401
-                     QueryEngineDtw, StatisticInfo, VerifyResult, rho_from_prompt)
+                     QueryEngineDtw, StatisticInfo, VerifyResult, WU_LIST, rho_from_prompt)

@@ -22,6 +22,7 @@
 
 #include "dtw_kernels.cuh"
 #include "stream_kernels.cuh"
+#include "wmean_kernels.cuh"
 #include "index_kernels.cuh"
 #include "index_file.hpp"
 
@@ -173,6 +174,17 @@ struct kvm_ctx {
   bool stream_dirty = true;          // need_bits / chain_last may hold leftovers (first use, or a call that failed)
   int opt_relay = 0, opt_force_all = 0, opt_plan_cache = 1;  // kvm_set_option (defaults from the environment)
   PinBuf sstage;
+  // fused window-mean pass: per width device buffers and the host-side result vectors
+  struct WmeanSlot {
+    DevBuf runs, seg_off, seg_cnt, need_bits, chain_last, flagged, x_off, x_ex, x_ex2;
+    long long run_cap = 0, x_cap = 0;
+    size_t need_words = 0, chains_n = 0, segs_n = 0;
+    std::vector<double> keys;
+    std::vector<int32_t> first, last;
+  };
+  WmeanSlot wm[kvm::kMaxWidths];
+  DevBuf wm_counters;
+  PinBuf wm_host;
   std::vector<BatchSlot> slots;      // query sets
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // query sets: per-query evaluator / exact stages run concurrently
   cudaEvent_t ev_set = nullptr;
@@ -1457,6 +1469,12 @@ void kvm_destroy(kvm_ctx* ctx) {
                    &ctx->need_bits, &ctx->chain_last, &ctx->flagged, &ctx->x_off, &ctx->x_ex, &ctx->x_ex2, &ctx->bmax};
   for (DevBuf* b : dev) b->release();
   for (BatchSlot& sl : ctx->slots) sl.release();
+  for (auto& w : ctx->wm) {
+    DevBuf* wb[] = {&w.runs, &w.seg_off, &w.seg_cnt, &w.need_bits, &w.chain_last, &w.flagged, &w.x_off, &w.x_ex, &w.x_ex2};
+    for (DevBuf* b : wb) b->release();
+  }
+  ctx->wm_counters.release();
+  ctx->wm_host.release();
   for (cudaStream_t st : ctx->aux)
     if (st) cudaStreamDestroy(st);
   if (ctx->ev_set) cudaEventDestroy(ctx->ev_set);
@@ -2152,6 +2170,297 @@ int kvm_window_mean_runs(kvm_ctx* ctx, int32_t w, kvm_runs* out) {
   out->keys = ctx->run_key_v.data();
   out->first = ctx->run_first_v.data();
   out->last = ctx->run_last_v.data();
+  return KVM_OK;
+}
+
+// Window positions and epoch chains of one width, as the reference's block iterator produces them
+// (K/IndexBuilder.java:152-180,194-301): `fed` = samples it feeds (125-sample nodes, the last one zero padded).
+static void wmean_geometry(int64_t n, int w, int64_t* n_win_out, int64_t* n_chains_out) {
+  constexpr int64_t kEpoch = 100000;
+  int64_t fed = 0;
+  {
+    const int64_t n_nodes = (n + 124) / 125;
+    int64_t cnt = 0;
+    for (int64_t b = 0; b < n_nodes; b++) {
+      const int64_t within = std::min<int64_t>(124, std::max<int64_t>(0, n - cnt));
+      fed += 1 + within;
+      cnt += within;
+      if (within < 124) break;
+    }
+  }
+  const int64_t stride = kEpoch - w + 1;
+  int64_t n_win = 0, n_chains = 0;
+  for (int64_t it = 0;; it++) {
+    const int64_t g0 = it * stride;
+    if (g0 + w - 1 >= fed) break;
+    const int64_t ep = std::min<int64_t>(kEpoch, fed - g0);
+    const int64_t nwin = std::min<int64_t>(ep - w + 1, n - g0);
+    if (nwin <= 0) break;
+    n_win = g0 + nwin;
+    n_chains = it + 1;
+    if (ep < kEpoch) break;
+  }
+  *n_win_out = n_win;
+  *n_chains_out = n_chains;
+}
+
+// All window widths of one index build in ONE pass over the series (wmean_kernels.cuh).  outs[q] is what
+// kvm_window_mean_runs(ctx, widths[q], ...) returns; its arrays stay valid until the next window-mean call on this ctx.
+int kvm_window_mean_runs_all(kvm_ctx* ctx, const int32_t* widths, int32_t n_widths, kvm_runs* outs) {
+  if (!ctx) return KVM_E_ARG;
+  if (!widths || !outs || n_widths < 1 || n_widths > kvm::kMaxWidths)
+    return fail(ctx, KVM_E_ARG, "1..%d window widths per call", kvm::kMaxWidths);
+  for (int q = 0; q < n_widths; q++) std::memset(&outs[q], 0, sizeof(kvm_runs));
+  constexpr int kEpoch = 100000;
+  int w_max = 0;
+  for (int q = 0; q < n_widths; q++) {
+    if (widths[q] < 2 || widths[q] > kEpoch) return fail(ctx, KVM_E_ARG, "window width %d", widths[q]);
+    w_max = std::max(w_max, widths[q]);
+  }
+  if (!ctx->series) return fail(ctx, KVM_E_STATE, "no series loaded");
+  if (ctx->first != 1 || ctx->count != ctx->n) return fail(ctx, KVM_E_RANGE, "index build needs the whole series on this ctx");
+  constexpr int NT = 256;
+  const size_t smem = kvm::wmean_smem_bytes(NT, w_max);
+  auto fallback = [&]() -> int {  // width by width through the exact walker
+    for (int q = 0; q < n_widths; q++) {
+      kvm_runs r;
+      int rc = kvm_window_mean_runs(ctx, widths[q], &r);
+      if (rc) return rc;
+      kvm_ctx::WmeanSlot& S = ctx->wm[q];
+      S.keys.assign(r.keys, r.keys + r.count);
+      S.first.assign(r.first, r.first + r.count);
+      S.last.assign(r.last, r.last + r.count);
+      outs[q] = r;
+      outs[q].keys = S.keys.data();
+      outs[q].first = S.first.data();
+      outs[q].last = S.last.data();
+    }
+    return KVM_OK;
+  };
+  if (smem > 110 * 1024 || !std::isfinite(ctx->absmax)) return fallback();
+  int rc = begin_call(ctx);
+  if (rc) return rc;
+  const int64_t n = ctx->n;
+  int64_t n_win[kvm::kMaxWidths] = {0}, n_chains[kvm::kMaxWidths] = {0};
+  int64_t total_pos = 0;
+  for (int q = 0; q < n_widths; q++) {
+    wmean_geometry(n, widths[q], &n_win[q], &n_chains[q]);
+    total_pos = std::max(total_pos, n_win[q]);
+  }
+  if (total_pos == 0) return KVM_OK;
+  const int W = kvm::kGroup * NT;
+  const int n_tiles = (int)((total_pos + W - 1) / W);
+  const size_t n_segs = (size_t)n_tiles * (NT / 32);
+  // counters: per width [n_runs, n_flagged, x_count], then the overflow flag
+  const size_t n_cnt = 3 * kvm::kMaxWidths + 1;
+  KVM_CUDA(ctx, ctx->wm_counters.ensure(sizeof(unsigned long long) * n_cnt));
+  KVM_CUDA(ctx, ctx->wm_host.ensure(sizeof(unsigned long long) * n_cnt));
+  unsigned long long* cnt_d = ctx->wm_counters.as<unsigned long long>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    KVM_CUDA(ctx, cudaFuncSetAttribute(kvm::wmean_stream_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr_set = true;
+  }
+  unsigned long long cnt[n_cnt];
+  double kernel_ms = 0;
+  int launches = 0;
+  for (int attempt = 0; attempt < 6; attempt++) {
+    kvm::WmeanParams P{};
+    P.T = ctx->series;
+    P.n_widths = n_widths;
+    P.w_max = w_max;
+    P.total_pos = (int)total_pos;
+    P.epoch = kEpoch;
+    P.bmax = ctx->bmax.as<double>();
+    P.n_bmax = (int)ctx->n_bmax;
+    P.overflow = reinterpret_cast<int*>(cnt_d + 3 * kvm::kMaxWidths);
+    for (int q = 0; q < n_widths; q++) {
+      kvm_ctx::WmeanSlot& S = ctx->wm[q];
+      const int w = widths[q];
+      if (S.run_cap == 0) {
+        S.run_cap = n_win[q] / 3 + n_win[q] / 33 + 4096;
+        KVM_CUDA(ctx, S.runs.ensure(sizeof(int2) * (size_t)S.run_cap));
+        S.run_cap = (long long)(S.runs.cap / sizeof(int2));
+      }
+      if (n_segs > S.segs_n) {
+        KVM_CUDA(ctx, S.seg_off.ensure(sizeof(int) * n_segs));
+        KVM_CUDA(ctx, S.seg_cnt.ensure(sizeof(int) * n_segs));
+        S.segs_n = n_segs;
+      }
+      const size_t words = (size_t)(n_win[q] + 63) / 32 + 4;
+      if (words > S.need_words) {
+        KVM_CUDA(ctx, S.need_bits.ensure(sizeof(unsigned) * words));
+        S.need_words = S.need_bits.cap / sizeof(unsigned);
+        KVM_CUDA(ctx, cudaMemsetAsync(S.need_bits.p, 0, S.need_bits.cap, ctx->stream));
+      }
+      if ((size_t)n_chains[q] > S.chains_n) {
+        KVM_CUDA(ctx, S.chain_last.ensure(sizeof(int32_t) * (size_t)n_chains[q]));
+        KVM_CUDA(ctx, S.flagged.ensure(sizeof(int32_t) * (size_t)n_chains[q]));
+        S.chains_n = std::min(S.chain_last.cap, S.flagged.cap) / sizeof(int32_t);
+        KVM_CUDA(ctx, cudaMemsetAsync(S.chain_last.p, 0xff, S.chain_last.cap, ctx->stream));
+      }
+      if (S.x_cap == 0) {
+        S.x_cap = 1 << 14;
+        KVM_CUDA(ctx, S.x_off.ensure(sizeof(int32_t) * (size_t)S.x_cap));
+        KVM_CUDA(ctx, S.x_ex.ensure(sizeof(double) * (size_t)S.x_cap));
+        KVM_CUDA(ctx, S.x_ex2.ensure(sizeof(double) * (size_t)S.x_cap));
+      }
+      kvm::WmeanWidth& Wq = P.W[q];
+      Wq.w = w;
+      Wq.n_win = (int)n_win[q];
+      Wq.c20w = 20.0 / (double)w;
+      {
+        // the chain does 2 roundings of size <= u*w*A per sample it consumes; the stream fewer than 320 on values
+        // <= (tile samples)*A (as stream_guard()); both doubled
+        const double u = kUlpHalf;
+        Wq.cd_chain = 2.0 * (2.0 * u * (double)w * 1.01) * 1.000001;
+        Wq.cd1 = 2.0 * (320.0 * u * ((double)W + w_max)) * 1.000001;
+      }
+      Wq.runs = S.runs.as<int2>();
+      Wq.run_cap = S.run_cap;
+      Wq.n_runs = cnt_d + 3 * q;
+      Wq.seg_off = S.seg_off.as<int>();
+      Wq.seg_cnt = S.seg_cnt.as<int>();
+      Wq.need_bits = S.need_bits.as<unsigned>();
+      Wq.chain_last = S.chain_last.as<int32_t>();
+      Wq.flagged = S.flagged.as<int32_t>();
+      Wq.n_flagged = cnt_d + 3 * q + 1;
+    }
+    KVM_CUDA(ctx, cudaMemsetAsync(cnt_d, 0, sizeof(unsigned long long) * n_cnt, ctx->stream));
+    KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    kvm::wmean_stream_kernel<NT><<<n_tiles, NT, smem, ctx->stream>>>(P);
+    KVM_CUDA(ctx, cudaGetLastError());
+    launches += 1;
+    {  // exact re-walk of the epochs that hold an ambiguous window: all widths in one launch
+      kvm::RewalkBatch B{};
+      int64_t most = 1;
+      for (int q = 0; q < n_widths; q++) {
+        kvm_ctx::WmeanSlot& S = ctx->wm[q];
+        kvm::RewalkParams& R = B.set[q];
+        R.T = ctx->series;
+        R.chains.regular = 1;
+        R.chains.s_base = 0;
+        R.chains.chunk = kEpoch - widths[q] + 1;
+        R.chains.total_win = (int32_t)n_win[q];
+        R.chains.n_chains = (int)n_chains[q];
+        R.m = widths[q];
+        R.first_global = 1;
+        R.need_bits = S.need_bits.as<unsigned>();
+        R.chain_last = S.chain_last.as<int32_t>();
+        R.flagged = S.flagged.as<int32_t>();
+        R.n_flagged = cnt_d + 3 * q + 1;
+        R.out = kvm::XList{S.x_off.as<int32_t>(), S.x_ex.as<double>(), S.x_ex2.as<double>(), cnt_d + 3 * q + 2, S.x_cap};
+        most = std::max(most, n_chains[q]);
+      }
+      kvm::chain_rewalk_batch_kernel<<<dim3((unsigned)std::min<int64_t>(most, ctx->n_sms * 4), (unsigned)n_widths), 32, 0, ctx->stream>>>(B);
+      KVM_CUDA(ctx, cudaGetLastError());
+      launches += 1;
+    }
+    KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    KVM_CUDA(ctx, cudaMemcpyAsync(ctx->wm_host.p, cnt_d, sizeof(unsigned long long) * n_cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::memcpy(cnt, ctx->wm_host.p, sizeof(unsigned long long) * n_cnt);
+    kernel_ms += elapsed_ms(ctx);
+    if (cnt[3 * kvm::kMaxWidths]) return fallback();  // bucket range / guard: the exact walker handles it
+    bool again = false;
+    for (int q = 0; q < n_widths; q++) {
+      kvm_ctx::WmeanSlot& S = ctx->wm[q];
+      if ((long long)cnt[3 * q] > S.run_cap) {
+        S.run_cap = (long long)cnt[3 * q] + 4096;
+        KVM_CUDA(ctx, S.runs.ensure(sizeof(int2) * (size_t)S.run_cap));
+        again = true;
+      }
+      if ((long long)cnt[3 * q + 2] > S.x_cap) {
+        S.x_cap = (long long)cnt[3 * q + 2] + 1024;
+        KVM_CUDA(ctx, S.x_off.ensure(sizeof(int32_t) * (size_t)S.x_cap));
+        KVM_CUDA(ctx, S.x_ex.ensure(sizeof(double) * (size_t)S.x_cap));
+        KVM_CUDA(ctx, S.x_ex2.ensure(sizeof(double) * (size_t)S.x_cap));
+        again = true;
+      }
+    }
+    if (!again) break;
+    if (attempt == 5) return fail(ctx, KVM_E_OOM, "run buffers kept overflowing");
+  }
+  // ---- host: stitch the warps' slices in position order, resolve the ambiguous windows with the reference's
+  // arithmetic, merge equal neighbours, split at 255 positions (K/IndexBuilder.java:268, MAXIMUM_DIFF - 1)
+  std::vector<int2> runs;
+  std::vector<int> seg_off, seg_cnt;
+  std::vector<int32_t> x_off;
+  std::vector<double> x_ex;
+  for (int q = 0; q < n_widths; q++) {
+    kvm_ctx::WmeanSlot& S = ctx->wm[q];
+    const long long n_runs = (long long)cnt[3 * q], n_x = (long long)cnt[3 * q + 2];
+    runs.resize((size_t)n_runs);
+    seg_off.resize(n_segs);
+    seg_cnt.resize(n_segs);
+    x_off.resize((size_t)n_x);
+    x_ex.resize((size_t)n_x);
+    KVM_CUDA(ctx, cudaMemcpyAsync(runs.data(), S.runs.p, sizeof(int2) * (size_t)n_runs, cudaMemcpyDeviceToHost, ctx->stream));
+    KVM_CUDA(ctx, cudaMemcpyAsync(seg_off.data(), S.seg_off.p, sizeof(int) * n_segs, cudaMemcpyDeviceToHost, ctx->stream));
+    KVM_CUDA(ctx, cudaMemcpyAsync(seg_cnt.data(), S.seg_cnt.p, sizeof(int) * n_segs, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_x) {
+      KVM_CUDA(ctx, cudaMemcpyAsync(x_off.data(), S.x_off.p, sizeof(int32_t) * (size_t)n_x, cudaMemcpyDeviceToHost, ctx->stream));
+      KVM_CUDA(ctx, cudaMemcpyAsync(x_ex.data(), S.x_ex.p, sizeof(double) * (size_t)n_x, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int w = widths[q];
+    // exact buckets of the ambiguous windows: b = floor(2 * fl(fl(ex / w) * 10)), K/utils/MeanIntervalUtils.java:51-61
+    std::vector<std::pair<int32_t, int>> exact((size_t)n_x);
+    for (long long i = 0; i < n_x; i++) {
+      const double v = (x_ex[i] / (double)w) * 10.0;
+      exact[i] = {x_off[i] - 1, (int)std::floor(v + v)};  // position = loc - 1
+    }
+    std::sort(exact.begin(), exact.end());
+    S.keys.clear();
+    S.first.clear();
+    S.last.clear();
+    const size_t est = (size_t)n_runs + (size_t)n_win[q] / 255 + 16;
+    S.keys.reserve(est);
+    S.first.reserve(est);
+    S.last.reserve(est);
+    auto close_run = [&](int b, int64_t first_pos, int64_t last_pos) {
+      const double int_value = std::floor((double)b * 0.5);
+      const double ret = (b & 1) ? int_value + 0.5 : int_value;
+      const double key = ret * 0.1;
+      for (int64_t f = first_pos; f <= last_pos; f += 255) {
+        S.keys.push_back(key);
+        S.first.push_back((int32_t)(f + 1));
+        S.last.push_back((int32_t)(std::min<int64_t>(f + 254, last_pos) + 1));
+      }
+    };
+    bool open = false;
+    int cur_b = 0;
+    int64_t cur_first = 0;
+    size_t xi = 0;
+    for (size_t sg = 0; sg < n_segs; sg++) {
+      const int c = seg_cnt[sg];
+      if (c <= 0) continue;
+      const int2* r = runs.data() + seg_off[sg];
+      for (int i = 0; i < c; i++) {
+        int b = r[i].y;
+        const int pos = r[i].x;
+        if (b == kvm::kAmbiguous) {
+          while (xi < exact.size() && exact[xi].first < pos) xi++;
+          if (xi >= exact.size() || exact[xi].first != pos)
+            return fail(ctx, KVM_E_CUDA, "window-mean pass: ambiguous window %d of width %d was not re-walked", pos, w);
+          b = exact[xi].second;
+        }
+        if (open && b == cur_b) continue;  // same key as the run before: one run
+        if (open) close_run(cur_b, cur_first, (int64_t)pos - 1);
+        open = true;
+        cur_b = b;
+        cur_first = pos;
+      }
+    }
+    if (open) close_run(cur_b, cur_first, n_win[q] - 1);
+    outs[q].count = (int64_t)S.keys.size();
+    outs[q].keys = S.keys.data();
+    outs[q].first = S.first.data();
+    outs[q].last = S.last.data();
+    outs[q].kernel_ms = kernel_ms;
+    outs[q].n_launches = launches;
+    outs[q].reserved = (int32_t)std::min<unsigned long long>(cnt[3 * q + 1], INT32_MAX);  // epochs re-walked exactly
+  }
   return KVM_OK;
 }
 

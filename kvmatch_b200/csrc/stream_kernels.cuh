@@ -618,7 +618,17 @@ constexpr int kRewalkStages = 6;  // 32-position tiles in flight per warp
 //   K/NormQueryEngine.java:523-524  ex -= T[j]; ex2 -= T[j]^2  (after each complete window)
 // Out-of-range slots of a 32-position tile are zero-filled: adding / subtracting +0.0 is the identity here (the sums
 // start at +0.0 and x + y is -0.0 only when both are).
-__global__ void __launch_bounds__(32) chain_rewalk_kernel(RewalkParams P) {
+__device__ __forceinline__ void chain_rewalk_body(const RewalkParams& P);
+
+__global__ void __launch_bounds__(32) chain_rewalk_kernel(RewalkParams P) { chain_rewalk_body(P); }
+
+// Several independent chain sets in one launch (the window-mean pass: one per width): blockIdx.y picks the set.
+struct RewalkBatch {
+  RewalkParams set[5];
+};
+__global__ void __launch_bounds__(32) chain_rewalk_batch_kernel(RewalkBatch B) { chain_rewalk_body(B.set[blockIdx.y]); }
+
+__device__ __forceinline__ void chain_rewalk_body(const RewalkParams& P) {
   __shared__ __align__(16) double s_in[kRewalkStages][32];
   __shared__ __align__(16) double s_out[kRewalkStages][32];
   __shared__ double s_ex[32], s_ex2[32];

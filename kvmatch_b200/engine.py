@@ -190,6 +190,31 @@ class GpuSeries:
         self._L.kvm_runs_free(self._h, C.byref(r))
         return keys, first, last, ms, nl
 
+    def window_mean_runs_all(self, widths=WU_LIST):
+        """kvm_window_mean_runs_all: every width of an index build in ONE pass over the series.  Returns WindowMeanRuns
+        with per-width (keys, first, last) tuples, the device time of the whole pass and the run / re-walk counts."""
+        ws = np.ascontiguousarray(widths, dtype=np.int32)
+        arr = (_lib.KvmRuns * len(ws))()
+        self._check(self._L.kvm_window_mean_runs_all(self._h, ws.ctypes.data, len(ws), arr))
+        per = []
+        for r in arr:
+            c = r.count
+            per.append((np.ctypeslib.as_array(r.keys, shape=(c,)).copy() if c else np.zeros(0),
+                        np.ctypeslib.as_array(r.first, shape=(c,)).copy() if c else np.zeros(0, np.int32),
+                        np.ctypeslib.as_array(r.last, shape=(c,)).copy() if c else np.zeros(0, np.int32)))
+        return WindowMeanRuns([int(w) for w in ws], per, float(arr[0].kernel_ms), int(arr[0].n_launches),
+                              int(sum(r.count for r in arr)), int(sum(r.reserved for r in arr)))
+
+
+@dataclass
+class WindowMeanRuns:
+    widths: list
+    runs: list             # per width: (keys f64, first i32, last i32)
+    kernel_ms: float
+    n_launches: int
+    n_runs: int
+    n_chains_rewalked: int
+
 
 def stable_sort_by_distance(offsets, distances):
     """answers.sort(Comparator.comparing(Pair::getSecond)) — stable, K/QueryEngine.java:373."""

@@ -108,3 +108,88 @@ def merge_answers(offsets: np.ndarray, distances: np.ndarray, counters: dict, de
         dist.all_reduce(cand, op=dist.ReduceOp.MIN)
         best = (float(local_min.item()), int(cand.item()))
     return offs, dists, totals, best
+
+
+class PackedMerger:
+    """The multi-GPU tail as ONE fixed-size collective per query: every rank packs
+    [#answers, best distance, best offset, counters..., first `cap` offsets, first `cap` distances] into a float64
+    buffer (offsets are int32: exact in float64), one all_gather moves it, every rank unpacks.  Only a query with more
+    than `cap` answers on some rank pays a second, padded all_gather for the overflow.  Buffers are allocated once.
+
+    merge() returns (offsets, distances, totals, best) like merge_answers(); `last_device_ms` is the device time of
+    the exchange (CUDA events on torch's current stream; 0 on CPU / single process)."""
+
+    def __init__(self, counter_keys, device=None, cap: int = 512):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.keys = list(counter_keys)
+        self.cap = int(cap)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.dev = device if device is not None else torch.device("cpu")
+        self.cuda = self.dev.type == "cuda"
+        self.head = 3 + len(self.keys)
+        self.len = self.head + 2 * self.cap
+        self.host = torch.zeros(self.len, dtype=torch.float64, pin_memory=self.cuda)
+        self.host_np = self.host.numpy()
+        self.all_host = torch.zeros(self.world * self.len, dtype=torch.float64, pin_memory=self.cuda)
+        if self.world > 1:
+            self.send = torch.zeros(self.len, dtype=torch.float64, device=self.dev)
+            self.recv = torch.zeros(self.world * self.len, dtype=torch.float64, device=self.dev)
+            if self.cuda:
+                self.ev0, self.ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.last_device_ms = 0.0
+        self.overflows = 0
+
+    def merge(self, offsets: np.ndarray, distances: np.ndarray, counters: dict):
+        n = len(offsets)
+        best_d, best_o = np.inf, float(np.iinfo(np.int64).max)
+        if n:
+            i = int(np.lexsort((offsets, distances))[0])
+            best_d, best_o = float(distances[i]), float(offsets[i])
+        if self.world == 1:
+            self.last_device_ms = 0.0
+            best = (best_d, int(best_o)) if n else None
+            return offsets, distances, dict(counters), best
+        torch, dist = self.torch, self.dist
+        h = self.host_np
+        h[0], h[1], h[2] = n, best_d, best_o
+        for j, k in enumerate(self.keys):
+            h[3 + j] = counters[k]
+        c = min(n, self.cap)
+        h[self.head:self.head + c] = offsets[:c]
+        h[self.head + self.cap:self.head + self.cap + c] = distances[:c]
+        if self.cuda:
+            self.ev0.record()
+        self.send.copy_(self.host, non_blocking=True)
+        dist.all_gather_into_tensor(self.recv, self.send)
+        self.all_host.copy_(self.recv, non_blocking=True)
+        if self.cuda:
+            self.ev1.record()
+            self.ev1.synchronize()
+            self.last_device_ms = float(self.ev0.elapsed_time(self.ev1))
+        a = self.all_host.numpy().reshape(self.world, self.len)
+        counts = a[:, 0].astype(np.int64)
+        totals = {k: int(a[:, 3 + j].sum()) for j, k in enumerate(self.keys)}
+        offs = [a[r, self.head:self.head + min(counts[r], self.cap)].astype(np.int32) for r in range(self.world)]
+        dists = [a[r, self.head + self.cap:self.head + self.cap + min(counts[r], self.cap)].copy() for r in range(self.world)]
+        over = int(counts.max()) - self.cap
+        if over > 0:  # rare: some rank holds more answers than the packed buffer carries
+            self.overflows += 1
+            pad = torch.zeros(2 * over, dtype=torch.float64)
+            k = max(0, n - self.cap)
+            pad[:k] = torch.from_numpy(np.ascontiguousarray(offsets[self.cap:], dtype=np.float64))
+            pad[over:over + k] = torch.from_numpy(np.ascontiguousarray(distances[self.cap:]))
+            pad = pad.to(self.dev)
+            got = torch.zeros(self.world * 2 * over, dtype=torch.float64, device=self.dev)
+            dist.all_gather_into_tensor(got, pad)
+            g = got.cpu().numpy().reshape(self.world, 2 * over)
+            for r in range(self.world):
+                k = max(0, int(counts[r]) - self.cap)
+                offs[r] = np.concatenate([offs[r], g[r, :k].astype(np.int32)])
+                dists[r] = np.concatenate([dists[r], g[r, over:over + k]])
+        best = None
+        if counts.sum() > 0:
+            r = int(np.lexsort((a[:, 2], a[:, 1]))[0])  # min distance, then the lowest offset (stable sort of the reference)
+            best = (float(a[r, 1]), int(a[r, 2]))
+        return np.concatenate(offs), np.concatenate(dists), totals, best

@@ -74,3 +74,44 @@ def test_two_rank_gloo_merge_equals_single_process(tmp_path, oracle):
     assert int(got["n_verified"]) == exp.n_verified and int(got["gate"]) == exp.n_gate_pass
     i = int(np.lexsort((exp.offsets, exp.distances))[0])
     assert got["best"].tolist() == [exp.distances[i], exp.offsets[i]] and exp.offsets[i] == 30_000
+
+
+def _packed_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    merger = sharding.PackedMerger(["n_verified", "gate"], cap=8)
+    rng = np.random.default_rng(100 + rank)
+    results = []
+    for step, n_ans in enumerate([0, 3, 8, 9, 40 if rank == 1 else 2, 0 if rank == 0 else 5]):
+        offs = np.sort(rng.choice(np.arange(1, 10_000), size=n_ans, replace=False)).astype(np.int32) + 10_000 * rank
+        dists = rng.random(n_ans)
+        if step == 2 and n_ans:
+            dists[:] = 0.125  # ties across ranks: the lowest offset must win
+        o, d, totals, best = merger.merge(offs, dists, {"n_verified": 1000 + rank, "gate": step})
+        results.append((o, d, totals, best, offs, dists))
+    np.save(os.path.join(out_dir, f"rank{rank}.npy"), np.array(results, dtype=object), allow_pickle=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_packed_merge_two_ranks_incl_overflow(tmp_path):
+    """PackedMerger: one fixed-size all_gather per query, a second one only when a rank holds more than `cap`
+    answers; both ranks must see the concatenation in rank order, the summed counters and the reference's best."""
+    import torch.multiprocessing as mp
+    mp.spawn(_packed_worker, args=(2, free_port(), str(tmp_path)), nprocs=2, join=True)
+    r0 = np.load(tmp_path / "rank0.npy", allow_pickle=True)
+    r1 = np.load(tmp_path / "rank1.npy", allow_pickle=True)
+    for step in range(len(r0)):
+        o0, d0, t0, b0, lo0, ld0 = r0[step]
+        o1, d1, t1, b1, lo1, ld1 = r1[step]
+        exp_o, exp_d = np.concatenate([lo0, lo1]), np.concatenate([ld0, ld1])
+        assert o0.tolist() == exp_o.tolist() == o1.tolist()
+        assert d0.tolist() == exp_d.tolist() == d1.tolist()
+        assert t0 == t1 == {"n_verified": 2001, "gate": 2 * step}
+        if len(exp_o):
+            i = int(np.lexsort((exp_o, exp_d))[0])
+            assert b0 == b1 == (float(exp_d[i]), int(exp_o[i]))
+        else:
+            assert b0 is None and b1 is None
