@@ -2352,7 +2352,7 @@ int kvm_window_mean_runs_all(kvm_ctx* ctx, const int32_t* widths, int32_t n_widt
         R.out = kvm::XList{S.x_off.as<int32_t>(), S.x_ex.as<double>(), S.x_ex2.as<double>(), cnt_d + 3 * q + 2, S.x_cap};
         most = std::max(most, n_chains[q]);
       }
-      kvm::chain_rewalk_batch_kernel<<<dim3((unsigned)std::min<int64_t>(most, ctx->n_sms * 4), (unsigned)n_widths), 32, 0, ctx->stream>>>(B);
+      kvm::chain_rewalk_batch_kernel<<<(unsigned)(std::min<int64_t>(most, ctx->n_sms * 4) * n_widths), 32, 0, ctx->stream>>>(B, n_widths);
       KVM_CUDA(ctx, cudaGetLastError());
       launches += 1;
     }

@@ -618,24 +618,31 @@ constexpr int kRewalkStages = 6;  // 32-position tiles in flight per warp
 //   K/NormQueryEngine.java:523-524  ex -= T[j]; ex2 -= T[j]^2  (after each complete window)
 // Out-of-range slots of a 32-position tile are zero-filled: adding / subtracting +0.0 is the identity here (the sums
 // start at +0.0 and x + y is -0.0 only when both are).
-__device__ __forceinline__ void chain_rewalk_body(const RewalkParams& P);
+template <bool kSq>
+__device__ __forceinline__ void chain_rewalk_body(const RewalkParams& P, int block, int n_blocks);
 
-__global__ void __launch_bounds__(32) chain_rewalk_kernel(RewalkParams P) { chain_rewalk_body(P); }
+__global__ void __launch_bounds__(32) chain_rewalk_kernel(RewalkParams P) { chain_rewalk_body<true>(P, blockIdx.x, gridDim.x); }
 
 // Several independent chain sets in one launch (the window-mean pass: one per width): blockIdx.y picks the set.
 struct RewalkBatch {
   RewalkParams set[5];
 };
-__global__ void __launch_bounds__(32) chain_rewalk_batch_kernel(RewalkBatch B) { chain_rewalk_body(B.set[blockIdx.y]); }
+// (window means need the sum only: kSq = false leaves the squares out; the sets are interleaved over the block index so
+// that the few busy warps of every set spread over different SMs)
+__global__ void __launch_bounds__(32) chain_rewalk_batch_kernel(RewalkBatch B, int n_sets) {
+  const int set = blockIdx.x % n_sets;
+  chain_rewalk_body<false>(B.set[set], blockIdx.x / n_sets, gridDim.x / n_sets);
+}
 
-__device__ __forceinline__ void chain_rewalk_body(const RewalkParams& P) {
+template <bool kSq>
+__device__ __forceinline__ void chain_rewalk_body(const RewalkParams& P, int block, int n_blocks) {
   __shared__ __align__(16) double s_in[kRewalkStages][32];
   __shared__ __align__(16) double s_out[kRewalkStages][32];
   __shared__ double s_ex[32], s_ex2[32];
   const int lane = threadIdx.x;
   const int m = P.m;
   const unsigned long long n = *P.n_flagged;
-  for (unsigned long long ci = blockIdx.x; ci < n; ci += gridDim.x) {
+  for (unsigned long long ci = block; ci < n; ci += n_blocks) {
     const int p = P.flagged[ci];
     const int cb = P.chains.begin(p);
     const int last = P.chain_last[p];
@@ -696,22 +703,22 @@ __device__ __forceinline__ void chain_rewalk_body(const RewalkParams& P) {
         for (int h = 0; h < 16; h++) {
           const double2 a = pin[h];
           ex = xadd(ex, a.x);
-          ex2 = xadd(ex2, xmul(a.x, a.x));
+          if (kSq) ex2 = xadd(ex2, xmul(a.x, a.x));
           ex = xadd(ex, a.y);
-          ex2 = xadd(ex2, xmul(a.y, a.y));
+          if (kSq) ex2 = xadd(ex2, xmul(a.y, a.y));
         }
       } else if (mask == 0) {
 #pragma unroll
         for (int h = 0; h < 16; h++) {
           const double2 a = pin[h], o = pout[h];
           ex = xadd(ex, a.x);
-          ex2 = xadd(ex2, xmul(a.x, a.x));
+          if (kSq) ex2 = xadd(ex2, xmul(a.x, a.x));
           ex = xsub(ex, o.x);
-          ex2 = xsub(ex2, xmul(o.x, o.x));
+          if (kSq) ex2 = xsub(ex2, xmul(o.x, o.x));
           ex = xadd(ex, a.y);
-          ex2 = xadd(ex2, xmul(a.y, a.y));
+          if (kSq) ex2 = xadd(ex2, xmul(a.y, a.y));
           ex = xsub(ex, o.y);
-          ex2 = xsub(ex2, xmul(o.y, o.y));
+          if (kSq) ex2 = xsub(ex2, xmul(o.y, o.y));
         }
       } else {
         // a tile with flagged windows: the same walk, every post-add state parked in shared memory; afterwards lane pp
@@ -720,17 +727,17 @@ __device__ __forceinline__ void chain_rewalk_body(const RewalkParams& P) {
         for (int h = 0; h < 16; h++) {
           const double2 a = pin[h], o = pout[h];
           ex = xadd(ex, a.x);
-          ex2 = xadd(ex2, xmul(a.x, a.x));
+          if (kSq) ex2 = xadd(ex2, xmul(a.x, a.x));
           s_ex[2 * h] = ex;
           s_ex2[2 * h] = ex2;
           ex = xsub(ex, o.x);
-          ex2 = xsub(ex2, xmul(o.x, o.x));
+          if (kSq) ex2 = xsub(ex2, xmul(o.x, o.x));
           ex = xadd(ex, a.y);
-          ex2 = xadd(ex2, xmul(a.y, a.y));
+          if (kSq) ex2 = xadd(ex2, xmul(a.y, a.y));
           s_ex[2 * h + 1] = ex;
           s_ex2[2 * h + 1] = ex2;
           ex = xsub(ex, o.y);
-          ex2 = xsub(ex2, xmul(o.y, o.y));
+          if (kSq) ex2 = xsub(ex2, xmul(o.y, o.y));
         }
         __syncwarp();
         const int j = j0 + lane;
