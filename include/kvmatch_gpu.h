@@ -147,6 +147,13 @@ int kvm_verify_cnsm_ed_batch(kvm_ctx* ctx, const double* queries, int32_t n_quer
 int kvm_scan_ucr_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int32_t rho, double alpha, double beta,
                      kvm_result* out);
 
+/* DtwUtils.lowerUpperLemire on the device (K/utils/DtwUtils.java:50-91, called on the data buffer at
+ * K/QueryEngineDtw.java:397-399): lower[i] / upper[i] = min / max of samples [max(first, first+i-r) ..
+ * min(first+len-1, first+i+r)] (1-based `first`, i = 0..len-1; r <= 512).  The verification entries do not need it
+ * (their third lower bound, LB_Keogh on the data envelope, K/utils/DtwUtils.java:238-257, forms the envelope of each
+ * surviving window on the fly); it is the reference's buffer-level operation offered as such.  Caller-owned outputs. */
+int kvm_envelope(kvm_ctx* ctx, int32_t r, int64_t first, int32_t len, double* lower, double* upper);
+
 /* IndexBuilder step 1 for window width w (K/IndexBuilder.java:194-301): sliding mean with the
  * reference's EPOCH=100000 restart structure, toRound key, run-length intervals split at 255.
  * Needs the whole series on this ctx (first == 1, count == n). */

@@ -174,6 +174,148 @@ __global__ void __launch_bounds__(128) cnsm_dtw_lb_list_kernel(LbListParams P) {
   if (my_gate) atomicAdd(P.gate_pass, (unsigned long long)my_gate);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// LB_Keogh on the DATA envelope (K/utils/DtwUtils.java:238-257, lbKeoghDataCumulative; fed by
+// lowerUpperLemire(data, ...) at K/QueryEngineDtw.java:397-399 / K/NormQueryEngineDtw.java:522-524): the third bound of
+// the reference's cascade.  One warp per survivor of the first stage: the (normalised) window goes to shared memory,
+// its sliding max / min of radius rho are formed with the van Herk / Gil-Werman block decomposition (block = 2 rho + 1:
+// a prefix maximum from each block start and a suffix maximum to each block end, then
+// U[i] = max(suffix[i - rho], prefix[i + rho])), and sum_i dist(q_i, [L_i, U_i])^2 is compared with eps^2.
+// The envelope is taken inside the window (the reference's runs over its whole read buffer, a superset: ours is the
+// tighter valid bound) and kept in single precision rounded outwards (a slightly wider, still valid envelope).
+struct Lb2Params {
+  const double* __restrict__ T;
+  int32_t first_global;
+  int m, rho;
+  const double* __restrict__ q;  // query in natural order (raw / z-normalised)
+  double eps2_hi;
+  CandList in, out;
+};
+
+constexpr size_t lb2_warp_bytes(int m) { return sizeof(double) * (size_t)m + 2 * sizeof(float) * (size_t)m; }
+
+__global__ void __launch_bounds__(256) dtw_lb_data_kernel(Lb2Params P) {
+  extern __shared__ __align__(16) unsigned char lb2_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const int m = P.m, rho = P.rho;
+  double* A = reinterpret_cast<double*>(lb2_smem + (size_t)warp * lb2_warp_bytes(m));
+  float* Pf = reinterpret_cast<float*>(A + m);  // prefix extremum from the block start
+  float* Sf = Pf + m;                            // suffix extremum to the block end
+  unsigned long long n = *P.in.count;
+  if ((long long)n > P.in.cap) n = (unsigned long long)P.in.cap;
+  const int blk = 2 * rho + 1;
+  const int n_blk = (m + blk - 1) / blk;
+  for (unsigned long long e = (unsigned long long)blockIdx.x * n_warps + warp; e < n;
+       e += (unsigned long long)gridDim.x * n_warps) {
+    const int32_t off = P.in.off[e];
+    const double mean = P.in.mean[e], stdv = P.in.stdv[e];
+    const double rstd = 1.0 / stdv;
+    const double* __restrict__ w = P.T + (off - P.first_global);
+    __syncwarp();
+    for (int k = lane; k < m; k += 32) A[k] = (w[k] - mean) * rstd;
+    __syncwarp();
+    double lb = 0.0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {  // pass 0: upper envelope (max), pass 1: lower envelope (min)
+      // blocks are independent: lane = (block, direction); forward prefix / backward suffix scans
+      for (int t = lane; t < 2 * n_blk; t += 32) {
+        const int b = t >> 1, lo = b * blk, hi = min(m, lo + blk) - 1;
+        if ((t & 1) == 0) {
+          float run = pass == 0 ? -INFINITY : INFINITY;
+          for (int k = lo; k <= hi; k++) {
+            const float v = pass == 0 ? __double2float_ru(A[k]) : __double2float_rd(A[k]);
+            run = pass == 0 ? fmaxf(run, v) : fminf(run, v);
+            Pf[k] = run;
+          }
+        } else {
+          float run = pass == 0 ? -INFINITY : INFINITY;
+          for (int k = hi; k >= lo; k--) {
+            const float v = pass == 0 ? __double2float_ru(A[k]) : __double2float_rd(A[k]);
+            run = pass == 0 ? fmaxf(run, v) : fminf(run, v);
+            Sf[k] = run;
+          }
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < m; i += 32) {
+        const int lo = max(0, i - rho), hi = min(m - 1, i + rho);
+        const double qv = __ldg(P.q + i);
+        if (pass == 0) {
+          const double up = (double)fmaxf(Sf[lo], Pf[hi]);
+          const double d = qv > up ? qv - up : 0.0;
+          lb = __fma_rn(d, d, lb);
+        } else {
+          const double dn = (double)fminf(Sf[lo], Pf[hi]);
+          const double d = qv < dn ? dn - qv : 0.0;
+          lb = __fma_rn(d, d, lb);
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lb += __shfl_xor_sync(kFullMask, lb, o);
+    if (lane == 0 && lb <= P.eps2_hi) cand_append(P.out, off, mean, stdv);
+  }
+}
+
+// lowerUpperLemire on the device (K/utils/DtwUtils.java:50-91): l[i] = min, u[i] = max of t[max(0,i-r) .. min(len-1,i+r)]
+// over a region of the series, exact doubles.  One CTA per tile of kEnvTile outputs: the tile plus its halo goes to
+// shared memory as order-preserving integer keys, a sparse table is built level by level (doubling), and every output
+// combines two overlapping power-of-two ranges.
+constexpr int kEnvTile = 2048;
+__device__ __forceinline__ long long env_key(double x) {  // monotone: a <= b  <=>  key(a) <= key(b)  (no NaNs)
+  const long long b = __double_as_longlong(x);
+  return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double env_unkey(long long k) { return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL)); }
+
+__global__ void __launch_bounds__(256) envelope_kernel(const double* __restrict__ t, int len, int r, double* __restrict__ lo_out,
+                                                       double* __restrict__ up_out) {
+  extern __shared__ long long env_smem[];
+  const int span = kEnvTile + 2 * r;  // keys of samples [i0 - r, i0 + kEnvTile + r)
+  long long* mx = env_smem;
+  long long* mn = env_smem + span;
+  const int i0 = (int)blockIdx.x * kEnvTile;
+  for (int k = threadIdx.x; k < span; k += blockDim.x) {
+    const int g = i0 - r + k;
+    const bool in = g >= 0 && g < len;
+    const long long key = in ? env_key(t[g]) : 0;
+    mx[k] = in ? key : LLONG_MIN;  // outside the region: neutral elements (the reference clamps the range)
+    mn[k] = in ? key : LLONG_MAX;
+  }
+  __syncthreads();
+  const int L = 2 * r + 1;
+  int levels = 0;
+  while ((2 << levels) <= L) levels++;  // 2^levels <= L < 2^(levels+1)
+  for (int lv = 0; lv < levels; lv++) {  // after level lv: mx[k] = max over [k, k + 2^(lv+1))
+    const int step = 1 << lv;
+    long long a[ (kEnvTile + 1024 + 255) / 256 ], b[ (kEnvTile + 1024 + 255) / 256 ];
+    int c = 0;
+    for (int k = threadIdx.x; k < span; k += blockDim.x, c++) {
+      const int k2 = min(k + step, span - 1);
+      a[c] = max(mx[k], (k + step < span) ? mx[k2] : LLONG_MIN);
+      b[c] = min(mn[k], (k + step < span) ? mn[k2] : LLONG_MAX);
+    }
+    __syncthreads();
+    c = 0;
+    for (int k = threadIdx.x; k < span; k += blockDim.x, c++) {
+      mx[k] = a[c];
+      mn[k] = b[c];
+    }
+    __syncthreads();
+  }
+  const int p2 = 1 << levels;
+  for (int k = threadIdx.x; k < kEnvTile; k += blockDim.x) {
+    const int i = i0 + k;
+    if (i >= len) break;
+    // window [i - r, i + r] = smem indices [k, k + 2r]: two ranges of length p2
+    const long long u = max(mx[k], mx[k + L - p2]);
+    const long long l = min(mn[k], mn[k + L - p2]);
+    up_out[i] = env_unkey(u);
+    lo_out[i] = env_unkey(l);
+  }
+}
+
 // min of two non-negative doubles through their bit patterns (for x, y >= +0 the IEEE order is the unsigned integer
 // order).  DTW costs are sums of squares, never negative and never -0.0, so this equals DtwUtils.min — and it runs on
 // the integer pipe: DMNMX issues at only ~1/5 of the DADD rate on B200 (tools/fp64_peak.cu) and two of them per cell

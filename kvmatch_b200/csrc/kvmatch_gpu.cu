@@ -95,7 +95,7 @@ struct Arena {
   }
 };
 
-enum Counter { kCntAnswers = 0, kCntCand = 1, kCntGate = 2, kCntTiles = 3, kCntEntries = 4, kCntFlag = 5, kCntDone = 6, kNumCounters = 8 };
+enum Counter { kCntAnswers = 0, kCntCand = 1, kCntGate = 2, kCntTiles = 3, kCntEntries = 4, kCntFlag = 5, kCntDone = 6, kCntCand2 = 7, kNumCounters = 10 };
 
 struct Plan {
   std::vector<int32_t> cbegin, nsamp, ncand;
@@ -161,6 +161,7 @@ struct kvm_ctx {
 
   DevBuf arena, qarena, counters, wl_off, wl_ex, wl_ex2, region_count, tile_prefix;
   DevBuf cand_off, cand_mean, cand_std, ans_off, ans_dist;
+  DevBuf cand2_off, cand2_mean, cand2_std;  // survivors of the data-envelope bound (same capacity as cand_*)
   DevBuf seg_b, seg_first, seg_last, chain_count, chain_prefix, run_key, run_b, run_first, run_last;
   long long cand_cap = 0, ans_cap = 0;
   NormPlanCache norm_cache;
@@ -358,16 +359,27 @@ int ensure_answers(kvm_ctx* ctx, long long cap) {
 
 int ensure_cands(kvm_ctx* ctx, long long cap) {
   if (cap <= ctx->cand_cap) return KVM_OK;
+  ctx->cand_cap = 0;
   KVM_CUDA(ctx, ctx->cand_off.ensure(sizeof(int32_t) * cap));
   KVM_CUDA(ctx, ctx->cand_mean.ensure(sizeof(double) * cap));
   KVM_CUDA(ctx, ctx->cand_std.ensure(sizeof(double) * cap));
+  KVM_CUDA(ctx, ctx->cand2_off.ensure(sizeof(int32_t) * cap));
+  KVM_CUDA(ctx, ctx->cand2_mean.ensure(sizeof(double) * cap));
+  KVM_CUDA(ctx, ctx->cand2_std.ensure(sizeof(double) * cap));
   ctx->cand_cap = cap;
   return KVM_OK;
 }
 
+CandList cands2_of(kvm_ctx* ctx);
+int launch_lb_data(kvm_ctx* ctx, const double* q, int m, int rho, double eps2_hi);
+
 AnswerSink sink_of(kvm_ctx* ctx) {
   return AnswerSink{ctx->ans_off.as<int32_t>(), ctx->ans_dist.as<double>(),
                     ctx->counters.as<unsigned long long>() + kCntAnswers, ctx->ans_cap};
+}
+CandList cands2_of(kvm_ctx* ctx) {
+  return CandList{ctx->cand2_off.as<int32_t>(), ctx->cand2_mean.as<double>(), ctx->cand2_std.as<double>(),
+                  ctx->counters.as<unsigned long long>() + kCntCand2, ctx->cand_cap};
 }
 CandList cands_of(kvm_ctx* ctx) {
   return CandList{ctx->cand_off.as<int32_t>(), ctx->cand_mean.as<double>(), ctx->cand_std.as<double>(),
@@ -1290,6 +1302,7 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
       L.out = cands_of(ctx);
       L.gate_pass = counters + kCntGate;
       cnsm_dtw_lb_list_kernel<<<ctx->n_sms * 8, 128, 0, ctx->stream>>>(L);
+      if ((rc = launch_lb_data(ctx, L.Q.q, m, rho, eps2_hi))) return rc;
       KVM_CUDA(ctx, cudaEventRecord(ctx->evs[2], ctx->stream));
       DtwParams D{};
       D.T = ctx->series;
@@ -1302,10 +1315,10 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
       D.eps2 = eps2;
       D.eps2_hi = eps2_hi;
       D.n_abandoned = counters + kCntFlag;
-      D.in = L.out;
+      D.in = cands2_of(ctx);
       D.sink = sink_of(ctx);
       if ((rc = launch_dtw(ctx, D))) return rc;
-      launches += 2;
+      launches += 3;
     }
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     KVM_CUDA(ctx, cudaGetLastError());
@@ -1342,10 +1355,39 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
   out->n_gate_pass = (int64_t)cnt[kCntGate];
   out->n_rewalked = (int64_t)cnt[kCntEntries];
   out->n_chains_rewalked = (int64_t)cnt[kCntTiles];
-  if (!dtw) out->n_exact = (int64_t)cnt[kCntFlag]; else out->n_lb_pass = (int64_t)cnt[kCntCand];
+  if (!dtw) out->n_exact = (int64_t)cnt[kCntFlag]; else out->n_lb_pass = (int64_t)cnt[kCntCand2];
   return fetch_answers(ctx, (long long)cnt[kCntAnswers], out);
 }
 
+}  // namespace
+
+// Third bound of the cascade (LB_Keogh on the data envelope) over the survivors of the first LB stage: cands -> cands2.
+namespace {
+int launch_lb_data(kvm_ctx* ctx, const double* q, int m, int rho, double eps2_hi) {
+  Lb2Params L{};
+  L.T = ctx->series;
+  L.first_global = (int32_t)ctx->first;
+  L.m = m;
+  L.rho = rho;
+  L.q = q;
+  L.eps2_hi = eps2_hi;
+  L.in = cands_of(ctx);
+  L.out = cands2_of(ctx);
+  const size_t per_warp = lb2_warp_bytes(m);
+  const size_t budget = 200 * 1024;
+  if (per_warp > budget) return fail(ctx, KVM_E_ARG, "DTW query length %d exceeds the shared-memory staging limit", m);
+  const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, budget / per_warp));
+  const size_t smem = per_warp * warps;
+  static bool attr = false;
+  if (!attr) {
+    KVM_CUDA(ctx, cudaFuncSetAttribute(dtw_lb_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    attr = true;
+  }
+  const int grid = ctx->n_sms * std::max(1, (int)(budget / smem));
+  dtw_lb_data_kernel<<<grid, warps * 32, smem, ctx->stream>>>(L);
+  KVM_CUDA(ctx, cudaGetLastError());
+  return KVM_OK;
+}
 }  // namespace
 
 int launch_dtw(kvm_ctx* ctx, const DtwParams& D) {
@@ -1463,7 +1505,7 @@ void kvm_destroy(kvm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* dev[] = {&ctx->series_buf, &ctx->arena, &ctx->qarena, &ctx->counters, &ctx->wl_off, &ctx->wl_ex, &ctx->wl_ex2,
-                   &ctx->region_count, &ctx->tile_prefix, &ctx->cand_off, &ctx->cand_mean, &ctx->cand_std,
+                   &ctx->region_count, &ctx->tile_prefix, &ctx->cand_off, &ctx->cand_mean, &ctx->cand_std, &ctx->cand2_off, &ctx->cand2_mean, &ctx->cand2_std,
                    &ctx->ans_off, &ctx->ans_dist, &ctx->seg_b, &ctx->seg_first, &ctx->seg_last, &ctx->chain_count,
                    &ctx->chain_prefix, &ctx->run_key, &ctx->run_b, &ctx->run_first, &ctx->run_last, &ctx->sarena,
                    &ctx->need_bits, &ctx->chain_last, &ctx->flagged, &ctx->x_off, &ctx->x_ex, &ctx->x_ex2, &ctx->bmax};
@@ -2029,6 +2071,8 @@ int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     dtw_lb_raw_kernel<<<(unsigned)n_tiles, kEdThreads, 0, ctx->stream>>>(L);
     KVM_CUDA(ctx, cudaEventRecord(ctx->evs[0], ctx->stream));
+    if ((rc = launch_lb_data(ctx, L.Q.q, m, rho, L.Q.eps2_hi))) return rc;  // LB_Keogh on the data envelope
+    D.in = cands2_of(ctx);
     KVM_CUDA(ctx, cudaEventRecord(ctx->evs[1], ctx->stream));
     if ((rc = launch_dtw(ctx, D))) return rc;
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -2036,14 +2080,14 @@ int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int
     if ((rc = read_counters(ctx, cnt))) return rc;
     out->kernel_ms += elapsed_ms(ctx);
     add_stage_ms(ctx, out);
-    out->n_launches += 2;
+    out->n_launches += 3;
     const bool cand_over = (long long)cnt[kCntCand] > ctx->cand_cap, ans_over = (long long)cnt[kCntAnswers] > ctx->ans_cap;
     if (!cand_over && !ans_over) break;
     if (attempt == 7) return fail(ctx, KVM_E_OOM, "result buffers kept overflowing");
     if (cand_over && (rc = ensure_cands(ctx, (long long)cnt[kCntCand] + 1024))) return rc;
     if (ans_over && (rc = ensure_answers(ctx, (long long)cnt[kCntAnswers] + 1024))) return rc;
   }
-  out->n_lb_pass = (int64_t)cnt[kCntCand];
+  out->n_lb_pass = (int64_t)cnt[kCntCand2];
   return fetch_answers(ctx, (long long)cnt[kCntAnswers], out);
 }
 
@@ -2461,6 +2505,35 @@ int kvm_window_mean_runs_all(kvm_ctx* ctx, const int32_t* widths, int32_t n_widt
     outs[q].n_launches = launches;
     outs[q].reserved = (int32_t)std::min<unsigned long long>(cnt[3 * q + 1], INT32_MAX);  // epochs re-walked exactly
   }
+  return KVM_OK;
+}
+
+// DtwUtils.lowerUpperLemire on the device: the envelope of samples [first, first + len - 1] (1-based) of the loaded
+// series, clamped at the ends of that region exactly as the reference clamps at the ends of its read buffer.
+int kvm_envelope(kvm_ctx* ctx, int32_t r, int64_t first, int32_t len, double* lower, double* upper) {
+  if (!ctx) return KVM_E_ARG;
+  if (!lower || !upper || len < 1 || r < 0) return fail(ctx, KVM_E_ARG, "null/invalid argument");
+  if (r > 512) return fail(ctx, KVM_E_ARG, "envelope radius %d exceeds the supported maximum 512", r);
+  if (!ctx->series) return fail(ctx, KVM_E_STATE, "no series loaded");
+  if (first < ctx->first || first + len - 1 > ctx->first + ctx->count - 1)
+    return fail(ctx, KVM_E_RANGE, "samples [%lld,%lld] are not on this ctx", (long long)first, (long long)(first + len - 1));
+  int rc = begin_call(ctx);
+  if (rc) return rc;
+  KVM_CUDA(ctx, ctx->run_key.ensure(sizeof(double) * 2 * (size_t)len));
+  double* lo_d = ctx->run_key.as<double>();
+  double* up_d = lo_d + len;
+  const size_t smem = sizeof(long long) * 2 * (size_t)(kvm::kEnvTile + 2 * r);
+  static bool attr = false;
+  if (!attr) {
+    KVM_CUDA(ctx, cudaFuncSetAttribute(kvm::envelope_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr = true;
+  }
+  kvm::envelope_kernel<<<(len + kvm::kEnvTile - 1) / kvm::kEnvTile, 256, smem, ctx->stream>>>(ctx->series + (first - ctx->first), len, r,
+                                                                                            lo_d, up_d);
+  KVM_CUDA(ctx, cudaGetLastError());
+  KVM_CUDA(ctx, cudaMemcpyAsync(lower, lo_d, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, ctx->stream));
+  KVM_CUDA(ctx, cudaMemcpyAsync(upper, up_d, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, ctx->stream));
+  KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return KVM_OK;
 }
 

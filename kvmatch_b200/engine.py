@@ -190,6 +190,13 @@ class GpuSeries:
         self._L.kvm_runs_free(self._h, C.byref(r))
         return keys, first, last, ms, nl
 
+    def envelope(self, r: int, first: int, length: int):
+        """kvm_envelope: (lower, upper) = DtwUtils.lowerUpperLemire over samples [first, first+length-1] (1-based)."""
+        lo = np.empty(length)
+        up = np.empty(length)
+        self._check(self._L.kvm_envelope(self._h, r, first, length, lo.ctypes.data, up.ctypes.data))
+        return lo, up
+
     def window_mean_runs_all(self, widths=WU_LIST):
         """kvm_window_mean_runs_all: every width of an index build in ONE pass over the series.  Returns WindowMeanRuns
         with per-width (keys, first, last) tuples, the device time of the whole pass and the run / re-walk counts."""

@@ -71,7 +71,16 @@ def run(iters=40, seed=2026, verbose=True):
         alpha, beta = float(rng.choice([1.1, 1.5, 3.0])), float(rng.choice([0.5, 5.0, 100.0]))
         rho = int(max(1, min(100, rng.choice([0.02, 0.05, 0.1]) * m)))
         ctx = f"it={it} n={n} m={m} K={len(iv)} kind={kind} shift={shift} eps={eps} a={alpha} b={beta} rho={rho}"
-        same(g.verify_cnsm_ed(q, eps, alpha, beta, iv, shift), o.verify_cnsm_ed(s, q, eps, alpha, beta, iv, shift), "cnsm-ed", ctx)
+        got_c, exp_c = g.verify_cnsm_ed(q, eps, alpha, beta, iv, shift), o.verify_cnsm_ed(s, q, eps, alpha, beta, iv, shift)
+        same(got_c, exp_c, "cnsm-ed", ctx)
+        if got_c.n_gate_pass != exp_c.n_gate_pass:
+            bad += 1
+            print("MISMATCH gate count", ctx, got_c.n_gate_pass, exp_c.n_gate_pass, flush=True)
+        if it % 3 == 0:  # the relay walker (every chain walked exactly) must agree with the stream
+            from kvmatch_b200 import _lib
+            g.set_option(_lib.KVM_OPT_CNSM_PATH, _lib.KVM_CNSM_RELAY)
+            same(g.verify_cnsm_ed(q, eps, alpha, beta, iv, shift), exp_c, "cnsm-ed (relay)", ctx)
+            g.set_option(_lib.KVM_OPT_CNSM_PATH, _lib.KVM_CNSM_STREAM)
         sc = float(np.sqrt(m))
         same(g.verify_ed(q, eps * sc, iv, shift), o.verify_ed(s, q, eps * sc, iv, shift), "ed", ctx)
         if m >= 16 and it % 2 == 0:
@@ -88,6 +97,13 @@ def run(iters=40, seed=2026, verbose=True):
             if not (f.tolist() == ef.tolist() and l.tolist() == el.tolist() and k.view(np.int64).tolist() == ek.view(np.int64).tolist()):
                 bad += 1
                 print("MISMATCH runs", ctx, w, flush=True)
+            ws = (25, 50, 100, 200, 400)
+            fused = g.window_mean_runs_all(ws)
+            for w2, (k2, f2, l2) in zip(ws, fused.runs):
+                ek2, ef2, el2 = o.window_mean_runs(s, w2)
+                if not (f2.tolist() == ef2.tolist() and l2.tolist() == el2.tolist() and k2.view(np.int64).tolist() == ek2.view(np.int64).tolist()):
+                    bad += 1
+                    print("MISMATCH fused runs", ctx, w2, flush=True)
             import tempfile
             with tempfile.TemporaryDirectory() as td:
                 path = os.path.join(td, "index")
