@@ -187,6 +187,27 @@ int kvm_index_image_from_runs(const double* keys, const int32_t* first, const in
                               unsigned char** image, kvm_index_info* info);
 void kvm_image_free(unsigned char* image);
 
+/* ---- several GPUs behind one handle (one process) -------------------------------------------------
+ * The series is sharded by offset range: device d owns window starts [d*per+1, (d+1)*per] (per = ceil(n / n_dev)
+ * rounded up to a multiple of `grid`) and holds `halo` more samples behind them.  Every interval is verified by the
+ * device that owns its first scanned sample max(left-shift, 1) — statistic chains are never split, so results are
+ * bit-identical to one device's — and must end within that device's halo (KVM_E_RANGE otherwise).  One host thread
+ * per device drives its context; the host concatenates the answers (device order = offset order), sums the
+ * counters and reports the slowest device's times.  No series data and no collective crosses GPUs.  (One process
+ * per GPU with an NCCL all_gather of the packed answers is the other supported layout: kvmatch_b200/sharding.py.)
+ * Precedent in the reference: the (w-1)-point overlap of K/mapreduce/BuildIndexMapReduce.java:216-221. */
+typedef struct kvm_multi kvm_multi;
+enum { KVM_ENGINE_ED = 0, KVM_ENGINE_CNSM_ED = 1, KVM_ENGINE_DTW = 2, KVM_ENGINE_CNSM_DTW = 3 };
+int kvm_multi_create(kvm_multi** out, const int32_t* device_ids, int32_t n_dev);
+void kvm_multi_destroy(kvm_multi* m);
+const char* kvm_multi_last_error(const kvm_multi* m);
+int32_t kvm_multi_devices(const kvm_multi* m);
+int kvm_multi_load_series_host(kvm_multi* m, const double* samples, int64_t n, int64_t halo, int64_t grid);
+/* engine selects kvm_verify_ed / _cnsm_ed / _dtw / _cnsm_dtw semantics (parameters the engine does not take are
+ * ignored); out->offsets / distances stay valid until the next call on this handle. */
+int kvm_multi_verify(kvm_multi* m, int32_t engine, const double* q, int32_t mq, double epsilon, int32_t rho, double alpha,
+                     double beta, const int32_t* lr, int32_t K, int32_t shift, kvm_result* out);
+
 void kvm_result_free(kvm_ctx* ctx, kvm_result* r);
 void kvm_runs_free(kvm_ctx* ctx, kvm_runs* r);
 

@@ -5,5 +5,5 @@ binding, the host-side mirror of the reference's engine classes, seeded DataGene
 and the multi-GPU offset sharding.  There is no CPU fallback.
 """
 from ._lib import KvmError, LIB_PATH  # noqa: F401
-from .engine import (GpuSeries, IndexBuilder, NormQueryEngine, NormQueryEngineDtw, QueryEngine,  # noqa: F401
+from .engine import (GpuSeries, IndexBuilder, MultiGpuSeries, NormQueryEngine, NormQueryEngineDtw, QueryEngine,  # noqa: F401
                      QueryEngineDtw, StatisticInfo, VerifyResult, WU_LIST, rho_from_prompt)

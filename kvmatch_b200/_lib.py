@@ -36,7 +36,10 @@ EXPORTS = [
     "kvm_verify_ed", "kvm_verify_cnsm_ed", "kvm_verify_dtw", "kvm_verify_cnsm_dtw", "kvm_verify_cnsm_ed_batch", "kvm_scan_ucr_dtw",
     "kvm_envelope", "kvm_window_mean_runs", "kvm_window_mean_runs_all", "kvm_build_index_file", "kvm_index_image_from_runs", "kvm_image_free",
     "kvm_result_free", "kvm_runs_free",
+    "kvm_multi_create", "kvm_multi_destroy", "kvm_multi_last_error", "kvm_multi_devices", "kvm_multi_load_series_host",
+    "kvm_multi_verify",
 ]
+KVM_ENGINE_ED, KVM_ENGINE_CNSM_ED, KVM_ENGINE_DTW, KVM_ENGINE_CNSM_DTW = 0, 1, 2, 3
 
 
 class KvmError(RuntimeError):
@@ -132,6 +135,15 @@ def load():
     L.kvm_result_free.restype = None
     L.kvm_runs_free.argtypes = [vp, C.POINTER(KvmRuns)]
     L.kvm_runs_free.restype = None
+    L.kvm_multi_create.argtypes = [C.POINTER(vp), vp, C.c_int32]
+    L.kvm_multi_destroy.argtypes = [vp]
+    L.kvm_multi_destroy.restype = None
+    L.kvm_multi_last_error.argtypes = [vp]
+    L.kvm_multi_last_error.restype = C.c_char_p
+    L.kvm_multi_devices.argtypes = [vp]
+    L.kvm_multi_load_series_host.argtypes = [vp, _dp, C.c_int64, C.c_int64, C.c_int64]
+    L.kvm_multi_verify.argtypes = [vp, C.c_int32, _dp, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_double, _ip,
+                                   C.c_int32, C.c_int32, R]
     _lib = L
     return L
 

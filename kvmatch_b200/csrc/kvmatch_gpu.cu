@@ -18,6 +18,7 @@
 #include <chrono>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "dtw_kernels.cuh"
@@ -2587,6 +2588,159 @@ int kvm_build_index_file(kvm_ctx* ctx, int32_t w, const char* path, kvm_index_in
   info->n_rows = ii.rows;
   info->kernel_ms = runs.kernel_ms;
   info->host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return KVM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Several GPUs behind one handle (single process): the series is sharded by offset range, every device verifies the
+// intervals whose first scanned sample it owns (chains are never split), one host thread per device drives its ctx,
+// and the host concatenates the answers — shards own ascending offset ranges, so device order is offset order.
+// No series data and no collective crosses GPUs; (the multi-process layout, one rank per GPU with an NCCL all_gather of
+// the packed answers, is kvmatch_b200/sharding.py.)
+struct kvm_multi {
+  std::vector<kvm_ctx*> ctx;
+  std::vector<int64_t> own_lo, own_hi;  // owned window starts (1-based, inclusive)
+  int64_t n = 0;
+  std::string err;
+  std::vector<int32_t> off;
+  std::vector<double> dist;
+};
+
+int kvm_multi_create(kvm_multi** out, const int32_t* device_ids, int32_t n_dev) {
+  if (!out) return KVM_E_ARG;
+  *out = nullptr;
+  if (!device_ids || n_dev < 1 || n_dev > 64) return fail(nullptr, KVM_E_ARG, "1..64 devices");
+  kvm_multi* M = new kvm_multi();
+  for (int d = 0; d < n_dev; d++) {
+    kvm_ctx* c = nullptr;
+    const int rc = kvm_create(&c, device_ids[d]);
+    if (rc) {
+      for (kvm_ctx* x : M->ctx) kvm_destroy(x);
+      delete M;
+      return rc;  // (message in kvm_last_error(NULL))
+    }
+    M->ctx.push_back(c);
+  }
+  *out = M;
+  return KVM_OK;
+}
+
+void kvm_multi_destroy(kvm_multi* M) {
+  if (!M) return;
+  for (kvm_ctx* c : M->ctx) kvm_destroy(c);
+  delete M;
+}
+
+const char* kvm_multi_last_error(const kvm_multi* M) { return M ? M->err.c_str() : g_create_error.c_str(); }
+
+int32_t kvm_multi_devices(const kvm_multi* M) { return M ? (int32_t)M->ctx.size() : 0; }
+
+// Shard `samples` (the whole series, length n) over the devices: device d owns window starts
+// [d*per + 1, (d+1)*per] with per = ceil(n / n_dev) rounded up to a multiple of `grid` (pass the chain chunk of an
+// index-free scan so that no chain straddles two devices; 1 otherwise) and holds `halo` more samples behind them
+// (at least the longest query minus one; longer if single intervals are longer than that).
+int kvm_multi_load_series_host(kvm_multi* M, const double* samples, int64_t n, int64_t halo, int64_t grid) {
+  if (!M) return KVM_E_ARG;
+  if (!samples || n < 1 || halo < 0 || grid < 1) {
+    M->err = "null/invalid argument";
+    return KVM_E_ARG;
+  }
+  const int D = (int)M->ctx.size();
+  int64_t per = (n + D - 1) / D;
+  per = (per + grid - 1) / grid * grid;
+  M->own_lo.assign(D, 0);
+  M->own_hi.assign(D, -1);
+  M->n = n;
+  std::vector<int> rcs(D, KVM_OK);
+  std::vector<std::thread> th;
+  for (int d = 0; d < D; d++) {
+    const int64_t lo = (int64_t)d * per + 1, hi = std::min<int64_t>(n, (int64_t)(d + 1) * per);
+    if (lo > n) continue;  // more devices than grid cells: this one stays empty
+    M->own_lo[d] = lo;
+    M->own_hi[d] = hi;
+    const int64_t last = std::min<int64_t>(n, hi + halo);
+    th.emplace_back([=, &rcs]() { rcs[d] = kvm_load_series_host(M->ctx[d], samples + (lo - 1), n, lo, last - lo + 1); });
+  }
+  for (std::thread& t : th) t.join();
+  for (int d = 0; d < D; d++)
+    if (rcs[d]) {
+      M->err = kvm_last_error(M->ctx[d]);
+      return rcs[d];
+    }
+  return KVM_OK;
+}
+
+// One verification call over all devices.  engine: KVM_ENGINE_ED / _CNSM_ED / _DTW / _CNSM_DTW (the unused parameters
+// are ignored).  out is what the single-device entry returns for the whole series: answers in ascending offset order,
+// counters summed, kernel_ms / stage_ms = the slowest device's.
+int kvm_multi_verify(kvm_multi* M, int32_t engine, const double* q, int32_t m, double epsilon, int32_t rho, double alpha,
+                     double beta, const int32_t* lr, int32_t K, int32_t shift, kvm_result* out) {
+  if (!M) return KVM_E_ARG;
+  if (!out || !q || K < 0 || (K > 0 && !lr) || engine < KVM_ENGINE_ED || engine > KVM_ENGINE_CNSM_DTW) {
+    M->err = "null/invalid argument";
+    return KVM_E_ARG;
+  }
+  std::memset(out, 0, sizeof(*out));
+  const int D = (int)M->ctx.size();
+  // intervals -> devices by their first scanned sample max(left - shift, 1)
+  std::vector<std::vector<int32_t>> part(D);
+  for (int p = 0; p < K; p++) {
+    const int64_t begin = std::max<int64_t>((int64_t)lr[2 * p] - shift, 1);
+    int d = 0;
+    while (d + 1 < D && M->own_hi[d] >= 0 && begin > M->own_hi[d]) d++;
+    if (M->own_hi[d] < 0) {
+      M->err = "an interval starts beyond the loaded series";
+      return KVM_E_RANGE;
+    }
+    part[d].push_back(lr[2 * p]);
+    part[d].push_back(lr[2 * p + 1]);
+  }
+  std::vector<kvm_result> res(D);
+  std::vector<int> rcs(D, KVM_OK);
+  std::vector<std::thread> th;
+  for (int d = 0; d < D; d++) {
+    std::memset(&res[d], 0, sizeof(kvm_result));
+    if (M->own_hi[d] < 0) continue;
+    th.emplace_back([&, d]() {
+      const int32_t* iv = part[d].data();
+      const int32_t k = (int32_t)(part[d].size() / 2);
+      kvm_ctx* c = M->ctx[d];
+      switch (engine) {
+        case KVM_ENGINE_ED: rcs[d] = kvm_verify_ed(c, q, m, epsilon, iv, k, shift, &res[d]); break;
+        case KVM_ENGINE_CNSM_ED: rcs[d] = kvm_verify_cnsm_ed(c, q, m, epsilon, alpha, beta, iv, k, shift, &res[d]); break;
+        case KVM_ENGINE_DTW: rcs[d] = kvm_verify_dtw(c, q, m, epsilon, rho, iv, k, shift, &res[d]); break;
+        default: rcs[d] = kvm_verify_cnsm_dtw(c, q, m, epsilon, rho, alpha, beta, iv, k, shift, &res[d]); break;
+      }
+    });
+  }
+  for (std::thread& t : th) t.join();
+  for (int d = 0; d < D; d++)
+    if (rcs[d]) {
+      M->err = std::string("device ") + std::to_string(d) + ": " + kvm_last_error(M->ctx[d]);
+      return rcs[d];
+    }
+  M->off.clear();
+  M->dist.clear();
+  for (int d = 0; d < D; d++) {
+    const kvm_result& r = res[d];
+    M->off.insert(M->off.end(), r.offsets, r.offsets + r.count);
+    M->dist.insert(M->dist.end(), r.distances, r.distances + r.count);
+    out->cnt_candidate += r.cnt_candidate;
+    out->n_verified += r.n_verified;
+    out->s_total += r.s_total;
+    out->n_gate_pass += r.n_gate_pass;
+    out->n_lb_pass += r.n_lb_pass;
+    out->n_exact += r.n_exact;
+    out->n_rewalked += r.n_rewalked;
+    out->n_chains_rewalked += r.n_chains_rewalked;
+    out->n_launches += r.n_launches;
+    out->h2d_bytes += r.h2d_bytes;
+    out->kernel_ms = std::max(out->kernel_ms, r.kernel_ms);
+    for (int i = 0; i < 4; i++) out->stage_ms[i] = std::max(out->stage_ms[i], r.stage_ms[i]);
+  }
+  out->count = (int64_t)M->off.size();
+  out->offsets = M->off.data();
+  out->distances = M->dist.data();
   return KVM_OK;
 }
 

@@ -213,6 +213,50 @@ class GpuSeries:
                               int(sum(r.count for r in arr)), int(sum(r.reserved for r in arr)))
 
 
+class MultiGpuSeries:
+    """kvm_multi: one process driving several GPUs; the series sharded by offset range with a halo (see
+    include/kvmatch_gpu.h).  verify(engine, ...) returns what the single-device call returns for the whole series."""
+
+    def __init__(self, device_ids):
+        self._L = _lib.load()
+        ids = np.ascontiguousarray(device_ids, dtype=np.int32)
+        h = C.c_void_p()
+        rc = self._L.kvm_multi_create(C.byref(h), ids.ctypes.data, len(ids))
+        if rc != 0:
+            raise _lib.KvmError(rc, self._L.kvm_last_error(None).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.kvm_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise _lib.KvmError(rc, self._L.kvm_multi_last_error(self._h).decode())
+
+    def load(self, samples, halo: int, grid: int = 1):
+        a, p = _lib.as_f64(samples)
+        self._check(self._L.kvm_multi_load_series_host(self._h, p, len(a), halo, grid))
+        return self
+
+    def verify(self, engine: int, q, epsilon, intervals, shift=0, rho=0, alpha=1.0, beta=0.0) -> VerifyResult:
+        q, qp = _lib.as_f64(q)
+        lr, lp, K = _lib.as_intervals(intervals)
+        r = _lib.KvmResult()
+        self._check(self._L.kvm_multi_verify(self._h, engine, qp, len(q), epsilon, rho, alpha, beta, lp, K, shift, C.byref(r)))
+        c = r.count
+        return VerifyResult(_lib.copy_out(r.offsets, c, np.int32), _lib.copy_out(r.distances, c, np.float64), r.cnt_candidate,
+                            r.n_verified, r.s_total, r.n_gate_pass, r.n_lb_pass, r.n_exact, r.kernel_ms, r.n_launches,
+                            tuple(r.stage_ms), int(r.h2d_bytes), int(r.n_rewalked), int(r.n_chains_rewalked))
+
+
 @dataclass
 class WindowMeanRuns:
     widths: list
