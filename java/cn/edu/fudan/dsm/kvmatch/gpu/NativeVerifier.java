@@ -159,7 +159,7 @@ public final class NativeVerifier implements AutoCloseable {
     public int buildIndexFile(int w, String path) throws IOException {
         try (Arena a = Arena.ofConfined()) {
             MemorySegment info = a.allocate(INDEX_INFO);
-            check((int) BUILD_INDEX_FILE.invokeExact(ctx, w, a.allocateUtf8String(path), info));
+            check((int) BUILD_INDEX_FILE.invokeExact(ctx, w, a.allocateFrom(path), info));
             return info.get(JAVA_INT, INDEX_INFO.byteOffset(MemoryLayout.PathElement.groupElement("n_rows")));
         } catch (IOException e) { throw e; } catch (Throwable t) { throw new IOException(t); }
     }

@@ -352,6 +352,7 @@ int check_common(kvm_ctx* ctx, const double* q, int m, double epsilon, const int
 
 int ensure_answers(kvm_ctx* ctx, long long cap) {
   if (cap <= ctx->ans_cap) return KVM_OK;
+  ctx->ans_cap = 0;  // (a failure below must not leave a stale capacity over a freed buffer)
   KVM_CUDA(ctx, ctx->ans_off.ensure(sizeof(int32_t) * cap));
   KVM_CUDA(ctx, ctx->ans_dist.ensure(sizeof(double) * cap));
   ctx->ans_cap = cap;
@@ -1955,7 +1956,8 @@ int kvm_verify_cnsm_ed_batch(kvm_ctx* ctx, const double* queries, int32_t n_quer
       if ((rc = launch_tail(q))) break;
       cudaStreamSynchronize(ctx->stream);
       std::memcpy(cnt, ctx->h_counters.p, sizeof(cnt));
-      if (attempt == 7) rc = fail(ctx, KVM_E_OOM, "candidate/answer buffers kept overflowing");
+      if (attempt == 7 && ((long long)cnt[kCntCand] > ctx->cand_cap || (long long)cnt[kCntAnswers] > ctx->ans_cap))
+        rc = fail(ctx, KVM_E_OOM, "candidate/answer buffers kept overflowing");
     }
     if (rc == KVM_OK) {
       out->n_gate_pass = (int64_t)cnt[kCntGate];
@@ -1996,7 +1998,22 @@ int kvm_scan_ucr_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, i
   if (ctx->first != 1 || ctx->count != ctx->n) return fail(ctx, KVM_E_STATE, "the UCR scan needs the whole series on this ctx");
   constexpr int64_t kEpoch = 100000;  // UcrDtwQueryExecutor.java:97
   if (m < 3 || m > kEpoch) return fail(ctx, KVM_E_ARG, "UCR-DTW needs 3 <= m <= EPOCH");
-  const int64_t per = kEpoch - m + 1, last = ctx->n - m + 1;  // window starts per buffer; last 1-based start
+  // The executor's block iterator feeds 125-sample nodes, the last one zero padded, and counts only within-node
+  // advances against n (K/experiments/ucr/UcrDtwQueryExecutor.java nextData(), as K/IndexBuilder.java:152-180): for
+  // n % 125 != 0 it also verifies the windows that run into the zero padding.  `fed` = samples it feeds; the series
+  // buffer keeps that many zeros behind the data (kTailPad).
+  int64_t fed = 0;
+  {
+    const int64_t n_nodes = (ctx->n + 124) / 125;
+    int64_t cnt = 0;
+    for (int64_t b = 0; b < n_nodes; b++) {
+      const int64_t within = std::min<int64_t>(124, std::max<int64_t>(0, ctx->n - cnt));
+      fed += 1 + within;
+      cnt += within;
+      if (within < 124) break;
+    }
+  }
+  const int64_t per = kEpoch - m + 1, last = fed - m + 1;  // window starts per buffer; last 1-based start
   std::vector<int32_t> lr;
   for (int64_t left = 1; left <= last; left += per) {
     lr.push_back((int32_t)left);
@@ -2007,7 +2024,16 @@ int kvm_scan_ucr_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, i
     std::memset(out, 0, sizeof(*out));
     return KVM_OK;
   }
+  const int64_t n_real = ctx->n, count_real = ctx->count;
+  ctx->n = fed;      // the phantom zeros count as samples for this scan
+  ctx->count = fed;
+  ctx->splan.valid = false;
+  ctx->norm_cache.valid = false;
   const int rc = verify_norm(ctx, Mode::kDtw, q, m, epsilon, rho, alpha, beta, lr.data(), (int)(lr.size() / 2), 0, out);
+  ctx->n = n_real;
+  ctx->count = count_real;
+  ctx->splan.valid = false;
+  ctx->norm_cache.valid = false;
   if (rc) return rc;
   for (int32_t& o : ctx->res_off) o -= 1;  // 0-based offsets, :278
   return KVM_OK;

@@ -324,6 +324,29 @@ def test_scan_ucr_dtw_matches_reference_executor(gpu, oracle, m, rho, eps):
     assert got.n_verified == n - m + 1
 
 
+@pytest.mark.parametrize("n", [250_007, 100_124, 199_999])
+def test_scan_ucr_dtw_phantom_samples(gpu, oracle, n):
+    """n % 125 != 0: the executor's block iterator zero-pads the last 1000-byte block and also verifies the windows
+    that run into the padding."""
+    s = datagen.generate(n, seed=n)
+    s[-300:] *= 0.01  # a quiet tail: windows over the zero padding can pass the gate
+    gpu.load(s)
+    m = 128
+    q = np.concatenate([s[-100:], np.zeros(m - 100)]) + 0.001 * np.cos(np.arange(m))
+    got = gpu.scan_ucr_dtw(q, 3.0, 6, 3.0, 50.0)
+    exp = oracle.ucr_dtw(s, q, 3.0, 6, 3.0, 50.0)
+    assert got.offsets.tolist() == exp.offsets.tolist()
+    assert got.distances.tolist() == exp.distances.tolist()
+    fed = cnt = 0  # samples the block iterator feeds: 125-sample nodes, only within-node advances count against n
+    for _ in range((n + 124) // 125):
+        within = min(124, max(0, n - cnt))
+        fed += 1 + within
+        cnt += within
+        if within < 124:
+            break
+    assert got.n_verified == fed - m + 1 and fed > n    # the windows over the zero padding were scanned
+
+
 def test_scan_ucr_dtw_needs_whole_series(gpu):
     import kvmatch_b200
     s = datagen.generate(50_000, seed=5)
