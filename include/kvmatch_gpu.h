@@ -187,6 +187,24 @@ int kvm_index_image_from_runs(const double* keys, const int32_t* first, const in
                               unsigned char** image, kvm_index_info* info);
 void kvm_image_free(unsigned char* image);
 
+/* ---- phase-1 tail on the host (no ctx, no GPU): the interval algebra between index probing and verification, on
+ * plain arrays so that the candidate list reaches kvm_verify_* without boxed Java lists.  Intervals are (left, right)
+ * int32 pairs with one lower-bound value (the reference's Interval.epsilon) each; outputs are caller-owned with room
+ * for `cap` intervals (*k_out is always set; KVM_E_ARG if it exceeds cap).
+ *   kvm_intervals_sort_merge     mode 0 = sortButNotMergeIntervals          K/QueryEngine.java:593-622
+ *                                mode 1 = sortButNotMergeIntervalsAndCount   :624-662 (cnt_disjoint, cnt_offsets)
+ *                                mode 2 = sortAndMergeIntervals              :664-693 (the list handed to phase 2)
+ *   kvm_intervals_intersect      CS ∩ CS_i with summed bounds <= eps2, shifted by delta_w          :282-308
+ *   kvm_intervals_first_segment  the first segment's positions clamped to window starts in [1, n-length+1]  :264-280 */
+int kvm_intervals_sort_merge(const int32_t* lr, const double* eps, int64_t k, int32_t mode, int32_t* lr_out, double* eps_out,
+                             int64_t cap, int64_t* k_out, int64_t* cnt_disjoint, int64_t* cnt_offsets);
+int kvm_intervals_intersect(const int32_t* cs_lr, const double* cs_eps, int64_t k1, const int32_t* csi_lr, const double* csi_eps,
+                            int64_t k2, double eps2, int32_t delta_w, int32_t* lr_out, double* eps_out, int64_t cap,
+                            int64_t* k_out, double* min_eps);
+int kvm_intervals_first_segment(const int32_t* lr, const double* eps, int64_t k, int32_t order, int32_t w0, int32_t length,
+                                int32_t n, int32_t delta_w, int32_t* lr_out, double* eps_out, int64_t cap, int64_t* k_out,
+                                double* min_eps);
+
 /* ---- several GPUs behind one handle (one process) -------------------------------------------------
  * The series is sharded by offset range: device d owns window starts [d*per+1, (d+1)*per] (per = ceil(n / n_dev)
  * rounded up to a multiple of `grid`) and holds `halo` more samples behind them.  Every interval is verified by the

@@ -37,7 +37,7 @@ EXPORTS = [
     "kvm_envelope", "kvm_window_mean_runs", "kvm_window_mean_runs_all", "kvm_build_index_file", "kvm_index_image_from_runs", "kvm_image_free",
     "kvm_result_free", "kvm_runs_free",
     "kvm_multi_create", "kvm_multi_destroy", "kvm_multi_last_error", "kvm_multi_devices", "kvm_multi_load_series_host",
-    "kvm_multi_verify",
+    "kvm_multi_verify", "kvm_intervals_sort_merge", "kvm_intervals_intersect", "kvm_intervals_first_segment",
 ]
 KVM_ENGINE_ED, KVM_ENGINE_CNSM_ED, KVM_ENGINE_DTW, KVM_ENGINE_CNSM_DTW = 0, 1, 2, 3
 
@@ -135,6 +135,11 @@ def load():
     L.kvm_result_free.restype = None
     L.kvm_runs_free.argtypes = [vp, C.POINTER(KvmRuns)]
     L.kvm_runs_free.restype = None
+    i64p, f64p = C.POINTER(C.c_int64), C.POINTER(C.c_double)
+    L.kvm_intervals_sort_merge.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, vp, C.c_int64, i64p, i64p, i64p]
+    L.kvm_intervals_intersect.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_int64, C.c_double, C.c_int32, vp, vp, C.c_int64, i64p, f64p]
+    L.kvm_intervals_first_segment.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp,
+                                              C.c_int64, i64p, f64p]
     L.kvm_multi_create.argtypes = [C.POINTER(vp), vp, C.c_int32]
     L.kvm_multi_destroy.argtypes = [vp]
     L.kvm_multi_destroy.restype = None

@@ -26,6 +26,7 @@
 #include "wmean_kernels.cuh"
 #include "index_kernels.cuh"
 #include "index_file.hpp"
+#include "phase1.hpp"
 
 using namespace kvm;
 
@@ -2562,6 +2563,54 @@ int kvm_envelope(kvm_ctx* ctx, int32_t r, int64_t first, int32_t len, double* lo
   KVM_CUDA(ctx, cudaMemcpyAsync(upper, up_d, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, ctx->stream));
   KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return KVM_OK;
+}
+
+// ---- phase-1 tail on the host (phase1.hpp): plain arrays in / out, no ctx, no GPU ----------------------------------
+static void to_ivs(const int32_t* lr, const double* eps, int64_t k, std::vector<kvm_phase1::Iv>& v) {
+  v.resize((size_t)k);
+  for (int64_t i = 0; i < k; i++) v[i] = kvm_phase1::Iv{lr[2 * i], lr[2 * i + 1], eps ? eps[i] : 0.0};
+}
+static int from_ivs(const std::vector<kvm_phase1::Iv>& v, int32_t* lr_out, double* eps_out, int64_t cap, int64_t* k_out) {
+  *k_out = (int64_t)v.size();
+  if ((int64_t)v.size() > cap) return KVM_E_ARG;
+  for (size_t i = 0; i < v.size(); i++) {
+    lr_out[2 * i] = v[i].left;
+    lr_out[2 * i + 1] = v[i].right;
+    if (eps_out) eps_out[i] = v[i].eps;
+  }
+  return KVM_OK;
+}
+
+int kvm_intervals_sort_merge(const int32_t* lr, const double* eps, int64_t k, int32_t mode, int32_t* lr_out, double* eps_out,
+                             int64_t cap, int64_t* k_out, int64_t* cnt_disjoint, int64_t* cnt_offsets) {
+  if (k < 0 || (k > 0 && !lr) || !lr_out || !k_out || mode < 0 || mode > 2) return KVM_E_ARG;
+  std::vector<kvm_phase1::Iv> v, out;
+  to_ivs(lr, eps, k, v);
+  kvm_phase1::sort_merge(v, mode, out, cnt_disjoint, cnt_offsets);
+  return from_ivs(out, lr_out, eps_out, cap, k_out);
+}
+
+int kvm_intervals_intersect(const int32_t* cs_lr, const double* cs_eps, int64_t k1, const int32_t* csi_lr, const double* csi_eps,
+                            int64_t k2, double eps2, int32_t delta_w, int32_t* lr_out, double* eps_out, int64_t cap, int64_t* k_out,
+                            double* min_eps) {
+  if (k1 < 0 || k2 < 0 || (k1 > 0 && (!cs_lr || !cs_eps)) || (k2 > 0 && (!csi_lr || !csi_eps)) || !lr_out || !eps_out || !k_out)
+    return KVM_E_ARG;
+  std::vector<kvm_phase1::Iv> a, b, out;
+  to_ivs(cs_lr, cs_eps, k1, a);
+  to_ivs(csi_lr, csi_eps, k2, b);
+  const double me = kvm_phase1::intersect(a, b, eps2, delta_w, out);
+  if (min_eps) *min_eps = me;
+  return from_ivs(out, lr_out, eps_out, cap, k_out);
+}
+
+int kvm_intervals_first_segment(const int32_t* lr, const double* eps, int64_t k, int32_t order, int32_t w0, int32_t length, int32_t n,
+                                int32_t delta_w, int32_t* lr_out, double* eps_out, int64_t cap, int64_t* k_out, double* min_eps) {
+  if (k < 0 || (k > 0 && (!lr || !eps)) || !lr_out || !eps_out || !k_out) return KVM_E_ARG;
+  std::vector<kvm_phase1::Iv> v, out;
+  to_ivs(lr, eps, k, v);
+  const double me = kvm_phase1::first_segment(v, order, w0, length, n, delta_w, out);
+  if (min_eps) *min_eps = me;
+  return from_ivs(out, lr_out, eps_out, cap, k_out);
 }
 
 int kvm_index_image_from_runs(const double* keys, const int32_t* first, const int32_t* last, int64_t n_runs,

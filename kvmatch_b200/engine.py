@@ -302,7 +302,20 @@ class _EngineBase:
 
 
 class QueryEngine(_EngineBase):
-    """RSM-ED — phase 2 of K/QueryEngine.java:162 (lines 341-363)."""
+    """RSM-ED — phase 2 of K/QueryEngine.java:162 (lines 341-363); query_with_index() adds phases 0 and 1
+    (kvmatch_b200/phase1.py) over index file images, i.e. the reference's whole query()."""
+
+    def query_with_index(self, statistics, query_data, epsilon, index_images):
+        from . import phase1
+        t0 = time.perf_counter()
+        indexes = [phase1.IndexFile(index_images[w]) for w in WU_LIST]
+        valid, last_segment, _ = phase1.phase1(query_data, epsilon, self.series.n, indexes)
+        self.phase1_ms = 1e3 * (time.perf_counter() - t0)
+        self.valid_positions, self.last_segment = valid, last_segment
+        if not valid:
+            self.answers = []
+            return False
+        return self.query(statistics, query_data, epsilon, valid, last_segment)
 
     def query(self, statistics, query_data, epsilon, valid_positions=None, last_segment=1, chunk=None):
         t0 = time.perf_counter()
@@ -357,6 +370,12 @@ class IndexBuilder:
     def window_mean_runs(self, w: int):
         keys, first, last, _, _ = self.series.window_mean_runs(w)
         return keys, first, last
+
+    def build_all(self, widths=WU_LIST):
+        """The whole index build for every width (K/IndexBuilder.java:98-120): ONE window-mean pass on the GPU
+        (kvm_window_mean_runs_all), then step 2 and the file image per width on the host.  Returns {w: file bytes}."""
+        res = self.series.window_mean_runs_all(widths)
+        return {w: _lib.index_image_from_runs(k, f, l)[0] for w, (k, f, l) in zip(res.widths, res.runs)}
 
     def build_rows(self, w: int):
         """{key: [(first, last), ...]} — what the reference's indexNodeMap holds after step 1."""

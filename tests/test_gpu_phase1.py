@@ -1,0 +1,59 @@
+"""End to end like the reference's README demo: build the five KV-indexes on the GPU (one fused window-mean pass), run
+phase 0 / phase 1 over them on the host (kvmatch_b200/phase1.py + kvm_intervals_*), verify the candidates on the GPU.
+KV-match guarantees no false dismissals, so the answers must equal a full scan's."""
+import numpy as np
+import pytest
+
+from kvmatch_b200 import datagen, phase1
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def world():
+    import kvmatch_b200
+    s = datagen.generate(1_000_000)
+    g = kvmatch_b200.GpuSeries(0)
+    g.load(s)
+    images = kvmatch_b200.IndexBuilder(g).build_all()
+    yield s, g, images
+    g.close()
+
+
+def test_fused_build_equals_single_width_files(world, oracle):
+    s, g, images = world
+    for w in (25, 400):
+        assert images[w] == oracle.index_file_image(s, w)[0]
+
+
+@pytest.mark.parametrize("off,length,eps", [(123456, 8192, 10.0), (500_000, 1024, 3.0), (777_000, 512, 1.0), (40_001, 2048, 40.0)])
+def test_index_pruned_query_equals_full_scan(world, oracle, off, length, eps):
+    import kvmatch_b200
+    s, g, images = world
+    q = s[off - 1:off - 1 + length].copy()
+    eng = kvmatch_b200.QueryEngine(g)
+    stats = [kvmatch_b200.StatisticInfo() for _ in range(6)]
+    assert eng.query_with_index(stats, q, eps, images) is True
+    full = oracle.verify_ed(s, q, eps, [(1, len(s) - length + 1)])
+    got = sorted(eng.answers)
+    assert [o for o, _ in got] == full.offsets.tolist()
+    assert sorted(d for _, d in got) == sorted(full.distances.tolist())
+    assert eng.answers[0] == (off, 0.0)  # Best: <offset>, distance: 0.0
+    n_cand = sum(r - l + 1 for l, r in eng.valid_positions)
+    assert n_cand < 0.2 * len(s)          # the index prunes
+    # the candidate list is what sortAndMergeIntervals returns: sorted, disjoint, non-adjacent
+    for (l1, r1), (l2, r2) in zip(eng.valid_positions, eng.valid_positions[1:]):
+        assert r1 + 1 < l2
+
+
+def test_query_plan_covers_the_query(world):
+    s, g, images = world
+    indexes = [phase1.IndexFile(images[w]) for w in phase1.WU_LIST]
+    q = s[200_000:200_000 + 1000]
+    plan = phase1.determine_query_plan(q, 5.0, [ix.stat for ix in indexes])
+    covered = sorted((seg.order, seg.wu) for seg in plan)
+    pos = 1
+    for order, wu in covered:      # disjoint windows tiling the first floor(1000/25)*25 points
+        assert order == pos and wu in phase1.WU_LIST
+        pos += wu // 25
+    assert pos - 1 == 1000 // 25
