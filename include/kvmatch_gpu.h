@@ -67,6 +67,7 @@ typedef struct kvm_result {
   int64_t n_rewalked;        /* cNSM: windows whose chain sums were recomputed exactly (ambiguous gate or surviving the
                                 in-stream lower bound) */
   int64_t n_chains_rewalked; /* cNSM: statistic chains (merged intervals) walked exactly for them */
+  int64_t n_dtw_cells;       /* DTW: band cells evaluated by the DTW kernel (5 FP64 operations each) */
 } kvm_result;
 
 /* IndexBuilder step-1 output for one window width w: the (key, first, last) intervals in the order

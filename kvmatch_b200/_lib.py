@@ -67,6 +67,7 @@ class KvmResult(C.Structure):
         ("h2d_bytes", C.c_int32),
         ("n_rewalked", C.c_int64),
         ("n_chains_rewalked", C.c_int64),
+        ("n_dtw_cells", C.c_int64),
     ]
 
 

@@ -337,6 +337,7 @@ struct DtwParams {
   CandList in;
   AnswerSink sink;
   unsigned long long* n_abandoned;
+  unsigned long long* n_cells;  // band cells evaluated (for the FP64 roofline: 5 flops per cell)
 };
 
 template <int R>
@@ -430,7 +431,12 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
       band_odd |= (u0 + 2 * r + 1 <= 2 * rho) ? (1u << r) : 0u;
     }
     bool abandoned = false;
+    unsigned long long cells = 0;  // (warp-uniform) cells inside matrix and band on the diagonals walked so far
     for (int d = 0; d <= last; d++) {
+      {
+        const int i_lo = max(max(0, d - (m - 1)), (d - rho + 1) >> 1), i_hi = min(min(m - 1, d), (d + rho) >> 1);
+        cells += (unsigned long long)max(0, i_hi - i_lo + 1);
+      }
       // Early abandon (the reference abandons per row with min_cost + cb[i+r+1], DtwUtils.java:324-326).  On the
       // wavefront: every warping path crosses one of the two most recent anti-diagonals, cell values only grow
       // along a path, and data points beyond imax = (d-1+rho)/2 have not been matched yet, so
@@ -522,6 +528,7 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
         }
       }
     }
+    if (lane == 0) atomicAdd(P.n_cells, cells);
     if (abandoned) {
       if (lane == 0) atomicAdd(P.n_abandoned, 1ULL);
       continue;

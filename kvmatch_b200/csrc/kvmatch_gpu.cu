@@ -97,7 +97,7 @@ struct Arena {
   }
 };
 
-enum Counter { kCntAnswers = 0, kCntCand = 1, kCntGate = 2, kCntTiles = 3, kCntEntries = 4, kCntFlag = 5, kCntDone = 6, kCntCand2 = 7, kNumCounters = 10 };
+enum Counter { kCntAnswers = 0, kCntCand = 1, kCntGate = 2, kCntTiles = 3, kCntEntries = 4, kCntFlag = 5, kCntDone = 6, kCntCand2 = 7, kCntCells = 8, kNumCounters = 10 };
 
 struct Plan {
   std::vector<int32_t> cbegin, nsamp, ncand;
@@ -796,6 +796,7 @@ int verify_norm(kvm_ctx* ctx, Mode mode, const double* q, int m, double epsilon,
       D.eps2 = eps2;
       D.eps2_hi = E.eps2_hi;
       D.n_abandoned = ctx->counters.as<unsigned long long>() + kCntFlag;
+      D.n_cells = ctx->counters.as<unsigned long long>() + kCntCells;
       D.in = E.out;
       D.sink = sink_of(ctx);
       if ((rc = launch_dtw(ctx, D))) return rc;
@@ -1318,6 +1319,7 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
       D.eps2 = eps2;
       D.eps2_hi = eps2_hi;
       D.n_abandoned = counters + kCntFlag;
+      D.n_cells = counters + kCntCells;
       D.in = cands2_of(ctx);
       D.sink = sink_of(ctx);
       if ((rc = launch_dtw(ctx, D))) return rc;
@@ -1359,6 +1361,7 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
   out->n_rewalked = (int64_t)cnt[kCntEntries];
   out->n_chains_rewalked = (int64_t)cnt[kCntTiles];
   if (!dtw) out->n_exact = (int64_t)cnt[kCntFlag]; else out->n_lb_pass = (int64_t)cnt[kCntCand2];
+  out->n_dtw_cells = (int64_t)cnt[kCntCells];
   return fetch_answers(ctx, (long long)cnt[kCntAnswers], out);
 }
 
@@ -2094,6 +2097,7 @@ int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int
     D.eps2 = eps2;
     D.eps2_hi = L.Q.eps2_hi;
     D.n_abandoned = ctx->counters.as<unsigned long long>() + kCntFlag;
+    D.n_cells = ctx->counters.as<unsigned long long>() + kCntCells;
     D.in = L.out;
     D.sink = sink_of(ctx);
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -2116,6 +2120,7 @@ int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int
     if (ans_over && (rc = ensure_answers(ctx, (long long)cnt[kCntAnswers] + 1024))) return rc;
   }
   out->n_lb_pass = (int64_t)cnt[kCntCand2];
+  out->n_dtw_cells = (int64_t)cnt[kCntCells];
   return fetch_answers(ctx, (long long)cnt[kCntAnswers], out);
 }
 
@@ -2807,6 +2812,7 @@ int kvm_multi_verify(kvm_multi* M, int32_t engine, const double* q, int32_t m, d
     out->n_lb_pass += r.n_lb_pass;
     out->n_exact += r.n_exact;
     out->n_rewalked += r.n_rewalked;
+    out->n_dtw_cells += r.n_dtw_cells;
     out->n_chains_rewalked += r.n_chains_rewalked;
     out->n_launches += r.n_launches;
     out->h2d_bytes += r.h2d_bytes;

@@ -42,6 +42,7 @@ class VerifyResult:
     h2d_bytes: int = 0
     n_rewalked: int = 0
     n_chains_rewalked: int = 0
+    n_dtw_cells: int = 0
 
     @property
     def count(self) -> int:
@@ -114,7 +115,7 @@ class GpuSeries:
         dist = _lib.copy_out(r.distances, c, np.float64)
         out = VerifyResult(off, dist, r.cnt_candidate, r.n_verified, r.s_total, r.n_gate_pass, r.n_lb_pass, r.n_exact,
                            r.kernel_ms, r.n_launches, tuple(r.stage_ms), int(r.h2d_bytes), int(r.n_rewalked),
-                           int(r.n_chains_rewalked))
+                           int(r.n_chains_rewalked), int(r.n_dtw_cells))
         self._L.kvm_result_free(self._h, C.byref(r))
         return out
 
@@ -141,7 +142,7 @@ class GpuSeries:
             out.append(VerifyResult(_lib.copy_out(r.offsets, c, np.int32), _lib.copy_out(r.distances, c, np.float64),
                                     r.cnt_candidate, r.n_verified, r.s_total, r.n_gate_pass, r.n_lb_pass, r.n_exact,
                                     r.kernel_ms, r.n_launches, tuple(r.stage_ms), int(r.h2d_bytes), int(r.n_rewalked),
-                           int(r.n_chains_rewalked)))
+                           int(r.n_chains_rewalked), int(r.n_dtw_cells)))
         return out
 
     def scan_ucr_dtw(self, q, epsilon, rho, alpha, beta) -> VerifyResult:
@@ -254,7 +255,8 @@ class MultiGpuSeries:
         c = r.count
         return VerifyResult(_lib.copy_out(r.offsets, c, np.int32), _lib.copy_out(r.distances, c, np.float64), r.cnt_candidate,
                             r.n_verified, r.s_total, r.n_gate_pass, r.n_lb_pass, r.n_exact, r.kernel_ms, r.n_launches,
-                            tuple(r.stage_ms), int(r.h2d_bytes), int(r.n_rewalked), int(r.n_chains_rewalked))
+                            tuple(r.stage_ms), int(r.h2d_bytes), int(r.n_rewalked), int(r.n_chains_rewalked),
+                            int(r.n_dtw_cells))
 
 
 @dataclass

@@ -20,7 +20,8 @@ import numpy as np
 
 from . import _lib
 
-WU_LIST = (25, 50, 100, 200, 400)
+WU_LIST = (25, 50, 100, 200, 400)                      # the enabled widths: the paper's Sigma
+WU_ALL = tuple(25 * k for k in range(1, 17))           # K/QueryEngine.java:51-52: WuList = 25..400 step 25, WuEnabled = Sigma
 
 
 # ---------------------------------------------------------------- MeanIntervalUtils (K/utils/MeanIntervalUtils.java)
@@ -181,8 +182,9 @@ def _counts(stat, wu: int, mean: float, epsilon: float):
     return upper1 - lower1, upper2 - lower2
 
 
-def determine_query_plan(q, epsilon: float, stats, enabled=(True,) * 5):
-    w0 = WU_LIST[0]
+def determine_query_plan(q, epsilon: float, stats):
+    """stats: {width: cumulative statistic table} for the widths of WU_LIST."""
+    w0 = WU_ALL[0]
     m = len(q) // w0
     sums, ex = [], 0.0
     for i, v in enumerate(q):
@@ -194,14 +196,14 @@ def determine_query_plan(q, epsilon: float, stats, enabled=(True,) * 5):
     prefix[0] = sums[0]
     for i in range(1, m):
         prefix[i] = prefix[i - 1] + sums[i]
-    total100 = stats[100 // 25 - 1][-1][1]
+    total100 = stats[100][-1][1]
     cost, cost2 = {}, {}
 
     def get_cost(l, r):
         if (l, r) not in cost:
             use = w0 * (r - l + 1)
             mean = (prefix[r] - (prefix[l - 1] if l > 0 else 0.0)) / use
-            c1, _ = _counts(stats[use // w0 - 1], use, mean, epsilon)
+            c1, _ = _counts(stats[use], use, mean, epsilon)
             cost[(l, r)] = math.log(1.0 * c1 / total100) if c1 > 0 else -math.inf
             cost2[(l, r)] = c1
         return cost[(l, r)]
@@ -211,10 +213,10 @@ def determine_query_plan(q, epsilon: float, stats, enabled=(True,) * 5):
     dp[0][0] = 0.0
     for i in range(1, m + 1):
         for j in range(1, min(i, 30) + 1):
-            for k in range(1, len(WU_LIST) + 1):
+            for k in range(1, len(WU_ALL) + 1):
                 if i - k < 0:
                     break
-                if not enabled[k - 1]:
+                if WU_ALL[k - 1] not in stats:   # WuEnabled
                     continue
                 tmp = ((j - 1) * dp[i - k][j - 1] + get_cost(i - k, i - 1)) / j
                 if tmp < dp[i][j]:
@@ -258,15 +260,15 @@ def scan_index(idx: IndexFile, seg: QuerySegment, begin: float, end: float):
 def phase1(q, epsilon: float, n: int, indexes):
     """Candidate intervals of an RSM-ED query: (valid_positions [(left, right)], last_segment, plan).  `indexes` = one
     IndexFile per width of WU_LIST."""
-    stats = [ix.stat for ix in indexes]
+    by_w = dict(zip(WU_LIST, indexes))
     length = len(q)
-    queries = determine_query_plan(q, epsilon, stats)
+    queries = determine_query_plan(q, epsilon, {w: ix.stat for w, ix in by_w.items()})
     valid = []
     last_min = 0.0
     range0 = epsilon * epsilon
     for i, seg in enumerate(queries):
         delta_w = 0 if i == len(queries) - 1 else (queries[i + 1].order - seg.order) * WU_LIST[0]
-        ix = indexes[seg.wu // WU_LIST[0] - 1]
+        ix = by_w[seg.wu]
         rng = math.sqrt((range0 - last_min) / seg.wu)
         begin = to_round_stat(seg.mean - rng, ix.stat_keys)
         end = to_round(seg.mean + rng)

@@ -46,14 +46,20 @@ def test_index_pruned_query_equals_full_scan(world, oracle, off, length, eps):
         assert r1 + 1 < l2
 
 
-def test_query_plan_covers_the_query(world):
+def test_query_plan_is_a_set_of_disjoint_windows(world):
+    """determineQueryPlan's DP: disjoint windows of the enabled widths inside the query.  (Like the reference's, the plan
+    need not reach back to the query's first point: its dp[i][1] accepts a first window anywhere, because
+    (j - 1) * Double.MAX_VALUE is 0 for j = 1, K/QueryEngine.java:466.)"""
     s, g, images = world
     indexes = [phase1.IndexFile(images[w]) for w in phase1.WU_LIST]
-    q = s[200_000:200_000 + 1000]
-    plan = phase1.determine_query_plan(q, 5.0, [ix.stat for ix in indexes])
-    covered = sorted((seg.order, seg.wu) for seg in plan)
-    pos = 1
-    for order, wu in covered:      # disjoint windows tiling the first floor(1000/25)*25 points
-        assert order == pos and wu in phase1.WU_LIST
-        pos += wu // 25
-    assert pos - 1 == 1000 // 25
+    for off, length in ((200_000, 1000), (5, 8192), (700_000, 512)):
+        q = s[off:off + length]
+        plan = phase1.determine_query_plan(q, 5.0, {w: ix.stat for w, ix in zip(phase1.WU_LIST, indexes)})
+        covered = sorted((seg.order, seg.wu) for seg in plan)
+        assert covered and len(covered) <= 30
+        end = 0
+        for order, wu in covered:
+            assert wu in phase1.WU_LIST and order > end
+            end = order + wu // 25 - 1
+        assert end == length // 25      # the reconstruction starts from the query's last full block
+        assert [seg.count for seg in plan] == sorted(seg.count for seg in plan)  # ENABLE_QUERY_REORDERING
