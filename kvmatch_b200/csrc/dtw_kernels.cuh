@@ -338,6 +338,9 @@ struct DtwParams {
   AnswerSink sink;
   unsigned long long* n_abandoned;
   unsigned long long* n_cells;  // band cells evaluated (for the FP64 roofline: 5 flops per cell)
+  // candidates below `coop_limit` belong to the CTA-cooperative kernel, the rest to the warp-per-candidate kernel
+  // (the host sends a query's whole list to one of the two: 0 or "all")
+  long long coop_limit;
 };
 
 template <int R>
@@ -359,7 +362,9 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
   const int tgt_u = rho;  // final cell (m-1, m-1): i-j = 0
   const int tgt_pair = tgt_u >> 1;
 
-  for (unsigned long long e = (unsigned long long)blockIdx.x * n_warps + warp; e < n;
+  // candidate e -> (warp, block) with the block index fastest: a short list spreads over all SMs, one warp per
+  // scheduler, instead of filling the first few CTAs
+  for (unsigned long long e = (unsigned long long)P.coop_limit + (unsigned long long)warp * gridDim.x + blockIdx.x; e < n;
        e += (unsigned long long)gridDim.x * n_warps) {
     const int32_t off = P.in.off[e];
     const double mean = P.in.mean[e], stdv = P.in.stdv[e];
@@ -432,7 +437,65 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
     }
     bool abandoned = false;
     unsigned long long cells = 0;  // (warp-uniform) cells inside matrix and band on the diagonals walked so far
+    // Interior diagonals (rho + 2 <= d, d + 1 < 2m - 2 - rho) are walked two at a time by the tight loop below: every
+    // band cell lies inside the matrix there, so no index test survives; cells beyond the band hold values >= INF
+    // (INF plus non-negative costs), which a band cell's min never selects because one of its three predecessors is
+    // always a band cell — exactly what the reference's INF neighbours do.
+    const int fast_begin = rho + 2, fast_pairs = m - 2 - rho;
     for (int d = 0; d <= last; d++) {
+      if (d == fast_begin && fast_pairs > 0) {
+        const int i_base = (d + u0 - rho) >> 1;  // (d + rho) is even here
+        int ia = i_base + R, jb = d - i_base;    // next A element (odd diagonal), next B element (even diagonal)
+        double a_new = A[min(ia, m - 1)], b_new = B[max(jb, 0)];
+        int p = 0;
+        for (; p < fast_pairs; p++) {
+          if ((p & 7) == 0 && p > 0) {
+            const int dc = d + 2 * p;
+            double mn = kDtwInf;
+#pragma unroll
+            for (int r = 0; r < R; r++) mn = umin_pos(mn, umin_pos(Ev[r], Od[r]));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mn = umin_pos(mn, __shfl_xor_sync(kFullMask, mn, o));
+            const int imax = min(m - 1, (dc - 1 + rho) >> 1);
+            if (mn + CBS[(imax + 1 + 7) >> 3] > P.eps2_hi) {
+              abandoned = true;
+              break;
+            }
+          }
+          // even diagonal: j grows by one
+          double left = __shfl_up_sync(kFullMask, Od[R - 1], 1);
+          if (lane == 0) left = kDtwInf;
+#pragma unroll
+          for (int r = R - 1; r > 0; r--) bv[r] = bv[r - 1];
+          bv[0] = b_new;
+          jb++;
+          b_new = B[min(max(jb, 0), m - 1)];
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const double own = umin_pos(Od[r], Ev[r]);  // ready before the neighbour arrives
+            const double x = (r == 0) ? left : Od[r - 1];
+            Ev[r] = xadd(umin_pos(x, own), xsqdist(av[r], bv[r]));
+          }
+          // odd diagonal: i grows by one
+          double right = __shfl_down_sync(kFullMask, Ev[0], 1);
+          if (lane == 31) right = kDtwInf;
+#pragma unroll
+          for (int r = 0; r < R - 1; r++) av[r] = av[r + 1];
+          av[R - 1] = a_new;
+          ia++;
+          a_new = A[min(ia, m - 1)];
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const double own = umin_pos(Ev[r], Od[r]);
+            const double y = (r == R - 1) ? right : Ev[r + 1];
+            const double v = xadd(umin_pos(y, own), xsqdist(av[r], bv[r]));
+            Od[r] = ((band_odd >> r) & 1u) ? v : kDtwInf;
+          }
+        }
+        cells += (unsigned long long)p * (unsigned long long)(2 * rho + 1);
+        if (abandoned) break;
+        d += 2 * p;  // p == fast_pairs: the edge diagonals follow
+      }
       {
         const int i_lo = max(max(0, d - (m - 1)), (d - rho + 1) >> 1), i_hi = min(min(m - 1, d), (d + rho) >> 1);
         cells += (unsigned long long)max(0, i_hi - i_lo + 1);
@@ -540,6 +603,237 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
     }
     res = __shfl_sync(kFullMask, res, tgt_pair / R);
     if (lane == 0 && res <= P.eps2) P.sink.emit(off, xsqrt(res));
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-cooperative band DTW: the same anti-diagonal sweep with the band split over kCoopThreads threads, one DTW per
+// CTA at a time.  Thread t owns RC consecutive (even, odd) band pairs; the two values that cross a thread boundary
+// per diagonal go through shared memory (one block barrier per diagonal).  A diagonal then costs one or two cells per
+// thread instead of R = 4..16 per lane: measured 0.33 ms per m = 2048 / rho = 102 DTW (153 cycles per diagonal:
+// barrier + LDS + two integer mins + DADD) against 0.52 ms on one warp.  Same operands, same unfused operations, same
+// INF = 1e20 conventions as dtw_band_kernel: bit-identical results.
+constexpr int kCoopThreads = 128;
+
+template <int RC>
+__global__ void __launch_bounds__(kCoopThreads) dtw_band_coop_kernel(DtwParams P) {
+  extern __shared__ double coop_smem[];
+  __shared__ double s_xo[kCoopThreads + 2], s_xe[kCoopThreads + 2];  // boundary cells: odd diagonals -> next even, even -> next odd
+  __shared__ double s_red[kCoopThreads / 32];
+  const int m = P.m, rho = P.rho;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cbs_len = (m >> 3) + 2;
+  double* B = coop_smem;           // query
+  double* A = coop_smem + m;       // normalised window
+  double* CBS = A + m;             // cumulative LB_Keogh remainder sampled every 8th position
+  for (int k = tid; k < m; k += kCoopThreads) B[k] = P.q[k];
+  unsigned long long n = *P.in.count;
+  if ((long long)n > P.in.cap) n = (unsigned long long)P.in.cap;
+  if ((long long)n > P.coop_limit) n = (unsigned long long)P.coop_limit;
+  const int tgt_u = rho, tgt_pair = tgt_u >> 1;
+  const int u0 = 2 * tid * RC;
+  const int last = 2 * m - 2;
+  for (unsigned long long e = blockIdx.x; e < n; e += gridDim.x) {
+    const int32_t off = P.in.off[e];
+    const double mean = P.in.mean[e], stdv = P.in.stdv[e];
+    const double* __restrict__ w = P.T + (off - P.first_global);
+    __syncthreads();
+    // window -> shared memory (the reference's arithmetic, NormQueryEngineDtw.java:564-567) + LB_Keogh group sums
+    for (int t = tid; t < cbs_len; t += kCoopThreads) {
+      double grp = 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int k = 8 * t + u;
+        if (k < m) {
+          const double a = xdiv(xsub(w[k], mean), stdv);
+          A[k] = a;
+          const double up = __ldg(P.uq + k), lo = __ldg(P.lq + k);
+          const double dd = (a > up) ? (a - up) : ((a < lo) ? (a - lo) : 0.0);
+          grp += dd * dd;
+        }
+      }
+      CBS[t] = grp;
+    }
+    s_xo[tid + 1] = kDtwInf;
+    s_xe[tid] = kDtwInf;
+    if (tid == 0) {
+      s_xo[0] = kDtwInf;
+      s_xe[kCoopThreads] = kDtwInf;
+    }
+    __syncthreads();
+    if (warp == 0) {  // suffix sums over the groups (sequential chunks per lane + a shuffle scan)
+      const int per = (cbs_len + 31) / 32;
+      const int t0 = lane * per, t1 = min(cbs_len, t0 + per);
+      double run = 0.0;
+      for (int t = t1 - 1; t >= t0; t--) {
+        run += CBS[t];
+        CBS[t] = run;
+      }
+      double tot = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double tt = __shfl_down_sync(kFullMask, tot, o);
+        if (lane + o < 32) tot += tt;
+      }
+      const double right = tot - run;
+      for (int t = t0; t < t1; t++) CBS[t] += right;
+    }
+    __syncthreads();
+
+    double Ev[RC], Od[RC];
+#pragma unroll
+    for (int r = 0; r < RC; r++) Ev[r] = Od[r] = kDtwInf;
+    unsigned band_odd = 0;  // this thread's odd cells that lie inside the band
+#pragma unroll
+    for (int r = 0; r < RC; r++) band_odd |= (u0 + 2 * r + 1 <= 2 * rho) ? (1u << r) : 0u;
+    bool abandoned = false;
+    unsigned long long cells = 0;
+    // lower bound of the final distance from the two most recent diagonals (see dtw_band_kernel); block-uniform
+    auto hopeless = [&](int d) {
+      double mn = kDtwInf;
+#pragma unroll
+      for (int r = 0; r < RC; r++) mn = umin_pos(mn, umin_pos(Ev[r], Od[r]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mn = umin_pos(mn, __shfl_xor_sync(kFullMask, mn, o));
+      if (lane == 0) s_red[warp] = mn;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < kCoopThreads / 32; k++) mn = umin_pos(mn, s_red[k]);
+      const int imax = min(m - 1, (d - 1 + rho) >> 1);
+      return mn + CBS[(imax + 1 + 7) >> 3] > P.eps2_hi;
+    };
+    // one edge diagonal (some band cells fall outside the matrix): the general form with per-cell index tests
+    auto edge_step = [&](int d) {
+      const int par = (d + rho) & 1;
+      const int i0 = (d + u0 + par - rho) >> 1;
+      if (par == 0) {
+        const double left = s_xo[tid];  // the previous thread's last odd cell of diagonal d - 1
+#pragma unroll
+        for (int r = 0; r < RC; r++) {
+          const int i = i0 + r, j = d - i;
+          const bool valid = (u0 + 2 * r <= 2 * rho) && i >= 0 && j >= 0 && i < m && j < m;
+          double v = kDtwInf;
+          if (valid) {
+            const double c = xsqdist(A[i], B[j]);
+            const double x = (r == 0) ? left : Od[r - 1];
+            v = (d == 0) ? c : xadd(umin_pos(umin_pos(x, Od[r]), Ev[r]), c);
+          }
+          Ev[r] = v;
+        }
+        s_xe[tid] = Ev[0];
+      } else {
+        const double right = s_xe[tid + 1];  // the next thread's first even cell of diagonal d - 1
+#pragma unroll
+        for (int r = 0; r < RC; r++) {
+          const int i = i0 + r, j = d - i;
+          const bool valid = (u0 + 2 * r + 1 <= 2 * rho) && i >= 0 && j >= 0 && i < m && j < m;
+          double v = kDtwInf;
+          if (valid) {
+            const double c = xsqdist(A[i], B[j]);
+            const double y = (r == RC - 1) ? right : Ev[r + 1];
+            v = (d == 0) ? c : xadd(umin_pos(umin_pos(Ev[r], y), Od[r]), c);
+          }
+          Od[r] = v;
+        }
+        s_xo[tid + 1] = Od[RC - 1];
+      }
+      const int i_lo = max(max(0, d - (m - 1)), (d - rho + 1) >> 1), i_hi = min(min(m - 1, d), (d + rho) >> 1);
+      cells += (unsigned long long)max(0, i_hi - i_lo + 1);
+      __syncthreads();
+    };
+    const int fast_begin = rho + 2, fast_pairs = max(0, m - 2 - rho);
+    int d = 0;
+    for (; d < min(fast_begin, last + 1) && !abandoned; d++) {
+      if ((d & 15) == 0 && d > 0 && hopeless(d)) abandoned = true;
+      else edge_step(d);
+    }
+    if (!abandoned && d == fast_begin && fast_pairs > 0) {
+      // Interior: two diagonals per iteration, operands carried in registers (even -> odd: every i grows by one;
+      // odd -> even: every j grows by one), no index tests; cells beyond the band hold values >= INF, which a band
+      // cell's min never selects.  Two block barriers per pair.
+      const int i_base = (d + u0 - rho) >> 1;
+      double av[RC], bv[RC];
+#pragma unroll
+      for (int r = 0; r < RC; r++) {
+        av[r] = A[min(i_base + r, m - 1)];
+        bv[r] = B[min(max(d - 1 - i_base - r, 0), m - 1)];  // as of diagonal d - 1; shifted on entry
+      }
+      int ia = i_base + RC, jb = d - i_base;
+      double a_new = A[min(ia, m - 1)], b_new = B[min(max(jb, 0), m - 1)];
+      int p = 0;
+      for (; p < fast_pairs; p++) {
+        const bool probe = (p & 15) == 15;
+        if (probe) {  // warp minima now, decision after this pair's first barrier (no barrier of its own)
+          double mn = kDtwInf;
+#pragma unroll
+          for (int r = 0; r < RC; r++) mn = umin_pos(mn, umin_pos(Ev[r], Od[r]));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mn = umin_pos(mn, __shfl_xor_sync(kFullMask, mn, o));
+          if (lane == 0) s_red[warp] = mn;
+        }
+        // even diagonal
+        const double left = s_xo[tid];
+#pragma unroll
+        for (int r = RC - 1; r > 0; r--) bv[r] = bv[r - 1];
+        bv[0] = b_new;
+        jb++;
+        b_new = B[min(max(jb, 0), m - 1)];
+#pragma unroll
+        for (int r = 0; r < RC; r++) {
+          const double own = umin_pos(Od[r], Ev[r]);
+          const double x = (r == 0) ? left : Od[r - 1];
+          Ev[r] = xadd(umin_pos(x, own), xsqdist(av[r], bv[r]));
+        }
+        s_xe[tid] = Ev[0];
+        __syncthreads();
+        if (probe) {
+          double mn = s_red[0];
+#pragma unroll
+          for (int k = 1; k < kCoopThreads / 32; k++) mn = umin_pos(mn, s_red[k]);
+          const int dc = d + 2 * p;  // the minima were taken over diagonals dc - 1 and dc - 2
+          const int imax = min(m - 1, (dc - 1 + rho) >> 1);
+          if (mn + CBS[(imax + 1 + 7) >> 3] > P.eps2_hi) {
+            abandoned = true;
+            break;
+          }
+        }
+        // odd diagonal
+        const double right = s_xe[tid + 1];
+#pragma unroll
+        for (int r = 0; r < RC - 1; r++) av[r] = av[r + 1];
+        av[RC - 1] = a_new;
+        ia++;
+        a_new = A[min(ia, m - 1)];
+#pragma unroll
+        for (int r = 0; r < RC; r++) {
+          const double own = umin_pos(Ev[r], Od[r]);
+          const double y = (r == RC - 1) ? right : Ev[r + 1];
+          const double v = xadd(umin_pos(y, own), xsqdist(av[r], bv[r]));
+          Od[r] = ((band_odd >> r) & 1u) ? v : kDtwInf;
+        }
+        s_xo[tid + 1] = Od[RC - 1];
+        __syncthreads();
+      }
+      cells += (unsigned long long)p * (unsigned long long)(2 * rho + 1);
+      d += 2 * p;
+    }
+    for (; d <= last && !abandoned; d++) {
+      if ((d & 15) == 0 && hopeless(d)) abandoned = true;
+      else edge_step(d);
+    }
+    if (tid == 0) {
+      atomicAdd(P.n_cells, cells);
+      if (abandoned) atomicAdd(P.n_abandoned, 1ULL);
+    }
+    if (!abandoned && tid == tgt_pair / RC) {
+      const int r = tgt_pair % RC;
+      double res = kDtwInf;
+#pragma unroll
+      for (int k = 0; k < RC; k++)
+        if (k == r) res = (tgt_u & 1) ? Od[k] : Ev[k];
+      if (res <= P.eps2) P.sink.emit(off, xsqrt(res));
+    }
   }
 }
 
