@@ -143,10 +143,21 @@ int kvm_verify_cnsm_ed_batch(kvm_ctx* ctx, const double* queries, int32_t n_quer
  * overlap by m-1 (:97-131), the running statistics restart per buffer (:133-134), every window goes through the
  * alpha/beta gate and the LB_Kim / LB_Keogh / DTW cascade, and answers carry 0-BASED offsets (:278).  Equivalent to
  * kvm_verify_cnsm_dtw over the intervals [it*(EPOCH-m+1)+1, ...] with shift 0.  Needs the whole series on this ctx.
- * (The ED baseline, UcrEdQueryExecutor.java:101-183, never restarts its statistics chain: one sequential chain over
- * the whole series has no parallel bit-exact equivalent, so it is not offered; use kvm_verify_cnsm_ed on a chain grid.) */
+ */
 int kvm_scan_ucr_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int32_t rho, double alpha, double beta,
                      kvm_result* out);
+
+/* The ED baseline executor (K/experiments/ucr/UcrEdQueryExecutor.java:101-183): every window of the series through the
+ * alpha/beta gate and the |zQ|-ordered early-abandoning distance, with ONE statistics chain that is never restarted
+ * (:138-176) and 1-BASED offsets (:166).  Equivalent to kvm_verify_cnsm_ed over the single interval [1, n-m+1]: the
+ * streaming pass screens every window in parallel, but each window that needs the chain's exact sums is re-walked from
+ * sample 1 by one warp (about 16 cycles per sample: ~10 ms per 1e6 samples up to the last such window), which is the
+ * price of bit-identical statistics on an unbroken chain; on long series prefer kvm_verify_cnsm_ed on a chain grid.
+ * The executor's distance loop runs `while sum < eps^2` (:91) where the engines use `<=` (K/NormQueryEngine.java:516):
+ * they differ only when a partial sum equals eps^2 exactly (the eps-tie exemption).  Needs the whole series on this ctx.
+ * The PAA variants (PaaUcrEdQueryExecutor / PaaUcrDtwQueryExecutor) add LB_PAA and a triangle-inequality skip, both
+ * pruning only: for eps >= 1 their answer set is this scan's (out of scope). */
+int kvm_scan_ucr_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, double alpha, double beta, kvm_result* out);
 
 /* DtwUtils.lowerUpperLemire on the device (K/utils/DtwUtils.java:50-91, called on the data buffer at
  * K/QueryEngineDtw.java:397-399): lower[i] / upper[i] = min / max of samples [max(first, first+i-r) ..

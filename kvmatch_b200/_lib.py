@@ -33,7 +33,7 @@ ERROR_NAMES = {
 EXPORTS = [
     "kvm_abi_version", "kvm_create", "kvm_destroy", "kvm_last_error", "kvm_set_option", "kvm_load_series_host",
     "kvm_load_series_file",
-    "kvm_verify_ed", "kvm_verify_cnsm_ed", "kvm_verify_dtw", "kvm_verify_cnsm_dtw", "kvm_verify_cnsm_ed_batch", "kvm_scan_ucr_dtw",
+    "kvm_verify_ed", "kvm_verify_cnsm_ed", "kvm_verify_dtw", "kvm_verify_cnsm_dtw", "kvm_verify_cnsm_ed_batch", "kvm_scan_ucr_dtw", "kvm_scan_ucr_ed",
     "kvm_envelope", "kvm_window_mean_runs", "kvm_window_mean_runs_all", "kvm_build_index_file", "kvm_index_image_from_runs", "kvm_image_free",
     "kvm_result_free", "kvm_runs_free",
     "kvm_multi_create", "kvm_multi_destroy", "kvm_multi_last_error", "kvm_multi_devices", "kvm_multi_load_series_host",
@@ -125,6 +125,7 @@ def load():
     L.kvm_verify_cnsm_ed_batch.argtypes = [vp, _dp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, _ip, C.c_int32,
                                            C.c_int32, R]
     L.kvm_scan_ucr_dtw.argtypes = [vp, _dp, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_double, R]
+    L.kvm_scan_ucr_ed.argtypes = [vp, _dp, C.c_int32, C.c_double, C.c_double, C.c_double, R]
     L.kvm_window_mean_runs.argtypes = [vp, C.c_int32, C.POINTER(KvmRuns)]
     L.kvm_envelope.argtypes = [vp, C.c_int32, C.c_int64, C.c_int32, vp, vp]
     L.kvm_window_mean_runs_all.argtypes = [vp, vp, C.c_int32, C.POINTER(KvmRuns)]

@@ -1240,8 +1240,8 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
     {
       const double c = (double)std::max<unsigned long long>(z16[8], 1);
       std::fprintf(stderr, "[stream prof] nt %d tiles %llu cycles/CTA (thread 0): setup %.0f guard+tma-wait %.0f group-sums %.0f warp-local %.0f "
-                   "end %.0f | chains needed %llu, warps slid %llu of %llu, candidates %llu\n", nt, z16[8], z16[0] / c, z16[1] / c, z16[2] / c,
-                   z16[5] / c, z16[6] / c, z16[10], z16[9], (unsigned long long)SP.n_tiles * (nt / 32), z16[11]);
+                   "end %.0f | chains needed %llu, warps slid %llu of %llu, candidates %llu | slowest CTA %llu cycles, %llu CTAs > 60k, slowest warp-0 local phase %llu\n", nt, z16[8], z16[0] / c, z16[1] / c, z16[2] / c,
+                   z16[5] / c, z16[6] / c, z16[10], z16[9], (unsigned long long)SP.n_tiles * (nt / 32), z16[11], z16[12], z16[13], z16[14]);
     }
 #endif
     KVM_CUDA(ctx, cudaEventRecord(ctx->evs[0], ctx->stream));
@@ -2021,6 +2021,43 @@ int kvm_verify_cnsm_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon
   return verify_norm(ctx, Mode::kDtw, q, m, epsilon, rho, alpha, beta, lr, K, shift, out);
 }
 
+// Samples the reference's block iterator feeds to a scan executor: 125-sample nodes, the last one zero padded, and only
+// within-node advances counted against n (nextData() of K/experiments/ucr/UcrDtwQueryExecutor.java and
+// UcrEdQueryExecutor.java:58-81, as K/IndexBuilder.java:152-180).  For n % 125 != 0 the executors therefore also
+// verify windows that run into the zero padding; the series buffer keeps that many zeros behind the data (kTailPad).
+static int64_t ucr_samples_fed(int64_t n) {
+  int64_t fed = 0, cnt = 0;
+  const int64_t n_nodes = (n + 124) / 125;
+  for (int64_t b = 0; b < n_nodes; b++) {
+    const int64_t within = std::min<int64_t>(124, std::max<int64_t>(0, n - cnt));
+    fed += 1 + within;
+    cnt += within;
+    if (within < 124) break;
+  }
+  return fed;
+}
+
+// One verify_norm call over `lr` with the phantom zeros counted as samples.
+static int ucr_scan(kvm_ctx* ctx, Mode mode, const double* q, int32_t m, double epsilon, int32_t rho, double alpha, double beta,
+                    int64_t fed, const std::vector<int32_t>& lr, kvm_result* out) {
+  if (!out) return fail(ctx, KVM_E_ARG, "null/invalid argument");
+  if (lr.empty()) {  // series shorter than the query: nothing to scan
+    std::memset(out, 0, sizeof(*out));
+    return KVM_OK;
+  }
+  const int64_t n_real = ctx->n, count_real = ctx->count;
+  ctx->n = fed;
+  ctx->count = fed;
+  ctx->splan.valid = false;
+  ctx->norm_cache.valid = false;
+  const int rc = verify_norm(ctx, mode, q, m, epsilon, rho, alpha, beta, lr.data(), (int)(lr.size() / 2), 0, out);
+  ctx->n = n_real;
+  ctx->count = count_real;
+  ctx->splan.valid = false;
+  ctx->norm_cache.valid = false;
+  return rc;
+}
+
 int kvm_scan_ucr_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int32_t rho, double alpha, double beta,
                      kvm_result* out) {
   if (!ctx) return KVM_E_ARG;
@@ -2028,45 +2065,33 @@ int kvm_scan_ucr_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, i
   if (ctx->first != 1 || ctx->count != ctx->n) return fail(ctx, KVM_E_STATE, "the UCR scan needs the whole series on this ctx");
   constexpr int64_t kEpoch = 100000;  // UcrDtwQueryExecutor.java:97
   if (m < 3 || m > kEpoch) return fail(ctx, KVM_E_ARG, "UCR-DTW needs 3 <= m <= EPOCH");
-  // The executor's block iterator feeds 125-sample nodes, the last one zero padded, and counts only within-node
-  // advances against n (K/experiments/ucr/UcrDtwQueryExecutor.java nextData(), as K/IndexBuilder.java:152-180): for
-  // n % 125 != 0 it also verifies the windows that run into the zero padding.  `fed` = samples it feeds; the series
-  // buffer keeps that many zeros behind the data (kTailPad).
-  int64_t fed = 0;
-  {
-    const int64_t n_nodes = (ctx->n + 124) / 125;
-    int64_t cnt = 0;
-    for (int64_t b = 0; b < n_nodes; b++) {
-      const int64_t within = std::min<int64_t>(124, std::max<int64_t>(0, ctx->n - cnt));
-      fed += 1 + within;
-      cnt += within;
-      if (within < 124) break;
-    }
-  }
+  const int64_t fed = ucr_samples_fed(ctx->n);
   const int64_t per = kEpoch - m + 1, last = fed - m + 1;  // window starts per buffer; last 1-based start
   std::vector<int32_t> lr;
   for (int64_t left = 1; left <= last; left += per) {
     lr.push_back((int32_t)left);
     lr.push_back((int32_t)std::min(left + per - 1, last));
   }
-  if (!out) return fail(ctx, KVM_E_ARG, "null/invalid argument");
-  if (lr.empty()) {  // series shorter than the query: nothing to scan
-    std::memset(out, 0, sizeof(*out));
-    return KVM_OK;
-  }
-  const int64_t n_real = ctx->n, count_real = ctx->count;
-  ctx->n = fed;      // the phantom zeros count as samples for this scan
-  ctx->count = fed;
-  ctx->splan.valid = false;
-  ctx->norm_cache.valid = false;
-  const int rc = verify_norm(ctx, Mode::kDtw, q, m, epsilon, rho, alpha, beta, lr.data(), (int)(lr.size() / 2), 0, out);
-  ctx->n = n_real;
-  ctx->count = count_real;
-  ctx->splan.valid = false;
-  ctx->norm_cache.valid = false;
+  const int rc = ucr_scan(ctx, Mode::kDtw, q, m, epsilon, rho, alpha, beta, fed, lr, out);
   if (rc) return rc;
   for (int32_t& o : ctx->res_off) o -= 1;  // 0-based offsets, :278
   return KVM_OK;
+}
+
+int kvm_scan_ucr_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, double alpha, double beta, kvm_result* out) {
+  if (!ctx) return KVM_E_ARG;
+  if (!ctx->series) return fail(ctx, KVM_E_STATE, "no series loaded");
+  if (ctx->first != 1 || ctx->count != ctx->n) return fail(ctx, KVM_E_STATE, "the UCR scan needs the whole series on this ctx");
+  if (m < 1) return fail(ctx, KVM_E_ARG, "UCR-ED needs m >= 1");
+  // UcrEdQueryExecutor.java:138-176: ONE statistics chain from the first sample to the last (ex / ex2 are never
+  // reset), 1-based offsets (:166) — i.e. the cNSM-ED engine's loop over the single interval [1, fed-m+1].
+  const int64_t fed = ucr_samples_fed(ctx->n);
+  std::vector<int32_t> lr;
+  if (fed - m + 1 >= 1) {
+    lr.push_back(1);
+    lr.push_back((int32_t)(fed - m + 1));
+  }
+  return ucr_scan(ctx, Mode::kEd, q, m, epsilon, 0, alpha, beta, fed, lr, out);
 }
 
 int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int32_t rho, const int32_t* lr, int32_t K,

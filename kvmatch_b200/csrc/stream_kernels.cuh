@@ -588,6 +588,9 @@ __global__ void __launch_bounds__(NT, NT <= 192 ? 3 : (NT <= 256 ? 2 : 1)) cnsm_
     const long long c6 = stream_clock();
     const long long d[9] = {c1 - c0, c2 - c1, c3 - c2, 0, 0, c5 - c3, c6 - c5, 0, 1};
     for (int i = 0; i < 9; i++) atomicAdd(&g_stream_prof[i], (unsigned long long)d[i]);
+    atomicMax(&g_stream_prof[12], (unsigned long long)(c6 - c0));        // the slowest CTA
+    if (c6 - c0 > 60000) atomicAdd(&g_stream_prof[13], 1ULL);           // CTAs slower than 60k cycles
+    atomicMax(&g_stream_prof[14], (unsigned long long)(c5 - c3));        // the slowest warp-local phase (thread 0's warp)
   }
 #endif
 }

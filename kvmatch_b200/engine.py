@@ -152,6 +152,14 @@ class GpuSeries:
         self._check(self._L.kvm_scan_ucr_dtw(self._h, qp, len(q), epsilon, rho, alpha, beta, C.byref(r)))
         return self._take(r)
 
+    def scan_ucr_ed(self, q, epsilon, alpha, beta) -> VerifyResult:
+        """K/experiments/ucr/UcrEdQueryExecutor.java:101-183: index-free cNSM-ED scan on ONE never-reset statistics
+        chain, 1-based offsets."""
+        q, qp = _lib.as_f64(q)
+        r = _lib.KvmResult()
+        self._check(self._L.kvm_scan_ucr_ed(self._h, qp, len(q), epsilon, alpha, beta, C.byref(r)))
+        return self._take(r)
+
     def build_index_file(self, w: int, path: str | None):
         """K/IndexBuilder.java:186-347 for one window width: returns the kvm_index_info fields."""
         info = _lib.KvmIndexInfo()

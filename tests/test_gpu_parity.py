@@ -347,6 +347,23 @@ def test_scan_ucr_dtw_phantom_samples(gpu, oracle, n):
     assert got.n_verified == fed - m + 1 and fed > n    # the windows over the zero padding were scanned
 
 
+@pytest.mark.parametrize("n,m,eps", [(250_000, 128, 3.0), (1_000_000, 1024, 8.0), (300_007, 256, 4.0)])
+def test_scan_ucr_ed_matches_reference_executor(gpu, oracle, n, m, eps):
+    """f4: kvm_scan_ucr_ed against the oracle's restatement of UcrEdQueryExecutor — ONE statistics chain over the whole
+    series (never reset), 1-based offsets, the block iterator's zero padding when n % 125 != 0."""
+    s = datagen.generate(n, seed=n + m)
+    gpu.load(s)
+    off = (2 * n) // 3
+    q = s[off:off + m].copy() + 0.01 * np.cos(np.arange(m))
+    got = gpu.scan_ucr_ed(q, eps, 1.5, 5.0)
+    exp = oracle.ucr_ed(s, q, eps, 1.5, 5.0)
+    assert got.offsets.tolist() == exp.offsets.tolist()
+    assert got.distances.tolist() == exp.distances.tolist()
+    assert got.n_gate_pass == exp.n_gate_pass
+    assert got.count > 0 and off + 1 in got.offsets.tolist()
+    assert got.n_verified == exp.n_verified
+
+
 def test_scan_ucr_dtw_needs_whole_series(gpu):
     import kvmatch_b200
     s = datagen.generate(50_000, seed=5)
@@ -410,6 +427,54 @@ def test_full_size_1e8_against_oracle_on_chain_subsets(oracle):
     assert off in d.offsets.tolist() and d.n_verified == n - m2 + 1
     sub2 = iv2[np.unique(np.concatenate([np.searchsorted(iv2[:, 0], d.offsets, side="right") - 1, rng.choice(len(iv2), 3)]))]
     assert_same(g.verify_cnsm_dtw(q2, 1.0, rho, 1.5, 5.0, sub2), oracle.verify_cnsm_dtw(s, q2, 1.0, rho, 1.5, 5.0, sub2))
+    # BASELINE configs[2]: RSM-DTW, m = 512, rho = 25 (5 %), the reference's raw-data epsilon grid; the engine's data
+    # envelope covers one interval read, so the scan is cut into EPOCH-sized intervals as the reference's executor does
+    for eps in (50.0, 75.0):
+        r = g.verify_dtw(q2, eps, rho, iv2)
+        assert off in r.offsets.tolist() and r.n_verified == n - m2 + 1
+        assert np.all(np.diff(r.offsets) > 0) and np.all(r.distances <= eps)
+        sub3 = iv2[np.unique(np.concatenate([np.searchsorted(iv2[:, 0], r.offsets, side="right") - 1, rng.choice(len(iv2), 3)]))][:8]
+        e3 = oracle.verify_dtw(s, q2, eps, rho, sub3)
+        g3 = g.verify_dtw(q2, eps, rho, sub3)
+        assert_same(g3, e3)
+        assert g3.n_lb_pass <= 1.5 * e3.n_dtw + 64     # the cascade prunes like the reference's
+    # one merged interval of 1e6 candidates (what an index-pruned phase 1 can hand over unchunked): a single
+    # statistics chain, K/NormQueryEngine.java:487
+    lo = max(1, off - 400_000)
+    one = [(lo, lo + 1_000_000 - 1)]
+    assert_same(g.verify_cnsm_ed(q, 5.0, 1.5, 5.0, one), oracle.verify_cnsm_ed(s, q, 5.0, 1.5, 5.0, one))
+    g.close()
+
+
+def test_full_size_1e9_against_oracle_on_chain_subsets(oracle):
+    """The metric's size (n = 1e9, 8 GB resident): whole-scan properties, and exact parity with the oracle on every chain
+    that holds an answer plus random other chains, for cNSM-ED (m = 1024) and cNSM-DTW (BASELINE configs[3]: m = 2048,
+    rho = 102).  The oracle only ever touches the chains it is given."""
+    import kvmatch_b200
+    n, chunk = 1_000_000_000, 2048
+    s = datagen.generate_range(n, 0, n, datagen.DEFAULT_SEED)
+    g = kvmatch_b200.GpuSeries(0)
+    g.load(s)
+    rng = np.random.default_rng(9)
+    off = 470_341_747
+    for m, rho, eps in ((1024, None, 5.0), (2048, 102, 1.0)):
+        iv = np.asarray(datagen.chain_intervals(n, m, chunk), dtype=np.int64).reshape(-1, 2)
+        q = s[off - 1:off - 1 + m].copy()
+        if rho is None:
+            full = g.verify_cnsm_ed(q, eps, 1.5, 5.0, iv)
+        else:
+            full = g.verify_cnsm_dtw(q, eps, rho, 1.5, 5.0, iv)
+        assert full.n_verified == n - m + 1
+        assert off in full.offsets.tolist() and np.all(np.diff(full.offsets) > 0) and np.all(full.distances <= eps)
+        hit = np.unique(np.searchsorted(iv[:, 0], full.offsets, side="right") - 1)
+        sub = iv[np.unique(np.concatenate([hit[:40], rng.choice(len(iv), size=24, replace=False)]))]
+        if rho is None:
+            got, exp = g.verify_cnsm_ed(q, eps, 1.5, 5.0, sub), oracle.verify_cnsm_ed(s, q, eps, 1.5, 5.0, sub)
+        else:
+            got, exp = g.verify_cnsm_dtw(q, eps, rho, 1.5, 5.0, sub), oracle.verify_cnsm_dtw(s, q, eps, rho, 1.5, 5.0, sub)
+        assert_same(got, exp)
+        assert got.n_gate_pass == exp.n_gate_pass
+        assert got.offsets.tolist() == [o for o in full.offsets.tolist() if np.any((sub[:, 0] <= o) & (o <= sub[:, 1]))]
     g.close()
 
 
