@@ -1131,8 +1131,10 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
     for (int k = 0; k < n_screen; k++) {
       const int i = (int)(((int64_t)(2 * k + 1) * m) / (2 * n_screen));  // evenly spread positions
       scr_i[k] = i;
-      scr_a[k] = uq[i];
-      scr_b[k] = lq[i];
+      // centre and half width of the envelope (the half width rounded up by more than the rounding of the centre,
+      // so that max(|x - centre| - half, 0) never exceeds the true excess over [lq, uq])
+      scr_a[k] = 0.5 * (uq[i] + lq[i]);
+      scr_b[k] = 0.5 * (uq[i] - lq[i]) + 4.0 * kUlpHalf * (std::fabs(uq[i]) + std::fabs(lq[i]) + 1.0);
     }
   }
   const kvm::GuardCoef GC = stream_guard(m, nt, SP.l_max, S, alpha, beta, epsilon, zmax, m);

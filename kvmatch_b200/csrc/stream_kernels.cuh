@@ -46,7 +46,21 @@ struct StreamTile {
 struct StreamGate {  // on ex (= m * mean) and t2 = m*ex2 - ex^2 (= m^2 * variance); out = may pass, in = certainly passes
   double e_lo_out, e_lo_in, e_hi_in, e_hi_out;
   double v_lo_out, v_lo_in, v_hi_in, v_hi_out;
+  // the same bands in centred form, |x - mid| <= rad, for the per-candidate tests: one DADD and an integer compare of
+  // the (non-negative) bit patterns instead of two DSETPs, which issue at about a fifth of the DADD rate on sm_100.
+  // rad_out is rounded outwards and rad_in inwards by more than the rounding of x - mid, so the centred tests admit
+  // every window the interval tests admit (out) and call a window certain only when the interval tests do (in).
+  double e_mid, e_rad_out, e_rad_in;
+  double v_mid, v_rad_out, v_rad_in;
 };
+
+// a <= b for doubles that are both >= +0 (or NaN, which then compares false for a and true for b): on the integer pipe
+__device__ __forceinline__ bool le_nonneg(double a, double b) { return __double_as_longlong(a) <= __double_as_longlong(b); }
+// min of two non-negative doubles on the integer pipe (DMNMX is as slow as DSETP)
+__device__ __forceinline__ double min_nonneg(double a, double b) {
+  const long long x = __double_as_longlong(a), y = __double_as_longlong(b);
+  return __longlong_as_double(x < y ? x : y);
+}
 
 // Guard bands as a function of A = max |sample| over everything a tile's chains have summed (stream_guard() on the
 // host explains every term).  Evaluated per tile on the device with the tile's own A, so that a series whose
@@ -78,6 +92,15 @@ __host__ __device__ inline void stream_guard_eval(const GuardCoef& C, double A, 
   G->v_lo_in = lo2 + g2;
   G->v_hi_in = hi2 - g2;
   G->v_hi_out = hi2 + g2;
+  {
+    const double up = 1.0 + 16.0 * u, dn = 1.0 - 16.0 * u;
+    G->e_mid = 0.5 * (G->e_lo_out + G->e_hi_out);
+    G->e_rad_out = fmax(G->e_hi_out - G->e_mid, G->e_mid - G->e_lo_out) * up + 1e-300;
+    G->e_rad_in = fmin(G->e_hi_in - G->e_mid, G->e_mid - G->e_lo_in) * dn - 1e-300;   // negative = no window is certain
+    G->v_mid = 0.5 * (G->v_lo_out + G->v_hi_out);
+    G->v_rad_out = fmax(G->v_hi_out - G->v_mid, G->v_mid - G->v_lo_out) * up + 1e-300;
+    G->v_rad_in = fmin(G->v_hi_in - G->v_mid, G->v_mid - G->v_lo_in) * dn - 1e-300;
+  }
   const double g_mean = g1 * C.inv_dm * (1.0 + 8.0 * u) + 4.0 * u * Mb;
   const double g_var = g2 * C.inv_dm * C.inv_dm * (1.0 + 8.0 * u);
   double t = 1.0 / 0.0;
@@ -131,7 +154,7 @@ struct StreamParams {
   int32_t s_base;
   int32_t total_win;
   // in-stream lower bound table (in the parameter block = constant memory).  ED: idx = order[k], a = zQ (sorted
-  // order); DTW: idx = evenly spread positions, a = upper, b = lower envelope
+  // order); DTW: idx = evenly spread positions, a = centre, b = half width of the query envelope there
   int32_t scr_idx[kScreenTerms];
   double scr_a[kScreenTerms];
   double scr_b[kScreenTerms];
@@ -195,22 +218,59 @@ constexpr size_t stream_smem_bytes(int nt, int m) {
          (size_t)(nt / 32) * kQ1Cap * (2 * sizeof(double) + sizeof(int32_t)) + 16;
 }
 
-// Flag the window that starts at local sample s (ordinal v).  p = a live chain at or before its chain, or -1 when the
-// tile was computed arithmetically (then the chain follows from the ordinal).  Rare path.
-__device__ __noinline__ void stream_flag(const ChainTable C, unsigned* need_bits, int32_t* chain_last, int32_t* flagged,
-                                         unsigned long long* n_flagged, unsigned long long* n_need, int s, int p, unsigned v) {
-  if (p < 0) {
-    p = C.chain_of(v);
-  } else {
-    while (s >= C.begin(p) + C.count(p)) p++;  // chains of one segment are consecutive
+// Flagging, warp-aggregated.  A warp's windows span at most 33*32 adjacent starts, i.e. a handful of chains, and a
+// near match flags hundreds of them: the per-chain maximum (chain_last) is therefore kept in warp-uniform registers
+// and written with ONE returning atomic when the chain changes or the warp is done, instead of one per window (32
+// lanes hammering one address per drain made the CTAs that hold a near match run for ~100 us — the tail of the whole
+// launch).  need_bits takes one fire-and-forget atomicOr per window; the window count is reduced at the end.
+struct FlagCache {
+  int p;        // chain whose maximum is pending (-1 = none); warp-uniform
+  int mx;       // pending maximum of (window start - chain begin); warp-uniform
+  unsigned n;   // this lane's flagged windows
+};
+
+__device__ __forceinline__ void flag_flush(const StreamParams& P, FlagCache& F, int lane) {
+  if (F.p >= 0 && lane == 0) {
+    const int old = atomicMax(P.chain_last + F.p, F.mx);
+    if (old < 0) {
+      const unsigned long long slot = atomicAdd(P.n_flagged, 1ULL);
+      P.flagged[slot] = F.p;
+    }
   }
-  atomicOr(need_bits + (v >> 5), 1u << (v & 31));
-  const int old = atomicMax(chain_last + p, s - C.begin(p));
-  if (old < 0) {
-    const unsigned long long slot = atomicAdd(n_flagged, 1ULL);
-    flagged[slot] = p;
+  F.p = -1;
+}
+
+// All 32 lanes call this; `mine` = this lane flags window w of the tile; fl = ballot of `mine` (non-zero).
+__device__ __forceinline__ void flag_warp(const StreamParams& P, const StreamTile& tile, int w, bool mine, unsigned fl,
+                                          FlagCache& F, int lane) {
+  int p = -1, rel = -1;
+  if (mine) {
+    const int s = tile.s0 + w;
+    const unsigned v = (unsigned)(tile.v0 + w);
+    if (tile.chain < 0) {
+      p = P.chains.chain_of(v);
+    } else {
+      p = tile.chain;
+      while (s >= P.chains.begin(p) + P.chains.count(p)) p++;  // chains of one segment are consecutive
+    }
+    atomicOr(P.need_bits + (v >> 5), 1u << (v & 31));
+    rel = s - P.chains.begin(p);
+    F.n++;
   }
-  atomicAdd(n_need, 1ULL);
+  unsigned rem = fl;
+  while (rem) {  // one round per distinct chain among the flagged lanes
+    const int pl = __shfl_sync(kFullMask, p, __ffs(rem) - 1);
+    const bool same = mine && p == pl;
+    const int mx = __reduce_max_sync(kFullMask, same ? rel : -1);
+    if (pl != F.p) {
+      flag_flush(P, F, lane);
+      F.p = pl;
+      F.mx = mx;
+    } else {
+      F.mx = max(F.mx, mx);
+    }
+    rem &= ~__ballot_sync(kFullMask, same);
+  }
 }
 
 #ifdef KVM_STREAM_PROF
@@ -240,20 +300,24 @@ struct WarpQueue {
 // One queued candidate per lane: the exact outer-band tests, then the table tier of the lower bound — ED: the 32
 // largest-|zQ| terms of the distance; DTW: LB_KimFL (K/utils/DtwUtils.java:149-189) and 32 evenly spread terms of
 // LB_Keogh on the query envelope.  Returns 1 when the window certainly passes the gate and certainly is no answer (it
-// is only counted).  A window that is ambiguous or survives the table is flagged: its chain is re-walked exactly and
+// is only counted), 2 when it is ambiguous or survives the table: the caller flags it, its chain is re-walked exactly and
 // the exact stage (cnsm_ed_exact_kernel / cnsm_dtw_lb_list_kernel, a warp resp. a thread per window over the whole
 // GPU) finishes the bound.  (A second in-stream tier over all m terms was measured: clusters of near matches made
 // single CTAs run for 0.3 ms.)  `wv` = the window's first sample in shared memory.
 template <int kMode>
 __device__ __forceinline__ unsigned stream_candidate(const StreamParams& P, const StreamTile& tile, const double* __restrict__ wv,
                                                      int w, double ex, double ex2, const StreamGate& G, const double thr) {
-  if (!(ex >= G.e_lo_out && ex <= G.e_hi_out)) return 0u;
+  // (centred band tests, see StreamGate; a NaN sum fails them like it fails the interval tests)
+  const double de = fabs(ex - G.e_mid);
+  if (!le_nonneg(de, G.e_rad_out)) return 0u;
   const double t2 = __fma_rn(P.dm, ex2, -__dmul_rn(ex, ex));
-  if (!(t2 >= G.v_lo_out && t2 <= G.v_hi_out)) return 0u;
-  const bool sure = ex >= G.e_lo_in && ex <= G.e_hi_in && t2 >= G.v_lo_in && t2 <= G.v_hi_in;
+  const double dv = fabs(t2 - G.v_mid);
+  if (!le_nonneg(dv, G.v_rad_out)) return 0u;
+  // rad_in < 0 (bit pattern negative as an integer) makes both tests false
+  const bool sure = __double_as_longlong(G.e_rad_in) >= __double_as_longlong(de) && __double_as_longlong(G.v_rad_in) >= __double_as_longlong(dv);
   bool survive = true;
   const int m = P.m;
-  if (t2 > 0.0 && !P.force_all) {
+  if (__double_as_longlong(t2) > 0LL && !P.force_all) {  // t2 > 0 (finite here: it passed the band test)
     const double mean = ex * P.inv_m;
     const double rstd = rsqrt(t2 * P.inv_m2);
     if (kMode == 1 && m >= 6) {
@@ -263,37 +327,58 @@ __device__ __forceinline__ unsigned stream_candidate(const StreamParams& P, cons
       const double q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
       const double p0 = __ldg(q + m - 1), p1 = __ldg(q + m - 2), p2 = __ldg(q + m - 3);
       auto sq = [](double a, double b) { const double d = a - b; return d * d; };
+      auto mn = [](double a, double b) { return min_nonneg(a, b); };
       double kim = sq(x0, q0) + sq(y0, p0);
-      kim += fmin(fmin(sq(x1, q0), sq(x0, q1)), sq(x1, q1));
-      kim += fmin(fmin(sq(y1, p0), sq(y0, p1)), sq(y1, p1));
-      kim += fmin(fmin(fmin(sq(x0, q2), sq(x1, q2)), sq(x2, q2)), fmin(sq(x2, q1), sq(x2, q0)));
-      kim += fmin(fmin(fmin(sq(y0, p2), sq(y1, p2)), sq(y2, p2)), fmin(sq(y2, p1), sq(y2, p0)));
-      survive = kim <= thr;
+      kim += mn(mn(sq(x1, q0), sq(x0, q1)), sq(x1, q1));
+      kim += mn(mn(sq(y1, p0), sq(y0, p1)), sq(y1, p1));
+      kim += mn(mn(mn(sq(x0, q2), sq(x1, q2)), sq(x2, q2)), mn(sq(x2, q1), sq(x2, q0)));
+      kim += mn(mn(mn(sq(y0, p2), sq(y1, p2)), sq(y2, p2)), mn(sq(y2, p1), sq(y2, p0)));
+      survive = le_nonneg(kim, thr);
     }
     const int n_scr = P.n_screen;
     double dist = 0.0;
-    for (int kk = 0; kk < n_scr && survive; kk += 4) {
+    auto term = [&](int k, double wk) {
+      const double x = (wk - mean) * rstd;
+      double d;
+      if (kMode == 0) {
+        d = x - P.scr_a[k];
+      } else {  // scr_a = centre, scr_b = half width of the envelope at this position: excess = max(|x - c| - h, 0)
+        const double e = fabs(x - P.scr_a[k]) - P.scr_b[k];
+        d = (__double2hiint(e) < 0) ? 0.0 : e;
+      }
+      return d;
+    };
+    if (n_scr == kScreenTerms) {
+      // The usual case (m >= 32), fully unrolled: every table entry is a constant-bank operand with an immediate
+      // offset, the eight window samples of a round are loaded up front and summed in two independent chains; the
+      // partial bound is tested once per round.  (With run-time indices each term was a serial LDC -> LDS -> 4 x FP64
+      // chain of its own, ~130 cycles: a tile full of candidates then ran for ~100 us and set the launch's tail.)
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        if (kk + u < n_scr) {
-          const double x = (wv[P.scr_idx[kk + u]] - mean) * rstd;
-          double d;
-          if (kMode == 0) {
-            d = x - P.scr_a[kk + u];
-          } else {
-            const double up = P.scr_a[kk + u], lo = P.scr_b[kk + u];
-            d = (x > up) ? (x - up) : ((x < lo) ? (x - lo) : 0.0);
+      for (int r = 0; r < kScreenTerms / 8; r++) {
+        if (survive) {
+          double wk[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) wk[u] = wv[P.scr_idx[8 * r + u]];
+          double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; u += 2) {
+            const double da = term(8 * r + u, wk[u]), db = term(8 * r + u + 1, wk[u + 1]);
+            acc0 = __fma_rn(da, da, acc0);
+            acc1 = __fma_rn(db, db, acc1);
           }
-          dist = __fma_rn(d, d, dist);
+          dist += acc0 + acc1;
+          survive = le_nonneg(dist, thr);
         }
       }
-      survive = dist <= thr;
+    } else {
+      for (int kk = 0; kk < n_scr && survive; kk++) {
+        const double d = term(kk, wv[P.scr_idx[kk]]);
+        dist = __fma_rn(d, d, dist);
+        survive = le_nonneg(dist, thr);
+      }
     }
   }
-  if (!survive && sure) return 1u;
-  stream_flag(P.chains, P.need_bits, P.chain_last, P.flagged, P.n_flagged, P.n_need, tile.s0 + w, tile.chain,
-              (unsigned)(tile.v0 + w));
-  return 0u;
+  return (!survive && sure) ? 1u : 2u;
 }
 
 // Drain up to 32 entries from the front of the queue (one per lane); the rest moves to the front.  n = entries
@@ -301,7 +386,7 @@ __device__ __forceinline__ unsigned stream_candidate(const StreamParams& P, cons
 template <int kMode>
 __device__ __forceinline__ int stream_drain(const StreamParams& P, const StreamTile& tile, const double* __restrict__ xs,
                                             const WarpQueue& Q, int n, int lane, const StreamGate& G, const double thr,
-                                            unsigned& my_gate) {
+                                            unsigned& my_gate, FlagCache& F) {
   const int nb = min(n, 32), rest = n - nb;
   int mw = 0;
   double mex = 0.0, mex2 = 0.0;
@@ -310,10 +395,15 @@ __device__ __forceinline__ int stream_drain(const StreamParams& P, const StreamT
     mex = Q.ex[nb + lane];
     mex2 = Q.ex2[nb + lane];
   }
+  int w = 0;
+  unsigned verdict = 0u;
   if (lane < nb) {
-    const int w = Q.w[lane];
-    my_gate += stream_candidate<kMode>(P, tile, xs + w, w, Q.ex[lane], Q.ex2[lane], G, thr);
+    w = Q.w[lane];
+    verdict = stream_candidate<kMode>(P, tile, xs + w, w, Q.ex[lane], Q.ex2[lane], G, thr);
   }
+  my_gate += verdict & 1u;
+  const unsigned fl = __ballot_sync(kFullMask, verdict == 2u);
+  if (fl) flag_warp(P, tile, w, verdict == 2u, fl, F, lane);
   __syncwarp();
   if (lane < rest) {
     Q.w[lane] = mw;
@@ -451,6 +541,7 @@ __global__ void __launch_bounds__(NT, NT <= 192 ? 3 : (NT <= 256 ? 2 : 1)) cnsm_
   // ---- warp-local from here on
   const int w0 = tid * kGroup;
   unsigned my_gate = 0;
+  FlagCache F{-1, -1, 0u};
   if (warp * 32 * kGroup < nwin) {  // (warp-uniform) the warp holds at least one window
     const int qa = m / kGroup, qb = m - qa * kGroup;
     const int gw = 32 * warp;  // the warp's first chain = group index
@@ -571,18 +662,18 @@ __global__ void __launch_bounds__(NT, NT <= 192 ? 3 : (NT <= 256 ? 2 : 1)) cnsm_
           rex += dl;
           rex2 = __fma_rn(dl, sm, rex2);
           __syncwarp();
-          if (n1 >= kQ1Drain) n1 = stream_drain<kMode>(P, tile, xs, Q, n1, lane, G, s_thr, my_gate);
+          if (n1 >= kQ1Drain) n1 = stream_drain<kMode>(P, tile, xs, Q, n1, lane, G, s_thr, my_gate, F);
         }
-        while (n1 > 0) n1 = stream_drain<kMode>(P, tile, xs, Q, n1, lane, G, s_thr, my_gate);
+        while (n1 > 0) n1 = stream_drain<kMode>(P, tile, xs, Q, n1, lane, G, s_thr, my_gate, F);
+        flag_flush(P, F, lane);
       }
     }
   }
   STREAM_T(c5);
-  // ---- certain gate passes
-  unsigned tot = my_gate;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFullMask, tot, o);
+  // ---- certain gate passes, flagged windows
+  const unsigned tot = __reduce_add_sync(kFullMask, my_gate), tot_flag = __reduce_add_sync(kFullMask, F.n);
   if (lane == 0 && tot) atomicAdd(P.gate_pass, (unsigned long long)tot);
+  if (lane == 0 && tot_flag) atomicAdd(P.n_need, (unsigned long long)tot_flag);
 #ifdef KVM_STREAM_PROF
   if (tid == 0) {
     const long long c6 = stream_clock();
