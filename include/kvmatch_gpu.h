@@ -55,7 +55,7 @@ typedef struct kvm_result {
   int64_t s_total;         /* series samples those windows cover, each counted once per interval */
   int64_t n_gate_pass;     /* cNSM: windows passing the exact alpha/beta gate */
   int64_t n_lb_pass;       /* DTW: windows surviving the GPU lower bounds, i.e. full DTWs computed */
-  int64_t n_exact;         /* ED: windows re-evaluated by the sequential reference-order path */
+  int64_t n_exact;         /* ED: windows re-evaluated by the sequential reference-order path; DTW: candidates that reached the band DTW (survivors of the corner probe, when it ran) */
   double kernel_ms;        /* device time of this call's kernels (CUDA events on the ctx stream) */
   double stage_ms[4];      /* the same, per stage.  cNSM engines: [0] streaming statistics pass (gate + in-stream lower
                               bound), [1] exact re-walk of the flagged chains, [2] exact stage (cNSM-ED: exact gate +

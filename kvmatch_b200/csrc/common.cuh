@@ -65,6 +65,14 @@ struct AnswerSink {
   }
 };
 
+// a <= b for doubles that are both >= +0 (or NaN, which then compares false for a and true for b): on the integer pipe
+__device__ __forceinline__ bool le_nonneg(double a, double b) { return __double_as_longlong(a) <= __double_as_longlong(b); }
+// min of two non-negative doubles on the integer pipe (DMNMX is as slow as DSETP)
+__device__ __forceinline__ double min_nonneg(double a, double b) {
+  const long long x = __double_as_longlong(a), y = __double_as_longlong(b);
+  return __longlong_as_double(x < y ? x : y);
+}
+
 // Per-candidate record handed from the statistics / lower-bound stages to the exact stages.
 struct CandList {
   int32_t* off;   // 1-based global window start
@@ -72,6 +80,7 @@ struct CandList {
   double* stdv;
   unsigned long long* count;
   long long cap;
+  double* lb = nullptr;  // optional: the candidate's LB_Keogh(EQ) total (0 when the producing stage did not form it)
 };
 
 }  // namespace kvm

@@ -76,12 +76,13 @@ __device__ __forceinline__ bool lb_cascade(const double* __restrict__ w, const L
   return lb <= Q.eps2_hi;
 }
 
-__device__ __forceinline__ void cand_append(const CandList& L, int32_t off, double mean, double stdv) {
+__device__ __forceinline__ void cand_append(const CandList& L, int32_t off, double mean, double stdv, double lb = 0.0) {
   const unsigned long long slot = atomicAdd(L.count, 1ULL);
   if ((long long)slot < L.cap) {
     L.off[slot] = off;
     L.mean[slot] = mean;
     L.stdv[slot] = stdv;
+    if (L.lb) L.lb[slot] = lb;
   }
 }
 
@@ -256,6 +257,367 @@ __global__ void __launch_bounds__(256) dtw_lb_data_kernel(Lb2Params P) {
     for (int o = 16; o > 0; o >>= 1) lb += __shfl_xor_sync(kFullMask, lb, o);
     if (lane == 0 && lb <= P.eps2_hi) cand_append(P.out, off, mean, stdv);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Both LB_Keogh bounds as ONE streaming kernel with survivor compaction.
+//   LB_Keogh(EQ): candidate against the query envelope   K/utils/DtwUtils.java:206-222
+//   LB_Keogh(EC): query against the DATA envelope        K/utils/DtwUtils.java:238-257
+// The data envelope does not depend on the window: l[i] / u[i] = min / max of the raw samples within rho of i
+// (the reference forms it over each read buffer, K/QueryEngineDtw.java:397-399 / K/NormQueryEngineDtw.java:522-524, and
+// normalises it per window, (l - mean) / std).  It is therefore built ONCE per (series, rho) by envelope_kernel over the
+// whole resident shard (16 bytes per sample, cached in the ctx) and every candidate reads it like it reads the series.
+// Taken over the shard rather than one read buffer it is never narrower than the reference's: still a valid bound.
+//
+// Thread per candidate, CTA = 256 candidates that walk the m terms together in chunks of kLbChunk: lanes hold
+// neighbouring window starts, so the series / envelope loads of a warp are coalesced and neighbouring lanes re-use each
+// other's lines out of L1, and the query terms of the chunk are broadcast from shared memory.  After every chunk the
+// candidates whose bound exceeds eps^2 (1 + 1e-9) are dropped and the survivors are COMPACTED to the front of the CTA,
+// so warps stay full of live candidates (a warp of the thread-per-candidate kernels this replaces ran as long as its
+// longest-lived lane — with 3 % survivors almost every warp ran all m terms — and the data-envelope bound rebuilt a
+// van Herk envelope per candidate: together 50 ns per candidate; this kernel: see DESIGN.md).
+// Arithmetic: x = (w - mean) * (1 / std) (well conditioned for any |mean| / std), excess outside [lo, up] as
+// max(|x - centre| - half, 0) with the clamp on the sign bit (no DSETP / DMNMX, which issue at a fifth of the DADD rate).
+constexpr int kLbChunk = 64;
+constexpr int kLbThreads = 256;
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+struct LbFusedParams {
+  const double* __restrict__ T;
+  const double* __restrict__ envL;  // data envelope, indexed like T
+  const double* __restrict__ envU;
+  int32_t first_global;
+  int m;
+  XList xin;    // kFromSums: (offset, ex, ex2) -> exact gate here
+  CandList cin; // else: (offset, mean, std)
+  double meanQ, stdQ, alpha, inv_alpha, beta;
+  const double* __restrict__ q;   // natural order (raw / z-normalised)
+  const double* __restrict__ uq;  // query envelope
+  const double* __restrict__ lq;
+  double eps2_hi;
+  CandList out;
+  unsigned long long* gate_pass;
+};
+
+// Block-wide stable compaction of the threads with `alive`: returns the number of live threads, `idx` = this thread's
+// new position.  Two barriers.
+__device__ __forceinline__ int lb_compact(bool alive, int& idx, int* s_wcount) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(kFullMask, alive);
+  __syncthreads();  // the previous round's readers of s_wcount are done
+  if (lane == 0) s_wcount[warp] = __popc(bal);
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kLbThreads / 32; w++) {
+    const int c = s_wcount[w];
+    before += (w < warp) ? c : 0;
+    total += c;
+  }
+  idx = before + __popc(bal & ((1u << lane) - 1u));
+  return total;
+}
+
+template <bool kFromSums, bool kEq>
+__global__ void __launch_bounds__(kLbThreads) dtw_lb_fused_kernel(LbFusedParams P) {
+  __shared__ double s_q[kLbChunk], s_c[kLbChunk], s_h[kLbChunk];
+  __shared__ int s_off[kLbThreads];
+  __shared__ double s_mean[kLbThreads], s_std[kLbThreads], s_rstd[kLbThreads], s_lbq[kLbThreads], s_lbc[kLbThreads];
+  __shared__ int s_wcount[kLbThreads / 32];
+  const int tid = threadIdx.x;
+  const int m = P.m;
+  unsigned long long n = kFromSums ? *P.xin.count : *P.cin.count;
+  const long long cap = kFromSums ? P.xin.cap : P.cin.cap;
+  if ((long long)n > cap) n = (unsigned long long)cap;
+  unsigned my_gate = 0;
+  for (unsigned long long base = (unsigned long long)blockIdx.x * kLbThreads; base < n; base += (unsigned long long)gridDim.x * kLbThreads) {
+    const unsigned long long e = base + tid;
+    bool alive = e < n;
+    int off = 0;
+    double mean = 0.0, stdv = 1.0;
+    if (alive) {
+      if (kFromSums) {
+        off = P.xin.off[e];
+        alive = cnsm_exact_gate(P.xin.ex[e], P.xin.ex2[e], m, P.meanQ, P.stdQ, P.alpha, P.inv_alpha, P.beta, mean, stdv);
+        my_gate += alive ? 1u : 0u;
+      } else {
+        off = P.cin.off[e];
+        mean = P.cin.mean[e];
+        stdv = P.cin.stdv[e];
+      }
+    }
+    double rstd = 1.0;
+    if (alive) {
+      rstd = 1.0 / stdv;
+      if (kEq && m >= 6) {  // LB_KimFL, K/utils/DtwUtils.java:149-189 (all five stages, no early return)
+        const double* __restrict__ w = P.T + (off - P.first_global);
+        const double* __restrict__ q = P.q;
+        const double x0 = (w[0] - mean) * rstd, x1 = (w[1] - mean) * rstd, x2 = (w[2] - mean) * rstd;
+        const double y0 = (w[m - 1] - mean) * rstd, y1 = (w[m - 2] - mean) * rstd, y2 = (w[m - 3] - mean) * rstd;
+        const double q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+        const double p0 = __ldg(q + m - 1), p1 = __ldg(q + m - 2), p2 = __ldg(q + m - 3);
+        auto mn = [](double a, double b) { return min_nonneg(a, b); };
+        double lb = fsq(x0, q0) + fsq(y0, p0);
+        lb += mn(mn(fsq(x1, q0), fsq(x0, q1)), fsq(x1, q1));
+        lb += mn(mn(fsq(y1, p0), fsq(y0, p1)), fsq(y1, p1));
+        lb += mn(mn(mn(fsq(x0, q2), fsq(x1, q2)), fsq(x2, q2)), mn(fsq(x2, q1), fsq(x2, q0)));
+        lb += mn(mn(mn(fsq(y0, p2), fsq(y1, p2)), fsq(y2, p2)), mn(fsq(y2, p1), fsq(y2, p0)));
+        alive = le_nonneg(lb, P.eps2_hi);
+      }
+    }
+    if (alive) {  // the first two chunks of this candidate's window (series and envelope)
+      const long long i0 = (long long)(off - P.first_global);
+#pragma unroll
+      for (int l = 0; l < 2 * kLbChunk * 8 / 128; l++) {
+        if (16 * l < m) {
+          if (kEq) prefetch_l2(P.T + i0 + 16 * l);
+          prefetch_l2(P.envL + i0 + 16 * l);
+          prefetch_l2(P.envU + i0 + 16 * l);
+        }
+      }
+    }
+    double lbq = 0.0, lbc = 0.0;
+    int n_live = kLbThreads;  // (first compaction always moves)
+    for (int k0 = 0;; k0 += kLbChunk) {
+      // ---- compaction: survivors to the front (state travels through shared memory only when somebody dropped out)
+      int idx;
+      const int total = lb_compact(alive, idx, s_wcount);
+      if (total != n_live) {
+        if (alive) {
+          s_off[idx] = off;
+          s_mean[idx] = mean;
+          s_std[idx] = stdv;
+          s_rstd[idx] = rstd;
+          s_lbq[idx] = lbq;
+          s_lbc[idx] = lbc;
+        }
+        __syncthreads();
+        n_live = total;
+        alive = tid < n_live;
+        if (alive) {
+          off = s_off[tid];
+          mean = s_mean[tid];
+          stdv = s_std[tid];
+          rstd = s_rstd[tid];
+          lbq = s_lbq[tid];
+          lbc = s_lbc[tid];
+        }
+      }
+      if (n_live == 0 || k0 >= m) break;  // (CTA-uniform)
+      // ---- the chunk's query terms: q, centre and half width of its envelope (half width rounded up)
+      const int kc = min(kLbChunk, m - k0);
+      if (tid < kLbChunk) {
+        double qv = 0.0, c = 0.0, h = 0.0;
+        if (tid < kc) {
+          qv = __ldg(P.q + k0 + tid);
+          const double up = __ldg(P.uq + k0 + tid), lo = __ldg(P.lq + k0 + tid);
+          c = 0.5 * (up + lo);
+          h = 0.5 * (up - lo) + 4.0 * 1.1102230246251565e-16 * (fabs(up) + fabs(lo) + 1.0);
+        }
+        s_q[tid] = qv;
+        s_c[tid] = c;
+        s_h[tid] = h;
+      }
+      __syncthreads();
+      if (alive) {
+        const long long i0 = (long long)(off - P.first_global) + k0;
+        const double* __restrict__ w = P.T + i0;
+        const double* __restrict__ el = P.envL + i0;
+        const double* __restrict__ eu = P.envU + i0;
+        // The windows were streamed long ago: their lines come from DRAM.  Ask for the lines of the chunk after the
+        // next one now (two chunks = ~2 us of work for a lone warp), so that a sparse candidate list does not pay one
+        // DRAM latency per group of loads (it did: 0.24 ms for a thousand candidates).
+        if (k0 + 2 * kLbChunk < m) {
+#pragma unroll
+          for (int l = 0; l < kLbChunk * 8 / 128; l++) {
+            if (kEq) prefetch_l2(w + 2 * kLbChunk + 16 * l);
+            prefetch_l2(el + 2 * kLbChunk + 16 * l);
+            prefetch_l2(eu + 2 * kLbChunk + 16 * l);
+          }
+        }
+        auto term = [&](int k, double wv, double lv, double uv) {
+          if (kEq) {
+            const double x = (wv - mean) * rstd;
+            const double ex = fabs(x - s_c[k]) - s_h[k];
+            const double d = (__double2hiint(ex) < 0) ? 0.0 : ex;
+            lbq = __fma_rn(d, d, lbq);
+          }
+          const double lo = (lv - mean) * rstd, up = (uv - mean) * rstd;
+          const double qk = s_q[k];
+          const double a = qk - up, b = lo - qk;
+          const double d2 = (__double2hiint(a) >= 0) ? a : ((__double2hiint(b) >= 0) ? b : 0.0);
+          lbc = __fma_rn(d2, d2, lbc);
+        };
+        if (kc == kLbChunk) {
+#pragma unroll 1
+          for (int kk = 0; kk < kLbChunk; kk += 8) {
+            double wv[8], lv[8], uv[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              wv[u] = kEq ? w[kk + u] : 0.0;
+              lv[u] = el[kk + u];
+              uv[u] = eu[kk + u];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) term(kk + u, wv[u], lv[u], uv[u]);
+          }
+        } else {
+          for (int kk = 0; kk < kc; kk++) term(kk, kEq ? w[kk] : 0.0, el[kk], eu[kk]);
+        }
+        alive = le_nonneg(lbq, P.eps2_hi) && le_nonneg(lbc, P.eps2_hi);
+      }
+    }
+    if (alive) cand_append(P.out, off, mean, stdv, kEq ? lbq : 0.0);  // (after the last compaction: tid < n_live)
+    __syncthreads();
+  }
+  if (kFromSums) {
+    const unsigned tot = __reduce_add_sync(kFullMask, my_gate);
+    if ((tid & 31) == 0 && tot) atomicAdd(P.gate_pass, (unsigned long long)tot);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Corner probe in front of the band DTW.  Most candidates that pass the lower bounds still abandon their DTW early:
+// measured on BASELINE configs[3]-shaped queries, 10 M DTWs per query gave up after ~6000 of 409 000 cells, i.e. right
+// after the top-left corner — and the wavefront kernels are at their worst there (a barrier or a shuffle per
+// anti-diagonal that holds a handful of cells).  The probe computes exactly that corner, the K x K square
+// (K = min(rho + 1, 128): every cell of it lies inside the band), one warp per candidate as a systolic array: lane l
+// owns columns 4l .. 4l+3 and works on row t - l at step t, so a step needs two shuffles and K + K/4 steps finish
+// the square.  Every warping path leaves the square through its last row or last column, and the rows it has not
+// matched by then each cost at least their LB_Keogh(EQ) term, so
+//     min( min_j D(K-1, j) + S(K),  min_i D(i, K-1) + S(i+1) ),   S(i) = sum of the Keogh terms of rows >= i,
+// is a lower bound of the band DTW.  S comes from the candidate's Keogh total (formed by the fused LB kernel) minus
+// the prefix over the first K rows, with the rounding slack on the safe side.  Candidates above eps^2 (1 + 1e-9) are
+// dropped; the rest go to the full DTW kernels unchanged (which start over: K^2 of m (2 rho + 1) cells).
+// Pruning only: answers and distances still come from dtw_band_*_kernel.
+constexpr int kProbeWarps = 8;
+constexpr int kProbeMaxK = 128;
+
+struct ProbeParams {
+  const double* __restrict__ T;
+  int32_t first_global;
+  int m, K;
+  const double* __restrict__ q;
+  const double* __restrict__ uq;
+  const double* __restrict__ lq;
+  double eps2_hi;
+  CandList in, out;
+  unsigned long long* n_cells;
+  int min_count;  // lists shorter than this are passed through
+};
+
+__global__ void __launch_bounds__(kProbeWarps * 32) dtw_probe_kernel(ProbeParams P) {
+  __shared__ double s_a[kProbeWarps][kProbeMaxK];
+  __shared__ double s_S[kProbeWarps][kProbeMaxK + 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int K = P.K;
+  double* A = s_a[warp];
+  double* S = s_S[warp];
+  double b[4], bu[4], bl[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const int col = min(4 * lane + c, K - 1);
+    b[c] = __ldg(P.q + col);
+    bu[c] = __ldg(P.uq + col);  // (rows and columns share the index range 0..K-1: the lane's four Keogh terms)
+    bl[c] = __ldg(P.lq + col);
+  }
+  unsigned long long n = *P.in.count;
+  if ((long long)n > P.in.cap) n = (unsigned long long)P.in.cap;
+  if (n < (unsigned long long)P.min_count) {  // a short list (mostly true matches): hand it on unprobed
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (unsigned long long)gridDim.x * blockDim.x)
+      cand_append(P.out, P.in.off[e], P.in.mean[e], P.in.stdv[e]);
+    return;
+  }
+  const int steps = K + (K + 3) / 4;
+  const int last_lane = (K - 1) >> 2, last_c = (K - 1) & 3;
+  unsigned long long probed = 0;
+  for (unsigned long long e = (unsigned long long)blockIdx.x * kProbeWarps + warp; e < n; e += (unsigned long long)gridDim.x * kProbeWarps) {
+    const int32_t off = P.in.off[e];
+    const double mean = P.in.mean[e], stdv = P.in.stdv[e];
+    const double total = P.in.lb ? P.in.lb[e] : 0.0;
+    const double rstd = 1.0 / stdv;
+    const double* __restrict__ w = P.T + (off - P.first_global);
+    __syncwarp();
+    // rows 4 lane .. 4 lane + 3: normalised samples and their Keogh terms
+    double kt[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int k = 4 * lane + c;
+      kt[c] = 0.0;
+      if (k < K) {
+        const double a = (w[k] - mean) * rstd;
+        A[k] = a;
+        const double dd = (a > bu[c]) ? (a - bu[c]) : ((a < bl[c]) ? (a - bl[c]) : 0.0);
+        kt[c] = dd * dd;
+      }
+    }
+    // S(i) = total - sum_{k < i} term_k, kept below the true remainder: total shrunk, prefix grown, clamped at 0
+    {
+      const double mine = (kt[0] + kt[1]) + (kt[2] + kt[3]);
+      double incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += t;
+      }
+      double pre = incl - mine;  // prefix before row 4 lane
+      const double tot = total * (1.0 - 1e-10);
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int k = 4 * lane + c;
+        if (k <= K) S[k] = fmax(tot - pre * (1.0 + 1e-10), 0.0);
+        pre += kt[c];
+      }
+      if (lane == 31 && K == kProbeMaxK) S[K] = fmax(tot - pre * (1.0 + 1e-10), 0.0);
+    }
+    __syncwarp();
+    double prev[4] = {kDtwInf, kDtwInf, kDtwInf, kDtwInf};
+    double last3 = kDtwInf, last3_prev = kDtwInf;
+    double best = kDtwInf;
+    const double s_end = S[K];
+    for (int t = 0; t < steps; t++) {
+      double left_in = __shfl_up_sync(kFullMask, last3, 1), diag_in = __shfl_up_sync(kFullMask, last3_prev, 1);
+      if (lane == 0) left_in = diag_in = kDtwInf;
+      const int r = t - lane;
+      if (r >= 0 && r < K) {
+        const double ar = A[r];
+        double x_left = left_in, x_diag = diag_in;
+        double cur[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const double d = ar - b[c];
+          const double cost = d * d;
+          const double up = prev[c];
+          double v = min_nonneg(min_nonneg(x_left, up), x_diag) + cost;
+          if (c == 0 && r == 0 && lane == 0) v = cost;
+          x_diag = up;
+          x_left = v;
+          cur[c] = v;
+        }
+        if (r == K - 1) {
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+            if (4 * lane + c < K) best = min_nonneg(best, cur[c] + s_end);
+        }
+        if (lane == last_lane) {
+          double v = cur[0];
+#pragma unroll
+          for (int c = 1; c < 4; c++) v = (c == last_c) ? cur[c] : v;
+          best = min_nonneg(best, v + S[r + 1]);
+        }
+        last3_prev = last3;
+        last3 = cur[3];
+#pragma unroll
+        for (int c = 0; c < 4; c++) prev[c] = cur[c];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min_nonneg(best, __shfl_xor_sync(kFullMask, best, o));
+    probed++;
+    if (lane == 0 && le_nonneg(best, P.eps2_hi)) cand_append(P.out, off, mean, stdv, total);
+  }
+  if (lane == 0 && probed) atomicAdd(P.n_cells, probed * (unsigned long long)K * (unsigned long long)K);
 }
 
 // lowerUpperLemire on the device (K/utils/DtwUtils.java:50-91): l[i] = min, u[i] = max of t[max(0,i-r) .. min(len-1,i+r)]
@@ -504,13 +866,15 @@ __global__ void __launch_bounds__(256) dtw_band_kernel(DtwParams P) {
       // wavefront: every warping path crosses one of the two most recent anti-diagonals, cell values only grow
       // along a path, and data points beyond imax = (d-1+rho)/2 have not been matched yet, so
       // min(cells on the last two diagonals) + cb[imax+1] is a lower bound of the final distance.
-      if ((d & 15) == 0 && d > 0) {
+      if ((d & 7) == 0 && d > 0) {
         double mn = kDtwInf;
 #pragma unroll
         for (int r = 0; r < R; r++) mn = umin_pos(mn, umin_pos(Ev[r], Od[r]));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mn = umin_pos(mn, __shfl_xor_sync(kFullMask, mn, o));
-        const int imax = min(m - 1, (d - 1 + rho) >> 1);
+        // (rows on diagonal d - 1: i <= d - 1 while the wavefront is still in the top-left corner, i <= (d - 1 + rho) / 2
+        // once the band binds)
+        const int imax = min(m - 1, min(d - 1, (d - 1 + rho) >> 1));
         const double rest = CBS[(imax + 1 + 7) >> 3];  // first sampled position >= imax+1: a (slightly smaller) valid remainder
         if (mn + rest > P.eps2_hi) {
           abandoned = true;
@@ -624,10 +988,10 @@ __global__ void __launch_bounds__(kCoopThreads) dtw_band_coop_kernel(DtwParams P
   const int m = P.m, rho = P.rho;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cbs_len = (m >> 3) + 2;
-  double* B = coop_smem;           // query
-  double* A = coop_smem + m;       // normalised window
+  const double* __restrict__ B = P.q;  // query: read through L1 (every CTA of the grid reads the same 8 m bytes; a private
+                                       // shared-memory copy halved the CTAs per SM)
+  double* A = coop_smem;           // normalised window
   double* CBS = A + m;             // cumulative LB_Keogh remainder sampled every 8th position
-  for (int k = tid; k < m; k += kCoopThreads) B[k] = P.q[k];
   unsigned long long n = *P.in.count;
   if ((long long)n > P.in.cap) n = (unsigned long long)P.in.cap;
   if ((long long)n > P.coop_limit) n = (unsigned long long)P.coop_limit;
@@ -700,7 +1064,7 @@ __global__ void __launch_bounds__(kCoopThreads) dtw_band_coop_kernel(DtwParams P
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < kCoopThreads / 32; k++) mn = umin_pos(mn, s_red[k]);
-      const int imax = min(m - 1, (d - 1 + rho) >> 1);
+      const int imax = min(m - 1, min(d - 1, (d - 1 + rho) >> 1));  // rows on diagonal d - 1 (corner: i <= d - 1)
       return mn + CBS[(imax + 1 + 7) >> 3] > P.eps2_hi;
     };
     // one edge diagonal (some band cells fall outside the matrix): the general form with per-cell index tests
@@ -745,7 +1109,7 @@ __global__ void __launch_bounds__(kCoopThreads) dtw_band_coop_kernel(DtwParams P
     const int fast_begin = rho + 2, fast_pairs = max(0, m - 2 - rho);
     int d = 0;
     for (; d < min(fast_begin, last + 1) && !abandoned; d++) {
-      if ((d & 15) == 0 && d > 0 && hopeless(d)) abandoned = true;
+      if ((d & 7) == 0 && d > 0 && hopeless(d)) abandoned = true;
       else edge_step(d);
     }
     if (!abandoned && d == fast_begin && fast_pairs > 0) {

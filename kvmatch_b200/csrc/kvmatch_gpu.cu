@@ -97,7 +97,7 @@ struct Arena {
   }
 };
 
-enum Counter { kCntAnswers = 0, kCntCand = 1, kCntGate = 2, kCntTiles = 3, kCntEntries = 4, kCntFlag = 5, kCntDone = 6, kCntCand2 = 7, kCntCells = 8, kNumCounters = 10 };
+enum Counter { kCntAnswers = 0, kCntCand = 1, kCntGate = 2, kCntTiles = 3, kCntEntries = 4, kCntFlag = 5, kCntDone = 6, kCntCand2 = 7, kCntCells = 8, kCntProbe = 9, kNumCounters = 10 };
 
 struct Plan {
   std::vector<int32_t> cbegin, nsamp, ncand;
@@ -163,7 +163,12 @@ struct kvm_ctx {
 
   DevBuf arena, qarena, counters, wl_off, wl_ex, wl_ex2, region_count, tile_prefix;
   DevBuf cand_off, cand_mean, cand_std, ans_off, ans_dist;
-  DevBuf cand2_off, cand2_mean, cand2_std;  // survivors of the data-envelope bound (same capacity as cand_*)
+  DevBuf cand2_off, cand2_mean, cand2_std, cand2_lb;  // survivors of the lower bounds (same capacity as cand_*) + their Keogh totals
+  // data envelope of the resident shard for one Sakoe-Chiba radius (lower / upper, laid out like series_buf): built at
+  // the first DTW call with that radius, dropped when a series is loaded
+  DevBuf env_lo, env_up;
+  int env_rho = -1;
+  bool env_failed = false;  // the allocation did not fit: DTW calls use the per-candidate envelope kernel instead
   DevBuf seg_b, seg_first, seg_last, chain_count, chain_prefix, run_key, run_b, run_first, run_last;
   long long cand_cap = 0, ans_cap = 0;
   NormPlanCache norm_cache;
@@ -369,12 +374,14 @@ int ensure_cands(kvm_ctx* ctx, long long cap) {
   KVM_CUDA(ctx, ctx->cand2_off.ensure(sizeof(int32_t) * cap));
   KVM_CUDA(ctx, ctx->cand2_mean.ensure(sizeof(double) * cap));
   KVM_CUDA(ctx, ctx->cand2_std.ensure(sizeof(double) * cap));
+  KVM_CUDA(ctx, ctx->cand2_lb.ensure(sizeof(double) * cap));
   ctx->cand_cap = cap;
   return KVM_OK;
 }
 
 CandList cands2_of(kvm_ctx* ctx);
-int launch_lb_data(kvm_ctx* ctx, const double* q, int m, int rho, double eps2_hi);
+int launch_lb_data(kvm_ctx* ctx, const double* q, const double* uq, const double* lq, int m, int rho, double eps2_hi);
+bool ensure_envelope(kvm_ctx* ctx, int rho);
 
 AnswerSink sink_of(kvm_ctx* ctx) {
   return AnswerSink{ctx->ans_off.as<int32_t>(), ctx->ans_dist.as<double>(),
@@ -382,7 +389,7 @@ AnswerSink sink_of(kvm_ctx* ctx) {
 }
 CandList cands2_of(kvm_ctx* ctx) {
   return CandList{ctx->cand2_off.as<int32_t>(), ctx->cand2_mean.as<double>(), ctx->cand2_std.as<double>(),
-                  ctx->counters.as<unsigned long long>() + kCntCand2, ctx->cand_cap};
+                  ctx->counters.as<unsigned long long>() + kCntCand2, ctx->cand_cap, ctx->cand2_lb.as<double>()};
 }
 CandList cands_of(kvm_ctx* ctx) {
   return CandList{ctx->cand_off.as<int32_t>(), ctx->cand_mean.as<double>(), ctx->cand_std.as<double>(),
@@ -1307,8 +1314,31 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
                     reinterpret_cast<const double*>(qbase + o_lq), m, eps2_hi};
       L.out = cands_of(ctx);
       L.gate_pass = counters + kCntGate;
-      cnsm_dtw_lb_list_kernel<<<ctx->n_sms * 8, 128, 0, ctx->stream>>>(L);
-      if ((rc = launch_lb_data(ctx, L.Q.q, m, rho, eps2_hi))) return rc;
+      if (ensure_envelope(ctx, rho)) {  // exact gate + LB_Kim + both LB_Keogh bounds in one pass: flagged windows -> cands2
+        kvm::LbFusedParams F{};
+        F.T = ctx->series;
+        F.envL = ctx->env_lo.as<double>() + kFrontPad;
+        F.envU = ctx->env_up.as<double>() + kFrontPad;
+        F.first_global = (int32_t)ctx->first;
+        F.m = m;
+        F.xin = R.out;
+        F.meanQ = S.meanQ;
+        F.stdQ = S.stdQ;
+        F.alpha = alpha;
+        F.inv_alpha = S.inv_alpha;
+        F.beta = beta;
+        F.q = L.Q.q;
+        F.uq = L.Q.uq;
+        F.lq = L.Q.lq;
+        F.eps2_hi = eps2_hi;
+        F.out = cands2_of(ctx);
+        F.gate_pass = counters + kCntGate;
+        kvm::dtw_lb_fused_kernel<true, true><<<ctx->n_sms * 6, kvm::kLbThreads, 0, ctx->stream>>>(F);
+        KVM_CUDA(ctx, cudaGetLastError());
+      } else {
+        cnsm_dtw_lb_list_kernel<<<ctx->n_sms * 8, 128, 0, ctx->stream>>>(L);
+        if ((rc = launch_lb_data(ctx, L.Q.q, L.Q.uq, L.Q.lq, m, rho, eps2_hi))) return rc;
+      }
       KVM_CUDA(ctx, cudaEventRecord(ctx->evs[2], ctx->stream));
       DtwParams D{};
       D.T = ctx->series;
@@ -1350,11 +1380,12 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
     }
     out->n_launches += launches;
     const bool x_over = (long long)cnt[kCntEntries] > ctx->x_cap;
-    const bool cand_over = dtw && (long long)cnt[kCntCand] > ctx->cand_cap, ans_over = (long long)cnt[kCntAnswers] > ctx->ans_cap;
+    const long long cand_need = (long long)std::max(cnt[kCntCand], cnt[kCntCand2]);
+    const bool cand_over = dtw && cand_need > ctx->cand_cap, ans_over = (long long)cnt[kCntAnswers] > ctx->ans_cap;
     if (!x_over && !cand_over && !ans_over) break;
     if (attempt == 7) return fail(ctx, KVM_E_OOM, "result buffers kept overflowing");
     if (x_over && (rc = ensure_xlist(ctx, (long long)cnt[kCntEntries] + 1024))) return rc;
-    if (cand_over && (rc = ensure_cands(ctx, (long long)cnt[kCntCand] + 1024))) return rc;
+    if (cand_over && (rc = ensure_cands(ctx, cand_need + 1024))) return rc;
     if (ans_over && (rc = ensure_answers(ctx, (long long)cnt[kCntAnswers] + 1024))) return rc;
   }
   ctx->stream_dirty = false;  // the re-walk consumed every flag it was given
@@ -1362,16 +1393,66 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
   out->n_gate_pass = (int64_t)cnt[kCntGate];
   out->n_rewalked = (int64_t)cnt[kCntEntries];
   out->n_chains_rewalked = (int64_t)cnt[kCntTiles];
-  if (!dtw) out->n_exact = (int64_t)cnt[kCntFlag]; else out->n_lb_pass = (int64_t)cnt[kCntCand2];
+  if (!dtw) out->n_exact = (int64_t)cnt[kCntFlag];
+  else {
+    out->n_lb_pass = (int64_t)cnt[kCntCand2];
+    out->n_exact = (int64_t)cnt[kCntProbe];  // DTW engines: candidates that reached the band DTW (after the corner probe)
+  }
   out->n_dtw_cells = (int64_t)cnt[kCntCells];
   return fetch_answers(ctx, (long long)cnt[kCntAnswers], out);
 }
 
 }  // namespace
 
-// Third bound of the cascade (LB_Keogh on the data envelope) over the survivors of the first LB stage: cands -> cands2.
+// Data envelope of the whole resident buffer (pads included: they hold the zeros some scans count as samples) for
+// radius rho, cached per ctx.  Returns false (and remembers it) when the 16 bytes per sample do not fit.
 namespace {
-int launch_lb_data(kvm_ctx* ctx, const double* q, int m, int rho, double eps2_hi) {
+bool ensure_envelope(kvm_ctx* ctx, int rho) {
+  static const int fused_on = env_int("KVM_LB_FUSED", 1);  // developer knob: 0 = the per-candidate kernels
+  if (!fused_on || rho > 512) return false;
+  if (ctx->env_rho == rho) return true;
+  if (ctx->env_failed) return false;
+  const size_t len = (size_t)(ctx->count + kFrontPad + kTailPad);
+  ctx->env_rho = -1;
+  if (ctx->env_lo.ensure(sizeof(double) * len) != cudaSuccess || ctx->env_up.ensure(sizeof(double) * len) != cudaSuccess) {
+    cudaGetLastError();
+    ctx->env_lo.release();
+    ctx->env_up.release();
+    ctx->env_failed = true;
+    return false;
+  }
+  const size_t smem = sizeof(long long) * 2 * (size_t)(kvm::kEnvTile + 2 * rho);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(kvm::envelope_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+  kvm::envelope_kernel<<<(unsigned)((len + kvm::kEnvTile - 1) / kvm::kEnvTile), 256, smem, ctx->stream>>>(
+      ctx->series_buf.as<double>(), (int)len, rho, ctx->env_lo.as<double>(), ctx->env_up.as<double>());
+  if (cudaGetLastError() != cudaSuccess) return false;
+  ctx->env_rho = rho;
+  return true;
+}
+
+// Third bound of the cascade (LB_Keogh on the data envelope) over the survivors of the first LB stage: cands -> cands2.
+int launch_lb_data(kvm_ctx* ctx, const double* q, const double* uq, const double* lq, int m, int rho, double eps2_hi) {
+  if (ensure_envelope(ctx, rho)) {
+    kvm::LbFusedParams F{};
+    F.T = ctx->series;
+    F.envL = ctx->env_lo.as<double>() + kFrontPad;
+    F.envU = ctx->env_up.as<double>() + kFrontPad;
+    F.first_global = (int32_t)ctx->first;
+    F.m = m;
+    F.cin = cands_of(ctx);
+    F.q = q;
+    F.uq = uq;
+    F.lq = lq;
+    F.eps2_hi = eps2_hi;
+    F.out = cands2_of(ctx);
+    kvm::dtw_lb_fused_kernel<false, false><<<ctx->n_sms * 6, kvm::kLbThreads, 0, ctx->stream>>>(F);
+    KVM_CUDA(ctx, cudaGetLastError());
+    return KVM_OK;
+  }
   Lb2Params L{};
   L.T = ctx->series;
   L.first_global = (int32_t)ctx->first;
@@ -1400,6 +1481,33 @@ int launch_lb_data(kvm_ctx* ctx, const double* q, int m, int rho, double eps2_hi
 
 int launch_dtw(kvm_ctx* ctx, const DtwParams& D_in) {
   DtwParams D = D_in;
+  // Corner probe (dtw_probe_kernel): survivors of the lower bounds whose K x K corner already exceeds eps^2 never reach
+  // the wavefront kernels.  Needs the list that carries the Keogh totals (the fused LB stage's output); its survivors
+  // go to the first candidate list, which no stage reads any more at this point.
+  {
+    static const int probe_on = env_int("KVM_DTW_PROBE", 1);
+    static const int probe_k = env_int("KVM_DTW_PROBE_K", kvm::kProbeMaxK);  // developer knob
+    const int K = std::min(std::min(D.rho + 1, std::min(probe_k, kvm::kProbeMaxK)), D.m);
+    if (probe_on && D.in.lb != nullptr && K >= 24) {
+      kvm::ProbeParams PP{};
+      PP.T = D.T;
+      PP.first_global = D.first_global;
+      PP.m = D.m;
+      PP.K = K;
+      PP.q = D.q;
+      PP.uq = D.uq;
+      PP.lq = D.lq;
+      PP.eps2_hi = D.eps2_hi;
+      PP.in = D.in;
+      PP.out = CandList{ctx->cand_off.as<int32_t>(), ctx->cand_mean.as<double>(), ctx->cand_std.as<double>(),
+                        ctx->counters.as<unsigned long long>() + kCntProbe, ctx->cand_cap};
+      PP.n_cells = D.n_cells;
+      PP.min_count = 4096;
+      kvm::dtw_probe_kernel<<<ctx->n_sms * 8, kvm::kProbeWarps * 32, 0, ctx->stream>>>(PP);
+      KVM_CUDA(ctx, cudaGetLastError());
+      D.in = PP.out;
+    }
+  }
   const int need = (D.rho + 1 + 31) / 32;  // (even,odd) pairs per lane
   const size_t bytes_per_row = sizeof(double) * (size_t)D.m;
   const size_t warp_bytes = sizeof(double) * (size_t)(D.m + ((((D.m >> 3) + 2) + 1) & ~1));  // window + sampled cb
@@ -1411,8 +1519,8 @@ int launch_dtw(kvm_ctx* ctx, const DtwParams& D_in) {
   // time: 0.33 ms per m = 2048 / rho = 102 DTW against 0.52 ms for one warp, and more DTWs per SM per ms as well
   // (five 4-warp CTAs per SM).  Narrow bands stay on the warp-per-candidate kernel.  KVM_DTW_COOP=0 disables.
   {
-    const size_t coop_smem = bytes_per_row + warp_bytes;
-    const int per_sm = std::max(1, (int)std::min<size_t>(smem_budget / coop_smem, 8));
+    const size_t coop_smem = warp_bytes;  // window + sampled cumulative bound (the query is read through L1)
+    const int per_sm = std::max(1, (int)std::min<size_t>(smem_budget / coop_smem, 9));
     const int need_c = (D.rho + 1 + kCoopThreads - 1) / kCoopThreads;
     static const int coop_on = env_int("KVM_DTW_COOP", 1);
     D.coop_limit = 0;
@@ -1577,6 +1685,8 @@ static int alloc_series(kvm_ctx* ctx, int64_t n, int64_t first, int64_t count) {
   // padding of the last 1000-byte block (K/operator/file/TimeSeriesNodeIterator.java:55-59).
   ctx->series = nullptr;
   ctx->norm_cache.valid = false;  // plans hold shard-relative indices
+  ctx->env_rho = -1;
+  ctx->env_failed = false;
   KVM_CUDA(ctx, ctx->series_buf.ensure(sizeof(double) * (size_t)(count + kFrontPad + kTailPad)));
   ctx->series = ctx->series_buf.as<double>() + kFrontPad;
   KVM_CUDA(ctx, cudaMemsetAsync(ctx->series_buf.p, 0, sizeof(double) * kFrontPad, ctx->stream));
@@ -2156,7 +2266,7 @@ int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     dtw_lb_raw_kernel<<<(unsigned)n_tiles, kEdThreads, 0, ctx->stream>>>(L);
     KVM_CUDA(ctx, cudaEventRecord(ctx->evs[0], ctx->stream));
-    if ((rc = launch_lb_data(ctx, L.Q.q, m, rho, L.Q.eps2_hi))) return rc;  // LB_Keogh on the data envelope
+    if ((rc = launch_lb_data(ctx, L.Q.q, L.Q.uq, L.Q.lq, m, rho, L.Q.eps2_hi))) return rc;  // LB_Keogh on the data envelope
     D.in = cands2_of(ctx);
     KVM_CUDA(ctx, cudaEventRecord(ctx->evs[1], ctx->stream));
     if ((rc = launch_dtw(ctx, D))) return rc;

@@ -54,14 +54,6 @@ struct StreamGate {  // on ex (= m * mean) and t2 = m*ex2 - ex^2 (= m^2 * varian
   double v_mid, v_rad_out, v_rad_in;
 };
 
-// a <= b for doubles that are both >= +0 (or NaN, which then compares false for a and true for b): on the integer pipe
-__device__ __forceinline__ bool le_nonneg(double a, double b) { return __double_as_longlong(a) <= __double_as_longlong(b); }
-// min of two non-negative doubles on the integer pipe (DMNMX is as slow as DSETP)
-__device__ __forceinline__ double min_nonneg(double a, double b) {
-  const long long x = __double_as_longlong(a), y = __double_as_longlong(b);
-  return __longlong_as_double(x < y ? x : y);
-}
-
 // Guard bands as a function of A = max |sample| over everything a tile's chains have summed (stream_guard() on the
 // host explains every term).  Evaluated per tile on the device with the tile's own A, so that a series whose
 // amplitude varies by orders of magnitude (random walks) keeps tight bands where the values are small.
@@ -704,7 +696,7 @@ __device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void* src, b
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 
-constexpr int kRewalkStages = 6;  // 32-position tiles in flight per warp
+constexpr int kRewalkStages = 12;  // 32-position tiles in flight per warp (covers ~2.5k cycles of DRAM latency at 16 cycles per position)
 
 // One warp per flagged chain.  All lanes run the same recurrence (the chain is sequential; what the warp buys is
 // coalesced, deeply prefetched sample rows and nothing but LDS + DADD/DMUL on the dependent path):
