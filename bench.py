@@ -12,9 +12,11 @@ chunking, K/experiments/ucr/UcrDtwQueryExecutor.java:97).
 
 N GPUs: STRONG scaling — the same series sharded by offset range (rank r holds its 1/N of the window starts plus an
 m-1 halo; chains are never split); every step ends with the multi-GPU tail inside the timed region: ONE packed
-all_gather (count, counters, best match, the first 512 answers of every rank; kvmatch_b200/sharding.PackedMerger).
+all_gather (count, counters, best match, the first 256 answers of every rank; kvm_gather_result in the library).
 `value` = window starts verified by all ranks / max-over-ranks device time of the K timed steps (the library's CUDA
-events per kernel stage + CUDA events around the exchange; series resident in HBM).  `e2e` = the same through the C
+events per kernel stage + CUDA events around the exchange; series resident in HBM).  The exchange is the library's own
+(kvm_comm_init / kvm_gather_result: ncclAllGather on the ctx's stream); torch.distributed carries the NCCL id, the
+barriers and the final statistics.  `e2e` = the same through the C
 ABI with host buffers (query + interval list in, answers out, exchange included), from the barrier-bracketed wall
 clock of the K steps.  At N=1 the line also carries BASELINE.json configs[1] itself (n = 1e8) as `cfg2_n1e8`.
 """
@@ -215,7 +217,11 @@ def timed_queries(g, queries, iv, steps, warmup, merger=None, barrier=None):
         r = g.verify_cnsm_ed(queries[i % len(queries)], EPSILON, ALPHA, BETA, iv)
         merged = None
         tail_ms = 0.0
-        if merger is not None:
+        if merger == "library":   # the library's own NCCL tail: one packed ncclAllGather on its stream (kvm_gather_result)
+            mr, best = g.gather(r)
+            merged = (mr.offsets, mr.distances, {"n_verified": mr.n_verified, "gate": mr.n_gate_pass}, best)
+            tail_ms = mr.stage_ms[0]
+        elif merger is not None:
             merged = merger.merge(r.offsets, r.distances, {"n_verified": r.n_verified, "gate": r.n_gate_pass})
             tail_ms = merger.last_device_ms
         return r, merged, tail_ms, time.perf_counter() - t
@@ -278,7 +284,12 @@ def main():
     iv = sharding.assign_intervals(all_iv, 0, M, shard)
     offs = query_offsets(n_total, M, N_QUERIES)
     queries = [query_of(n_total, o, M) for o in offs]
-    merger = sharding.PackedMerger(["n_verified", "gate"], device=dev)
+    # multi-GPU tail: the library's communicator (KVM_BENCH_TAIL=torch selects the torch.distributed PackedMerger instead)
+    if world > 1 and os.environ.get("KVM_BENCH_TAIL", "library") == "library":
+        g.comm_init(rank, world)
+        merger = "library"
+    else:
+        merger = sharding.PackedMerger(["n_verified", "gate"], device=dev)
 
     def barrier():
         if world > 1:
@@ -312,6 +323,9 @@ def main():
     rewalked = sum(r.n_rewalked for r, _, _, _ in rows)
     last, last_merged = rows[-1][0], rows[-1][1]
 
+    tail_min = torch.tensor([tail_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tail_min, op=dist.ReduceOp.MIN)
     stats = torch.tensor([dev_ms, t_wall, kern_ms, stream_ms, tail_ms], dtype=torch.float64, device=dev)
     sums = torch.tensor([verified, launches, answers, gate, rewalked], dtype=torch.float64, device=dev)
     if world > 1:
@@ -352,8 +366,14 @@ def main():
                          "stage_ms_per_step": {"stream": stream_ms / k,
                                                "rewalk": sum(r.stage_ms[1] for r, _, _, _ in rows) / k,
                                                "exact": sum(r.stage_ms[2] for r, _, _, _ in rows) / k}},
-            "tail": {"ms_per_step_device_max_over_ranks": tail_ms_max / k, "collectives_per_step": 1 if world > 1 else 0,
-                     "overflow_rounds": merger.overflows, "packed_bytes_per_rank": 8 * merger.len},
+            "tail": {"ms_per_step_device_max_over_ranks": tail_ms_max / k,
+                     # the rank that arrives last at the collective waits for nobody: its time is the exchange itself, the
+                     # difference to the maximum is load imbalance between the shards of one query
+                     "ms_per_step_device_min_over_ranks": float(tail_min.item()) / k,
+                     "collectives_per_step": 1 if world > 1 else 0,
+                     "implementation": "kvm_gather_result: one packed ncclAllGather on the library's stream (copies + collective timed by CUDA events)"
+                     if merger == "library" else "torch.distributed all_gather_into_tensor (sharding.PackedMerger)",
+                     "packed_bytes_per_rank": 8 * (16 + 2 * 256) if merger == "library" else 8 * merger.len},
             "parity": "oracle-only (reference unpinned: Java 8, no JVM in this image)",
             "answers_per_step": answers_all / k, "gate_pass_per_step": gate_all / k, "rewalked_windows_per_step": rewalked_all / k,
             "wall_s_timed_region": t_wall_max, "datagen_s": t_gen,

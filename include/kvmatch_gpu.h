@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KVM_ABI_VERSION 2
+#define KVM_ABI_VERSION 3
 
 enum {
   KVM_OK = 0,
@@ -37,9 +37,10 @@ enum {
   KVM_E_CUDA = -4,     /* CUDA runtime error (message has the detail) */
   KVM_E_IO = -5,       /* series file could not be read */
   KVM_E_STATE = -6,    /* no series loaded */
-  KVM_E_RANGE = -7     /* an interval needs samples outside [1,n] or outside this ctx's shard; the
+  KVM_E_RANGE = -7,    /* an interval needs samples outside [1,n] or outside this ctx's shard; the
                           reference throws IllegalArgumentException for the former
                           (K/operator/file/TimeSeriesFileOperator.java:55-57) */
+  KVM_E_NCCL = -8      /* NCCL could not be loaded or a collective failed (kvm_comm_*, kvm_gather_result) */
 };
 
 typedef struct kvm_ctx kvm_ctx;
@@ -237,6 +238,26 @@ int kvm_multi_load_series_host(kvm_multi* m, const double* samples, int64_t n, i
  * ignored); out->offsets / distances stay valid until the next call on this handle. */
 int kvm_multi_verify(kvm_multi* m, int32_t engine, const double* q, int32_t mq, double epsilon, int32_t rho, double alpha,
                      double beta, const int32_t* lr, int32_t K, int32_t shift, kvm_result* out);
+
+/* ---- One process per GPU: the multi-GPU tail inside the library --------------------------------
+ * The series shards by offset range, every rank verifies its own slice with the entries above, and the only exchange is
+ * the tail: per-rank counts, the sparse answers and the best match.  The reference has no counterpart (single JVM); its
+ * MapReduce index build shards the same way (K/mapreduce/BuildIndexMapReduce.java:216-221).
+ * kvm_comm_unique_id: rank 0 obtains a 128-byte NCCL id and distributes it to the other ranks by any means (the
+ * Python host code broadcasts it through torch.distributed; a Java driver would send it over its own RPC).
+ * kvm_comm_init: every rank joins the communicator with its ctx (ncclCommInitRank on the ctx's device).  NCCL is
+ * resolved with dlopen("libnccl.so.2") at the first call: the library has no link-time dependency on it.
+ * kvm_gather_result: COLLECTIVE — every rank passes the result of its own verify call; ONE fixed-size ncclAllGather on
+ * the ctx's stream carries [count, counters, best match, first 256 answers] of every rank (a second, padded one only
+ * when some rank holds more); every rank receives the merged result: answers of all ranks in ascending offset order
+ * (ranks must own ascending, disjoint offset ranges), counters summed, kernel_ms = max over ranks, stage_ms[0] = device
+ * time of the exchange itself (CUDA events around the copies and the collective), and the reference's
+ * `Best:` line (lowest distance, lowest offset among equals, K/QueryEngine.java:373-376) in best_distance /
+ * best_offset (may be NULL).  merged->offsets / distances are library-owned, valid until the next call on the ctx. */
+int kvm_comm_unique_id(unsigned char* id128);
+int kvm_comm_init(kvm_ctx* ctx, const unsigned char* id128, int32_t rank, int32_t world);
+int kvm_gather_result(kvm_ctx* ctx, const kvm_result* local, kvm_result* merged, double* best_distance,
+                      int32_t* best_offset);
 
 void kvm_result_free(kvm_ctx* ctx, kvm_result* r);
 void kvm_runs_free(kvm_ctx* ctx, kvm_runs* r);

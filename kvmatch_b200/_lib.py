@@ -21,12 +21,13 @@ KVM_E_CUDA = -4
 KVM_E_IO = -5
 KVM_E_STATE = -6
 KVM_E_RANGE = -7
+KVM_E_NCCL = -8
 KVM_OPT_CNSM_PATH, KVM_OPT_STREAM_FLAG_ALL, KVM_OPT_PLAN_CACHE = 1, 2, 3
 KVM_CNSM_STREAM, KVM_CNSM_RELAY = 0, 1
 
 ERROR_NAMES = {
     KVM_E_NODEVICE: "KVM_E_NODEVICE", KVM_E_ARG: "KVM_E_ARG", KVM_E_OOM: "KVM_E_OOM", KVM_E_CUDA: "KVM_E_CUDA",
-    KVM_E_IO: "KVM_E_IO", KVM_E_STATE: "KVM_E_STATE", KVM_E_RANGE: "KVM_E_RANGE",
+    KVM_E_IO: "KVM_E_IO", KVM_E_STATE: "KVM_E_STATE", KVM_E_RANGE: "KVM_E_RANGE", KVM_E_NCCL: "KVM_E_NCCL",
 }
 
 # every symbol include/kvmatch_gpu.h declares
@@ -37,7 +38,7 @@ EXPORTS = [
     "kvm_envelope", "kvm_window_mean_runs", "kvm_window_mean_runs_all", "kvm_build_index_file", "kvm_index_image_from_runs", "kvm_image_free",
     "kvm_result_free", "kvm_runs_free",
     "kvm_multi_create", "kvm_multi_destroy", "kvm_multi_last_error", "kvm_multi_devices", "kvm_multi_load_series_host",
-    "kvm_multi_verify", "kvm_intervals_sort_merge", "kvm_intervals_intersect", "kvm_intervals_first_segment",
+    "kvm_multi_verify", "kvm_comm_unique_id", "kvm_comm_init", "kvm_gather_result", "kvm_intervals_sort_merge", "kvm_intervals_intersect", "kvm_intervals_first_segment",
 ]
 KVM_ENGINE_ED, KVM_ENGINE_CNSM_ED, KVM_ENGINE_DTW, KVM_ENGINE_CNSM_DTW = 0, 1, 2, 3
 
@@ -126,6 +127,9 @@ def load():
                                            C.c_int32, R]
     L.kvm_scan_ucr_dtw.argtypes = [vp, _dp, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_double, R]
     L.kvm_scan_ucr_ed.argtypes = [vp, _dp, C.c_int32, C.c_double, C.c_double, C.c_double, R]
+    L.kvm_comm_unique_id.argtypes = [vp]
+    L.kvm_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    L.kvm_gather_result.argtypes = [vp, R, R, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     L.kvm_window_mean_runs.argtypes = [vp, C.c_int32, C.POINTER(KvmRuns)]
     L.kvm_envelope.argtypes = [vp, C.c_int32, C.c_int64, C.c_int32, vp, vp]
     L.kvm_window_mean_runs_all.argtypes = [vp, vp, C.c_int32, C.POINTER(KvmRuns)]

@@ -11,6 +11,7 @@
 #include "../../include/kvmatch_gpu.h"
 
 #include <algorithm>
+#include <dlfcn.h>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -166,6 +167,13 @@ struct kvm_ctx {
   DevBuf cand2_off, cand2_mean, cand2_std, cand2_lb;  // survivors of the lower bounds (same capacity as cand_*) + their Keogh totals
   // data envelope of the resident shard for one Sakoe-Chiba radius (lower / upper, laid out like series_buf): built at
   // the first DTW call with that radius, dropped when a series is loaded
+  // multi-GPU tail (kvm_comm_*): one NCCL communicator per ctx = per rank, packed all-gather buffers
+  void* comm = nullptr;      // ncclComm_t
+  int comm_rank = 0, comm_world = 1;
+  DevBuf g_send, g_recv;
+  PinBuf g_hsend, g_hrecv;
+  std::vector<int32_t> g_off;
+  std::vector<double> g_dist;
   DevBuf env_lo, env_up;
   int env_rho = -1;
   bool env_failed = false;  // the allocation did not fit: DTW calls use the per-candidate envelope kernel instead
@@ -206,6 +214,10 @@ struct kvm_ctx {
   std::vector<int32_t> res_off, run_first_v, run_last_v;
   std::vector<double> res_dist, run_key_v;
 };
+
+extern "C" {
+static void kvm_comm_release(kvm_ctx* ctx);
+}
 
 namespace {
 
@@ -1650,8 +1662,12 @@ void kvm_destroy(kvm_ctx* ctx) {
                    &ctx->region_count, &ctx->tile_prefix, &ctx->cand_off, &ctx->cand_mean, &ctx->cand_std, &ctx->cand2_off, &ctx->cand2_mean, &ctx->cand2_std,
                    &ctx->ans_off, &ctx->ans_dist, &ctx->seg_b, &ctx->seg_first, &ctx->seg_last, &ctx->chain_count,
                    &ctx->chain_prefix, &ctx->run_key, &ctx->run_b, &ctx->run_first, &ctx->run_last, &ctx->sarena,
-                   &ctx->need_bits, &ctx->chain_last, &ctx->flagged, &ctx->x_off, &ctx->x_ex, &ctx->x_ex2, &ctx->bmax};
+                   &ctx->need_bits, &ctx->chain_last, &ctx->flagged, &ctx->x_off, &ctx->x_ex, &ctx->x_ex2, &ctx->bmax,
+                   &ctx->cand2_lb, &ctx->env_lo, &ctx->env_up, &ctx->g_send, &ctx->g_recv};
   for (DevBuf* b : dev) b->release();
+  kvm_comm_release(ctx);
+  ctx->g_hsend.release();
+  ctx->g_hrecv.release();
   for (BatchSlot& sl : ctx->slots) sl.release();
   for (auto& w : ctx->wm) {
     DevBuf* wb[] = {&w.runs, &w.seg_off, &w.seg_cnt, &w.need_bits, &w.chain_last, &w.flagged, &w.x_off, &w.x_ex, &w.x_ex2};
@@ -2987,6 +3003,213 @@ int kvm_multi_verify(kvm_multi* M, int32_t engine, const double* q, int32_t m, d
   out->distances = M->dist.data();
   return KVM_OK;
 }
+
+// ---- multi-GPU tail inside the library: NCCL resolved at run time (no link dependency; a process that already
+// loaded an NCCL, e.g. through torch, shares that copy) ---------------------------------------------------------------
+namespace {
+struct NcclId {  // ncclUniqueId: 128 opaque bytes, passed by value
+  char b[128];
+};
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+      api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+      api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
+      api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+      api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+      if (api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy) api.h = h;
+    }
+  }
+  return api.h ? &api : nullptr;
+}
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+constexpr int kGatherHead = 16;  // doubles in front of the answers of one rank
+constexpr int kGatherCap = 256;  // answers per rank carried by the first (fixed-size) all-gather
+
+int nccl_fail(kvm_ctx* ctx, NcclApi* N, int rc, const char* what) {
+  return fail(ctx, KVM_E_NCCL, "%s: %s", what, N && N->GetErrorString ? N->GetErrorString(rc) : "NCCL error");
+}
+}  // namespace
+
+static void kvm_comm_release(kvm_ctx* ctx) {
+  if (ctx->comm) {
+    if (NcclApi* N = nccl_api()) N->CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+}
+
+extern "C" {
+
+int kvm_comm_unique_id(unsigned char* id128) {
+  NcclApi* N = nccl_api();
+  if (!N || !id128) return KVM_E_NCCL;
+  NcclId id;
+  if (N->GetUniqueId(&id) != 0) return KVM_E_NCCL;
+  std::memcpy(id128, id.b, 128);
+  return KVM_OK;
+}
+
+int kvm_comm_init(kvm_ctx* ctx, const unsigned char* id128, int32_t rank, int32_t world) {
+  if (!ctx) return KVM_E_ARG;
+  if (!id128 || world < 1 || rank < 0 || rank >= world) return fail(ctx, KVM_E_ARG, "null/invalid argument");
+  NcclApi* N = nccl_api();
+  if (!N) return fail(ctx, KVM_E_NCCL, "libnccl.so.2 could not be loaded");
+  KVM_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->comm) {
+    N->CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+  NcclId id;
+  std::memcpy(id.b, id128, 128);
+  const int rc = N->CommInitRank(&ctx->comm, world, id, rank);
+  if (rc != 0) {
+    ctx->comm = nullptr;
+    return nccl_fail(ctx, N, rc, "ncclCommInitRank");
+  }
+  ctx->comm_rank = rank;
+  ctx->comm_world = world;
+  return KVM_OK;
+}
+
+int kvm_gather_result(kvm_ctx* ctx, const kvm_result* local, kvm_result* merged, double* best_distance, int32_t* best_offset) {
+  if (!ctx) return KVM_E_ARG;
+  if (!local || !merged) return fail(ctx, KVM_E_ARG, "null/invalid argument");
+  if (!ctx->comm) return fail(ctx, KVM_E_STATE, "kvm_comm_init has not been called on this ctx");
+  NcclApi* N = nccl_api();
+  const int W = ctx->comm_world;
+  KVM_CUDA(ctx, cudaSetDevice(ctx->device));
+  // Best match of this rank: lowest distance, lowest offset among equals (the reference's stable sort by distance over
+  // the scan order, K/QueryEngine.java:373-376)
+  double bd = INFINITY, bo = 4e18;
+  for (int64_t i = 0; i < local->count; i++)
+    if (local->distances[i] < bd) {  // (offsets ascend: the first minimum is the lowest offset)
+      bd = local->distances[i];
+      bo = (double)local->offsets[i];
+    }
+  double exchange_ms = 0.0;  // device time of the exchange (CUDA events on the ctx stream: copies + collective)
+  auto round_trip = [&](size_t len_per_rank, auto fill) -> int {
+    KVM_CUDA(ctx, ctx->g_hsend.ensure(sizeof(double) * len_per_rank));
+    KVM_CUDA(ctx, ctx->g_hrecv.ensure(sizeof(double) * len_per_rank * W));
+    KVM_CUDA(ctx, ctx->g_send.ensure(sizeof(double) * len_per_rank));
+    KVM_CUDA(ctx, ctx->g_recv.ensure(sizeof(double) * len_per_rank * W));
+    fill(static_cast<double*>(ctx->g_hsend.p));
+    KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    KVM_CUDA(ctx, cudaMemcpyAsync(ctx->g_send.p, ctx->g_hsend.p, sizeof(double) * len_per_rank, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = N->AllGather(ctx->g_send.p, ctx->g_recv.p, len_per_rank, kNcclFloat64, ctx->comm, ctx->stream);
+    if (rc != 0) return nccl_fail(ctx, N, rc, "ncclAllGather");
+    KVM_CUDA(ctx, cudaMemcpyAsync(ctx->g_hrecv.p, ctx->g_recv.p, sizeof(double) * len_per_rank * W, cudaMemcpyDeviceToHost, ctx->stream));
+    KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    exchange_ms += ms;
+    return KVM_OK;
+  };
+  // ---- round 1, fixed size: header + the first kGatherCap answers of every rank
+  const size_t len1 = kGatherHead + 2 * (size_t)kGatherCap;
+  int rc = round_trip(len1, [&](double* h) {
+    std::memset(h, 0, sizeof(double) * len1);
+    h[0] = (double)local->count;
+    h[1] = (double)local->n_verified;
+    h[2] = (double)local->cnt_candidate;
+    h[3] = (double)local->s_total;
+    h[4] = (double)local->n_gate_pass;
+    h[5] = (double)local->n_lb_pass;
+    h[6] = (double)local->n_exact;
+    h[7] = (double)local->n_rewalked;
+    h[8] = (double)local->n_chains_rewalked;
+    h[9] = (double)local->n_dtw_cells;
+    h[10] = local->kernel_ms;
+    h[11] = bd;
+    h[12] = bo;
+    h[13] = (double)local->n_launches;
+    const int64_t c = std::min<int64_t>(local->count, kGatherCap);
+    for (int64_t i = 0; i < c; i++) {
+      h[kGatherHead + i] = (double)local->offsets[i];
+      h[kGatherHead + kGatherCap + i] = local->distances[i];
+    }
+  });
+  if (rc) return rc;
+  const double* a = static_cast<const double*>(ctx->g_hrecv.p);
+  int64_t total = 0, max_count = 0;
+  std::memset(merged, 0, sizeof(*merged));
+  double gbd = INFINITY, gbo = 4e18;
+  for (int r = 0; r < W; r++) {
+    const double* h = a + (size_t)r * len1;
+    total += (int64_t)h[0];
+    max_count = std::max<int64_t>(max_count, (int64_t)h[0]);
+    merged->n_verified += (int64_t)h[1];
+    merged->cnt_candidate += (int64_t)h[2];
+    merged->s_total += (int64_t)h[3];
+    merged->n_gate_pass += (int64_t)h[4];
+    merged->n_lb_pass += (int64_t)h[5];
+    merged->n_exact += (int64_t)h[6];
+    merged->n_rewalked += (int64_t)h[7];
+    merged->n_chains_rewalked += (int64_t)h[8];
+    merged->n_dtw_cells += (int64_t)h[9];
+    merged->kernel_ms = std::max(merged->kernel_ms, h[10]);
+    if (h[11] < gbd || (h[11] == gbd && h[12] < gbo)) {
+      gbd = h[11];
+      gbo = h[12];
+    }
+    merged->n_launches += (int32_t)h[13];
+  }
+  ctx->g_off.clear();
+  ctx->g_dist.clear();
+  ctx->g_off.reserve((size_t)total);
+  ctx->g_dist.reserve((size_t)total);
+  if (max_count <= kGatherCap) {
+    for (int r = 0; r < W; r++) {  // ranks own ascending offset ranges: concatenation is the scan order
+      const double* h = a + (size_t)r * len1;
+      for (int64_t i = 0; i < (int64_t)h[0]; i++) {
+        ctx->g_off.push_back((int32_t)h[kGatherHead + i]);
+        ctx->g_dist.push_back(h[kGatherHead + kGatherCap + i]);
+      }
+    }
+  } else {
+    // ---- round 2 (a rank holds more answers than the fixed block carries; every rank sees the same max_count, so
+    // every rank takes this branch): all answers, padded to the largest count
+    std::vector<int64_t> counts(W);
+    for (int r = 0; r < W; r++) counts[r] = (int64_t)a[(size_t)r * len1];
+    const size_t len2 = 2 * (size_t)max_count;
+    rc = round_trip(len2, [&](double* h) {
+      for (int64_t i = 0; i < local->count; i++) {
+        h[i] = (double)local->offsets[i];
+        h[max_count + i] = local->distances[i];
+      }
+    });
+    if (rc) return rc;
+    const double* b = static_cast<const double*>(ctx->g_hrecv.p);
+    for (int r = 0; r < W; r++)
+      for (int64_t i = 0; i < counts[r]; i++) {
+        ctx->g_off.push_back((int32_t)b[(size_t)r * len2 + i]);
+        ctx->g_dist.push_back(b[(size_t)r * len2 + max_count + i]);
+      }
+  }
+  merged->stage_ms[0] = exchange_ms;
+  merged->count = total;
+  merged->offsets = ctx->g_off.data();
+  merged->distances = ctx->g_dist.data();
+  if (best_distance) *best_distance = gbd;
+  if (best_offset) *best_offset = total > 0 ? (int32_t)gbo : 0;
+  return KVM_OK;
+}
+
+}  // extern "C"
 
 void kvm_result_free(kvm_ctx* ctx, kvm_result* r) {
   (void)ctx;

@@ -119,6 +119,47 @@ class GpuSeries:
         self._L.kvm_result_free(self._h, C.byref(r))
         return out
 
+    # ---- one process per GPU: the multi-GPU tail inside the library (kvm_comm_*, kvm_gather_result) ----
+    def comm_init(self, rank: int | None = None, world: int | None = None):
+        """Join the library's NCCL communicator.  The 128-byte id is obtained on rank 0 and broadcast through
+        torch.distributed (any backend); rank / world default to the process group's."""
+        import torch.distributed as dist
+        rank = dist.get_rank() if rank is None else rank
+        world = dist.get_world_size() if world is None else world
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            self._check(self._L.kvm_comm_unique_id(ident))
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=0)
+        ident = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        self._check(self._L.kvm_comm_init(self._h, ident, rank, world))
+        self.comm_world = world
+        return self
+
+    def gather(self, local: VerifyResult):
+        """COLLECTIVE: merge this rank's result with every other rank's (one packed ncclAllGather on the library's
+        stream).  Returns (merged VerifyResult, best) with best = (distance, offset) of the reference's `Best:` line or
+        None when nobody has an answer."""
+        lo = np.ascontiguousarray(local.offsets, dtype=np.int32)
+        ld = np.ascontiguousarray(local.distances, dtype=np.float64)
+        a = _lib.KvmResult()
+        a.count = len(lo)
+        a.offsets = lo.ctypes.data
+        a.distances = ld.ctypes.data
+        a.cnt_candidate, a.n_verified, a.s_total = local.cnt_candidate, local.n_verified, local.s_total
+        a.n_gate_pass, a.n_lb_pass, a.n_exact = local.n_gate_pass, local.n_lb_pass, local.n_exact
+        a.kernel_ms, a.n_launches = local.kernel_ms, local.n_launches
+        a.n_rewalked, a.n_chains_rewalked, a.n_dtw_cells = local.n_rewalked, local.n_chains_rewalked, local.n_dtw_cells
+        m = _lib.KvmResult()
+        bd, bo = C.c_double(), C.c_int32()
+        self._check(self._L.kvm_gather_result(self._h, C.byref(a), C.byref(m), C.byref(bd), C.byref(bo)))
+        c = m.count
+        out = VerifyResult(_lib.copy_out(m.offsets, c, np.int32), _lib.copy_out(m.distances, c, np.float64), m.cnt_candidate,
+                           m.n_verified, m.s_total, m.n_gate_pass, m.n_lb_pass, m.n_exact, m.kernel_ms, m.n_launches,
+                           tuple(m.stage_ms), int(local.h2d_bytes), int(m.n_rewalked), int(m.n_chains_rewalked),
+                           int(m.n_dtw_cells))
+        return out, ((bd.value, bo.value) if c > 0 else None)
+
     def verify_ed(self, q, epsilon, intervals, shift=0) -> VerifyResult:
         q, qp = _lib.as_f64(q)
         lr, lp, K = _lib.as_intervals(intervals)
