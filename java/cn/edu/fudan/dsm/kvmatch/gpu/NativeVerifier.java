@@ -70,6 +70,8 @@ public final class NativeVerifier implements AutoCloseable {
     private static final MethodHandle SCAN_UCR_DTW = fn("kvm_scan_ucr_dtw",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_DOUBLE, JAVA_INT, JAVA_DOUBLE, JAVA_DOUBLE,
                     ADDRESS));
+    private static final MethodHandle SCAN_UCR_ED = fn("kvm_scan_ucr_ed",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_DOUBLE, ADDRESS));
     // struct kvm_index_info
     private static final StructLayout INDEX_INFO = MemoryLayout.structLayout(
             JAVA_LONG.withName("file_bytes"), JAVA_LONG.withName("n_runs"), JAVA_LONG.withName("n_intervals"),
@@ -169,6 +171,15 @@ public final class NativeVerifier implements AutoCloseable {
         try (Arena a = Arena.ofConfined()) {
             MemorySegment res = a.allocate(RESULT);
             check((int) SCAN_UCR_DTW.invokeExact(ctx, doubles(a, q), q.size(), epsilon, rho, alpha, beta, res));
+            return take(res);
+        } catch (IOException e) { throw e; } catch (Throwable t) { throw new IOException(t); }
+    }
+
+    /** Index-free scan, UcrEdQueryExecutor semantics (one never-reset statistics chain, 1-based offsets). */
+    public List<Answer> scanUcrEd(List<Double> q, double epsilon, double alpha, double beta) throws IOException {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment res = a.allocate(RESULT);
+            check((int) SCAN_UCR_ED.invokeExact(ctx, doubles(a, q), q.size(), epsilon, alpha, beta, res));
             return take(res);
         } catch (IOException e) { throw e; } catch (Throwable t) { throw new IOException(t); }
     }
