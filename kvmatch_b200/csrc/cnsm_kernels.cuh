@@ -801,6 +801,50 @@ struct ExactEdParams {
   int q_cap;    // doubles (and ints) of the per-CTA staging of zQ / order (0 = none)
 };
 
+// Screen in front of the exact stage (streaming path): one warp per re-walked window — exact statistics and gate from
+// the chain sums (K/NormQueryEngine.java:508-511, counted), then the 128 largest-|zQ| terms of the distance in fast
+// arithmetic, straight from global memory.  No shared memory, so the SM holds 64 warps of it and the scattered window
+// gathers (the windows were streamed long ago: DRAM) overlap; survivors (rare: near matches) go to
+// cnsm_ed_exact_kernel<false> as (offset, mean, std).  Inside the exact kernel the same screen ran at 8-12 warps per
+// SM (its staging buffers): 105 us for 65 k windows at n = 1e9.
+__global__ void __launch_bounds__(256) cnsm_ed_screen_kernel(ExactEdParams P) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long gwarp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  unsigned long long n = *P.xin.count;
+  if ((long long)n > P.xin.cap) n = (unsigned long long)P.xin.cap;
+  const int m = P.m;
+  unsigned my_gate = 0;
+  for (unsigned long long e = gwarp; e < n; e += n_warps) {
+    double mean, stdv;
+    const int32_t off = P.xin.off[e];
+    if (!cnsm_exact_gate(P.xin.ex[e], P.xin.ex2[e], m, P.meanQ, P.stdQ, P.alpha, P.inv_alpha, P.beta, mean, stdv)) continue;
+    my_gate++;
+    const double* __restrict__ wg = P.T + (off - P.first_global);
+    const double rstd = 1.0 / stdv;
+    double part = 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int k = u * 32 + lane;
+      if (k < m) {
+        const double df = (wg[__ldg(P.order + k)] - mean) * rstd - __ldg(P.zq + k);
+        part = __fma_rn(df, df, part);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFullMask, part, o);
+    if (lane == 0 && part <= P.eps2_hi) {
+      const unsigned long long slot = atomicAdd(P.in.count, 1ULL);
+      if ((long long)slot < P.in.cap) {
+        P.in.off[slot] = off;
+        P.in.mean[slot] = mean;
+        P.in.stdv[slot] = stdv;
+      }
+    }
+  }
+  if (lane == 0 && my_gate) atomicAdd(P.gate_pass, (unsigned long long)my_gate);
+}
+
 constexpr int kExactChunk = 1024;  // terms staged in shared memory per pass (8 KB per warp)
 
 // K/NormQueryEngine.java:513-520 verbatim arithmetic: x = (T[order[k]+j]-mean)/std; dist += (x-zQ[k])^2.

@@ -42,15 +42,16 @@ __global__ void __launch_bounds__(kEdThreads) ed_verify_kernel(EdParams P) {
   const int m = P.m;
   const double eps2 = P.eps2;
   const double q0 = __ldg(q);
-  for (int c = c0 + (int)threadIdx.x; c < min(c0 + kEdTile, ncand); c += kEdThreads) {
-    const int start = cbegin + c;
+  // On a scan almost every window is hopeless after its first sample, so a thread's work per window is one 8-byte load
+  // and a compare: the kernel is bound by the bytes in flight.  The first samples of four of the thread's windows are
+  // therefore requested together (4 x 256 B per warp in flight instead of one load and a dependent branch).
+  const int c_end = min(c0 + kEdTile, ncand);
+  auto finish = [&](int start, double first) {
     const double* __restrict__ w = P.T + start;
-    // The first abandon tests come after 1 and 4 terms: on a scan almost every window is hopeless after its
-    // first sample, and each thread then costs 8 bytes of L1 traffic instead of 64.
-    double dist = xsqdist(w[0], q0);
-    bool alive = dist <= eps2;
+    double dist = first;
+    bool alive = true;
     int j = 1;
-    if (alive && m >= 4) {
+    if (m >= 4) {
 #pragma unroll
       for (int u = 1; u < 4; u++) dist = xadd(dist, xsqdist(w[u], __ldg(q + u)));
       alive = dist <= eps2;
@@ -68,6 +69,19 @@ __global__ void __launch_bounds__(kEdThreads) ed_verify_kernel(EdParams P) {
       for (; j < m; j++) dist = xadd(dist, xsqdist(w[j], __ldg(q + j)));
     }
     if (dist <= eps2) P.sink.emit(P.first_global + start, xsqrt(dist));
+  };
+  for (int c = c0 + (int)threadIdx.x; c < c_end; c += 4 * kEdThreads) {
+    double f[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int cu = c + u * kEdThreads;
+      f[u] = (cu < c_end) ? P.T[cbegin + cu] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const double d0 = xsqdist(f[u], q0);
+      if (c + u * kEdThreads < c_end && d0 <= eps2) finish(cbegin + c + u * kEdThreads, d0);
+    }
   }
 }
 

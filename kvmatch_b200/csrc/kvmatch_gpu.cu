@@ -359,6 +359,25 @@ int make_plan(kvm_ctx* ctx, const int32_t* lr, int K, int shift, int m, Plan* P)
   return KVM_OK;
 }
 
+// The raw-series engines keep no state across window starts, so intervals whose window starts are adjacent are one
+// run of candidates for them: merge such neighbours (and drop empty intervals) in place.  An index-free scan handed over
+// as 488 k chain-sized intervals becomes ONE run: no per-CTA search through the tile table (19 dependent loads in front
+// of 2048 windows of work), 24 bytes of plan instead of 5.9 MB on the wire.  Returns the new interval count.
+int coalesce_runs(int32_t* cb, int32_t* nc, int K) {
+  int k2 = 0;
+  for (int p = 0; p < K; p++) {
+    if (nc[p] <= 0) continue;
+    if (k2 > 0 && (int64_t)cb[k2 - 1] + nc[k2 - 1] == cb[p] && (int64_t)nc[k2 - 1] + nc[p] <= 0x7fff0000LL) {
+      nc[k2 - 1] += nc[p];
+    } else {
+      cb[k2] = cb[p];
+      nc[k2] = nc[p];
+      k2++;
+    }
+  }
+  return k2;
+}
+
 int check_common(kvm_ctx* ctx, const double* q, int m, double epsilon, const int32_t* lr, int K, kvm_result* out) {
   if (!ctx) return KVM_E_ARG;
   if (!out || !q || m < 1 || K < 0 || (K > 0 && !lr)) return fail(ctx, KVM_E_ARG, "null/invalid argument");
@@ -1178,7 +1197,7 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
   ctx->stream_dirty = true;  // until this call has completed
   if ((rc = ensure_xlist(ctx, std::max<long long>(ctx->x_cap, 1 << 18)))) return rc;
   if ((rc = ensure_answers(ctx, std::max<long long>(ctx->ans_cap, 1 << 16)))) return rc;
-  if (mode == Mode::kDtw && (rc = ensure_cands(ctx, std::max<long long>(ctx->cand_cap, 1 << 18)))) return rc;
+  if ((rc = ensure_cands(ctx, std::max<long long>(ctx->cand_cap, 1 << 18)))) return rc;
 
   // ---- query block: [scr_idx | scr_a | scr_b | zq | order | uq | lq]; the screen part goes up before the stream
   auto up256 = [](size_t x) { return (x + 255) & ~size_t(255); };
@@ -1309,8 +1328,16 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
       X.inv_alpha = S.inv_alpha;
       X.beta = beta;
       X.gate_pass = counters + kCntGate;
-      launch_exact<true>(ctx, X);
-      launches += 1;
+      X.in = cands_of(ctx);
+      static const int split = env_int("KVM_EXACT_SPLIT", 1);  // developer knob: 0 = gate and screen inside the exact kernel
+      if (split) {
+        cnsm_ed_screen_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(X);
+        launch_exact<false>(ctx, X);
+        launches += 2;
+      } else {
+        launch_exact<true>(ctx, X);
+        launches += 1;
+      }
     } else {
       LbListParams L{};
       L.T = ctx->series;
@@ -1393,7 +1420,7 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
     out->n_launches += launches;
     const bool x_over = (long long)cnt[kCntEntries] > ctx->x_cap;
     const long long cand_need = (long long)std::max(cnt[kCntCand], cnt[kCntCand2]);
-    const bool cand_over = dtw && cand_need > ctx->cand_cap, ans_over = (long long)cnt[kCntAnswers] > ctx->ans_cap;
+    const bool cand_over = cand_need > ctx->cand_cap, ans_over = (long long)cnt[kCntAnswers] > ctx->ans_cap;
     if (!x_over && !cand_over && !ans_over) break;
     if (attempt == 7) return fail(ctx, KVM_E_OOM, "result buffers kept overflowing");
     if (x_over && (rc = ensure_xlist(ctx, (long long)cnt[kCntEntries] + 1024))) return rc;
@@ -1801,17 +1828,47 @@ int kvm_verify_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, cons
   int32_t* nc = reinterpret_cast<int32_t*>(st + o_ncand);
   int32_t* tp = reinterpret_cast<int32_t*>(st + o_tp);
   Plan& P = ctx->plan_scratch;
-  P.nsamp.resize(K);
-  int64_t totals[3];
-  if (plan_pass(lr, K, shift, m, ctx->n, ctx->first, ctx->first + ctx->count - 1, cb, P.nsamp.data(), nc, totals))
-    return make_plan(ctx, lr, K, shift, m, &P);  // locates the offending interval and sets the error
-  P.cnt_candidate = totals[0];
-  P.S = totals[1];
-  P.V = totals[2];
+  // An index-free scan arrives as a regular grid (adjacent intervals of one length, nothing clamped): recognised in one
+  // vectorised pass over the list, it is ONE run of window starts and needs no per-interval planning.
+  bool regular = false;
+  if (K >= 2) {
+    const int64_t c0 = (int64_t)lr[1] - lr[0] + 1;
+    const int64_t first_begin = (int64_t)lr[0] - shift, last_end = (int64_t)lr[2 * K - 1] - shift + m - 1;
+    const int64_t lo = ctx->first, hi = ctx->first + ctx->count - 1;
+    if (c0 >= 1 && c0 <= INT32_MAX / 2 && first_begin >= 1 && first_begin >= lo && last_end <= ctx->n && last_end <= hi &&
+        !regular_grid_pass(lr, K, (int32_t)c0)) {
+      const int64_t V = (int64_t)lr[2 * K - 1] - lr[0] + 1;
+      if (V <= 0x7fff0000LL) {
+        regular = true;
+        cb[0] = (int32_t)(first_begin - lo);
+        nc[0] = (int32_t)V;
+        P.cnt_candidate = V;
+        P.V = V;
+        P.S = V + (int64_t)K * (m - 1);
+      }
+    }
+  }
+  if (!regular) {
+    P.nsamp.resize(K);
+    int64_t totals[3];
+    if (plan_pass(lr, K, shift, m, ctx->n, ctx->first, ctx->first + ctx->count - 1, cb, P.nsamp.data(), nc, totals))
+      return make_plan(ctx, lr, K, shift, m, &P);  // locates the offending interval and sets the error
+    P.cnt_candidate = totals[0];
+    P.S = totals[1];
+    P.V = totals[2];
+  }
   out->cnt_candidate = P.cnt_candidate;
   out->n_verified = P.V;
   out->s_total = P.S;
   if (P.V == 0) return fetch_answers(ctx, 0, out);
+  // adjacent intervals are one run for this engine: re-pack the plan for the K2 runs
+  K = regular ? 1 : coalesce_runs(cb, nc, K);
+  const size_t o_ncand2 = up256(o_cbegin + sizeof(int32_t) * (size_t)K);
+  const size_t o_tp2 = up256(o_ncand2 + sizeof(int32_t) * (size_t)K);
+  const size_t bytes2 = o_tp2 + sizeof(int32_t) * ((size_t)K + 1);
+  std::memmove(st + o_ncand2, nc, sizeof(int32_t) * (size_t)K);  // (o_ncand2 <= o_ncand: moving towards the front)
+  nc = reinterpret_cast<int32_t*>(st + o_ncand2);
+  tp = reinterpret_cast<int32_t*>(st + o_tp2);
   int64_t n_tiles = 0;
   for (int p = 0; p < K; p++) {
     tp[p] = (int32_t)n_tiles;
@@ -1819,8 +1876,8 @@ int kvm_verify_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, cons
   }
   tp[K] = (int32_t)n_tiles;
   std::memcpy(st + o_q, q, sizeof(double) * (size_t)m);
-  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->arena.p, ctx->stage.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  ctx->h2d_bytes += (long long)bytes;
+  KVM_CUDA(ctx, cudaMemcpyAsync(ctx->arena.p, ctx->stage.p, bytes2, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->h2d_bytes += (long long)bytes2;
   if ((rc = ensure_answers(ctx, std::max<long long>(ctx->ans_cap, 1 << 16)))) return rc;
   const unsigned char* base = ctx->arena.as<unsigned char>();
   unsigned long long cnt[kNumCounters];
@@ -1830,8 +1887,8 @@ int kvm_verify_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, cons
     E.T = ctx->series;
     E.q = reinterpret_cast<const double*>(base + o_q);
     E.cbegin = reinterpret_cast<const int32_t*>(base + o_cbegin);
-    E.ncand = reinterpret_cast<const int32_t*>(base + o_ncand);
-    E.tile_prefix = reinterpret_cast<const int32_t*>(base + o_tp);
+    E.ncand = reinterpret_cast<const int32_t*>(base + o_ncand2);
+    E.tile_prefix = reinterpret_cast<const int32_t*>(base + o_tp2);
     E.K = K;
     E.m = m;
     E.eps2 = epsilon * epsilon;
@@ -2234,6 +2291,9 @@ int kvm_verify_dtw(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, int
   out->n_verified = P.V;
   out->s_total = P.S;
   if (P.V == 0) return fetch_answers(ctx, 0, out);
+  K = coalesce_runs(P.cbegin.data(), P.ncand.data(), K);  // (the data envelope is the shard's: interval borders do not matter)
+  P.cbegin.resize(K);
+  P.ncand.resize(K);
   std::vector<double> qv(q, q + m), uq, lq;
   envelope(qv, rho, lq, uq);  // K/QueryEngineDtw.java:362
   int64_t n_tiles = 0;

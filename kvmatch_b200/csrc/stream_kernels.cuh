@@ -29,6 +29,7 @@
 // Every reported number (answers, distances, n_gate_pass) therefore still comes from the reference's arithmetic; the
 // stream only decides which windows can be skipped, and the guard (host: stream_guard()) is a worst-case bound.
 #pragma once
+#include <type_traits>
 #include "cnsm_kernels.cuh"
 
 namespace kvm {
@@ -345,23 +346,29 @@ __device__ __forceinline__ unsigned stream_candidate(const StreamParams& P, cons
       // offset, the eight window samples of a round are loaded up front and summed in two independent chains; the
       // partial bound is tested once per round.  (With run-time indices each term was a serial LDC -> LDS -> 4 x FP64
       // chain of its own, ~130 cycles: a tile full of candidates then ran for ~100 us and set the launch's tail.)
+      // rounds of 4, 4, 8, 8, 8 terms: with eps^2 ~ 25 and |zQ| ~ 2.5 .. 3 on the leading terms a window that is no match
+      // is over the threshold after three or four of them, so the first test comes early
+      auto round = [&](auto k0c, auto cntc) {
+        constexpr int k0 = decltype(k0c)::value, cnt = decltype(cntc)::value;
+        double wk[cnt];
 #pragma unroll
-      for (int r = 0; r < kScreenTerms / 8; r++) {
-        if (survive) {
-          double wk[8];
+        for (int u = 0; u < cnt; u++) wk[u] = wv[P.scr_idx[k0 + u]];
+        double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-          for (int u = 0; u < 8; u++) wk[u] = wv[P.scr_idx[8 * r + u]];
-          double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-          for (int u = 0; u < 8; u += 2) {
-            const double da = term(8 * r + u, wk[u]), db = term(8 * r + u + 1, wk[u + 1]);
-            acc0 = __fma_rn(da, da, acc0);
-            acc1 = __fma_rn(db, db, acc1);
-          }
-          dist += acc0 + acc1;
-          survive = le_nonneg(dist, thr);
+        for (int u = 0; u < cnt; u += 2) {
+          const double da = term(k0 + u, wk[u]), db = term(k0 + u + 1, wk[u + 1]);
+          acc0 = __fma_rn(da, da, acc0);
+          acc1 = __fma_rn(db, db, acc1);
         }
-      }
+        dist += acc0 + acc1;
+        survive = le_nonneg(dist, thr);
+      };
+      using std::integral_constant;
+      if (survive) round(integral_constant<int, 0>{}, integral_constant<int, 4>{});
+      if (survive) round(integral_constant<int, 4>{}, integral_constant<int, 4>{});
+      if (survive) round(integral_constant<int, 8>{}, integral_constant<int, 8>{});
+      if (survive) round(integral_constant<int, 16>{}, integral_constant<int, 8>{});
+      if (survive) round(integral_constant<int, 24>{}, integral_constant<int, 8>{});
     } else {
       for (int kk = 0; kk < n_scr && survive; kk++) {
         const double d = term(kk, wv[P.scr_idx[kk]]);
