@@ -63,10 +63,13 @@ constexpr size_t wmean_smem_bytes(int nt, int w_max) {
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT, 2) wmean_stream_kernel(WmeanParams P) {
+__global__ void __launch_bounds__(NT, 3) wmean_stream_kernel(WmeanParams P) {
   constexpr int NW = kMaxWidths;
   extern __shared__ __align__(16) unsigned char wm_smem[];
   __shared__ double s_amax;
+  __shared__ int s_wtot[kMaxWidths][NT / 32];
+  __shared__ int s_cta_tot[kMaxWidths];
+  __shared__ long long s_cta_base[kMaxWidths];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(kFullMask, tid >> 5, 0);
   constexpr int kW = kGroup * NT;
@@ -123,12 +126,9 @@ __global__ void __launch_bounds__(NT, 2) wmean_stream_kernel(WmeanParams P) {
     }
     gs1[g] = (a[0] + a[1]) + a[2];
   }
-  __syncthreads();  // (2) group sums ready; warp-local from here on
-  if (warp * 32 * kGroup >= npos) {  // (warp-uniform) no position for this warp: empty slices
-    if (lane == 0)
-      for (int q = 0; q < P.n_widths; q++) P.W[q].seg_cnt[(int)blockIdx.x * (NT / 32) + warp] = 0;
-    return;
-  }
+  __syncthreads();  // (2) group sums ready
+  // (a warp without positions — the last tile — keeps running with zero valid windows: it takes part in the barriers
+  // of the slice reservation below)
 
   const double A = s_amax;
   const int p0 = tid * kGroup;  // this thread's first position within the tile
@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(NT, 2) wmean_stream_kernel(WmeanParams P) {
       }
     }
   }
-  // ---- per width: validity, slice reservation, flags
-  int slot[NW];
+  // ---- per width: validity and run counts
+  int slot[NW], incl_q[NW], cnt_q[NW];
 #pragma unroll
   for (int q = 0; q < NW; q++) {
     slot[q] = 0;
@@ -227,17 +227,41 @@ __global__ void __launch_bounds__(NT, 2) wmean_stream_kernel(WmeanParams P) {
       const int t = __shfl_up_sync(kFullMask, incl, o);
       if (lane >= o) incl += t;
     }
-    const int total = __shfl_sync(kFullMask, incl, 31);
-    long long base = 0;
-    if (lane == 0 && total > 0) base = (long long)atomicAdd(Wq.n_runs, (unsigned long long)total);
-    base = __shfl_sync(kFullMask, base, 0);
-    const int seg = (int)blockIdx.x * (NT / 32) + warp;
-    if (lane == 0) {
-      Wq.seg_off[seg] = (int)base;
-      Wq.seg_cnt[seg] = total;
+    incl_q[q] = incl;
+    cnt_q[q] = cnt;
+    if (lane == 31) s_wtot[q][warp] = incl;  // the warp's runs of this width
+  }
+  // ---- slice reservation: ONE atomic per CTA and width (thread q), the warps' slices follow each other in warp order.
+  // (One returning atomic per warp and width put 95 k serialised updates on each of five addresses at n = 1e8 and
+  // every warp waited for its turn.)
+  __syncthreads();
+  if (tid < P.n_widths) {
+    int tot = 0;
+#pragma unroll
+    for (int w8 = 0; w8 < NT / 32; w8++) {
+      const int c = s_wtot[tid][w8];
+      s_wtot[tid][w8] = tot;  // exclusive prefix over the warps
+      tot += c;
     }
-    if (base + total > Wq.run_cap) starts[q] = 0ULL;  // overflow: counted, not stored (the host grows the list and re-runs)
-    slot[q] = (int)base + (incl - cnt);
+    s_cta_tot[tid] = tot;
+    s_cta_base[tid] = tot > 0 ? (long long)atomicAdd(P.W[tid].n_runs, (unsigned long long)tot) : 0LL;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NW; q++) {
+    if (q >= P.n_widths) continue;
+    const WmeanWidth& Wq = P.W[q];
+    {
+      const long long base = s_cta_base[q] + s_wtot[q][warp];
+      const int total = __shfl_sync(kFullMask, incl_q[q], 31);
+      const int seg = (int)blockIdx.x * (NT / 32) + warp;
+      if (lane == 0) {
+        Wq.seg_off[seg] = (int)base;
+        Wq.seg_cnt[seg] = total;
+      }
+      if (s_cta_base[q] + s_cta_tot[q] > Wq.run_cap) starts[q] = 0ULL;  // overflow: counted, not stored (the host grows the list and re-runs)
+      slot[q] = (int)base + (incl_q[q] - cnt_q[q]);
+    }
     unsigned long long m2 = amb[q];
     if (m2) {  // flag the ambiguous windows for the exact re-walk
       const int chunk = P.epoch - Wq.w + 1;
