@@ -175,6 +175,7 @@ struct kvm_ctx {
   std::vector<int32_t> g_off;
   std::vector<double> g_dist;
   DevBuf env_lo, env_up;
+  int64_t series_len = 0;  // samples in series_buf, pads included (the UCR scans change `count` for the duration of a call)
   int env_rho = -1;
   bool env_failed = false;  // the allocation did not fit: DTW calls use the per-candidate envelope kernel instead
   DevBuf seg_b, seg_first, seg_last, chain_count, chain_prefix, run_key, run_b, run_first, run_last;
@@ -1451,7 +1452,7 @@ bool ensure_envelope(kvm_ctx* ctx, int rho) {
   if (!fused_on || rho > 512) return false;
   if (ctx->env_rho == rho) return true;
   if (ctx->env_failed) return false;
-  const size_t len = (size_t)(ctx->count + kFrontPad + kTailPad);
+  const size_t len = (size_t)ctx->series_len;
   ctx->env_rho = -1;
   if (ctx->env_lo.ensure(sizeof(double) * len) != cudaSuccess || ctx->env_up.ensure(sizeof(double) * len) != cudaSuccess) {
     cudaGetLastError();
@@ -1732,6 +1733,7 @@ static int alloc_series(kvm_ctx* ctx, int64_t n, int64_t first, int64_t count) {
   ctx->env_failed = false;
   KVM_CUDA(ctx, ctx->series_buf.ensure(sizeof(double) * (size_t)(count + kFrontPad + kTailPad)));
   ctx->series = ctx->series_buf.as<double>() + kFrontPad;
+  ctx->series_len = count + kFrontPad + kTailPad;
   KVM_CUDA(ctx, cudaMemsetAsync(ctx->series_buf.p, 0, sizeof(double) * kFrontPad, ctx->stream));
   KVM_CUDA(ctx, cudaMemsetAsync(ctx->series + count, 0, sizeof(double) * kTailPad, ctx->stream));
   ctx->n = n;
