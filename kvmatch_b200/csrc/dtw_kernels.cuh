@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(256) dtw_lb_data_kernel(Lb2Params P) {
 // max(|x - centre| - half, 0) with the clamp on the sign bit (no DSETP / DMNMX, which issue at a fifth of the DADD rate).
 constexpr int kLbChunk = 64;
 constexpr int kLbThreads = 256;
+constexpr int kLbWarpPathMax = 32768;  // lists up to this length take the warp-per-candidate path
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -331,9 +332,90 @@ __global__ void __launch_bounds__(kLbThreads) dtw_lb_fused_kernel(LbFusedParams 
   const long long cap = kFromSums ? P.xin.cap : P.cin.cap;
   if ((long long)n > cap) n = (unsigned long long)cap;
   unsigned my_gate = 0;
-  for (unsigned long long base = (unsigned long long)blockIdx.x * kLbThreads; base < n; base += (unsigned long long)gridDim.x * kLbThreads) {
+  // Short lists (a selective query: a few hundred to a few thousand flagged windows): one WARP per candidate, lanes
+  // split the m terms (coalesced loads, 64 iterations for m = 2048) — microseconds, where a cohort would walk its 2048
+  // terms in 32 barrier-separated rounds on a single SM (0.2 ms).  Long lists take the cohort path below: there the
+  // warp-per-candidate form would re-read 48 KB per candidate from L2.
+  if (n <= (unsigned long long)kLbWarpPathMax) {
+    const int lane = tid & 31;
+    const unsigned long long gwarp = ((unsigned long long)blockIdx.x * kLbThreads + tid) >> 5;
+    const unsigned long long n_warps = ((unsigned long long)gridDim.x * kLbThreads) >> 5;
+    for (unsigned long long e = gwarp; e < n; e += n_warps) {
+      int off;
+      double mean = 0.0, stdv = 1.0;
+      if (kFromSums) {
+        off = P.xin.off[e];
+        if (!cnsm_exact_gate(P.xin.ex[e], P.xin.ex2[e], m, P.meanQ, P.stdQ, P.alpha, P.inv_alpha, P.beta, mean, stdv)) continue;
+        my_gate += (lane == 0) ? 1u : 0u;
+      } else {
+        off = P.cin.off[e];
+        mean = P.cin.mean[e];
+        stdv = P.cin.stdv[e];
+      }
+      const double rstd = 1.0 / stdv;
+      const long long i0 = (long long)(off - P.first_global);
+      const double* __restrict__ w = P.T + i0;
+      if (kEq && m >= 6) {  // LB_KimFL (every lane computes it: six loads per end, all of them broadcasts)
+        const double* __restrict__ q = P.q;
+        const double x0 = (w[0] - mean) * rstd, x1 = (w[1] - mean) * rstd, x2 = (w[2] - mean) * rstd;
+        const double y0 = (w[m - 1] - mean) * rstd, y1 = (w[m - 2] - mean) * rstd, y2 = (w[m - 3] - mean) * rstd;
+        const double q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+        const double p0 = __ldg(q + m - 1), p1 = __ldg(q + m - 2), p2 = __ldg(q + m - 3);
+        auto mn = [](double a, double b) { return min_nonneg(a, b); };
+        double lb = fsq(x0, q0) + fsq(y0, p0);
+        lb += mn(mn(fsq(x1, q0), fsq(x0, q1)), fsq(x1, q1));
+        lb += mn(mn(fsq(y1, p0), fsq(y0, p1)), fsq(y1, p1));
+        lb += mn(mn(mn(fsq(x0, q2), fsq(x1, q2)), fsq(x2, q2)), mn(fsq(x2, q1), fsq(x2, q0)));
+        lb += mn(mn(mn(fsq(y0, p2), fsq(y1, p2)), fsq(y2, p2)), mn(fsq(y2, p1), fsq(y2, p0)));
+        if (!le_nonneg(lb, P.eps2_hi)) continue;
+      }
+      double lbq = 0.0, lbc = 0.0;
+      bool alive = true;
+      for (int k0 = 0; k0 < m && alive; k0 += 256) {  // 8 terms per lane between two abandon tests
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int k = k0 + 32 * u + lane;
+          if (k < m) {
+            const double qk = __ldg(P.q + k);
+            if (kEq) {
+              const double up = __ldg(P.uq + k), lo = __ldg(P.lq + k);
+              const double c = 0.5 * (up + lo);
+              const double h = 0.5 * (up - lo) + 4.0 * 1.1102230246251565e-16 * (fabs(up) + fabs(lo) + 1.0);
+              const double x = (w[k] - mean) * rstd;
+              const double ex = fabs(x - c) - h;
+              const double d = (__double2hiint(ex) < 0) ? 0.0 : ex;
+              lbq = __fma_rn(d, d, lbq);
+            }
+            const double lo2 = (P.envL[i0 + k] - mean) * rstd, up2 = (P.envU[i0 + k] - mean) * rstd;
+            const double a = qk - up2, b = lo2 - qk;
+            const double d2 = (__double2hiint(a) >= 0) ? a : ((__double2hiint(b) >= 0) ? b : 0.0);
+            lbc = __fma_rn(d2, d2, lbc);
+          }
+        }
+        double tq = lbq, tc = lbc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          tq += __shfl_xor_sync(kFullMask, tq, o);
+          tc += __shfl_xor_sync(kFullMask, tc, o);
+        }
+        alive = le_nonneg(tq, P.eps2_hi) && le_nonneg(tc, P.eps2_hi);
+        if (k0 + 256 >= m && alive && lane == 0) cand_append(P.out, off, mean, stdv, kEq ? tq : 0.0);
+      }
+    }
+    if (kFromSums) {
+      const unsigned tot = __reduce_add_sync(kFullMask, my_gate);
+      if ((tid & 31) == 0 && tot) atomicAdd(P.gate_pass, (unsigned long long)tot);
+    }
+    return;
+  }
+  // Cohort size: 256 candidates when the list fills the grid, down to 32 when it is short — a cohort lives on one SM and
+  // its 2048-term walk is bound by that SM's FP64 pipe (256 candidates x 2048 terms x 12 operations = 0.1 M cycles), so
+  // a short list is spread over as many SMs as it has warps.
+  const unsigned long long per_cta = (n + gridDim.x - 1) / gridDim.x;
+  const int B = (int)min((unsigned long long)kLbThreads, max(32ULL, (per_cta + 31ULL) & ~31ULL));
+  for (unsigned long long base = (unsigned long long)blockIdx.x * B; base < n; base += (unsigned long long)gridDim.x * B) {
     const unsigned long long e = base + tid;
-    bool alive = e < n;
+    bool alive = tid < B && e < n;
     int off = 0;
     double mean = 0.0, stdv = 1.0;
     if (alive) {
