@@ -525,3 +525,26 @@ def test_every_window_is_an_answer_buffers_regrow(oracle):
     small = g.verify_cnsm_ed(q, 0.01, 1.1, 0.1, iv)                     # and a selective call on the grown buffers
     assert_same(small, oracle.verify_cnsm_ed(s, q, 0.01, 1.1, 0.1, iv))
     g.close()
+
+
+def test_rsm_engines_coalesce_adjacent_intervals(gpu, oracle):
+    """The raw-series engines merge intervals whose window starts are adjacent into one run of candidates (and recognise
+    a regular grid without per-interval planning): answers, #candidates, #verified and s_total must not change — mixed
+    adjacent / separate / clamped intervals, with a shift, against the oracle."""
+    n, m = 400_000, 256
+    s = datagen.generate(n, seed=909)
+    gpu.load(s)
+    off = 123_457
+    q = s[off - 1:off - 1 + m].copy()
+    shift = 50
+    iv = [(60, 5_000), (5_001, 9_000), (9_001, 9_001), (20_000, 30_000), (30_001, 30_500), (off + shift - 40, off + shift + 40),
+          (off + shift + 41, off + shift + 2_000), (n - m - 3_000 + shift, n - m + 1 + shift), (n - m + 2 + shift, n + shift)]
+    assert_same(gpu.verify_ed(q, 12.0, iv, shift), oracle.verify_ed(s, q, 12.0, iv, shift))
+    g2, e2 = gpu.verify_dtw(q, 12.0, 12, iv, shift), oracle.verify_dtw(s, q, 12.0, 12, iv, shift)
+    assert_same(g2, e2)
+    assert off in g2.offsets.tolist()
+    grid = datagen.chain_intervals(n, m, 1000)                       # a regular grid: one run
+    assert_same(gpu.verify_ed(q, 12.0, grid), oracle.verify_ed(s, q, 12.0, grid))
+    ragged = [tuple(x) for x in np.asarray(grid).reshape(-1, 2)]
+    ragged[7] = (ragged[7][0], ragged[7][1] - 1)                     # one gap: not regular any more
+    assert_same(gpu.verify_ed(q, 12.0, ragged), oracle.verify_ed(s, q, 12.0, ragged))
