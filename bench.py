@@ -459,7 +459,10 @@ def side_measurements(line, g, kvmatch_b200, local, n_total, chunk, queries, off
     # ---- the metric's other half: cNSM-DTW, BASELINE configs[3] (n = 1e9, m = 2048, rho = 5 % = 102), the seeded
     # queries at eps in {1, 5, 10} within a time budget; DTW roofline = 5 flops per executed band cell / FP64 peak
     try:
+        smp = ClockSampler(0)   # the heavy queries run seconds of FP64 / integer work: the clocks they ran at belong beside them
+        smp.start()
         line["cnsm_dtw"] = dtw_block(g, n_total, chunk, offs)
+        line["cnsm_dtw"]["clocks"] = smp.stop()
     except Exception as e:
         line["cnsm_dtw"] = {"error": repr(e)}
     # ---- IndexBuilder's window-mean pass, all five windows of Sigma

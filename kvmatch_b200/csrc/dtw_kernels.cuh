@@ -299,6 +299,7 @@ struct LbFusedParams {
   double eps2_hi;
   CandList out;
   unsigned long long* gate_pass;
+  int warp_path_max;  // lists up to this length take the warp-per-candidate path (kLbWarpPathMax; a developer knob lowers it)
 };
 
 // Block-wide stable compaction of the threads with `alive`: returns the number of live threads, `idx` = this thread's
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(kLbThreads) dtw_lb_fused_kernel(LbFusedParams 
   // split the m terms (coalesced loads, 64 iterations for m = 2048) — microseconds, where a cohort would walk its 2048
   // terms in 32 barrier-separated rounds on a single SM (0.2 ms).  Long lists take the cohort path below: there the
   // warp-per-candidate form would re-read 48 KB per candidate from L2.
-  if (n <= (unsigned long long)kLbWarpPathMax) {
+  if (n <= (unsigned long long)P.warp_path_max) {
     const int lane = tid & 31;
     const unsigned long long gwarp = ((unsigned long long)blockIdx.x * kLbThreads + tid) >> 5;
     const unsigned long long n_warps = ((unsigned long long)gridDim.x * kLbThreads) >> 5;

@@ -414,6 +414,7 @@ int ensure_cands(kvm_ctx* ctx, long long cap) {
 CandList cands2_of(kvm_ctx* ctx);
 int launch_lb_data(kvm_ctx* ctx, const double* q, const double* uq, const double* lq, int m, int rho, double eps2_hi);
 bool ensure_envelope(kvm_ctx* ctx, int rho);
+int lb_warp_path_max();
 
 AnswerSink sink_of(kvm_ctx* ctx) {
   return AnswerSink{ctx->ans_off.as<int32_t>(), ctx->ans_dist.as<double>(),
@@ -1373,6 +1374,7 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
         F.eps2_hi = eps2_hi;
         F.out = cands2_of(ctx);
         F.gate_pass = counters + kCntGate;
+        F.warp_path_max = lb_warp_path_max();
         kvm::dtw_lb_fused_kernel<true, true><<<ctx->n_sms * 6, kvm::kLbThreads, 0, ctx->stream>>>(F);
         KVM_CUDA(ctx, cudaGetLastError());
       } else {
@@ -1447,6 +1449,11 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
 // Data envelope of the whole resident buffer (pads included: they hold the zeros some scans count as samples) for
 // radius rho, cached per ctx.  Returns false (and remembers it) when the 16 bytes per sample do not fit.
 namespace {
+int lb_warp_path_max() {
+  static const int v = env_int("KVM_LB_WARP_MAX", kvm::kLbWarpPathMax);  // developer knob (0: every list takes the cohort path)
+  return v;
+}
+
 bool ensure_envelope(kvm_ctx* ctx, int rho) {
   static const int fused_on = env_int("KVM_LB_FUSED", 1);  // developer knob: 0 = the per-candidate kernels
   if (!fused_on || rho > 512) return false;
@@ -1489,6 +1496,7 @@ int launch_lb_data(kvm_ctx* ctx, const double* q, const double* uq, const double
     F.lq = lq;
     F.eps2_hi = eps2_hi;
     F.out = cands2_of(ctx);
+    F.warp_path_max = lb_warp_path_max();
     kvm::dtw_lb_fused_kernel<false, false><<<ctx->n_sms * 6, kvm::kLbThreads, 0, ctx->stream>>>(F);
     KVM_CUDA(ctx, cudaGetLastError());
     return KVM_OK;
@@ -1542,7 +1550,8 @@ int launch_dtw(kvm_ctx* ctx, const DtwParams& D_in) {
       PP.out = CandList{ctx->cand_off.as<int32_t>(), ctx->cand_mean.as<double>(), ctx->cand_std.as<double>(),
                         ctx->counters.as<unsigned long long>() + kCntProbe, ctx->cand_cap};
       PP.n_cells = D.n_cells;
-      PP.min_count = 4096;
+      static const int probe_min = env_int("KVM_DTW_PROBE_MIN", 4096);  // developer knob
+      PP.min_count = probe_min;
       kvm::dtw_probe_kernel<<<ctx->n_sms * 8, kvm::kProbeWarps * 32, 0, ctx->stream>>>(PP);
       KVM_CUDA(ctx, cudaGetLastError());
       D.in = PP.out;
