@@ -197,3 +197,36 @@ def test_two_contexts_interleaved(oracle):
         assert same(r2, oracle.verify_cnsm_ed(s2, q2, 4.0, 1.5, 5.0, iv2))
     g1.close()
     g2.close()
+
+
+def test_deferred_regular_grid_check_catches_an_irregular_list(oracle):
+    """A long interval list that looks like a regular chain grid from its first and last entries is planned as one
+    while the full check runs behind the kernel launches (plan cache off, K >= 4096).  A list with one hole in the
+    middle must be caught by that check and re-planned: same answers as the oracle, and as the truly regular list
+    except inside the hole."""
+    import os
+    import kvmatch_b200
+    from kvmatch_b200 import _lib
+    n, m, chunk = 3_000_000, 128, 512
+    s = datagen.generate(n, seed=4711)
+    g = kvmatch_b200.GpuSeries(0)
+    g.load(s)
+    g.set_option(_lib.KVM_OPT_PLAN_CACHE, 0)
+    off = 1_500_123
+    q = s[off - 1:off - 1 + m].copy()
+    iv = np.asarray(datagen.chain_intervals(n, m, chunk), dtype=np.int32).reshape(-1, 2)
+    assert len(iv) >= 4096
+    full = g.verify_cnsm_ed(q, 3.0, 1.5, 5.0, iv)
+    e = oracle.verify_cnsm_ed(s, q, 3.0, 1.5, 5.0, iv)
+    assert full.offsets.tolist() == e.offsets.tolist() and full.distances.tolist() == e.distances.tolist()
+    assert off in full.offsets.tolist()
+    holed = iv.copy()
+    k = int(np.searchsorted(iv[:, 0], off, side="right") - 1)
+    holed[k, 1] -= 7                                   # interval k loses its last 7 starts: both ends still look regular
+    got = g.verify_cnsm_ed(q, 3.0, 1.5, 5.0, holed)
+    exp = oracle.verify_cnsm_ed(s, q, 3.0, 1.5, 5.0, holed)
+    assert got.offsets.tolist() == exp.offsets.tolist() and got.distances.tolist() == exp.distances.tolist()
+    assert got.n_verified == full.n_verified - 7 and got.n_gate_pass == exp.n_gate_pass
+    again = g.verify_cnsm_ed(q, 3.0, 1.5, 5.0, iv)    # and the state left behind by the discarded attempt does no harm
+    assert again.offsets.tolist() == full.offsets.tolist() and again.n_gate_pass == full.n_gate_pass
+    g.close()
