@@ -642,7 +642,26 @@ __global__ void __launch_bounds__(NT, NT <= 192 ? 3 : (NT <= 256 ? 2 : 1)) cnsm_
       STREAM_COUNT(11, __popcll(mk));  // candidates (hot-loop bits)
       const unsigned any_lo = __reduce_or_sync(kFullMask, (unsigned)mk), any_hi = __reduce_or_sync(kFullMask, (unsigned)(mk >> 32));
       const unsigned long long all = ((unsigned long long)any_hi << 32) | any_lo;
-      if (all != 0ULL) {
+      const int dens = __reduce_add_sync(kFullMask, __popcll(mk));
+      if (dens >= 16 * kGroup) {
+        // A warp at least half full of candidates (a region whose statistics match the query's) finishes them in place:
+        // the replay hands every lane its own window sums, so no queue, no compaction — what those buy when one lane
+        // in ten holds a candidate costs a third of the instructions when nearly all of them do.
+        double rex = ex, rex2 = ex2;
+#pragma unroll 1
+        for (int j = 0; (all >> j) != 0ULL; j++) {
+          unsigned verdict = 0u;
+          if ((mk >> j) & 1ULL) verdict = stream_candidate<kMode>(P, tile, xs + w0 + j, w0 + j, rex, rex2, G, s_thr);
+          my_gate += verdict & 1u;
+          const unsigned fl = __ballot_sync(kFullMask, verdict == 2u);
+          if (fl) flag_warp(P, tile, w0 + j, verdict == 2u, fl, F, lane);
+          const double av = xi[j], ov = xo[j];
+          const double dl = av - ov, sm = av + ov;
+          rex += dl;
+          rex2 = __fma_rn(dl, sm, rex2);
+        }
+        flag_flush(P, F, lane);
+      } else if (all != 0ULL) {
         // replay (same operations, same values) step by step, each step pushing its candidates into the queue
         int n1 = 0;
         double rex = ex, rex2 = ex2;
