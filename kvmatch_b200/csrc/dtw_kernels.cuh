@@ -38,18 +38,24 @@ __device__ __forceinline__ bool lb_cascade(const double* __restrict__ w, const L
   const int m = Q.m;
   const double* __restrict__ q = Q.q;
   double lb = 0.0;
-  if (m >= 6) {  // LB_KimFL, K/utils/DtwUtils.java:149-189 (all five stages, no early return)
-    const double x0 = ((w[0] - mean) * rstd), x1 = ((w[1] - mean) * rstd), x2 = ((w[2] - mean) * rstd);
-    const double y0 = ((w[m - 1] - mean) * rstd), y1 = ((w[m - 2] - mean) * rstd),
-                 y2 = ((w[m - 3] - mean) * rstd);
-    const double q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-    const double p0 = __ldg(q + m - 1), p1 = __ldg(q + m - 2), p2 = __ldg(q + m - 3);
+  if (m >= 6) {  // LB_KimFL, K/utils/DtwUtils.java:149-189, with the reference's early returns: on a raw-series scan the two
+                 // end points alone reject almost every window (one load per end, 5 FP64 operations); the minima run on the
+                 // integer pipe (DMNMX issues at a fifth of the DADD rate)
+    const double q0 = __ldg(q), p0 = __ldg(q + m - 1);
+    const double x0 = ((w[0] - mean) * rstd), y0 = ((w[m - 1] - mean) * rstd);
     lb = fsq(x0, q0) + fsq(y0, p0);
-    lb += fmin(fmin(fsq(x1, q0), fsq(x0, q1)), fsq(x1, q1));
-    lb += fmin(fmin(fsq(y1, p0), fsq(y0, p1)), fsq(y1, p1));
-    lb += fmin(fmin(fmin(fsq(x0, q2), fsq(x1, q2)), fsq(x2, q2)), fmin(fsq(x2, q1), fsq(x2, q0)));
-    lb += fmin(fmin(fmin(fsq(y0, p2), fsq(y1, p2)), fsq(y2, p2)), fmin(fsq(y2, p1), fsq(y2, p0)));
-    if (!(lb <= Q.eps2_hi)) return false;
+    if (!le_nonneg(lb, Q.eps2_hi)) return false;
+    auto mn = [](double a, double b) { return min_nonneg(a, b); };
+    const double x1 = ((w[1] - mean) * rstd), y1 = ((w[m - 2] - mean) * rstd);
+    const double q1 = __ldg(q + 1), p1 = __ldg(q + m - 2);
+    lb += mn(mn(fsq(x1, q0), fsq(x0, q1)), fsq(x1, q1));
+    lb += mn(mn(fsq(y1, p0), fsq(y0, p1)), fsq(y1, p1));
+    if (!le_nonneg(lb, Q.eps2_hi)) return false;
+    const double x2 = ((w[2] - mean) * rstd), y2 = ((w[m - 3] - mean) * rstd);
+    const double q2 = __ldg(q + 2), p2 = __ldg(q + m - 3);
+    lb += mn(mn(mn(fsq(x0, q2), fsq(x1, q2)), fsq(x2, q2)), mn(fsq(x2, q1), fsq(x2, q0)));
+    lb += mn(mn(mn(fsq(y0, p2), fsq(y1, p2)), fsq(y2, p2)), mn(fsq(y2, p1), fsq(y2, p0)));
+    if (!le_nonneg(lb, Q.eps2_hi)) return false;
   }
   // LB_Keogh on the query envelope, K/utils/DtwUtils.java:206-222
   lb = 0.0;
@@ -105,9 +111,27 @@ __global__ void __launch_bounds__(kEdThreads) dtw_lb_raw_kernel(LbRawParams P) {
   const int p = s_p;
   const int c0 = ((int)blockIdx.x - P.tile_prefix[p]) * kEdTile;
   const int ncand = P.ncand[p], cbegin = P.cbegin[p];
-  for (int c = c0 + (int)threadIdx.x; c < min(c0 + kEdTile, ncand); c += kEdThreads) {
-    const int start = cbegin + c;
-    if (lb_cascade(P.T + start, P.Q, 1.0, 0.0)) cand_append(P.out, P.first_global + start, 0.0, 1.0);
+  // Almost every window of a raw-series scan fails on its two end points: those are requested for four of the thread's
+  // windows together (eight loads in flight per thread), only the windows that pass go through the cascade.
+  const int c_end = min(c0 + kEdTile, ncand);
+  const int m = P.Q.m;
+  const double q0 = __ldg(P.Q.q), p0 = __ldg(P.Q.q + m - 1);
+  for (int c = c0 + (int)threadIdx.x; c < c_end; c += 4 * kEdThreads) {
+    double a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int cu = c + u * kEdThreads;
+      a[u] = (cu < c_end) ? P.T[cbegin + cu] : 0.0;
+      b[u] = (cu < c_end) ? P.T[cbegin + cu + m - 1] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int cu = c + u * kEdThreads;
+      if (cu >= c_end) continue;
+      if (m >= 6 && !le_nonneg(fsq(a[u], q0) + fsq(b[u], p0), P.Q.eps2_hi)) continue;
+      const int start = cbegin + cu;
+      if (lb_cascade(P.T + start, P.Q, 1.0, 0.0)) cand_append(P.out, P.first_global + start, 0.0, 1.0);
+    }
   }
 }
 
