@@ -3201,10 +3201,19 @@ int kvm_gather_result(kvm_ctx* ctx, const kvm_result* local, kvm_result* merged,
     KVM_CUDA(ctx, ctx->g_recv.ensure(sizeof(double) * len_per_rank * W));
     fill(static_cast<double*>(ctx->g_hsend.p));
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    KVM_CUDA(ctx, cudaMemcpyAsync(ctx->g_send.p, ctx->g_hsend.p, sizeof(double) * len_per_rank, cudaMemcpyHostToDevice, ctx->stream));
-    const int rc = N->AllGather(ctx->g_send.p, ctx->g_recv.p, len_per_rank, kNcclFloat64, ctx->comm, ctx->stream);
-    if (rc != 0) return nccl_fail(ctx, N, rc, "ncclAllGather");
-    KVM_CUDA(ctx, cudaMemcpyAsync(ctx->g_hrecv.p, ctx->g_recv.p, sizeof(double) * len_per_rank * W, cudaMemcpyDeviceToHost, ctx->stream));
+    // The blocks are a few KB: the collective reads and writes the pinned host buffers directly (they are device
+    // accessible through unified addressing), which saves the two staging copies around it.  KVM_GATHER_ZEROCOPY=0
+    // stages through device buffers instead.
+    static const int zero_copy = env_int("KVM_GATHER_ZEROCOPY", 1);
+    if (zero_copy) {
+      const int rc = N->AllGather(ctx->g_hsend.p, ctx->g_hrecv.p, len_per_rank, kNcclFloat64, ctx->comm, ctx->stream);
+      if (rc != 0) return nccl_fail(ctx, N, rc, "ncclAllGather");
+    } else {
+      KVM_CUDA(ctx, cudaMemcpyAsync(ctx->g_send.p, ctx->g_hsend.p, sizeof(double) * len_per_rank, cudaMemcpyHostToDevice, ctx->stream));
+      const int rc = N->AllGather(ctx->g_send.p, ctx->g_recv.p, len_per_rank, kNcclFloat64, ctx->comm, ctx->stream);
+      if (rc != 0) return nccl_fail(ctx, N, rc, "ncclAllGather");
+      KVM_CUDA(ctx, cudaMemcpyAsync(ctx->g_hrecv.p, ctx->g_recv.p, sizeof(double) * len_per_rank * W, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
