@@ -15,7 +15,8 @@ m-1 halo; chains are never split); every step ends with the multi-GPU tail insid
 all_gather (count, counters, best match, the first 256 answers of every rank; kvm_gather_result in the library).
 `value` = window starts verified by all ranks / max-over-ranks device time of the K timed steps (the library's CUDA
 events per kernel stage + CUDA events around the exchange; series resident in HBM).  The exchange is the library's own
-(kvm_comm_init / kvm_gather_result: ncclAllGather on the ctx's stream); torch.distributed carries the NCCL id, the
+(kvm_comm_init / kvm_gather_result: a peer-memory exchange kernel on the ctx's stream, NCCL for the overflow round);
+torch.distributed carries the NCCL id and the IPC handles, the
 barriers and the final statistics.  `e2e` = the same through the C
 ABI with host buffers (query + interval list in, answers out, exchange included), from the barrier-bracketed wall
 clock of the K steps.  At N=1 the line also carries BASELINE.json configs[1] itself (n = 1e8) as `cfg2_n1e8`.
@@ -371,7 +372,10 @@ def main():
                      # difference to the maximum is load imbalance between the shards of one query
                      "ms_per_step_device_min_over_ranks": float(tail_min.item()) / k,
                      "collectives_per_step": 1 if world > 1 else 0,
-                     "implementation": "kvm_gather_result: one packed ncclAllGather on the library's stream (copies + collective timed by CUDA events)"
+                     "implementation": ("kvm_gather_result: one peer-memory exchange kernel on the library's stream (CUDA IPC over NVLink / NVSwitch; "
+                                        "ncclAllGather only for a rank with more than 256 answers), timed by CUDA events"
+                                        if os.environ.get("KVM_GATHER_P2P", "1") != "0" and world <= 8 else
+                                        "kvm_gather_result: one packed ncclAllGather on the library's stream, timed by CUDA events")
                      if merger == "library" else "torch.distributed all_gather_into_tensor (sharding.PackedMerger)",
                      "packed_bytes_per_rank": 8 * (16 + 2 * 256) if merger == "library" else 8 * merger.len},
             "parity": "oracle-only (reference unpinned: Java 8, no JVM in this image)",

@@ -258,6 +258,15 @@ int kvm_comm_unique_id(unsigned char* id128);
 int kvm_comm_init(kvm_ctx* ctx, const unsigned char* id128, int32_t rank, int32_t world);
 int kvm_gather_result(kvm_ctx* ctx, const kvm_result* local, kvm_result* merged, double* best_distance,
                       int32_t* best_offset);
+/* Optional fast path of kvm_gather_result for ranks on one node (up to 8, NVLink / NVSwitch peer access): the fixed-size
+ * round runs as ONE kernel over peer memory instead of an ncclAllGather — every rank writes its 4 KB block straight into
+ * every other rank's exchange buffer and waits for theirs (sequence numbers behind a system-scope fence).
+ * kvm_comm_ipc_handle: after kvm_comm_init, every rank exports the 64-byte CUDA IPC handle of its exchange buffer;
+ * the handles travel like the NCCL id; kvm_comm_ipc_attach(ctx, handles: world x 64 bytes in rank order) maps the
+ * peers' buffers.  Results are identical to the NCCL path; a rank that never arrives makes the others return KVM_E_NCCL
+ * after ~3 s instead of hanging.  The overflow round (a rank with more than 256 answers) still uses NCCL. */
+int kvm_comm_ipc_handle(kvm_ctx* ctx, unsigned char* handle64);
+int kvm_comm_ipc_attach(kvm_ctx* ctx, const unsigned char* handles);
 
 void kvm_result_free(kvm_ctx* ctx, kvm_result* r);
 void kvm_runs_free(kvm_ctx* ctx, kvm_runs* r);

@@ -38,7 +38,7 @@ EXPORTS = [
     "kvm_envelope", "kvm_window_mean_runs", "kvm_window_mean_runs_all", "kvm_build_index_file", "kvm_index_image_from_runs", "kvm_image_free",
     "kvm_result_free", "kvm_runs_free",
     "kvm_multi_create", "kvm_multi_destroy", "kvm_multi_last_error", "kvm_multi_devices", "kvm_multi_load_series_host",
-    "kvm_multi_verify", "kvm_comm_unique_id", "kvm_comm_init", "kvm_gather_result", "kvm_intervals_sort_merge", "kvm_intervals_intersect", "kvm_intervals_first_segment",
+    "kvm_multi_verify", "kvm_comm_unique_id", "kvm_comm_init", "kvm_gather_result", "kvm_comm_ipc_handle", "kvm_comm_ipc_attach", "kvm_intervals_sort_merge", "kvm_intervals_intersect", "kvm_intervals_first_segment",
 ]
 KVM_ENGINE_ED, KVM_ENGINE_CNSM_ED, KVM_ENGINE_DTW, KVM_ENGINE_CNSM_DTW = 0, 1, 2, 3
 
@@ -129,6 +129,8 @@ def load():
     L.kvm_scan_ucr_ed.argtypes = [vp, _dp, C.c_int32, C.c_double, C.c_double, C.c_double, R]
     L.kvm_comm_unique_id.argtypes = [vp]
     L.kvm_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    L.kvm_comm_ipc_handle.argtypes = [vp, vp]
+    L.kvm_comm_ipc_attach.argtypes = [vp, vp]
     L.kvm_gather_result.argtypes = [vp, R, R, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     L.kvm_window_mean_runs.argtypes = [vp, C.c_int32, C.POINTER(KvmRuns)]
     L.kvm_envelope.argtypes = [vp, C.c_int32, C.c_int64, C.c_int32, vp, vp]

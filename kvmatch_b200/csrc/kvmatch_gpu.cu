@@ -171,6 +171,12 @@ struct kvm_ctx {
   // multi-GPU tail (kvm_comm_*): one NCCL communicator per ctx = per rank, packed all-gather buffers
   void* comm = nullptr;      // ncclComm_t
   int comm_rank = 0, comm_world = 1;
+  // peer-memory exchange (kvm_comm_ipc_*): every rank's exchange buffer mapped into every other rank
+  DevBuf xbuf;                       // [2 parities][world][kXchgSlot doubles] then [2][world] sequence numbers
+  void* xpeer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // peers' xbuf (own: xbuf.p)
+  bool xattached = false;
+  unsigned long long xseq = 0;       // exchanges done
+  DevBuf xerr;
   DevBuf g_send, g_recv;
   PinBuf g_hsend, g_hrecv;
   std::vector<int32_t> g_off;
@@ -3139,6 +3145,13 @@ int nccl_fail(kvm_ctx* ctx, NcclApi* N, int rc, const char* what) {
 }  // namespace
 
 static void kvm_comm_release(kvm_ctx* ctx) {
+  if (ctx->xattached) {
+    for (int r = 0; r < ctx->comm_world; r++)
+      if (r != ctx->comm_rank && ctx->xpeer[r]) cudaIpcCloseMemHandle(ctx->xpeer[r]);
+    ctx->xattached = false;
+  }
+  ctx->xbuf.release();
+  ctx->xerr.release();
   if (ctx->comm) {
     if (NcclApi* N = nccl_api()) N->CommDestroy(ctx->comm);
     ctx->comm = nullptr;
@@ -3178,6 +3191,47 @@ int kvm_comm_init(kvm_ctx* ctx, const unsigned char* id128, int32_t rank, int32_
   return KVM_OK;
 }
 
+int kvm_comm_ipc_handle(kvm_ctx* ctx, unsigned char* handle64) {
+  if (!ctx) return KVM_E_ARG;
+  if (!handle64) return fail(ctx, KVM_E_ARG, "null/invalid argument");
+  if (!ctx->comm) return fail(ctx, KVM_E_STATE, "kvm_comm_init has not been called on this ctx");
+  if (ctx->comm_world > 8) return fail(ctx, KVM_E_ARG, "the peer-memory exchange serves up to 8 ranks");
+  KVM_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t bytes = sizeof(double) * 2 * (size_t)ctx->comm_world * kvm::kXchgSlot + sizeof(unsigned long long) * 2 * (size_t)ctx->comm_world;
+  // (a dedicated allocation: cudaIpcGetMemHandle exports the whole cudaMalloc block)
+  ctx->xbuf.release();
+  KVM_CUDA(ctx, cudaMalloc(&ctx->xbuf.p, bytes));
+  ctx->xbuf.cap = bytes;
+  KVM_CUDA(ctx, cudaMemsetAsync(ctx->xbuf.p, 0, bytes, ctx->stream));
+  KVM_CUDA(ctx, ctx->xerr.ensure(sizeof(int)));
+  KVM_CUDA(ctx, cudaMemsetAsync(ctx->xerr.p, 0, sizeof(int), ctx->stream));
+  KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaIpcMemHandle_t h;
+  KVM_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->xbuf.p));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(handle64, &h, 64);
+  return KVM_OK;
+}
+
+int kvm_comm_ipc_attach(kvm_ctx* ctx, const unsigned char* handles) {
+  if (!ctx) return KVM_E_ARG;
+  if (!handles) return fail(ctx, KVM_E_ARG, "null/invalid argument");
+  if (!ctx->comm || !ctx->xbuf.p) return fail(ctx, KVM_E_STATE, "kvm_comm_ipc_handle has not been called on this ctx");
+  KVM_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (int r = 0; r < ctx->comm_world; r++) {
+    if (r == ctx->comm_rank) {
+      ctx->xpeer[r] = ctx->xbuf.p;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + 64 * (size_t)r, 64);
+    KVM_CUDA(ctx, cudaIpcOpenMemHandle(&ctx->xpeer[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  ctx->xattached = true;
+  ctx->xseq = 0;
+  return KVM_OK;
+}
+
 int kvm_gather_result(kvm_ctx* ctx, const kvm_result* local, kvm_result* merged, double* best_distance, int32_t* best_offset) {
   if (!ctx) return KVM_E_ARG;
   if (!local || !merged) return fail(ctx, KVM_E_ARG, "null/invalid argument");
@@ -3195,12 +3249,38 @@ int kvm_gather_result(kvm_ctx* ctx, const kvm_result* local, kvm_result* merged,
     }
   double exchange_ms = 0.0;  // device time of the exchange (CUDA events on the ctx stream: copies + collective)
   auto round_trip = [&](size_t len_per_rank, auto fill) -> int {
-    KVM_CUDA(ctx, ctx->g_hsend.ensure(sizeof(double) * len_per_rank));
+    KVM_CUDA(ctx, ctx->g_hsend.ensure(sizeof(double) * (len_per_rank + 2)));
     KVM_CUDA(ctx, ctx->g_hrecv.ensure(sizeof(double) * len_per_rank * W));
     KVM_CUDA(ctx, ctx->g_send.ensure(sizeof(double) * len_per_rank));
     KVM_CUDA(ctx, ctx->g_recv.ensure(sizeof(double) * len_per_rank * W));
     fill(static_cast<double*>(ctx->g_hsend.p));
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    static const int p2p_on = env_int("KVM_GATHER_P2P", 1);
+    if (p2p_on && ctx->xattached && len_per_rank == (size_t)kvm::kXchgSlot) {
+      // round 1 over peer memory: one kernel pushes this rank's block to every rank and waits for theirs
+      kvm::XchgParams X{};
+      for (int r = 0; r < W; r++) X.peer[r] = static_cast<double*>(ctx->xpeer[r]);
+      X.send = static_cast<const double*>(ctx->g_hsend.p);
+      X.rank = ctx->comm_rank;
+      X.world = W;
+      ctx->xseq++;
+      X.seq = ctx->xseq;
+      X.parity = (int)(ctx->xseq & 1ULL);
+      X.err = ctx->xerr.as<int>();
+      kvm::xchg_kernel<<<1, 256, 0, ctx->stream>>>(X);
+      KVM_CUDA(ctx, cudaGetLastError());
+      const double* area = static_cast<const double*>(ctx->xbuf.p) + (size_t)X.parity * W * kvm::kXchgSlot;
+      KVM_CUDA(ctx, cudaMemcpyAsync(ctx->g_hrecv.p, area, sizeof(double) * len_per_rank * W, cudaMemcpyDeviceToHost, ctx->stream));
+      int* herr = reinterpret_cast<int*>(static_cast<double*>(ctx->g_hsend.p) + len_per_rank);  // (spare pinned slot behind the block)
+      KVM_CUDA(ctx, cudaMemcpyAsync(herr, ctx->xerr.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+      KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+      exchange_ms += ms;
+      if (*herr) return fail(ctx, KVM_E_NCCL, "peer-memory exchange timed out: a rank did not arrive");
+      return KVM_OK;
+    }
     // The blocks are a few KB: the collective reads and writes the pinned host buffers directly (they are device
     // accessible through unified addressing), which saves the two staging copies around it.  KVM_GATHER_ZEROCOPY=0
     // stages through device buffers instead.

@@ -878,4 +878,47 @@ __device__ __forceinline__ void chain_rewalk_body(const RewalkParams& P, int blo
   }
 }
 
+// ---- The same tail over peer memory (NVLink / NVSwitch P2P), one kernel: every rank writes its packed block straight
+// into every other rank's exchange buffer, publishes a sequence number behind a system-scope fence, and waits until
+// the sequence numbers of all ranks have arrived in its own buffer.  No library call on the data path; the blocks are
+// 4 KB, so latency is everything (an ncclAllGather of them costs ~65 us, this kernel a few us plus the wait for the
+// slowest rank).  Two alternating areas: a rank can run at most one exchange ahead of the slowest one (it needs that
+// rank's sequence number to finish), and the slowest rank reads area k before it starts exchange k + 1 (stream order).
+constexpr int kXchgSlot = 16 + 2 * 256;  // = kGatherHead + 2 * kGatherCap doubles per rank
+struct XchgParams {
+  double* peer[8];              // base of every rank's exchange buffer as mapped here
+  const double* send;           // this rank's block (pinned host memory, read once)
+  int rank, world, parity;
+  unsigned long long seq;
+  int* err;
+};
+__device__ __forceinline__ size_t xchg_seq_base(int world) { return (size_t)2 * world * kXchgSlot; }
+__global__ void __launch_bounds__(256) xchg_kernel(XchgParams P) {
+  const int tid = threadIdx.x;
+  const size_t area = (size_t)P.parity * P.world * kXchgSlot;
+  for (int p = 0; p < P.world; p++) {
+    double* dst = P.peer[p] + area + (size_t)P.rank * kXchgSlot;
+    for (int i = tid; i < kXchgSlot; i += blockDim.x) dst[i] = P.send[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < P.world) {
+    unsigned long long* flag = reinterpret_cast<unsigned long long*>(P.peer[tid] + xchg_seq_base(P.world)) + (size_t)P.parity * P.world + P.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(P.seq) : "memory");
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(P.peer[P.rank] + xchg_seq_base(P.world)) + (size_t)P.parity * P.world + tid;
+    const long long t0 = clock64();
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+      if (v >= P.seq) break;
+      if (clock64() - t0 > 6000000000LL) {  // ~3 s: a rank never arrived
+        *P.err = 1;
+        break;
+      }
+      __nanosleep(64);
+    } while (true);
+  }
+  __syncthreads();
+}
+
 }  // namespace kvm

@@ -120,7 +120,7 @@ class GpuSeries:
         return out
 
     # ---- one process per GPU: the multi-GPU tail inside the library (kvm_comm_*, kvm_gather_result) ----
-    def comm_init(self, rank: int | None = None, world: int | None = None):
+    def comm_init(self, rank: int | None = None, world: int | None = None, p2p: bool = True):
         """Join the library's NCCL communicator.  The 128-byte id is obtained on rank 0 and broadcast through
         torch.distributed (any backend); rank / world default to the process group's."""
         import torch.distributed as dist
@@ -134,6 +134,14 @@ class GpuSeries:
         ident = (C.c_ubyte * 128).from_buffer_copy(box[0])
         self._check(self._L.kvm_comm_init(self._h, ident, rank, world))
         self.comm_world = world
+        if p2p and 1 < world <= 8:
+            # the peer-memory fast path of the exchange: every rank's buffer mapped into every other rank (CUDA IPC)
+            mine = (C.c_ubyte * 64)()
+            self._check(self._L.kvm_comm_ipc_handle(self._h, mine))
+            every = [None] * world
+            dist.all_gather_object(every, bytes(mine))
+            blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(every))
+            self._check(self._L.kvm_comm_ipc_attach(self._h, blob))
         return self
 
     def gather(self, local: VerifyResult):
