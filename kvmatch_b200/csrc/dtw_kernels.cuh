@@ -620,20 +620,24 @@ __global__ void __launch_bounds__(kProbeWarps * 32) dtw_probe_kernel(ProbeParams
   __shared__ double s_exit[kProbeWarps][2 * kProbeMaxK + 2 * 64];  // exit cells: last column / last row of the square and of the sub-square
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int K = P.K;
-  double* A = s_a[warp];
+  float* Af = reinterpret_cast<float*>(s_a[warp]);  // normalised rows, FP32
   double* S = s_S[warp];
   double* COL = s_exit[warp];
   double* ROW = COL + kProbeMaxK;
   double* COL1 = ROW + kProbeMaxK;
   double* ROW1 = COL1 + 64;
-  double b[4], bu[4], bl[4];
+  double bu[4], bl[4];
+  float bf[4];
+  float bmax = 0.f;
 #pragma unroll
   for (int c = 0; c < 4; c++) {
     const int col = min(4 * lane + c, K - 1);
-    b[c] = __ldg(P.q + col);
+    bf[c] = (float)__ldg(P.q + col);
+    bmax = fmaxf(bmax, fabsf(bf[c]));
     bu[c] = __ldg(P.uq + col);  // (rows and columns share the index range 0..K-1: the lane's four Keogh terms)
     bl[c] = __ldg(P.lq + col);
   }
+  bmax = __uint_as_float(__reduce_max_sync(kFullMask, __float_as_uint(bmax)));  // (non-negative floats order like their bit patterns)
   unsigned long long n = *P.in.count;
   if ((long long)n > P.in.cap) n = (unsigned long long)P.in.cap;
   if (n < (unsigned long long)P.min_count) {  // a short list (mostly true matches): hand it on unprobed
@@ -653,17 +657,26 @@ __global__ void __launch_bounds__(kProbeWarps * 32) dtw_probe_kernel(ProbeParams
     __syncwarp();
     // rows 4 lane .. 4 lane + 3: normalised samples and their Keogh terms
     double kt[4];
+    float amax = 0.f;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
       const int k = 4 * lane + c;
       kt[c] = 0.0;
       if (k < K) {
         const double a = (w[k] - mean) * rstd;
-        A[k] = a;
+        Af[k] = (float)a;
+        amax = fmaxf(amax, fabsf((float)a));
         const double dd = (a > bu[c]) ? (a - bu[c]) : ((a < bl[c]) ? (a - bl[c]) : 0.0);
         kt[c] = dd * dd;
       }
     }
+    amax = __uint_as_float(__reduce_max_sync(kFullMask, __float_as_uint(amax)));
+    // The square itself runs in FP32 with every rounding on the safe side (a 4-column systolic step is issue bound: FP32
+    // min / fused multiply-add are one instruction where the binary64 forms were five).  |a - b| is lowered by
+    // e >= the two conversion errors plus the subtraction's own rounding ((|a| + |b|) 2^-22 covers 2 * 2^-24 * (|a| + |b|)
+    // four times over), the product and the sum round towards zero, the minimum is exact: every cell is a lower bound
+    // of the binary64 cell, and so is the exit bound built from them.
+    const float e_sub = __fmul_ru(__fadd_ru(amax, bmax), 2.3841858e-7f);  // 2^-22
     // S(i) = total - sum_{k < i} term_k, kept below the true remainder: total shrunk, prefix grown, clamped at 0
     {
       const double mine = (kt[0] + kt[1]) + (kt[2] + kt[3]);
@@ -687,8 +700,9 @@ __global__ void __launch_bounds__(kProbeWarps * 32) dtw_probe_kernel(ProbeParams
     // The systolic sweep.  Nothing but the recurrence sits in the loop: the exit cells (last row / last column of the
     // square and of the K1 sub-square) are parked in shared memory with predicated stores and reduced afterwards by
     // all lanes.  Cell (0, 0) needs no special case: its diagonal predecessor is seeded with 0.
-    double prev[4] = {kDtwInf, kDtwInf, kDtwInf, kDtwInf};
-    double last3 = kDtwInf, last3_prev = kDtwInf;
+    const float kInfF = 9.9999e19f;  // (below the reference INF = 1e20: a lower bound of it)
+    float prev[4] = {kInfF, kInfF, kInfF, kInfF};
+    float last3 = kInfF, last3_prev = kInfF;
     // The same bound on the sub-square K1 x K1 (K1 = 64 when K >= 96) is complete after step K1 - 1 + K1/4 - 1: most
     // candidates are already over eps^2 there (86 % on the measured queries) and skip the remaining 40 % of the steps.
     const int K1 = (K >= 96) ? 64 : 0;
@@ -710,20 +724,20 @@ __global__ void __launch_bounds__(kProbeWarps * 32) dtw_probe_kernel(ProbeParams
           break;
         }
       }
-      double x_left = __shfl_up_sync(kFullMask, last3, 1), x_diag = __shfl_up_sync(kFullMask, last3_prev, 1);
+      float x_left = __shfl_up_sync(kFullMask, last3, 1), x_diag = __shfl_up_sync(kFullMask, last3_prev, 1);
       if (lane == 0) {
-        x_left = kDtwInf;
-        x_diag = (t == 0) ? 0.0 : kDtwInf;
+        x_left = kInfF;
+        x_diag = (t == 0) ? 0.f : kInfF;
       }
       const int r = t - lane;
       if (r >= 0 && r < K) {
-        const double ar = A[r];
-        double cur[4];
+        const float ar = Af[r];
+        float cur[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-          const double d = ar - b[c];
-          const double up = prev[c];
-          const double v = __fma_rn(d, d, min_nonneg(min_nonneg(x_left, up), x_diag));
+          const float d = fmaxf(__fadd_rd(fabsf(ar - bf[c]), -e_sub), 0.f);
+          const float up = prev[c];
+          const float v = __fmaf_rz(d, d, fminf(fminf(x_left, up), x_diag));
           x_diag = up;
           x_left = v;
           cur[c] = v;
@@ -731,16 +745,16 @@ __global__ void __launch_bounds__(kProbeWarps * 32) dtw_probe_kernel(ProbeParams
         }
         last3_prev = last3;
         last3 = cur[3];
-        if (lane == last_lane) COL[r] = (last_c == 0) ? cur[0] : (last_c == 1) ? cur[1] : (last_c == 2) ? cur[2] : cur[3];
+        if (lane == last_lane) COL[r] = (double)((last_c == 0) ? cur[0] : (last_c == 1) ? cur[1] : (last_c == 2) ? cur[2] : cur[3]);
         if (r == K - 1) {
 #pragma unroll
-          for (int c = 0; c < 4; c++) ROW[min(4 * lane + c, kProbeMaxK - 1)] = cur[c];
+          for (int c = 0; c < 4; c++) ROW[min(4 * lane + c, kProbeMaxK - 1)] = (double)cur[c];
         }
         if (K1) {
-          if (lane == k1_lane && r < K1) COL1[r] = cur[3];
+          if (lane == k1_lane && r < K1) COL1[r] = (double)cur[3];
           if (r == K1 - 1 && lane <= k1_lane) {
 #pragma unroll
-            for (int c = 0; c < 4; c++) ROW1[4 * lane + c] = cur[c];
+            for (int c = 0; c < 4; c++) ROW1[4 * lane + c] = (double)cur[c];
           }
         }
       }
