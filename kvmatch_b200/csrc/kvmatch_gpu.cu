@@ -1846,8 +1846,19 @@ int kvm_load_series_file(kvm_ctx* ctx, const char* path, int64_t n, int64_t firs
   return measure_absmax(ctx);
 }
 
+static int verify_ed_impl(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, const int32_t* lr, int32_t K, int32_t shift,
+                          kvm_result* out, bool may_defer);
+
 int kvm_verify_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, const int32_t* lr, int32_t K, int32_t shift,
                   kvm_result* out) {
+  return verify_ed_impl(ctx, q, m, epsilon, lr, K, shift, out, true);
+}
+
+static int verify_ed_impl(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, const int32_t* lr, int32_t K, int32_t shift,
+                          kvm_result* out, bool may_defer) {
+  const int32_t K_list = K;
+  bool unchecked = false;  // regular by its two ends only: the pass over the whole list runs behind the kernel launch
+  int32_t c0_list = 0;
   int rc = check_common(ctx, q, m, epsilon, lr, K, out);
   if (rc) return rc;
   if ((rc = begin_call(ctx))) return rc;
@@ -1874,8 +1885,14 @@ int kvm_verify_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, cons
     const int64_t c0 = (int64_t)lr[1] - lr[0] + 1;
     const int64_t first_begin = (int64_t)lr[0] - shift, last_end = (int64_t)lr[2 * K - 1] - shift + m - 1;
     const int64_t lo = ctx->first, hi = ctx->first + ctx->count - 1;
-    if (c0 >= 1 && c0 <= INT32_MAX / 2 && first_begin >= 1 && first_begin >= lo && last_end <= ctx->n && last_end <= hi &&
-        !regular_grid_pass(lr, K, (int32_t)c0)) {
+    bool ends_ok = c0 >= 1 && c0 <= INT32_MAX / 2 && first_begin >= 1 && first_begin >= lo && last_end <= ctx->n && last_end <= hi;
+    if (ends_ok && may_defer && K >= 4096) {  // (as in the streaming path: check the list while the kernel runs)
+      const int64_t V0 = (int64_t)lr[2 * K - 1] - lr[0] + 1;
+      unchecked = V0 > (int64_t)(K - 1) * c0 && V0 <= (int64_t)K * c0 && (int64_t)lr[2 * (K - 1)] == (int64_t)lr[0] + (int64_t)(K - 1) * c0;
+      c0_list = (int32_t)c0;
+    }
+    if (ends_ok && !unchecked) ends_ok = !regular_grid_pass(lr, K, (int32_t)c0);
+    if (ends_ok) {
       const int64_t V = (int64_t)lr[2 * K - 1] - lr[0] + 1;
       if (V <= 0x7fff0000LL) {
         regular = true;
@@ -1937,6 +1954,13 @@ int kvm_verify_ed(kvm_ctx* ctx, const double* q, int32_t m, double epsilon, cons
     ed_verify_kernel<<<(unsigned)n_tiles, kEdThreads, 0, ctx->stream>>>(E);
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     KVM_CUDA(ctx, cudaGetLastError());
+    if (unchecked) {
+      unchecked = false;
+      if (regular_grid_pass(lr, K_list, c0_list)) {  // not a regular grid after all: discard, plan interval by interval
+        KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return verify_ed_impl(ctx, q, m, epsilon, lr, K_list, shift, out, false);
+      }
+    }
     if ((rc = read_counters(ctx, cnt))) return rc;
     out->kernel_ms += elapsed_ms(ctx);
     out->stage_ms[0] += elapsed_ms(ctx);

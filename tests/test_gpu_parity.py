@@ -548,3 +548,22 @@ def test_rsm_engines_coalesce_adjacent_intervals(gpu, oracle):
     ragged = [tuple(x) for x in np.asarray(grid).reshape(-1, 2)]
     ragged[7] = (ragged[7][0], ragged[7][1] - 1)                     # one gap: not regular any more
     assert_same(gpu.verify_ed(q, 12.0, ragged), oracle.verify_ed(s, q, 12.0, ragged))
+
+
+def test_rsm_ed_deferred_grid_check_catches_a_holed_list(gpu, oracle):
+    """RSM-ED takes a long list that looks regular from its two ends as one run and checks it in full behind the kernel
+    launch; a hole in the middle must be caught and the list planned interval by interval."""
+    n, m, chunk = 3_000_000, 128, 512
+    s = datagen.generate(n, seed=4712)
+    gpu.load(s)
+    off = 2_000_321
+    q = s[off - 1:off - 1 + m].copy()
+    iv = np.asarray(datagen.chain_intervals(n, m, chunk), dtype=np.int32).reshape(-1, 2)
+    assert len(iv) >= 4096
+    assert_same(gpu.verify_ed(q, 15.0, iv), oracle.verify_ed(s, q, 15.0, iv))
+    holed = iv.copy()
+    k = int(np.searchsorted(iv[:, 0], off, side="right") - 1)
+    holed[k] = (off + 1, holed[k, 1])                  # the interval that holds the planted match now starts behind it
+    got, exp = gpu.verify_ed(q, 15.0, holed), oracle.verify_ed(s, q, 15.0, holed)
+    assert_same(got, exp)
+    assert off not in got.offsets.tolist()
