@@ -1108,24 +1108,16 @@ int stream_plan(kvm_ctx* ctx, const int32_t* lr, int K, int shift, int m, int nt
 // fit shared memory.
 template <bool kFromSums>
 void launch_exact(kvm_ctx* ctx, ExactEdParams& X) {
-  const size_t budget = 200 * 1024;
-  auto bytes = [&](int warps) {
-    return sizeof(double) * ((size_t)X.q_cap + (X.q_cap + 1) / 2 + (size_t)warps * (kExactChunk + X.win_cap));
-  };
-  int warps = 4;
-  X.win_cap = (X.m + 1) & ~1;
-  X.q_cap = (X.m + 1) & ~1;
-  while (warps > 1 && bytes(warps) > budget) warps >>= 1;
-  if (bytes(warps) > budget) {
-    X.q_cap = 0;
-    warps = 4;
-    while (warps > 1 && bytes(warps) > budget) warps >>= 1;
-  }
-  if (bytes(warps) > budget) {
-    warps = 4;
-    X.win_cap = 0;
-  }
-  cnsm_ed_exact_kernel<kFromSums><<<ctx->n_sms * 6, warps * 32, bytes(warps), ctx->stream>>>(X);
+  // Shared memory per CTA: the |zQ|-ordered query (12 m bytes, once per CTA) and per warp the term buffer (8 KB) plus,
+  // for short queries, the window itself.  What matters is how many warps the SM holds: survivors are worked on one
+  // warp each and every one of them costs microseconds (m dependent additions in the reference's order), so a long
+  // query must not buy its staging with parallelism — with everything staged an m = 8192 query ran ONE warp per SM and
+  // its exact stage took 3-4 ms for a few thousand survivors.  Window staged up to m = 1024, query up to m = 4096.
+  const int warps = 4;
+  X.win_cap = X.m <= 1024 ? ((X.m + 1) & ~1) : 0;
+  X.q_cap = X.m <= 4096 ? ((X.m + 1) & ~1) : 0;
+  const size_t bytes = sizeof(double) * ((size_t)X.q_cap + (X.q_cap + 1) / 2 + (size_t)warps * (kExactChunk + X.win_cap));
+  cnsm_ed_exact_kernel<kFromSums><<<ctx->n_sms * 6, warps * 32, bytes, ctx->stream>>>(X);
 }
 
 int ensure_xlist(kvm_ctx* ctx, long long cap) {
