@@ -495,7 +495,7 @@ def dtw_block(g, n_total, chunk, offs, budget_s=25.0):
             r2 = g.verify_cnsm_dtw(q2, eps, rho2, ALPHA, BETA, iv2)
             rows.append({"offset": int(o2), "kernel_ms": r2.kernel_ms, "wall_ms": 1e3 * (time.perf_counter() - t0),
                          "verified": int(r2.n_verified), "gate_pass": int(r2.n_gate_pass), "dtws": int(r2.n_lb_pass),
-                         "cells": int(r2.n_dtw_cells), "answers": int(r2.count),
+                         "cells": int(r2.n_dtw_cells), "answers": int(r2.count), "band_dtws": int(r2.n_exact),
                          "stage_ms": [float(x) for x in r2.stage_ms]})
         kt = sum(r["kernel_ms"] for r in rows) * 1e-3
         dtw_t = sum(r["stage_ms"][3] for r in rows) * 1e-3
