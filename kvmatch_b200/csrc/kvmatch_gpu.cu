@@ -3191,10 +3191,7 @@ int kvm_comm_init(kvm_ctx* ctx, const unsigned char* id128, int32_t rank, int32_
   NcclApi* N = nccl_api();
   if (!N) return fail(ctx, KVM_E_NCCL, "libnccl.so.2 could not be loaded");
   KVM_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (ctx->comm) {
-    N->CommDestroy(ctx->comm);
-    ctx->comm = nullptr;
-  }
+  kvm_comm_release(ctx);  // a second init replaces the communicator and drops the peer-memory mappings of the first
   NcclId id;
   std::memcpy(id.b, id128, 128);
   const int rc = N->CommInitRank(&ctx->comm, world, id, rank);
@@ -3250,7 +3247,7 @@ int kvm_comm_ipc_attach(kvm_ctx* ctx, const unsigned char* handles) {
 
 int kvm_gather_result(kvm_ctx* ctx, const kvm_result* local, kvm_result* merged, double* best_distance, int32_t* best_offset) {
   if (!ctx) return KVM_E_ARG;
-  if (!local || !merged) return fail(ctx, KVM_E_ARG, "null/invalid argument");
+  if (!local || !merged || local == merged) return fail(ctx, KVM_E_ARG, "null/invalid argument (local and merged must be distinct)");
   if (!ctx->comm) return fail(ctx, KVM_E_STATE, "kvm_comm_init has not been called on this ctx");
   NcclApi* N = nccl_api();
   const int W = ctx->comm_world;
