@@ -41,7 +41,8 @@ public final class NativeVerifier implements AutoCloseable {
             JAVA_LONG.withName("cnt_candidate"), JAVA_LONG.withName("n_verified"), JAVA_LONG.withName("s_total"),
             JAVA_LONG.withName("n_gate_pass"), JAVA_LONG.withName("n_lb_pass"), JAVA_LONG.withName("n_exact"),
             JAVA_DOUBLE.withName("kernel_ms"), MemoryLayout.sequenceLayout(4, JAVA_DOUBLE).withName("stage_ms"),
-            JAVA_INT.withName("n_launches"), JAVA_INT.withName("h2d_bytes"));
+            JAVA_INT.withName("n_launches"), JAVA_INT.withName("h2d_bytes"),
+            JAVA_LONG.withName("n_rewalked"), JAVA_LONG.withName("n_chains_rewalked"), JAVA_LONG.withName("n_dtw_cells"));
     // struct kvm_runs
     private static final StructLayout RUNS = MemoryLayout.structLayout(
             JAVA_LONG.withName("count"), ADDRESS.withName("keys"), ADDRESS.withName("first"), ADDRESS.withName("last"),
