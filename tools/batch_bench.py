@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("KVM_PLAN_CACHE", "0")
 import numpy as np, kvmatch_b200, bench
 from kvmatch_b200 import datagen
-n = int(float(sys.argv[1])) if len(sys.argv) > 1 else bench.N_PER_GPU
+n = int(float(sys.argv[1])) if len(sys.argv) > 1 else bench.N_CFG2
 chunk = int(sys.argv[2]) if len(sys.argv) > 2 else bench.DEFAULT_CHUNK
 m = bench.M
 s = datagen.generate(n); g = kvmatch_b200.GpuSeries(0); g.load(s)
