@@ -612,6 +612,8 @@ struct ProbeParams {
   CandList in, out;
   unsigned long long* n_cells;
   int min_count;  // lists shorter than this are passed through
+  int skip_sub;   // the 64 x 64 sub-square was already probed (dtw_probe64_kernel): no early exit on it
+  unsigned long long* handed_on;  // set by the first stage when it handed a short list on unprobed: the second stage does the same
 };
 
 __global__ void __launch_bounds__(kProbeWarps * 32) dtw_probe_kernel(ProbeParams P) {
@@ -640,9 +642,9 @@ __global__ void __launch_bounds__(kProbeWarps * 32) dtw_probe_kernel(ProbeParams
   bmax = __uint_as_float(__reduce_max_sync(kFullMask, __float_as_uint(bmax)));  // (non-negative floats order like their bit patterns)
   unsigned long long n = *P.in.count;
   if ((long long)n > P.in.cap) n = (unsigned long long)P.in.cap;
-  if (n < (unsigned long long)P.min_count) {  // a short list (mostly true matches): hand it on unprobed
+  if (n < (unsigned long long)P.min_count || (P.skip_sub && P.handed_on && *P.handed_on)) {  // a short list (mostly true matches): hand it on unprobed
     for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (unsigned long long)gridDim.x * blockDim.x)
-      cand_append(P.out, P.in.off[e], P.in.mean[e], P.in.stdv[e]);
+      cand_append(P.out, P.in.off[e], P.in.mean[e], P.in.stdv[e], P.in.lb ? P.in.lb[e] : 0.0);
     return;
   }
   const int steps = K + (K + 3) / 4;
@@ -705,7 +707,7 @@ __global__ void __launch_bounds__(kProbeWarps * 32) dtw_probe_kernel(ProbeParams
     float last3 = kInfF, last3_prev = kInfF;
     // The same bound on the sub-square K1 x K1 (K1 = 64 when K >= 96) is complete after step K1 - 1 + K1/4 - 1: most
     // candidates are already over eps^2 there (86 % on the measured queries) and skip the remaining 40 % of the steps.
-    const int K1 = (K >= 96) ? 64 : 0;
+    const int K1 = (K >= 96 && !P.skip_sub) ? 64 : 0;
     const int k1_lane = (K1 >> 2) - 1, k1_step = K1 - 1 + k1_lane;
     bool dead = false;
     auto exit_bound = [&](const double* col, const double* row, int kk) {  // kk x kk square: min over its exit cells
@@ -767,6 +769,132 @@ __global__ void __launch_bounds__(kProbeWarps * 32) dtw_probe_kernel(ProbeParams
     }
   }
   if (lane == 0 && probed_cells) atomicAdd(P.n_cells, probed_cells);
+}
+
+// First stage of the probe for wide bands (K >= 96): the 64 x 64 sub-square alone, TWO candidates per warp (a half-warp
+// of 16 lanes x 4 columns each).  86 % of the measured candidates are already over eps^2 on this sub-square; they cost
+// half a warp for 79 steps here instead of a whole warp for 79 of its 129 steps, and only the survivors go through
+// dtw_probe_kernel's full square.  Same arithmetic and the same bound as there (FP32 cells rounded to the safe side,
+// exit cells + remaining Keogh).
+__global__ void __launch_bounds__(kProbeWarps * 32) dtw_probe64_kernel(ProbeParams P) {
+  constexpr int K1 = 64;
+  __shared__ float s_af[kProbeWarps][2][K1];
+  __shared__ double s_S[kProbeWarps][2][K1 + 2];
+  __shared__ double s_exit[kProbeWarps][2][2 * K1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = lane >> 4, hl = lane & 15;
+  float* Af = s_af[warp][half];
+  double* S = s_S[warp][half];
+  double* COL = s_exit[warp][half];
+  double* ROW = COL + K1;
+  double bu[4], bl[4];
+  float bf[4];
+  float bmax = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const int col = 4 * hl + c;
+    bf[c] = (float)__ldg(P.q + col);
+    bmax = fmaxf(bmax, fabsf(bf[c]));
+    bu[c] = __ldg(P.uq + col);
+    bl[c] = __ldg(P.lq + col);
+  }
+  bmax = __uint_as_float(__reduce_max_sync(kFullMask, __float_as_uint(bmax)));
+  unsigned long long n = *P.in.count;
+  if ((long long)n > P.in.cap) n = (unsigned long long)P.in.cap;
+  if (n < (unsigned long long)P.min_count) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P.handed_on) *P.handed_on = 1ULL;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (unsigned long long)gridDim.x * blockDim.x)
+      cand_append(P.out, P.in.off[e], P.in.mean[e], P.in.stdv[e], P.in.lb ? P.in.lb[e] : 0.0);
+    return;
+  }
+  const float kInfF = 9.9999e19f;
+  unsigned long long probed = 0;
+  for (unsigned long long e0 = 2ULL * ((unsigned long long)blockIdx.x * kProbeWarps + warp); e0 < n; e0 += 2ULL * gridDim.x * kProbeWarps) {
+    const bool valid = e0 + half < n;
+    const unsigned long long e = valid ? e0 + half : n - 1;  // (an odd tail: the idle half repeats the last candidate)
+    const int32_t off = P.in.off[e];
+    const double mean = P.in.mean[e], stdv = P.in.stdv[e];
+    const double total = P.in.lb ? P.in.lb[e] : 0.0;
+    const double rstd = 1.0 / stdv;
+    const double* __restrict__ w = P.T + (off - P.first_global);
+    __syncwarp();
+    double kt[4];
+    float amax = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int k = 4 * hl + c;
+      const double a = (w[k] - mean) * rstd;
+      Af[k] = (float)a;
+      amax = fmaxf(amax, fabsf((float)a));
+      const double dd = (a > bu[c]) ? (a - bu[c]) : ((a < bl[c]) ? (a - bl[c]) : 0.0);
+      kt[c] = dd * dd;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(kFullMask, amax, o, 16));
+    const float e_sub = __fmul_ru(__fadd_ru(amax, bmax), 2.3841858e-7f);  // 2^-22, as in dtw_probe_kernel
+    {
+      const double mine = (kt[0] + kt[1]) + (kt[2] + kt[3]);
+      double incl = mine;
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        const double t = __shfl_up_sync(kFullMask, incl, o, 16);
+        if (hl >= o) incl += t;
+      }
+      double pre = incl - mine;
+      const double tot = total * (1.0 - 1e-10);
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        S[4 * hl + c] = fmax(tot - pre * (1.0 + 1e-10), 0.0);
+        pre += kt[c];
+      }
+      if (hl == 15) S[K1] = fmax(tot - pre * (1.0 + 1e-10), 0.0);
+    }
+    __syncwarp();
+    float prev[4] = {kInfF, kInfF, kInfF, kInfF};
+    float last3 = kInfF, last3_prev = kInfF;
+#pragma unroll 1
+    for (int t = 0; t < K1 + 15; t++) {
+      float x_left = __shfl_up_sync(kFullMask, last3, 1, 16), x_diag = __shfl_up_sync(kFullMask, last3_prev, 1, 16);
+      if (hl == 0) {
+        x_left = kInfF;
+        x_diag = (t == 0) ? 0.f : kInfF;
+      }
+      const int r = t - hl;
+      if (r >= 0 && r < K1) {
+        const float ar = Af[r];
+        float cur[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const float d = fmaxf(__fadd_rd(fabsf(ar - bf[c]), -e_sub), 0.f);
+          const float up = prev[c];
+          const float v = __fmaf_rz(d, d, fminf(fminf(x_left, up), x_diag));
+          x_diag = up;
+          x_left = v;
+          cur[c] = v;
+          prev[c] = v;
+        }
+        last3_prev = last3;
+        last3 = cur[3];
+        if (hl == 15) COL[r] = (double)cur[3];
+        if (r == K1 - 1) {
+#pragma unroll
+          for (int c = 0; c < 4; c++) ROW[4 * hl + c] = (double)cur[c];
+        }
+      }
+    }
+    __syncwarp();
+    double bb = kDtwInf;
+    const double s_last = S[K1];
+    for (int i = hl; i < K1; i += 16) bb = min_nonneg(bb, min_nonneg(COL[i] + S[i + 1], ROW[i] + s_last));
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) bb = min_nonneg(bb, __shfl_xor_sync(kFullMask, bb, o, 16));
+    if (valid && hl == 0) {
+      probed++;
+      if (le_nonneg(bb, P.eps2_hi)) cand_append(P.out, off, mean, stdv, total);
+    }
+  }
+  probed = __reduce_add_sync(kFullMask, (unsigned)probed);
+  if (lane == 0 && probed) atomicAdd(P.n_cells, probed * (unsigned long long)(K1 * K1));
 }
 
 // lowerUpperLemire on the device (K/utils/DtwUtils.java:50-91): l[i] = min, u[i] = max of t[max(0,i-r) .. min(len-1,i+r)]

@@ -98,7 +98,7 @@ struct Arena {
   }
 };
 
-enum Counter { kCntAnswers = 0, kCntCand = 1, kCntGate = 2, kCntTiles = 3, kCntEntries = 4, kCntFlag = 5, kCntDone = 6, kCntCand2 = 7, kCntCells = 8, kCntProbe = 9, kNumCounters = 10 };
+enum Counter { kCntAnswers = 0, kCntCand = 1, kCntGate = 2, kCntTiles = 3, kCntEntries = 4, kCntFlag = 5, kCntDone = 6, kCntCand2 = 7, kCntCells = 8, kCntProbe = 9, kCntProbe2 = 10, kNumCounters = 12 };
 
 struct Plan {
   std::vector<int32_t> cbegin, nsamp, ncand;
@@ -165,6 +165,8 @@ struct kvm_ctx {
 
   DevBuf arena, qarena, counters, wl_off, wl_ex, wl_ex2, region_count, tile_prefix;
   DevBuf cand_off, cand_mean, cand_std, ans_off, ans_dist;
+  DevBuf cand_lb;  // Keogh totals beside cand_* (between the two probe stages)
+  int dtw_final_counter = 9;  // counter that holds the candidates handed to the band DTW (kCntProbe / kCntProbe2)
   DevBuf cand2_off, cand2_mean, cand2_std, cand2_lb;  // survivors of the lower bounds (same capacity as cand_*) + their Keogh totals
   // data envelope of the resident shard for one Sakoe-Chiba radius (lower / upper, laid out like series_buf): built at
   // the first DTW call with that radius, dropped when a series is loaded
@@ -414,6 +416,7 @@ int ensure_cands(kvm_ctx* ctx, long long cap) {
   KVM_CUDA(ctx, ctx->cand2_mean.ensure(sizeof(double) * cap));
   KVM_CUDA(ctx, ctx->cand2_std.ensure(sizeof(double) * cap));
   KVM_CUDA(ctx, ctx->cand2_lb.ensure(sizeof(double) * cap));
+  KVM_CUDA(ctx, ctx->cand_lb.ensure(sizeof(double) * cap));
   ctx->cand_cap = cap;
   return KVM_OK;
 }
@@ -1458,7 +1461,7 @@ int verify_norm_stream(kvm_ctx* ctx, Mode mode, const double* q, int m, double e
   if (!dtw) out->n_exact = (int64_t)cnt[kCntFlag];
   else {
     out->n_lb_pass = (int64_t)cnt[kCntCand2];
-    out->n_exact = (int64_t)cnt[kCntProbe];  // DTW engines: candidates that reached the band DTW (after the corner probe)
+    out->n_exact = (int64_t)cnt[ctx->dtw_final_counter];  // DTW engines: candidates that reached the band DTW (after the corner probe)
   }
   out->n_dtw_cells = (int64_t)cnt[kCntCells];
   return fetch_answers(ctx, (long long)cnt[kCntAnswers], out);
@@ -1566,14 +1569,35 @@ int launch_dtw(kvm_ctx* ctx, const DtwParams& D_in) {
       PP.uq = D.uq;
       PP.lq = D.lq;
       PP.eps2_hi = D.eps2_hi;
-      PP.in = D.in;
-      PP.out = CandList{ctx->cand_off.as<int32_t>(), ctx->cand_mean.as<double>(), ctx->cand_std.as<double>(),
-                        ctx->counters.as<unsigned long long>() + kCntProbe, ctx->cand_cap};
       PP.n_cells = D.n_cells;
       static const int probe_min = env_int("KVM_DTW_PROBE_MIN", 4096);  // developer knob
       PP.min_count = probe_min;
-      kvm::dtw_probe_kernel<<<ctx->n_sms * 8, kvm::kProbeWarps * 32, 0, ctx->stream>>>(PP);
-      KVM_CUDA(ctx, cudaGetLastError());
+      unsigned long long* counters = ctx->counters.as<unsigned long long>();
+      const CandList first_list{ctx->cand_off.as<int32_t>(), ctx->cand_mean.as<double>(), ctx->cand_std.as<double>(),
+                                counters + kCntProbe, ctx->cand_cap, ctx->cand_lb.as<double>()};
+      static const int two_stage = env_int("KVM_DTW_PROBE64", 1);  // developer knob
+      if (two_stage && K >= 96) {
+        // wide bands: the 64 x 64 sub-square first, two candidates per warp; its survivors through the full square
+        PP.in = D.in;
+        PP.out = first_list;
+        PP.handed_on = counters + 11;  // (a free counter slot, zeroed with the others)
+        kvm::dtw_probe64_kernel<<<ctx->n_sms * 8, kvm::kProbeWarps * 32, 0, ctx->stream>>>(PP);
+        KVM_CUDA(ctx, cudaGetLastError());
+        PP.in = first_list;
+        PP.out = CandList{ctx->cand2_off.as<int32_t>(), ctx->cand2_mean.as<double>(), ctx->cand2_std.as<double>(),
+                          counters + kCntProbe2, ctx->cand_cap};
+        PP.skip_sub = 1;
+        PP.min_count = 0;  // (a short list was already handed on by the first stage; what arrives here is probed)
+        kvm::dtw_probe_kernel<<<ctx->n_sms * 8, kvm::kProbeWarps * 32, 0, ctx->stream>>>(PP);
+        KVM_CUDA(ctx, cudaGetLastError());
+        ctx->dtw_final_counter = kCntProbe2;
+      } else {
+        PP.in = D.in;
+        PP.out = first_list;
+        kvm::dtw_probe_kernel<<<ctx->n_sms * 8, kvm::kProbeWarps * 32, 0, ctx->stream>>>(PP);
+        KVM_CUDA(ctx, cudaGetLastError());
+        ctx->dtw_final_counter = kCntProbe;
+      }
       D.in = PP.out;
     }
   }
@@ -1720,7 +1744,7 @@ void kvm_destroy(kvm_ctx* ctx) {
                    &ctx->ans_off, &ctx->ans_dist, &ctx->seg_b, &ctx->seg_first, &ctx->seg_last, &ctx->chain_count,
                    &ctx->chain_prefix, &ctx->run_key, &ctx->run_b, &ctx->run_first, &ctx->run_last, &ctx->sarena,
                    &ctx->need_bits, &ctx->chain_last, &ctx->flagged, &ctx->x_off, &ctx->x_ex, &ctx->x_ex2, &ctx->bmax,
-                   &ctx->cand2_lb, &ctx->env_lo, &ctx->env_up, &ctx->g_send, &ctx->g_recv};
+                   &ctx->cand2_lb, &ctx->cand_lb, &ctx->env_lo, &ctx->env_up, &ctx->g_send, &ctx->g_recv};
   for (DevBuf* b : dev) b->release();
   kvm_comm_release(ctx);
   ctx->g_hsend.release();
