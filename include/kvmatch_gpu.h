@@ -218,6 +218,31 @@ int kvm_intervals_first_segment(const int32_t* lr, const double* eps, int64_t k,
                                 int32_t n, int32_t delta_w, int32_t* lr_out, double* eps_out, int64_t cap, int64_t* k_out,
                                 double* min_eps);
 
+/* The same tail for the cNSM engines (K/NormQueryEngine.java, K/NormQueryEngineDtw.java): an interval carries the lower
+ * and (DTW engine) upper sums of the segments seen so far (K/common/NormInterval.java exLower / ex2Lower / exUpper /
+ * ex2Upper, in blocks of w0 points) and the bit set of beta partitions its index rows fell into.
+ *   kvm_norm_intervals_sort_merge     mode 0 = sortButNotMergeIntervals         K/NormQueryEngine.java:788-823 (Dtw :926-967)
+ *                                     mode 1 = sortButNotMergeIntervalsAndCount  :825-869 (Dtw :969-1019)
+ *                                     mode 2 = sortAndMergeIntervals             :871-896 (Dtw :1021-1046), handed to phase 2
+ *   kvm_norm_intervals_intersect      CS ∩ CS_i with the beta-partition and variance filters (ENABLE_BETA_PARTITION,
+ *                                     ENABLE_STD_FILTER), shifted by delta_w; pre_length = blocks covered so far;
+ *                                     dtw = 0: NormQueryEngine :333-397, dtw = 1: NormQueryEngineDtw :349-425
+ *   kvm_norm_intervals_first_segment  the first segment's positions clamped to window starts in [1, n-length+1]
+ *                                     :313-332 (Dtw :326-348) */
+typedef struct kvm_norm_interval {
+  int32_t left, right;
+  double ex_lower, ex2_lower;
+  double ex_upper, ex2_upper; /* DTW engine only; zero otherwise */
+  int64_t beta_partitions;
+} kvm_norm_interval;
+int kvm_norm_intervals_sort_merge(const kvm_norm_interval* in, int64_t k, int32_t mode, kvm_norm_interval* out, int64_t cap,
+                                  int64_t* k_out, int64_t* cnt_disjoint, int64_t* cnt_offsets);
+int kvm_norm_intervals_intersect(const kvm_norm_interval* cs, int64_t k1, const kvm_norm_interval* csi, int64_t k2,
+                                 int32_t pre_length, int32_t w0, int32_t query_length, double mean_q, double std_q, double alpha,
+                                 double beta, int32_t delta_w, int32_t dtw, kvm_norm_interval* out, int64_t cap, int64_t* k_out);
+int kvm_norm_intervals_first_segment(const kvm_norm_interval* in, int64_t k, int32_t order, int32_t w0, int32_t length, int32_t n,
+                                     int32_t delta_w, kvm_norm_interval* out, int64_t cap, int64_t* k_out);
+
 /* ---- several GPUs behind one handle (one process) -------------------------------------------------
  * The series is sharded by offset range: device d owns window starts [d*per+1, (d+1)*per] (per = ceil(n / n_dev)
  * rounded up to a multiple of `grid`) and holds `halo` more samples behind them.  Every interval is verified by the

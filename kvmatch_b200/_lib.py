@@ -39,6 +39,7 @@ EXPORTS = [
     "kvm_result_free", "kvm_runs_free",
     "kvm_multi_create", "kvm_multi_destroy", "kvm_multi_last_error", "kvm_multi_devices", "kvm_multi_load_series_host",
     "kvm_multi_verify", "kvm_comm_unique_id", "kvm_comm_init", "kvm_gather_result", "kvm_comm_ipc_handle", "kvm_comm_ipc_attach", "kvm_intervals_sort_merge", "kvm_intervals_intersect", "kvm_intervals_first_segment",
+    "kvm_norm_intervals_sort_merge", "kvm_norm_intervals_intersect", "kvm_norm_intervals_first_segment",
 ]
 KVM_ENGINE_ED, KVM_ENGINE_CNSM_ED, KVM_ENGINE_DTW, KVM_ENGINE_CNSM_DTW = 0, 1, 2, 3
 
@@ -148,6 +149,11 @@ def load():
     L.kvm_intervals_intersect.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_int64, C.c_double, C.c_int32, vp, vp, C.c_int64, i64p, f64p]
     L.kvm_intervals_first_segment.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp,
                                               C.c_int64, i64p, f64p]
+    L.kvm_norm_intervals_sort_merge.argtypes = [vp, C.c_int64, C.c_int32, vp, C.c_int64, i64p, i64p, i64p]
+    L.kvm_norm_intervals_intersect.argtypes = [vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                               C.c_double, C.c_double, C.c_int32, C.c_int32, vp, C.c_int64, i64p]
+    L.kvm_norm_intervals_first_segment.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int64,
+                                                   i64p]
     L.kvm_multi_create.argtypes = [C.POINTER(vp), vp, C.c_int32]
     L.kvm_multi_destroy.argtypes = [vp]
     L.kvm_multi_destroy.restype = None

@@ -109,4 +109,150 @@ inline double first_segment(const std::vector<Iv>& pos, int32_t order, int32_t w
   return min_eps;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// cNSM variants (K/NormQueryEngine.java:313-397, 788-896; K/NormQueryEngineDtw.java:326-425, 926-1046): an interval carries
+// the lower (and, for DTW, upper) sums of the segments seen so far, in blocks of w0 points, and the bit set of beta
+// partitions its rows fell into (K/common/NormInterval.java).  Layout = kvm_norm_interval.
+struct NormIv {
+  int32_t left, right;
+  double ex, ex2;    // exLower, ex2Lower
+  double exu, ex2u;  // exUpper, ex2Upper (DTW engine; zero in the ED engine)
+  int64_t bp;
+};
+
+// Double.compare(a, b) == 0: same value with the same sign of zero, or both NaN
+inline bool jcompare_eq(double a, double b) {
+  if (a != a || b != b) return a != a && b != b;
+  return a == b && std::signbit(a) == std::signbit(b);
+}
+// Double.compare(a, b) <= 0 (NaN sorts above everything, -0.0 below +0.0)
+inline bool jcompare_le(double a, double b) {
+  if (a != a) return b != b;
+  if (b != b) return true;
+  if (a < b) return true;
+  if (a > b) return false;
+  return !(std::signbit(b) && !std::signbit(a));
+}
+
+// mode 0: sortButNotMergeIntervals (:788-823 / Dtw :926-967)          merge overlaps, or neighbours with bit-equal LOWER sums
+// mode 1: sortButNotMergeIntervalsAndCount (:825-869 / Dtw :969-1019)  the same + the two counts of the phase-2 time estimate
+// mode 2: sortAndMergeIntervals (:871-896 / Dtw :1021-1046)            merge overlaps and neighbours; sums and partitions dropped
+// (a merged interval keeps the MINIMUM of every sum, the upper ones included: Dtw :949-950)
+inline void norm_sort_merge(std::vector<NormIv>& v, int mode, std::vector<NormIv>& out, int64_t* cnt_disjoint, int64_t* cnt_offsets) {
+  out.clear();
+  if (cnt_disjoint) *cnt_disjoint = (int64_t)v.size();
+  if (cnt_offsets) *cnt_offsets = v.empty() ? 0 : (int64_t)v[0].right - v[0].left + 1;
+  if (v.size() <= 1) {
+    out = v;
+    return;
+  }
+  std::stable_sort(v.begin(), v.end(), [](const NormIv& a, const NormIv& b) { return a.left < b.left; });
+  NormIv cur = v[0];
+  int64_t disjoint = (int64_t)v.size(), offsets = 0;
+  auto emit = [&]() {
+    out.push_back(mode == 2 ? NormIv{cur.left, cur.right, 0.0, 0.0, 0.0, 0.0, 0} : cur);
+    offsets += (int64_t)cur.right - cur.left + 1;
+  };
+  for (size_t i = 1; i < v.size(); i++) {
+    const NormIv& c = v[i];
+    const int64_t gap = (int64_t)c.left - 1;
+    if (gap <= cur.right) disjoint--;
+    const bool merge = (mode == 2) ? (gap <= cur.right)
+                                   : (gap < cur.right || (gap == cur.right && jcompare_eq(c.ex, cur.ex) && jcompare_eq(c.ex2, cur.ex2)));
+    if (merge) {
+      cur.right = std::max(c.right, cur.right);
+      cur.ex = std::min(c.ex, cur.ex);  // (Math.min; the sums are finite products of row keys)
+      cur.ex2 = std::min(c.ex2, cur.ex2);
+      cur.exu = std::min(c.exu, cur.exu);
+      cur.ex2u = std::min(c.ex2u, cur.ex2u);
+      cur.bp |= c.bp;
+    } else {
+      emit();
+      cur = c;
+    }
+  }
+  emit();
+  if (cnt_disjoint) *cnt_disjoint = disjoint;
+  if (cnt_offsets) *cnt_offsets = offsets;
+}
+
+// CS ∩ CS_i (:333-397 / Dtw :349-425) with ENABLE_BETA_PARTITION and ENABLE_STD_FILTER: an overlap survives when the two
+// sides share a beta partition and the smallest variance any window with these block sums can have stays within
+// (alpha * stdQ)^2.  pre_length = blocks of w0 points covered by the segments so far (this one included).  dtw = the
+// DTW engine's form: the same test from the lower sums, then — overwriting it — from the upper sums.
+inline void norm_intersect(const std::vector<NormIv>& cs, const std::vector<NormIv>& csi, int32_t pre_length, int32_t w0,
+                           int32_t query_length, double mean_q, double std_q, double alpha, double beta, int32_t delta_w, bool dtw,
+                           std::vector<NormIv>& out) {
+  out.clear();
+  const double limit = alpha * alpha * std_q * std_q;
+  size_t i1 = 0, i2 = 0;
+  while (i1 < cs.size() && i2 < csi.size()) {
+    const NormIv& a = cs[i1];
+    const NormIv& b = csi[i2];
+    if (a.right < b.left) {
+      i1++;
+    } else if (b.right < a.left) {
+      i2++;
+    } else {
+      const int64_t common = a.bp & b.bp;
+      if (common == 0) {
+        if (a.right < b.right) i1++; else i2++;
+        continue;
+      }
+      const double rest = query_length - pre_length * 1.0 * w0;
+      const double sum_ex = a.ex + b.ex, sum_ex2 = a.ex2 + b.ex2;
+      double sum_exu = 0.0, sum_ex2u = 0.0;
+      double mean = sum_ex / pre_length;
+      double std2 = 0.0;
+      if (mean > mean_q + beta) {
+        const double nv = mean_q + beta - (mean - mean_q - beta) * pre_length * w0 / rest;
+        mean = mean_q + beta;
+        std2 = (sum_ex2 * w0 + (query_length - pre_length * w0) * nv * nv) / query_length - mean * mean;
+      }
+      if (dtw) {
+        sum_exu = a.exu + b.exu;
+        sum_ex2u = a.ex2u + b.ex2u;
+        double mean_u = sum_exu / pre_length;
+        if (mean_u < mean_q - beta) {
+          const double nv = mean_q - beta - (mean_q - beta - mean_u) * pre_length * w0 / rest;
+          mean_u = mean_q - beta;
+          std2 = (sum_ex2u * w0 + (query_length - pre_length * w0) * nv * nv) / query_length - mean_u * mean_u;
+        }
+      }
+      const bool keep = jcompare_le(std2, limit);
+      const int32_t l = std::max(a.left, b.left) + delta_w;
+      if (a.right < b.right) {
+        if (keep) out.push_back(NormIv{l, a.right + delta_w, sum_ex, sum_ex2, sum_exu, sum_ex2u, common});
+        i1++;
+      } else {
+        if (keep) out.push_back(NormIv{l, b.right + delta_w, sum_ex, sum_ex2, sum_exu, sum_ex2u, common});
+        i2++;
+      }
+    }
+  }
+}
+
+// The first segment's positions clamped to window starts inside the series (:313-332 / Dtw :326-348).
+inline void norm_first_segment(const std::vector<NormIv>& pos, int32_t order, int32_t w0, int32_t length, int32_t n, int32_t delta_w,
+                               std::vector<NormIv>& out) {
+  out.clear();
+  const int64_t sh = (int64_t)(order - 1) * w0;
+  for (const NormIv& p : pos) {
+    NormIv o = p;
+    if ((int64_t)p.right - sh + length - 1 > n) {
+      if ((int64_t)p.left - sh + length - 1 > n) continue;
+      o.left = p.left + delta_w;
+      o.right = (int32_t)(n - length + 1 + sh + delta_w);
+    } else if ((int64_t)p.left - sh < 1) {
+      if ((int64_t)p.right - sh < 1) continue;
+      o.left = (int32_t)(1 + sh + delta_w);
+      o.right = p.right + delta_w;
+    } else {
+      o.left = p.left + delta_w;
+      o.right = p.right + delta_w;
+    }
+    out.push_back(o);
+  }
+}
+
 }  // namespace kvm_phase1

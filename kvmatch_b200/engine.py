@@ -345,6 +345,18 @@ class _EngineBase:
             return chain_intervals(s.n, m, chunk or (EPOCH - m + 1), lo=s.first, hi=hi)
         return np.asarray(valid_positions, dtype=np.int32).reshape(-1, 2)
 
+    def _phase1(self, fn, query_data, *args):
+        """Phases 0 / 1 over index file images (kvmatch_b200/phase1.py): sets valid_positions / last_segment / phase1_ms."""
+        from . import phase1
+        t0 = time.perf_counter()
+        indexes = [phase1.IndexFile(self._images[w]) for w in WU_LIST]
+        valid, last_segment, _ = getattr(phase1, fn)(query_data, *args, self.series.n, indexes)
+        self.phase1_ms = 1e3 * (time.perf_counter() - t0)
+        self.valid_positions, self.last_segment = valid, last_segment
+        if not valid:
+            self.answers = []
+        return valid, last_segment
+
     def _finish(self, statistics, res: VerifyResult, t0, t1_ms=0.0):
         t2_ms = (time.perf_counter() - t0) * 1e3
         off, dist = stable_sort_by_distance(res.offsets, res.distances)
@@ -384,7 +396,13 @@ class QueryEngine(_EngineBase):
 
 
 class NormQueryEngine(_EngineBase):
-    """cNSM-ED — phase 2 of K/NormQueryEngine.java:177 (lines 432-528)."""
+    """cNSM-ED — phase 2 of K/NormQueryEngine.java:177 (lines 432-528); query_with_index() adds phases 0 and 1
+    (phase1.phase1_norm, :190-430) over index file images."""
+
+    def query_with_index(self, statistics, query_data, epsilon, alpha, beta, index_images):
+        self._images = index_images
+        valid, last_segment = self._phase1("phase1_norm", query_data, epsilon, alpha, beta)
+        return bool(valid) and self.query(statistics, query_data, epsilon, alpha, beta, valid, last_segment)
 
     def query(self, statistics, query_data, epsilon, alpha, beta, valid_positions=None, last_segment=1, chunk=None):
         t0 = time.perf_counter()
@@ -394,7 +412,13 @@ class NormQueryEngine(_EngineBase):
 
 
 class QueryEngineDtw(_EngineBase):
-    """RSM-DTW — phase 2 of K/QueryEngineDtw.java:172 (lines 349-452)."""
+    """RSM-DTW — phase 2 of K/QueryEngineDtw.java:172 (lines 349-452); query_with_index() adds phases 0 and 1
+    (phase1.phase1_dtw, :185-347)."""
+
+    def query_with_index(self, statistics, query_data, epsilon, rho, index_images):
+        self._images = index_images
+        valid, last_segment = self._phase1("phase1_dtw", query_data, epsilon, rho)
+        return bool(valid) and self.query(statistics, query_data, epsilon, rho, valid, last_segment)
 
     def query(self, statistics, query_data, epsilon, rho, valid_positions=None, last_segment=1, chunk=None):
         t0 = time.perf_counter()
@@ -404,7 +428,13 @@ class QueryEngineDtw(_EngineBase):
 
 
 class NormQueryEngineDtw(_EngineBase):
-    """cNSM-DTW — phase 2 of K/NormQueryEngineDtw.java:190 (lines 457-603)."""
+    """cNSM-DTW — phase 2 of K/NormQueryEngineDtw.java:190 (lines 457-603); query_with_index() adds phases 0 and 1
+    (phase1.phase1_norm_dtw, :203-455)."""
+
+    def query_with_index(self, statistics, query_data, epsilon, rho, alpha, beta, index_images):
+        self._images = index_images
+        valid, last_segment = self._phase1("phase1_norm_dtw", query_data, epsilon, rho, alpha, beta)
+        return bool(valid) and self.query(statistics, query_data, epsilon, rho, alpha, beta, valid, last_segment)
 
     def query(self, statistics, query_data, epsilon, rho, alpha, beta, valid_positions=None, last_segment=1,
               chunk=None):

@@ -182,28 +182,51 @@ def _counts(stat, wu: int, mean: float, epsilon: float):
     return upper1 - lower1, upper2 - lower2
 
 
-def determine_query_plan(q, epsilon: float, stats):
-    """stats: {width: cumulative statistic table} for the widths of WU_LIST."""
-    w0 = WU_ALL[0]
-    m = len(q) // w0
+@dataclass
+class RangeQuerySegment:
+    mean_min: float
+    mean_max: float
+    order: int
+    count: int
+    wu: int
+
+
+def _block_prefix(values, w0: int):
+    """Sums of the disjoint blocks of w0 points and their running prefix (:597-606, :627-629)."""
     sums, ex = [], 0.0
-    for i, v in enumerate(q):
+    for i, v in enumerate(values):
         ex += float(v)
         if (i + 1) % w0 == 0:
             sums.append(ex)
             ex = 0.0
-    prefix = [0.0] * m
+    prefix = [0.0] * len(sums)
     prefix[0] = sums[0]
-    for i in range(1, m):
+    for i in range(1, len(sums)):
         prefix[i] = prefix[i - 1] + sums[i]
+    return prefix
+
+
+def determine_query_plan(q, epsilon: float, stats, counts=None, bounds=None):
+    """stats: {width: cumulative statistic table} for the widths of WU_LIST.  `counts(stat, wu, *means)` = the engine's
+    getCountsFromStatisticInfo (default: the RSM-ED one); the DP itself is the same in K/QueryEngine.java:398-503,
+    K/NormQueryEngine.java:593-671 and, over the block means of the query's lower / upper envelope (`bounds` = (L, U),
+    segments become RangeQuerySegments), in K/NormQueryEngineDtw.java:670-799."""
+    if counts is None:
+        counts = lambda stat, wu, mean: _counts(stat, wu, mean, epsilon)
+    w0 = WU_ALL[0]
+    m = len(q) // w0
+    prefixes = [_block_prefix(q, w0)] if bounds is None else [_block_prefix(bounds[0], w0), _block_prefix(bounds[1], w0)]
     total100 = stats[100][-1][1]
     cost, cost2 = {}, {}
+
+    def means(l, r):
+        use = w0 * (r - l + 1)
+        return [(p[r] - (p[l - 1] if l > 0 else 0.0)) / use for p in prefixes]
 
     def get_cost(l, r):
         if (l, r) not in cost:
             use = w0 * (r - l + 1)
-            mean = (prefix[r] - (prefix[l - 1] if l > 0 else 0.0)) / use
-            c1, _ = _counts(stats[use], use, mean, epsilon)
+            c1, _ = counts(stats[use], use, *means(l, r))
             cost[(l, r)] = math.log(1.0 * c1 / total100) if c1 > 0 else -math.inf
             cost2[(l, r)] = c1
         return cost[(l, r)]
@@ -233,9 +256,10 @@ def determine_query_plan(q, epsilon: float, stats):
         use = w0 * (r - l + 1)
         if use < 0:
             break
-        mean = (prefix[r] - (prefix[l - 1] if l > 0 else 0.0)) / use
         get_cost(l, r)
-        queries.append(QuerySegment(mean, l + 1, cost2[(l, r)], use))
+        mm = means(l, r)
+        queries.append(QuerySegment(mm[0], l + 1, cost2[(l, r)], use) if bounds is None
+                       else RangeQuerySegment(mm[0], mm[1], l + 1, cost2[(l, r)], use))
         index -= pre[index][i]
     queries.sort(key=lambda s: s.count)   # ENABLE_QUERY_REORDERING (stable sort)
     return queries
@@ -283,3 +307,324 @@ def phase1(q, epsilon: float, n: int, indexes):
     last_segment = queries[-1].order
     merged, _, _ = sort_merge(valid, 2)
     return [(l, r) for l, r, _ in merged], last_segment, queries
+
+
+# ---------------------------------------------------------------- cNSM-ED: phases 0 / 1 of K/NormQueryEngine.java:177-430
+NORM_IV = np.dtype([("left", "<i4"), ("right", "<i4"), ("ex", "<f8"), ("ex2", "<f8"), ("exu", "<f8"), ("ex2u", "<f8"), ("bp", "<i8")])   # = kvm_norm_interval
+BETA_PARTITION_WIDTH = 10.0   # :59
+
+
+def _norm_out(k):
+    return np.zeros(max(k, 1), dtype=NORM_IV)
+
+
+def norm_sort_merge(ivs: np.ndarray, mode: int):
+    """kvm_norm_intervals_sort_merge -> (intervals, cnt_disjoint, cnt_offsets)."""
+    L = _lib.load()
+    ivs = np.ascontiguousarray(ivs, dtype=NORM_IV)
+    out = _norm_out(len(ivs))
+    ko, cd, co = C.c_int64(), C.c_int64(), C.c_int64()
+    rc = L.kvm_norm_intervals_sort_merge(ivs.ctypes.data, len(ivs), mode, out.ctypes.data, len(out), C.byref(ko), C.byref(cd), C.byref(co))
+    if rc:
+        raise _lib.KvmError(rc, "kvm_norm_intervals_sort_merge")
+    return out[:ko.value], cd.value, co.value
+
+
+def norm_intersect(cs, csi, pre_length: int, query_length: int, mean_q: float, std_q: float, alpha: float, beta: float, delta_w: int,
+                   dtw: bool = False):
+    L = _lib.load()
+    cs, csi = np.ascontiguousarray(cs, dtype=NORM_IV), np.ascontiguousarray(csi, dtype=NORM_IV)
+    out = _norm_out(len(cs) + len(csi))
+    ko = C.c_int64()
+    rc = L.kvm_norm_intervals_intersect(cs.ctypes.data, len(cs), csi.ctypes.data, len(csi), pre_length, WU_LIST[0], query_length,
+                                        mean_q, std_q, alpha, beta, delta_w, int(dtw), out.ctypes.data, len(out), C.byref(ko))
+    if rc:
+        raise _lib.KvmError(rc, "kvm_norm_intervals_intersect")
+    return out[:ko.value]
+
+
+def norm_first_segment(pos, order: int, length: int, n: int, delta_w: int):
+    L = _lib.load()
+    pos = np.ascontiguousarray(pos, dtype=NORM_IV)
+    out = _norm_out(len(pos))
+    ko = C.c_int64()
+    rc = L.kvm_norm_intervals_first_segment(pos.ctypes.data, len(pos), order, WU_LIST[0], length, n, delta_w, out.ctypes.data, len(out),
+                                            C.byref(ko))
+    if rc:
+        raise _lib.KvmError(rc, "kvm_norm_intervals_first_segment")
+    return out[:ko.value]
+
+
+def norm_mean_range(mean: float, wu: int, epsilon: float, alpha: float, beta: float, mean_q: float, std_q: float, lo_shift=0.0, hi_shift=None):
+    """The window-mean range a segment of mean `mean` admits under (alpha, beta): the expressions of :225-231 (whole range:
+    lo_shift = 0, hi_shift = 2 beta) and :244-250 (one beta partition), operation for operation."""
+    if hi_shift is None:
+        hi_shift = 2.0 * beta
+        begin = 1.0 / alpha * mean + (1 - 1.0 / alpha) * mean_q - beta - math.sqrt(1.0 / (alpha * alpha) * std_q * std_q * epsilon * epsilon / wu)
+        begin1 = alpha * mean + (1 - alpha) * mean_q - beta - math.sqrt(alpha * alpha * std_q * std_q * epsilon * epsilon / wu)
+        end = alpha * mean + (1 - alpha) * mean_q + beta + math.sqrt(alpha * alpha * std_q * std_q * epsilon * epsilon / wu)
+        end1 = 1.0 / alpha * mean + (1 - 1.0 / alpha) * mean_q + beta + math.sqrt(1.0 / (alpha * alpha) * std_q * std_q * epsilon * epsilon / wu)
+    else:
+        begin = 1.0 / alpha * mean + (1 - 1.0 / alpha) * mean_q - beta + lo_shift - math.sqrt(1.0 / (alpha * alpha) * std_q * std_q * epsilon * epsilon / wu)
+        begin1 = alpha * mean + (1 - alpha) * mean_q - beta + lo_shift - math.sqrt(alpha * alpha * std_q * std_q * epsilon * epsilon / wu)
+        end = alpha * mean + (1 - alpha) * mean_q - beta + hi_shift + math.sqrt(alpha * alpha * std_q * std_q * epsilon * epsilon / wu)
+        end1 = 1.0 / alpha * mean + (1 - 1.0 / alpha) * mean_q - beta + hi_shift + math.sqrt(1.0 / (alpha * alpha) * std_q * std_q * epsilon * epsilon / wu)
+    return min(begin, begin1), max(end, end1)
+
+
+def _counts_norm(stat, wu: int, mean: float, epsilon: float, alpha: float, beta: float, mean_q: float, std_q: float):
+    """getCountsFromStatisticInfo :547-572 (both ends through the plain toRound)."""
+    keys = [t[0] for t in stat]
+    lo, hi = norm_mean_range(mean, wu, epsilon, alpha, beta, mean_q, std_q)
+    begin, end = to_round(lo), to_round(hi)
+
+    def search(key):
+        return min(bisect.bisect_left(keys, key), len(stat) - 1)
+    i = search(begin)
+    lower1 = stat[i - 1][1] if i > 0 else 0
+    lower2 = stat[i - 1][2] if i > 0 else 0
+    i = search(end)
+    upper1 = stat[i][1] if i > 0 else 0
+    upper2 = stat[i][2] if i > 0 else 0
+    return upper1 - lower1, upper2 - lower2
+
+
+def beta_partitions(seg: QuerySegment, epsilon: float, alpha: float, beta: float, mean_q: float, std_q: float, stat_keys):
+    """:233-254: (int)(2 beta / 10) partitions (at most 64) of the beta range, each with its own rounded mean range.  beta < 5
+    gives ZERO partitions, hence empty bit sets and — from the second segment on — an empty candidate set: the reference's
+    behaviour, kept."""
+    num = min(int(2.0 * beta / BETA_PARTITION_WIDTH), 64)
+    parts = []
+    for idx in range(num):
+        width = 2.0 * beta / num
+        lo, hi = norm_mean_range(seg.mean, seg.wu, epsilon, alpha, beta, mean_q, std_q, width * idx, width * (idx + 1))
+        parts.append((to_round_stat(lo, stat_keys), to_round(hi)))
+    return parts
+
+
+def _java_int_shl1(idx: int) -> int:
+    """`1 << idx` on a Java int (:692: the shift distance wraps at 32 and bit 31 sign-extends into the long it is or-ed to)."""
+    v = (1 << (idx & 31)) & 0xFFFFFFFF
+    return v - (1 << 32) if v & 0x80000000 else v
+
+
+def scan_index_norm(idx: IndexFile, seg: QuerySegment, begin: float, end: float, parts) -> np.ndarray:
+    """scanIndex :673-701: positions with the row's lower block sums (key * blocks, key'^2 * blocks with key' = the row's
+    upper end for negative keys) and the beta partitions the row key falls into."""
+    blocks = seg.wu // WU_ALL[0]
+    rows = idx.read_indexes(begin, end + 0.01)
+    out = np.zeros(sum(len(p) for _, p in rows), dtype=NORM_IV)
+    at = 0
+    for key, positions in rows:
+        key2 = to_upper_stat(key, idx.stat_keys) if key < 0 else key
+        bits = 0
+        for j, (p_lo, p_hi) in enumerate(parts):
+            if p_lo > key:
+                break
+            if p_lo <= key <= p_hi:
+                bits |= _java_int_shl1(j)
+        k = len(positions)
+        if k:
+            blk = out[at:at + k]
+            lr = np.asarray(positions, dtype=np.int32)
+            blk["left"], blk["right"] = lr[:, 0], lr[:, 1]
+            blk["ex"], blk["ex2"], blk["bp"] = key * blocks, key2 * key2 * blocks, bits
+            at += k
+    return out
+
+
+def query_statistics(q):
+    """Phase 0 :192-198: sequential sums."""
+    ex = ex2 = 0.0
+    for v in q:
+        v = float(v)
+        ex += v
+        ex2 += v * v
+    mean_q = ex / len(q)
+    return mean_q, math.sqrt(ex2 / len(q) - mean_q * mean_q)
+
+
+def phase1_norm(q, epsilon: float, alpha: float, beta: float, n: int, indexes):
+    """Candidate intervals of a cNSM-ED query: (valid_positions [(left, right)], last_segment, plan).  Same deviations as
+    phase1(): the index is scanned directly (the reference's incremental-visiting cache returns the same rows where its
+    five cases apply and NOTHING where they do not — a range spanning a whole cached range matches no case, :258-309) and
+    the wall-clock early termination (:410-421) is off."""
+    by_w = dict(zip(WU_LIST, indexes))
+    length = len(q)
+    mean_q, std_q = query_statistics(q)
+    queries = determine_query_plan(q, epsilon, {w: ix.stat for w, ix in by_w.items()},
+                                   counts=lambda stat, wu, mean: _counts_norm(stat, wu, mean, epsilon, alpha, beta, mean_q, std_q))
+    valid = np.zeros(0, dtype=NORM_IV)
+    pre_length = 0
+    for i, seg in enumerate(queries):
+        delta_w = 0 if i == len(queries) - 1 else (queries[i + 1].order - seg.order) * WU_LIST[0]
+        pre_length += seg.wu // WU_ALL[0]
+        ix = by_w[seg.wu]
+        lo, hi = norm_mean_range(seg.mean, seg.wu, epsilon, alpha, beta, mean_q, std_q)
+        begin, end = to_round_stat(lo, ix.stat_keys), to_round(hi)
+        parts = beta_partitions(seg, epsilon, alpha, beta, mean_q, std_q, ix.stat_keys)
+        positions, _, _ = norm_sort_merge(scan_index_norm(ix, seg, begin, end, parts), 0)
+        if i == 0:
+            nxt = norm_first_segment(positions, seg.order, length, n, delta_w)
+        else:
+            nxt = norm_intersect(valid, positions, pre_length, length, mean_q, std_q, alpha, beta, delta_w)
+        valid, _, _ = norm_sort_merge(nxt, 1)
+        if len(valid) == 0:
+            break
+    merged, _, _ = norm_sort_merge(valid, 2)
+    return [(int(l), int(r)) for l, r in zip(merged["left"], merged["right"])], queries[-1].order, queries
+
+
+# ---------------------------------------------------------------- cNSM-DTW: phases 0 / 1 of K/NormQueryEngineDtw.java:190-455
+def query_envelope_padded(q, rho: int):
+    """:673-715: the raw query padded with rho copies of its first and last value, then the sliding maximum / minimum over
+    2 rho + 1 points: U[i] = max q[i-rho .. i+rho], L[i] = min (indexes clamped into the query)."""
+    v = np.asarray(q, dtype=np.float64)
+    if rho <= 0:
+        return v.copy(), v.copy()
+    pad = np.concatenate([np.full(rho, v[0]), v, np.full(rho, v[-1])])
+    win = np.lib.stride_tricks.sliding_window_view(pad, 2 * rho + 1)
+    return win.min(axis=1), win.max(axis=1)
+
+
+def norm_mean_range_dtw(mean_min: float, mean_max: float, wu: int, epsilon: float, alpha: float, beta: float, mean_q: float, std_q: float,
+                        lo_shift=0.0, hi_shift=None):
+    """:238-244 (whole beta range) and :259-265 (one beta partition), operation for operation."""
+    if hi_shift is None:
+        begin = 1.0 / alpha * mean_min + (1 - 1.0 / alpha) * mean_q - beta - 1.0 / alpha * epsilon * std_q / math.sqrt(wu)
+        begin1 = alpha * mean_min + (1 - alpha) * mean_q - beta - alpha * epsilon * std_q / math.sqrt(wu)
+        end = alpha * mean_max + (1 - alpha) * mean_q + beta + alpha * epsilon * std_q / math.sqrt(wu)
+        end1 = 1.0 / alpha * mean_max + (1 - 1.0 / alpha) * mean_q + beta + 1.0 / alpha * epsilon * std_q / math.sqrt(wu)
+    else:
+        begin = 1.0 / alpha * mean_min + (1 - 1.0 / alpha) * mean_q - beta + lo_shift - 1.0 / alpha * epsilon * std_q / math.sqrt(wu)
+        begin1 = alpha * mean_min + (1 - alpha) * mean_q - beta + lo_shift - alpha * epsilon * std_q / math.sqrt(wu)
+        end = alpha * mean_max + (1 - alpha) * mean_q - beta + hi_shift + alpha * epsilon * std_q / math.sqrt(wu)
+        end1 = 1.0 / alpha * mean_max + (1 - 1.0 / alpha) * mean_q - beta + hi_shift + 1.0 / alpha * epsilon * std_q / math.sqrt(wu)
+    return min(begin, begin1), max(end, end1)
+
+
+def _cumulative_counts(stat, begin: float, end: float):
+    """The table lookups shared by every getCountsFromStatisticInfo (e.g. K/NormQueryEngineDtw.java:633-645)."""
+    keys = [t[0] for t in stat]
+
+    def search(key):
+        return min(bisect.bisect_left(keys, key), len(stat) - 1)
+    i = search(begin)
+    lower1 = stat[i - 1][1] if i > 0 else 0
+    lower2 = stat[i - 1][2] if i > 0 else 0
+    i = search(end)
+    upper1 = stat[i][1] if i > 0 else 0
+    upper2 = stat[i][2] if i > 0 else 0
+    return upper1 - lower1, upper2 - lower2
+
+
+def scan_index_norm_dtw(idx: IndexFile, seg: RangeQuerySegment, begin: float, end: float, parts) -> np.ndarray:
+    """scanIndex :802-833: like the ED engine's, plus the row's upper block sums (upper = the next row key)."""
+    blocks = seg.wu // WU_ALL[0]
+    rows = idx.read_indexes(begin, end + 0.01)
+    out = np.zeros(sum(len(p) for _, p in rows), dtype=NORM_IV)
+    at = 0
+    for key, positions in rows:
+        upper = to_upper_stat(key, idx.stat_keys)
+        sq_lower = upper * upper if key < 0 else key * key
+        sq_upper = key * key if upper < 0 else upper * upper
+        bits = 0
+        for j, (p_lo, p_hi) in enumerate(parts):
+            if p_lo > key:
+                break
+            if p_lo <= key <= p_hi:
+                bits |= _java_int_shl1(j)
+        k = len(positions)
+        if k:
+            blk = out[at:at + k]
+            lr = np.asarray(positions, dtype=np.int32)
+            blk["left"], blk["right"] = lr[:, 0], lr[:, 1]
+            blk["ex"], blk["ex2"], blk["exu"], blk["ex2u"], blk["bp"] = key * blocks, sq_lower * blocks, upper * blocks, sq_upper * blocks, bits
+            at += k
+    return out
+
+
+def phase1_norm_dtw(q, epsilon: float, rho: int, alpha: float, beta: float, n: int, indexes):
+    """Candidate intervals of a cNSM-DTW query: (valid_positions, last_segment, plan); deviations as in phase1_norm()."""
+    by_w = dict(zip(WU_LIST, indexes))
+    length = len(q)
+    mean_q, std_q = query_statistics(q)
+    rng = lambda a, b, wu, lo=0.0, hi=None: norm_mean_range_dtw(a, b, wu, epsilon, alpha, beta, mean_q, std_q, lo, hi)
+
+    def counts(stat, wu, mean_min, mean_max):   # getCountsFromStatisticInfo :622-646 (both ends through the plain toRound)
+        lo, hi = rng(mean_min, mean_max, wu)
+        return _cumulative_counts(stat, to_round(lo), to_round(hi))
+    queries = determine_query_plan(q, epsilon, {w: ix.stat for w, ix in by_w.items()}, counts=counts, bounds=query_envelope_padded(q, rho))
+    valid = np.zeros(0, dtype=NORM_IV)
+    pre_length = 0
+    for i, seg in enumerate(queries):
+        delta_w = 0 if i == len(queries) - 1 else (queries[i + 1].order - seg.order) * WU_LIST[0]
+        pre_length += seg.wu // WU_ALL[0]
+        ix = by_w[seg.wu]
+        lo, hi = rng(seg.mean_min, seg.mean_max, seg.wu)
+        begin, end = to_round_stat(lo, ix.stat_keys), to_round(hi)
+        num = min(int(2.0 * beta / BETA_PARTITION_WIDTH), 64)   # :246-268
+        parts = []
+        for j in range(num):
+            width = 2.0 * beta / num
+            p_lo, p_hi = rng(seg.mean_min, seg.mean_max, seg.wu, width * j, width * (j + 1))
+            parts.append((to_round_stat(p_lo, ix.stat_keys), to_round(p_hi)))
+        positions, _, _ = norm_sort_merge(scan_index_norm_dtw(ix, seg, begin, end, parts), 0)
+        if i == 0:
+            nxt = norm_first_segment(positions, seg.order, length, n, delta_w)
+        else:
+            nxt = norm_intersect(valid, positions, pre_length, length, mean_q, std_q, alpha, beta, delta_w, dtw=True)
+        valid, _, _ = norm_sort_merge(nxt, 1)
+        if len(valid) == 0:
+            break
+    merged, _, _ = norm_sort_merge(valid, 2)
+    return [(int(l), int(r)) for l, r in zip(merged["left"], merged["right"])], queries[-1].order, queries
+
+
+# ---------------------------------------------------------------- RSM-DTW: phases 0 / 1 of K/QueryEngineDtw.java:172-347
+def scan_index_dtw(idx: IndexFile, seg: RangeQuerySegment, begin: float, end: float):
+    """scanIndex :647-661 with getDistanceLowerBound :721-734: the row's mean range against the segment's mean range."""
+    out = []
+    for key, positions in idx.read_indexes(begin, end + 0.01):
+        upper = to_upper_stat(key, idx.stat_keys)
+        if key > seg.mean_max:
+            delta = (key - seg.mean_max) * (key - seg.mean_max)
+        elif upper < seg.mean_min:
+            delta = (seg.mean_min - upper) * (seg.mean_min - upper)
+        else:
+            delta = 0.0
+        out.extend((l, r, seg.wu * delta) for l, r in positions)
+    return out
+
+
+def phase1_dtw(q, epsilon: float, rho: int, n: int, indexes):
+    """Candidate intervals of an RSM-DTW query: (valid_positions, last_segment, plan).  The RSM-ED loop over segments that
+    carry the mean range of the query's envelope; the interval algebra is the same (kvm_intervals_*)."""
+    by_w = dict(zip(WU_LIST, indexes))
+    length = len(q)
+
+    def counts(stat, wu, mean_min, mean_max):   # getCountsFromStatisticInfo :471-491
+        rng = epsilon / math.sqrt(wu)
+        return _cumulative_counts(stat, to_round(mean_min - rng), to_round(mean_max + rng))
+    queries = determine_query_plan(q, epsilon, {w: ix.stat for w, ix in by_w.items()}, counts=counts, bounds=query_envelope_padded(q, rho))
+    valid = []
+    last_min = 0.0
+    range0 = epsilon * epsilon
+    for i, seg in enumerate(queries):
+        delta_w = 0 if i == len(queries) - 1 else (queries[i + 1].order - seg.order) * WU_LIST[0]
+        ix = by_w[seg.wu]
+        if last_min > range0:   # :210
+            last_min = 0.0
+        rng = math.sqrt((range0 - last_min) / seg.wu)
+        begin = to_round_stat(seg.mean_min - rng, ix.stat_keys)
+        end = to_round(seg.mean_max + rng)
+        positions, _, _ = sort_merge(scan_index_dtw(ix, seg, begin, end), 0)
+        if i == 0:
+            nxt, last_min = first_segment(positions, seg.order, length, n, delta_w)
+        else:
+            nxt, last_min = intersect(valid, positions, range0, delta_w)
+        valid, _, _ = sort_merge(nxt, 1)
+        if not valid:
+            break
+    merged, _, _ = sort_merge(valid, 2)
+    return [(l, r) for l, r, _ in merged], queries[-1].order, queries

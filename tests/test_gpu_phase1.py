@@ -63,3 +63,50 @@ def test_query_plan_is_a_set_of_disjoint_windows(world):
             end = order + wu // 25 - 1
         assert end == length // 25      # the reconstruction starts from the query's last full block
         assert [seg.count for seg in plan] == sorted(seg.count for seg in plan)  # ENABLE_QUERY_REORDERING
+
+
+@pytest.mark.parametrize("off,length,eps,alpha,beta", [(123456, 1024, 5.0, 1.5, 5.0), (500_000, 512, 3.0, 1.2, 5.0), (777_000, 2048, 8.0, 2.0, 10.0)])
+def test_cnsm_ed_index_pruned_query_equals_full_scan(world, oracle, off, length, eps, alpha, beta):
+    """The cNSM-ED engine end to end (K/NormQueryEngine.java:177-545): phases 0 / 1 with beta partitions and the variance
+    filter over the GPU-built indexes, phase 2 on the GPU.  Bit-exact against the oracle on the same candidate list;
+    the same answer offsets as a full scan (no false dismissals)."""
+    import kvmatch_b200
+    s, g, images = world
+    q = s[off - 1:off - 1 + length].copy()
+    eng = kvmatch_b200.NormQueryEngine(g)
+    stats = [kvmatch_b200.StatisticInfo() for _ in range(6)]
+    assert eng.query_with_index(stats, q, eps, alpha, beta, images) is True
+    shift = (eng.last_segment - 1) * 25
+    same_list = oracle.verify_cnsm_ed(s, q, eps, alpha, beta, eng.valid_positions, shift)
+    assert eng.last.offsets.tolist() == same_list.offsets.tolist() and eng.last.distances.tolist() == same_list.distances.tolist()
+    full = oracle.verify_cnsm_ed(s, q, eps, alpha, beta, [(1, len(s) - length + 1)])
+    assert eng.last.offsets.tolist() == full.offsets.tolist() and off in full.offsets.tolist()
+    assert sum(r - l + 1 for l, r in eng.valid_positions) < len(s)
+    assert eng.answers[0][0] == off
+
+
+@pytest.mark.parametrize("off,length,eps,rho", [(123456, 512, 12.0, 25), (640_000, 1024, 30.0, 51)])
+def test_rsm_dtw_index_pruned_query_equals_full_scan(world, oracle, off, length, eps, rho):
+    import kvmatch_b200
+    s, g, images = world
+    q = s[off - 1:off - 1 + length].copy()
+    eng = kvmatch_b200.QueryEngineDtw(g)
+    assert eng.query_with_index(None, q, eps, rho, images) is True
+    full = oracle.verify_dtw(s, q, eps, rho, [(1, len(s) - length + 1)])
+    assert eng.last.offsets.tolist() == full.offsets.tolist() and eng.last.distances.tolist() == full.distances.tolist()
+    assert eng.answers[0] == (off, 0.0)
+    assert sum(r - l + 1 for l, r in eng.valid_positions) < 0.5 * len(s)
+
+
+@pytest.mark.parametrize("off,length,eps,rho,alpha,beta", [(123456, 512, 3.0, 25, 1.5, 5.0), (500_000, 1024, 5.0, 51, 1.2, 5.0)])
+def test_cnsm_dtw_index_pruned_query_equals_full_scan(world, oracle, off, length, eps, rho, alpha, beta):
+    import kvmatch_b200
+    s, g, images = world
+    q = s[off - 1:off - 1 + length].copy()
+    eng = kvmatch_b200.NormQueryEngineDtw(g)
+    assert eng.query_with_index(None, q, eps, rho, alpha, beta, images) is True
+    shift = (eng.last_segment - 1) * 25
+    same_list = oracle.verify_cnsm_dtw(s, q, eps, rho, alpha, beta, eng.valid_positions, shift)
+    assert eng.last.offsets.tolist() == same_list.offsets.tolist() and eng.last.distances.tolist() == same_list.distances.tolist()
+    full = oracle.verify_cnsm_dtw(s, q, eps, rho, alpha, beta, [(1, len(s) - length + 1)])
+    assert eng.last.offsets.tolist() == full.offsets.tolist() and off in full.offsets.tolist()
