@@ -199,6 +199,10 @@ int kvm_build_index_file(kvm_ctx* ctx, int32_t w, const char* path, kvm_index_in
 int kvm_index_image_from_runs(const double* keys, const int32_t* first, const int32_t* last, int64_t n_runs,
                               unsigned char** image, kvm_index_info* info);
 void kvm_image_free(unsigned char* image);
+/* The reader's half (host only): the (left, right) pairs of ONE index row from its compact bytes, the 8-byte key
+ * excluded (IndexNode.parseBytesCompact, K/common/entity/IndexNode.java:108-128).  *k_out is always set; KVM_E_ARG if
+ * the row holds more than `cap` pairs (row_bytes / 2 always suffices), KVM_E_RANGE on a truncated row. */
+int kvm_index_row_positions(const unsigned char* row, int64_t row_bytes, int32_t* lr_out, int64_t cap, int64_t* k_out);
 
 /* ---- phase-1 tail on the host (no ctx, no GPU): the interval algebra between index probing and verification, on
  * plain arrays so that the candidate list reaches kvm_verify_* without boxed Java lists.  Intervals are (left, right)

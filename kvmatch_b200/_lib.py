@@ -35,7 +35,7 @@ EXPORTS = [
     "kvm_abi_version", "kvm_create", "kvm_destroy", "kvm_last_error", "kvm_set_option", "kvm_load_series_host",
     "kvm_load_series_file",
     "kvm_verify_ed", "kvm_verify_cnsm_ed", "kvm_verify_dtw", "kvm_verify_cnsm_dtw", "kvm_verify_cnsm_ed_batch", "kvm_scan_ucr_dtw", "kvm_scan_ucr_ed",
-    "kvm_envelope", "kvm_window_mean_runs", "kvm_window_mean_runs_all", "kvm_build_index_file", "kvm_index_image_from_runs", "kvm_image_free",
+    "kvm_envelope", "kvm_window_mean_runs", "kvm_window_mean_runs_all", "kvm_build_index_file", "kvm_index_image_from_runs", "kvm_image_free", "kvm_index_row_positions",
     "kvm_result_free", "kvm_runs_free",
     "kvm_multi_create", "kvm_multi_destroy", "kvm_multi_last_error", "kvm_multi_devices", "kvm_multi_load_series_host",
     "kvm_multi_verify", "kvm_comm_unique_id", "kvm_comm_init", "kvm_gather_result", "kvm_comm_ipc_handle", "kvm_comm_ipc_attach", "kvm_intervals_sort_merge", "kvm_intervals_intersect", "kvm_intervals_first_segment",
@@ -140,6 +140,7 @@ def load():
     L.kvm_index_image_from_runs.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(KvmIndexInfo)]
     L.kvm_image_free.argtypes = [vp]
     L.kvm_image_free.restype = None
+    L.kvm_index_row_positions.argtypes = [vp, C.c_int64, vp, C.c_int64, C.POINTER(C.c_int64)]
     L.kvm_result_free.argtypes = [vp, R]
     L.kvm_result_free.restype = None
     L.kvm_runs_free.argtypes = [vp, C.POINTER(KvmRuns)]

@@ -99,6 +99,35 @@ inline void append_compact(std::vector<unsigned char>& f, const Iv* p, size_t n)
   }
 }
 
+// IndexNode.parseBytesCompact (:108-128): the inverse of append_compact over one row's bytes (the key excluded).
+// Returns the number of (left, right) pairs, written to lr_out while they fit `cap`; -1 on a truncated row.
+inline int64_t parse_compact(const unsigned char* b, int64_t nb, int32_t* lr_out, int64_t cap) {
+  int64_t k = 0, idx = 0;
+  auto put = [&](int32_t l, int32_t r) {
+    if (k < cap) {
+      lr_out[2 * k] = l;
+      lr_out[2 * k + 1] = r;
+    }
+    ++k;
+  };
+  while (idx < nb) {
+    if (idx + 6 > nb) return -1;
+    int32_t left = (int32_t)(((uint32_t)b[idx] << 24) | ((uint32_t)b[idx + 1] << 16) | ((uint32_t)b[idx + 2] << 8) | (uint32_t)b[idx + 3]);
+    const int count = (int)(b[idx + 4] ^ 0x80);  // (signed byte) + 128
+    int32_t right = left + (int32_t)(b[idx + 5] ^ 0x80);
+    idx += 6;
+    put(left, right);
+    if (idx + 2 * (int64_t)count > nb) return -1;
+    for (int j = 0; j < count; j++) {
+      left = right + (int32_t)(b[idx] ^ 0x80);
+      right = left + (int32_t)(b[idx + 1] ^ 0x80);
+      idx += 2;
+      put(left, right);
+    }
+  }
+  return k;
+}
+
 struct ImageInfo {
   int32_t rows_step1 = 0, rows = 0;
   int64_t intervals = 0, offsets = 0;

@@ -3002,6 +3002,14 @@ int kvm_index_image_from_runs(const double* keys, const int32_t* first, const in
   return KVM_OK;
 }
 
+int kvm_index_row_positions(const unsigned char* row, int64_t row_bytes, int32_t* lr_out, int64_t cap, int64_t* k_out) {
+  if (!row || row_bytes < 0 || !k_out || (cap > 0 && !lr_out) || cap < 0) return KVM_E_ARG;
+  const int64_t k = kvm_index::parse_compact(row, row_bytes, lr_out, cap);
+  *k_out = k < 0 ? 0 : k;
+  if (k < 0) return KVM_E_RANGE;
+  return k > cap ? KVM_E_ARG : KVM_OK;
+}
+
 void kvm_image_free(unsigned char* image) { std::free(image); }
 
 int kvm_build_index_file(kvm_ctx* ctx, int32_t w, const char* path, kvm_index_info* info) {

@@ -146,7 +146,17 @@ inline void norm_sort_merge(std::vector<NormIv>& v, int mode, std::vector<NormIv
     out = v;
     return;
   }
-  std::stable_sort(v.begin(), v.end(), [](const NormIv& a, const NormIv& b) { return a.left < b.left; });
+  // List.sort(comparingInt(getLeft)) is a stable merge sort.  The lists are millions of 48-byte intervals at n = 1e8:
+  // already sorted ones (every intersection output) are left alone, the others are ordered through (left, position)
+  // pairs — unique keys, so any sort of them is the stable order — and gathered once.
+  if (!std::is_sorted(v.begin(), v.end(), [](const NormIv& a, const NormIv& b) { return a.left < b.left; })) {
+    std::vector<uint64_t> key(v.size());
+    for (size_t i = 0; i < v.size(); i++) key[i] = ((uint64_t)((uint32_t)v[i].left ^ 0x80000000u) << 32) | (uint64_t)i;
+    std::sort(key.begin(), key.end());
+    std::vector<NormIv> sorted(v.size());
+    for (size_t i = 0; i < v.size(); i++) sorted[i] = v[(size_t)(key[i] & 0xffffffffu)];
+    v.swap(sorted);
+  }
   NormIv cur = v[0];
   int64_t disjoint = (int64_t)v.size(), offsets = 0;
   auto emit = [&]() {

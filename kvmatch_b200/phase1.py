@@ -58,6 +58,8 @@ class IndexFile:
 
     def __init__(self, data: bytes):
         self.data = data
+        self._buf = np.frombuffer(data, dtype=np.uint8)      # (keeps the bytes addressable for the library's row decoder)
+        self._base = self._buf.ctypes.data
         n = len(data)
         last = struct.unpack(">i", data[n - 4:n])[0]                   # readOffsetInfo :52-62
         self.offsets = list(struct.unpack(f">{(n - last) // 4}i", data[last:n]))
@@ -72,33 +74,36 @@ class IndexFile:
         with open(path, "rb") as f:
             return cls(f.read())
 
+    def row_array(self, i: int):
+        """(key, int32 array [k, 2] of (left, right)) of row i: IndexNode.parseBytesCompact, K/common/entity/IndexNode.java:108-128.
+        A group is [left i32][count][right - left] followed by `count` (gap, width) byte pairs, every byte stored as
+        value - 128 (a signed Java byte); decoded by the library (kvm_index_row_positions, csrc/index_file.hpp)."""
+        lo, hi = self.offsets[i], self.offsets[i + 1]
+        key = struct.unpack(">d", self.data[lo:lo + 8])[0]
+        nb = hi - lo - 8
+        out = np.empty((max(nb // 2, 1), 2), dtype=np.int32)
+        k = C.c_int64()
+        rc = _lib.load().kvm_index_row_positions(self._base + lo + 8, nb, out.ctypes.data, len(out), C.byref(k))
+        if rc:
+            raise _lib.KvmError(rc, "kvm_index_row_positions")
+        return key, out[:k.value]
+
     def row(self, i: int):
-        """(key, [(left, right), ...]) of row i: IndexNode.parseBytesCompact, K/common/entity/IndexNode.java:108-128."""
-        b = self.data[self.offsets[i]:self.offsets[i + 1]]
-        key = struct.unpack(">d", b[:8])[0]
-        v = memoryview(b)[8:]
-        out = []
-        idx = 0
-        while idx < len(v):
-            left = struct.unpack(">i", v[idx:idx + 4])[0]
-            idx += 4
-            count = int.from_bytes(v[idx:idx + 1], "big", signed=True) + 128
-            idx += 1
-            right = left + int.from_bytes(v[idx:idx + 1], "big", signed=True) + 128
-            idx += 1
-            out.append((left, right))
-            for _ in range(count):
-                left = right + int.from_bytes(v[idx:idx + 1], "big", signed=True) + 128
-                right = left + int.from_bytes(v[idx + 1:idx + 2], "big", signed=True) + 128
-                idx += 2
-                out.append((left, right))
-        return key, out
+        """(key, [(left, right), ...]) of row i."""
+        key, arr = self.row_array(i)
+        return key, [tuple(p) for p in arr.tolist()]
 
     def read_indexes(self, key_from: float, key_to: float):
         """readIndexes :64-83: rows with key_from <= key <= key_to (lowerBound / upperBound on the row keys)."""
         lo = bisect.bisect_left(self.keys, key_from)
         hi = bisect.bisect_right(self.keys, key_to) - 1
         return [self.row(i) for i in range(lo, hi + 1)] if lo < self.n_rows and hi >= 0 else []
+
+    def read_index_arrays(self, key_from: float, key_to: float):
+        """read_indexes with the positions as int32 arrays (the cNSM scans fill structured arrays from them)."""
+        lo = bisect.bisect_left(self.keys, key_from)
+        hi = bisect.bisect_right(self.keys, key_to) - 1
+        return [self.row_array(i) for i in range(lo, hi + 1)] if lo < self.n_rows and hi >= 0 else []
 
 
 # ---------------------------------------------------------------- interval algebra: the library's host functions
@@ -412,7 +417,7 @@ def scan_index_norm(idx: IndexFile, seg: QuerySegment, begin: float, end: float,
     """scanIndex :673-701: positions with the row's lower block sums (key * blocks, key'^2 * blocks with key' = the row's
     upper end for negative keys) and the beta partitions the row key falls into."""
     blocks = seg.wu // WU_ALL[0]
-    rows = idx.read_indexes(begin, end + 0.01)
+    rows = idx.read_index_arrays(begin, end + 0.01)
     out = np.zeros(sum(len(p) for _, p in rows), dtype=NORM_IV)
     at = 0
     for key, positions in rows:
@@ -426,8 +431,7 @@ def scan_index_norm(idx: IndexFile, seg: QuerySegment, begin: float, end: float,
         k = len(positions)
         if k:
             blk = out[at:at + k]
-            lr = np.asarray(positions, dtype=np.int32)
-            blk["left"], blk["right"] = lr[:, 0], lr[:, 1]
+            blk["left"], blk["right"] = positions[:, 0], positions[:, 1]
             blk["ex"], blk["ex2"], blk["bp"] = key * blocks, key2 * key2 * blocks, bits
             at += k
     return out
@@ -521,7 +525,7 @@ def _cumulative_counts(stat, begin: float, end: float):
 def scan_index_norm_dtw(idx: IndexFile, seg: RangeQuerySegment, begin: float, end: float, parts) -> np.ndarray:
     """scanIndex :802-833: like the ED engine's, plus the row's upper block sums (upper = the next row key)."""
     blocks = seg.wu // WU_ALL[0]
-    rows = idx.read_indexes(begin, end + 0.01)
+    rows = idx.read_index_arrays(begin, end + 0.01)
     out = np.zeros(sum(len(p) for _, p in rows), dtype=NORM_IV)
     at = 0
     for key, positions in rows:
@@ -537,8 +541,7 @@ def scan_index_norm_dtw(idx: IndexFile, seg: RangeQuerySegment, begin: float, en
         k = len(positions)
         if k:
             blk = out[at:at + k]
-            lr = np.asarray(positions, dtype=np.int32)
-            blk["left"], blk["right"] = lr[:, 0], lr[:, 1]
+            blk["left"], blk["right"] = positions[:, 0], positions[:, 1]
             blk["ex"], blk["ex2"], blk["exu"], blk["ex2u"], blk["bp"] = key * blocks, sq_lower * blocks, upper * blocks, sq_upper * blocks, bits
             at += k
     return out

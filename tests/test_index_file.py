@@ -127,3 +127,30 @@ def test_oracle_agrees_on_hand_cases(oracle):
     assert got == exp
     dec, _ = decode_image(exp)
     assert sum(b - a + 1 for _, pos in dec for a, b in pos) == len(s) - w + 1
+
+
+def test_library_row_decoder_matches_independent_decoder():
+    """kvm_index_row_positions (the reader's half, used by kvmatch_b200/phase1.IndexFile) against decode_image above, plus its
+    error behaviour: capacity too small -> KVM_E_ARG with the count reported, truncated row -> KVM_E_RANGE."""
+    import ctypes as C
+    from kvmatch_b200 import phase1
+    s = datagen.generate(150_000, seed=21)
+    from oracle import kvm_oracle
+    image = kvm_oracle.index_file_image(s, 50)[0]
+    rows, table = decode_image(image)
+    ix = phase1.IndexFile(image)
+    assert ix.n_rows == len(rows) and [tuple(t) for t in ix.stat] == table
+    for i, (key, pos) in enumerate(rows):
+        k2, arr = ix.row_array(i)
+        assert k2 == key and arr.dtype == np.int32 and [tuple(p) for p in arr.tolist()] == pos
+    L = _lib.load()
+    lo, hi = ix.offsets[0] + 8, ix.offsets[1]
+    row = np.frombuffer(image, dtype=np.uint8)[lo:hi].copy()
+    k = C.c_int64()
+    out = np.zeros((1, 2), dtype=np.int32)
+    n_pos = len(rows[0][1])
+    assert n_pos > 1
+    assert L.kvm_index_row_positions(row.ctypes.data, len(row), out.ctypes.data, 1, C.byref(k)) == _lib.KVM_E_ARG and k.value == n_pos
+    assert tuple(out[0]) == rows[0][1][0]
+    assert L.kvm_index_row_positions(row.ctypes.data, len(row) - 1, out.ctypes.data, 1, C.byref(k)) == _lib.KVM_E_RANGE
+    assert L.kvm_index_row_positions(row.ctypes.data, 0, out.ctypes.data, 1, C.byref(k)) == 0 and k.value == 0

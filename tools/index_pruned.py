@@ -1,0 +1,66 @@
+"""BASELINE configs[1] (ii): INDEX-PRUNED cNSM-ED queries — the reference's whole query() with phase 2 on the GPU.
+
+Builds the five KV-indexes of one n-sample series on the GPU (one fused window-mean pass + host step 2 / file image),
+then for each seeded query: phases 0 / 1 on the host (kvmatch_b200/phase1.phase1_norm over kvm_norm_intervals_* and the
+library's row decoder), phase 2 on the GPU over the resulting interval list (kvm_verify_cnsm_ed with
+shift = (lastSegment - 1) * 25), and the same query as an index-free full scan for comparison.  Checks: the index-pruned
+answer offsets equal the full scan's (no false dismissals).  Writes a markdown table.
+
+usage: python tools/index_pruned.py [n=1e8] [queries=4] [eps=5] [out=gpurun_out/index_pruned_r02.md]
+"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import kvmatch_b200, bench
+from kvmatch_b200 import datagen, phase1
+
+n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
+n_q = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+eps = float(sys.argv[3]) if len(sys.argv) > 3 else bench.EPSILON
+out = sys.argv[4] if len(sys.argv) > 4 else "gpurun_out/index_pruned_r02.md"
+m = bench.M
+s = datagen.generate_range(n, 0, n, bench.SEED)
+g = kvmatch_b200.GpuSeries(0)
+g.load(s)
+t0 = time.perf_counter()
+images = kvmatch_b200.IndexBuilder(g).build_all()
+build_s = time.perf_counter() - t0
+t0 = time.perf_counter()
+indexes = [phase1.IndexFile(images[w]) for w in phase1.WU_LIST]
+open_s = time.perf_counter() - t0
+full_iv = datagen.chain_intervals(n, m, bench.DEFAULT_CHUNK)
+rows = []
+for off in bench.query_offsets(n, m, bench.N_QUERIES)[:n_q]:
+    q = s[off - 1:off - 1 + m].copy()
+    t0 = time.perf_counter()
+    valid, last_segment, plan = phase1.phase1_norm(q, eps, bench.ALPHA, bench.BETA, n, indexes)
+    t1_ms = 1e3 * (time.perf_counter() - t0)
+    iv = np.asarray(valid, dtype=np.int32).reshape(-1, 2)
+    shift = (last_segment - 1) * 25
+    g.verify_cnsm_ed(q, eps, bench.ALPHA, bench.BETA, iv, shift)
+    t0 = time.perf_counter()
+    r = g.verify_cnsm_ed(q, eps, bench.ALPHA, bench.BETA, iv, shift)
+    t2_ms = 1e3 * (time.perf_counter() - t0)
+    g.verify_cnsm_ed(q, eps, bench.ALPHA, bench.BETA, full_iv)
+    t0 = time.perf_counter()
+    f = g.verify_cnsm_ed(q, eps, bench.ALPHA, bench.BETA, full_iv)
+    tf_ms = 1e3 * (time.perf_counter() - t0)
+    assert r.offsets.tolist() == f.offsets.tolist(), off
+    assert off in r.offsets.tolist(), off
+    lens = iv[:, 1] - iv[:, 0] + 1
+    row = (off, len(plan), last_segment, t1_ms, len(iv), int(lens.sum()), int(lens.max()), r.kernel_ms, t2_ms, f.kernel_ms, tf_ms, r.count)
+    rows.append(row)
+    print(row, flush=True)
+with open(out, "w") as fh:
+    fh.write(f"# Index-pruned cNSM-ED queries (BASELINE configs[1] (ii)), n = {n}, m = {m}, eps = {eps}, alpha = {bench.ALPHA}, beta = {bench.BETA} (round 2)\n\n"
+             f"`python tools/index_pruned.py {n} {n_q} {eps}` on one B200.  Index build (five widths: one fused window-mean pass on the GPU, "
+             f"runs to the host, step 2 + file images on the host): {build_s:.2f} s, {sum(len(b) for b in images.values()) / 1e6:.0f} MB of index files; "
+             f"opening them (offset + statistic tables): {open_s:.2f} s.  T_1 = phases 0 / 1 on ONE host core (plan DP, index range scans, "
+             f"`kvm_norm_intervals_*`); T_2 = `kvm_verify_cnsm_ed` over the phase-1 interval list with host buffers (wall) and its CUDA-event "
+             f"kernel time; full scan = the same query over every window start (chains of {bench.DEFAULT_CHUNK}).  Every row: index-pruned answer "
+             f"offsets == full-scan answer offsets.\n\n"
+             "| query offset | segments | lastSegment | T_1 host ms | intervals | candidates | longest interval | T_2 kernel ms | T_2 wall ms | full-scan kernel ms | full-scan wall ms | answers |\n"
+             "|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+    for r in rows:
+        fh.write(f"| {r[0]} | {r[1]} | {r[2]} | {r[3]:.0f} | {r[4]} | {r[5]} ({100.0 * r[5] / n:.1f} % of n) | {r[6]} | {r[7]:.3f} | {r[8]:.3f} | {r[9]:.3f} | {r[10]:.3f} | {r[11]} |\n")
+print(open(out).read())
