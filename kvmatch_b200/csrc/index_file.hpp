@@ -146,19 +146,44 @@ inline bool build_image(const double* keys, const int32_t* first, const int32_t*
     std::memcpy(&u, &d, 8);
     return (d != d) ? 0x7ff8000000000000ULL : u;  // Double.equals: NaNs are one key
   };
-  std::unordered_map<uint64_t, int32_t> id_of;
-  id_of.reserve(1 << 14);
+  // open addressing on the key bits (a node-based map costs 30 ns per run here; this one 5): slot = id + 1, 0 = empty
+  int cap_bits = 12;
+  size_t cap = (size_t)1 << cap_bits;
+  std::vector<uint64_t> slot_key(cap);
+  std::vector<int32_t> slot_id(cap, 0);
   std::vector<int32_t> run_id((size_t)n_runs);
   std::vector<double> id_key;
   std::vector<int64_t> id_count;
+  auto slot_of = [&](uint64_t b) {
+    size_t h = (size_t)((b * 0x9E3779B97F4A7C15ULL) >> (64 - cap_bits));  // the product's top bits
+    while (slot_id[h] != 0 && slot_key[h] != b) h = (h + 1) & (cap - 1);
+    return h;
+  };
   for (int64_t r = 0; r < n_runs; r++) {
-    auto it = id_of.emplace(bits_of(keys[r]), (int32_t)id_key.size());
-    if (it.second) {
+    const uint64_t b = bits_of(keys[r]);
+    size_t h = slot_of(b);
+    if (slot_id[h] == 0) {
+      if (2 * (id_key.size() + 1) > cap) {  // keep the load under one half
+        cap_bits += 2;
+        cap = (size_t)1 << cap_bits;
+        slot_key.assign(cap, 0);
+        slot_id.assign(cap, 0);
+        for (size_t i = 0; i < id_key.size(); i++) {
+          const uint64_t bi = bits_of(id_key[i]);
+          const size_t hi = slot_of(bi);
+          slot_key[hi] = bi;
+          slot_id[hi] = (int32_t)i + 1;
+        }
+        h = slot_of(b);
+      }
+      slot_key[h] = b;
+      slot_id[h] = (int32_t)id_key.size() + 1;
       id_key.push_back(keys[r]);
       id_count.push_back(0);
     }
-    run_id[(size_t)r] = it.first->second;
-    id_count[(size_t)it.first->second]++;
+    const int32_t id = slot_id[h] - 1;
+    run_id[(size_t)r] = id;
+    id_count[(size_t)id]++;
   }
   const size_t n_ids = id_key.size();
   std::vector<int32_t> by_key(n_ids);

@@ -2777,39 +2777,40 @@ int kvm_window_mean_runs_all(kvm_ctx* ctx, const int32_t* widths, int32_t n_widt
     if (attempt == 5) return fail(ctx, KVM_E_OOM, "run buffers kept overflowing");
   }
   // ---- host: stitch the warps' slices in position order, resolve the ambiguous windows with the reference's
-  // arithmetic, merge equal neighbours, split at 255 positions (K/IndexBuilder.java:268, MAXIMUM_DIFF - 1)
-  std::vector<int2> runs;
-  std::vector<int> seg_off, seg_cnt;
-  std::vector<int32_t> x_off;
-  std::vector<double> x_ex;
-  for (int q = 0; q < n_widths; q++) {
-    kvm_ctx::WmeanSlot& S = ctx->wm[q];
-    const long long n_runs = (long long)cnt[3 * q], n_x = (long long)cnt[3 * q + 2];
-    runs.resize((size_t)n_runs);
-    seg_off.resize(n_segs);
-    seg_cnt.resize(n_segs);
-    x_off.resize((size_t)n_x);
-    x_ex.resize((size_t)n_x);
-    KVM_CUDA(ctx, cudaMemcpyAsync(runs.data(), S.runs.p, sizeof(int2) * (size_t)n_runs, cudaMemcpyDeviceToHost, ctx->stream));
-    KVM_CUDA(ctx, cudaMemcpyAsync(seg_off.data(), S.seg_off.p, sizeof(int) * n_segs, cudaMemcpyDeviceToHost, ctx->stream));
-    KVM_CUDA(ctx, cudaMemcpyAsync(seg_cnt.data(), S.seg_cnt.p, sizeof(int) * n_segs, cudaMemcpyDeviceToHost, ctx->stream));
-    if (n_x) {
-      KVM_CUDA(ctx, cudaMemcpyAsync(x_off.data(), S.x_off.p, sizeof(int32_t) * (size_t)n_x, cudaMemcpyDeviceToHost, ctx->stream));
-      KVM_CUDA(ctx, cudaMemcpyAsync(x_ex.data(), S.x_ex.p, sizeof(double) * (size_t)n_x, cudaMemcpyDeviceToHost, ctx->stream));
+  // arithmetic, merge equal neighbours, split at 255 positions (K/IndexBuilder.java:268, MAXIMUM_DIFF - 1).  The widths
+  // are independent: each one is stitched on its own host thread while the next one's runs are still being copied.
+  struct WmHost {
+    std::vector<int2> runs;
+    std::vector<int> seg_off, seg_cnt;
+    std::vector<int32_t> x_off;
+    std::vector<double> x_ex;
+    int bad_pos = -1;  // an ambiguous window the re-walk did not deliver
+  };
+  std::vector<WmHost> host((size_t)n_widths);
+  std::vector<std::thread> workers;
+  struct Joiner {
+    std::vector<std::thread>& w;
+    ~Joiner() {
+      for (std::thread& t : w)
+        if (t.joinable()) t.join();
     }
-    KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  } joiner{workers};
+  auto stitch = [&](int q) {
+    kvm_ctx::WmeanSlot& S = ctx->wm[q];
+    WmHost& H = host[(size_t)q];
     const int w = widths[q];
+    const size_t n_x = H.x_off.size();
     // exact buckets of the ambiguous windows: b = floor(2 * fl(fl(ex / w) * 10)), K/utils/MeanIntervalUtils.java:51-61
-    std::vector<std::pair<int32_t, int>> exact((size_t)n_x);
-    for (long long i = 0; i < n_x; i++) {
-      const double v = (x_ex[i] / (double)w) * 10.0;
-      exact[i] = {x_off[i] - 1, (int)std::floor(v + v)};  // position = loc - 1
+    std::vector<std::pair<int32_t, int>> exact(n_x);
+    for (size_t i = 0; i < n_x; i++) {
+      const double v = (H.x_ex[i] / (double)w) * 10.0;
+      exact[i] = {H.x_off[i] - 1, (int)std::floor(v + v)};  // position = loc - 1
     }
     std::sort(exact.begin(), exact.end());
     S.keys.clear();
     S.first.clear();
     S.last.clear();
-    const size_t est = (size_t)n_runs + (size_t)n_win[q] / 255 + 16;
+    const size_t est = H.runs.size() + (size_t)n_win[q] / 255 + 16;
     S.keys.reserve(est);
     S.first.reserve(est);
     S.last.reserve(est);
@@ -2828,16 +2829,18 @@ int kvm_window_mean_runs_all(kvm_ctx* ctx, const int32_t* widths, int32_t n_widt
     int64_t cur_first = 0;
     size_t xi = 0;
     for (size_t sg = 0; sg < n_segs; sg++) {
-      const int c = seg_cnt[sg];
+      const int c = H.seg_cnt[sg];
       if (c <= 0) continue;
-      const int2* r = runs.data() + seg_off[sg];
+      const int2* r = H.runs.data() + H.seg_off[sg];
       for (int i = 0; i < c; i++) {
         int b = r[i].y;
         const int pos = r[i].x;
         if (b == kvm::kAmbiguous) {
           while (xi < exact.size() && exact[xi].first < pos) xi++;
-          if (xi >= exact.size() || exact[xi].first != pos)
-            return fail(ctx, KVM_E_CUDA, "window-mean pass: ambiguous window %d of width %d was not re-walked", pos, w);
+          if (xi >= exact.size() || exact[xi].first != pos) {
+            H.bad_pos = pos;
+            return;
+          }
           b = exact[xi].second;
         }
         if (open && b == cur_b) continue;  // same key as the run before: one run
@@ -2855,7 +2858,30 @@ int kvm_window_mean_runs_all(kvm_ctx* ctx, const int32_t* widths, int32_t n_widt
     outs[q].kernel_ms = kernel_ms;
     outs[q].n_launches = launches;
     outs[q].reserved = (int32_t)std::min<unsigned long long>(cnt[3 * q + 1], INT32_MAX);  // epochs re-walked exactly
+  };
+  for (int q = 0; q < n_widths; q++) {
+    kvm_ctx::WmeanSlot& S = ctx->wm[q];
+    WmHost& H = host[(size_t)q];
+    const long long n_runs = (long long)cnt[3 * q], n_x = (long long)cnt[3 * q + 2];
+    H.runs.resize((size_t)n_runs);
+    H.seg_off.resize(n_segs);
+    H.seg_cnt.resize(n_segs);
+    H.x_off.resize((size_t)n_x);
+    H.x_ex.resize((size_t)n_x);
+    KVM_CUDA(ctx, cudaMemcpyAsync(H.runs.data(), S.runs.p, sizeof(int2) * (size_t)n_runs, cudaMemcpyDeviceToHost, ctx->stream));
+    KVM_CUDA(ctx, cudaMemcpyAsync(H.seg_off.data(), S.seg_off.p, sizeof(int) * n_segs, cudaMemcpyDeviceToHost, ctx->stream));
+    KVM_CUDA(ctx, cudaMemcpyAsync(H.seg_cnt.data(), S.seg_cnt.p, sizeof(int) * n_segs, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_x) {
+      KVM_CUDA(ctx, cudaMemcpyAsync(H.x_off.data(), S.x_off.p, sizeof(int32_t) * (size_t)n_x, cudaMemcpyDeviceToHost, ctx->stream));
+      KVM_CUDA(ctx, cudaMemcpyAsync(H.x_ex.data(), S.x_ex.p, sizeof(double) * (size_t)n_x, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    KVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    workers.emplace_back(stitch, q);
   }
+  for (std::thread& t : workers) t.join();
+  for (int q = 0; q < n_widths; q++)
+    if (host[(size_t)q].bad_pos >= 0)
+      return fail(ctx, KVM_E_CUDA, "window-mean pass: ambiguous window %d of width %d was not re-walked", host[(size_t)q].bad_pos, widths[q]);
   return KVM_OK;
 }
 

@@ -255,18 +255,20 @@ class GpuSeries:
         self._check(self._L.kvm_envelope(self._h, r, first, length, lo.ctypes.data, up.ctypes.data))
         return lo, up
 
-    def window_mean_runs_all(self, widths=WU_LIST):
+    def window_mean_runs_all(self, widths=WU_LIST, copy=True):
         """kvm_window_mean_runs_all: every width of an index build in ONE pass over the series.  Returns WindowMeanRuns
-        with per-width (keys, first, last) tuples, the device time of the whole pass and the run / re-walk counts."""
+        with per-width (keys, first, last) tuples, the device time of the whole pass and the run / re-walk counts.
+        copy=False hands out views of the library's buffers (valid until the next window-mean call on this series)."""
         ws = np.ascontiguousarray(widths, dtype=np.int32)
         arr = (_lib.KvmRuns * len(ws))()
         self._check(self._L.kvm_window_mean_runs_all(self._h, ws.ctypes.data, len(ws), arr))
+        take = (lambda a: a.copy()) if copy else (lambda a: a)
         per = []
         for r in arr:
             c = r.count
-            per.append((np.ctypeslib.as_array(r.keys, shape=(c,)).copy() if c else np.zeros(0),
-                        np.ctypeslib.as_array(r.first, shape=(c,)).copy() if c else np.zeros(0, np.int32),
-                        np.ctypeslib.as_array(r.last, shape=(c,)).copy() if c else np.zeros(0, np.int32)))
+            per.append((take(np.ctypeslib.as_array(r.keys, shape=(c,))) if c else np.zeros(0),
+                        take(np.ctypeslib.as_array(r.first, shape=(c,))) if c else np.zeros(0, np.int32),
+                        take(np.ctypeslib.as_array(r.last, shape=(c,))) if c else np.zeros(0, np.int32)))
         return WindowMeanRuns([int(w) for w in ws], per, float(arr[0].kernel_ms), int(arr[0].n_launches),
                               int(sum(r.count for r in arr)), int(sum(r.reserved for r in arr)))
 
@@ -463,8 +465,11 @@ class IndexBuilder:
     def build_all(self, widths=WU_LIST):
         """The whole index build for every width (K/IndexBuilder.java:98-120): ONE window-mean pass on the GPU
         (kvm_window_mean_runs_all), then step 2 and the file image per width on the host.  Returns {w: file bytes}."""
-        res = self.series.window_mean_runs_all(widths)
-        return {w: _lib.index_image_from_runs(k, f, l)[0] for w, (k, f, l) in zip(res.widths, res.runs)}
+        res = self.series.window_mean_runs_all(widths, copy=False)   # consumed right here
+        from concurrent.futures import ThreadPoolExecutor   # the widths are independent; the library call drops the GIL
+        with ThreadPoolExecutor(max_workers=len(res.widths)) as pool:
+            images = list(pool.map(lambda kfl: _lib.index_image_from_runs(*kfl)[0], res.runs))
+        return dict(zip(res.widths, images))
 
     def build_rows(self, w: int):
         """{key: [(first, last), ...]} — what the reference's indexNodeMap holds after step 1."""
