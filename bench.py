@@ -531,8 +531,46 @@ def window_mean_block(kvmatch_b200, peak):
                         "roofline": {"bound": "hbm", "kernel": "window_mean_stream_kernel", "unit": "GB/s", "peak": peak,
                                      "achieved": (8.0 * n + 16.0 * res.n_runs) / (ms * 1e-3) / 1e9,
                                      "frac": (8.0 * n + 16.0 * res.n_runs) / (ms * 1e-3) / 1e9 / peak}}
+        if n == N_CFG2:  # BASELINE configs[1] (ii): the whole index-pruned query on this series
+            try:
+                out["index_pruned_n1e8"] = index_pruned_block(kvmatch_b200, g, s, n)
+            except Exception as e:
+                out["index_pruned_n1e8"] = {"error": repr(e)}
         g.close()
     return out
+
+
+def index_pruned_block(kvmatch_b200, g, s, n, n_queries=3):
+    """The reference's whole query() for cNSM-ED: the five indexes built from the fused window-mean pass (+ host step 2 and
+    file images), phases 0 / 1 on one host core (kvmatch_b200/phase1.py over kvm_norm_intervals_*), phase 2 on the GPU over
+    the phase-1 interval list; beside it the same query as a full scan, whose answer offsets it must reproduce."""
+    from kvmatch_b200 import phase1
+    t0 = time.perf_counter()
+    images = kvmatch_b200.IndexBuilder(g).build_all()
+    build_s = time.perf_counter() - t0
+    indexes = [phase1.IndexFile(images[w]) for w in phase1.WU_LIST]
+    full_iv = datagen.chain_intervals(n, M, DEFAULT_CHUNK)
+    rows = []
+    for off in query_offsets(n, M, N_QUERIES)[:n_queries]:
+        q = query_of(n, off, M)
+        t0 = time.perf_counter()
+        valid, last_segment, plan = phase1.phase1_norm(q, EPSILON, ALPHA, BETA, n, indexes)
+        t1_ms = 1e3 * (time.perf_counter() - t0)
+        iv = np.asarray(valid, dtype=np.int32).reshape(-1, 2)
+        shift = (last_segment - 1) * 25
+        g.verify_cnsm_ed(q, EPSILON, ALPHA, BETA, iv, shift)
+        t0 = time.perf_counter()
+        r = g.verify_cnsm_ed(q, EPSILON, ALPHA, BETA, iv, shift)
+        t2_ms = 1e3 * (time.perf_counter() - t0)
+        g.verify_cnsm_ed(q, EPSILON, ALPHA, BETA, full_iv)
+        f = g.verify_cnsm_ed(q, EPSILON, ALPHA, BETA, full_iv)
+        lens = iv[:, 1] - iv[:, 0] + 1
+        rows.append({"query_offset": int(off), "segments": len(plan), "last_segment": int(last_segment), "phase1_host_ms": t1_ms,
+                     "intervals": int(len(iv)), "candidates": int(lens.sum()), "longest_interval": int(lens.max()),
+                     "phase2_kernel_ms": r.kernel_ms, "phase2_wall_ms": t2_ms, "full_scan_kernel_ms": f.kernel_ms,
+                     "answers": int(r.count), "same_answer_offsets_as_full_scan": bool(r.offsets.tolist() == f.offsets.tolist())})
+    return {"index_build_s": build_s, "index_bytes": int(sum(len(b) for b in images.values())), "queries": rows,
+            "note": "phase 1 = one host core; incremental index visiting and wall-clock early termination off (DESIGN 1, row f1)"}
 
 
 if __name__ == "__main__":
