@@ -2965,45 +2965,53 @@ int kvm_intervals_first_segment(const int32_t* lr, const double* eps, int64_t k,
 // ---- the same tail for the cNSM engines (K/NormQueryEngine.java:313-397, 788-896 and NormQueryEngineDtw.java:326-426,
 // 926-1046): kvm_norm_interval = kvm_phase1::NormIv
 static_assert(sizeof(kvm_norm_interval) == sizeof(kvm_phase1::NormIv) && sizeof(kvm_norm_interval) == 48, "kvm_norm_interval layout");
-static void to_nivs(const kvm_norm_interval* in, int64_t k, std::vector<kvm_phase1::NormIv>& v) {
-  v.resize((size_t)k);
-  for (int64_t i = 0; i < k; i++) v[i] = kvm_phase1::NormIv{in[i].left, in[i].right, in[i].ex_lower, in[i].ex2_lower, in[i].ex_upper, in[i].ex2_upper, in[i].beta_partitions};
-}
-static int from_nivs(const std::vector<kvm_phase1::NormIv>& v, kvm_norm_interval* out, int64_t cap, int64_t* k_out) {
-  *k_out = (int64_t)v.size();
-  if ((int64_t)v.size() > cap) return KVM_E_ARG;
-  for (size_t i = 0; i < v.size(); i++) out[i] = kvm_norm_interval{v[i].left, v[i].right, v[i].ex, v[i].ex2, v[i].exu, v[i].ex2u, v[i].bp};
-  return KVM_OK;
-}
-
 int kvm_norm_intervals_sort_merge(const kvm_norm_interval* in, int64_t k, int32_t mode, kvm_norm_interval* out, int64_t cap,
                                   int64_t* k_out, int64_t* cnt_disjoint, int64_t* cnt_offsets) {
-  if (k < 0 || (k > 0 && !in) || !out || !k_out || mode < 0 || mode > 2) return KVM_E_ARG;
-  std::vector<kvm_phase1::NormIv> v, o;
-  to_nivs(in, k, v);
-  kvm_phase1::norm_sort_merge(v, mode, o, cnt_disjoint, cnt_offsets);
-  return from_nivs(o, out, cap, k_out);
+  if (k < 0 || (k > 0 && !in) || !out || !k_out || mode < 0 || mode > 2 || k > (int64_t)0xffffffffLL) return KVM_E_ARG;
+  // same layout (static_assert above): the lists are read and written in place, no staging copies
+  const kvm_phase1::NormIv* v = reinterpret_cast<const kvm_phase1::NormIv*>(in);
+  int64_t n_out = 0;
+  kvm_phase1::norm_sort_merge_core(
+      v, (size_t)k, mode,
+      [&](const kvm_phase1::NormIv& x) {
+        if (n_out < cap) out[n_out] = kvm_norm_interval{x.left, x.right, x.ex, x.ex2, x.exu, x.ex2u, x.bp};
+        n_out++;
+      },
+      cnt_disjoint, cnt_offsets);
+  *k_out = n_out;
+  return n_out > cap ? KVM_E_ARG : KVM_OK;
 }
+
+// (writes results straight into the caller's array; counts on past `cap`)
+struct NormSink {
+  kvm_norm_interval* out;
+  int64_t cap, n = 0;
+  void operator()(const kvm_phase1::NormIv& x) {
+    if (n < cap) out[n] = kvm_norm_interval{x.left, x.right, x.ex, x.ex2, x.exu, x.ex2u, x.bp};
+    n++;
+  }
+};
 
 int kvm_norm_intervals_intersect(const kvm_norm_interval* cs, int64_t k1, const kvm_norm_interval* csi, int64_t k2, int32_t pre_length,
                                  int32_t w0, int32_t query_length, double mean_q, double std_q, double alpha, double beta,
                                  int32_t delta_w, int32_t dtw, kvm_norm_interval* out, int64_t cap, int64_t* k_out) {
   if (k1 < 0 || k2 < 0 || (k1 > 0 && !cs) || (k2 > 0 && !csi) || !out || !k_out || pre_length < 1 || w0 < 1 || query_length < 1)
     return KVM_E_ARG;
-  std::vector<kvm_phase1::NormIv> a, b, o;
-  to_nivs(cs, k1, a);
-  to_nivs(csi, k2, b);
-  kvm_phase1::norm_intersect(a, b, pre_length, w0, query_length, mean_q, std_q, alpha, beta, delta_w, dtw != 0, o);
-  return from_nivs(o, out, cap, k_out);
+  NormSink sink{out, cap};
+  kvm_phase1::norm_intersect_core(reinterpret_cast<const kvm_phase1::NormIv*>(cs), (size_t)k1,
+                                  reinterpret_cast<const kvm_phase1::NormIv*>(csi), (size_t)k2, pre_length, w0, query_length, mean_q,
+                                  std_q, alpha, beta, delta_w, dtw != 0, sink);
+  *k_out = sink.n;
+  return sink.n > cap ? KVM_E_ARG : KVM_OK;
 }
 
 int kvm_norm_intervals_first_segment(const kvm_norm_interval* in, int64_t k, int32_t order, int32_t w0, int32_t length, int32_t n,
                                      int32_t delta_w, kvm_norm_interval* out, int64_t cap, int64_t* k_out) {
   if (k < 0 || (k > 0 && !in) || !out || !k_out) return KVM_E_ARG;
-  std::vector<kvm_phase1::NormIv> v, o;
-  to_nivs(in, k, v);
-  kvm_phase1::norm_first_segment(v, order, w0, length, n, delta_w, o);
-  return from_nivs(o, out, cap, k_out);
+  NormSink sink{out, cap};
+  kvm_phase1::norm_first_segment_core(reinterpret_cast<const kvm_phase1::NormIv*>(in), (size_t)k, order, w0, length, n, delta_w, sink);
+  *k_out = sink.n;
+  return sink.n > cap ? KVM_E_ARG : KVM_OK;
 }
 
 int kvm_index_image_from_runs(const double* keys, const int32_t* first, const int32_t* last, int64_t n_runs,

@@ -138,33 +138,48 @@ inline bool jcompare_le(double a, double b) {
 // mode 1: sortButNotMergeIntervalsAndCount (:825-869 / Dtw :969-1019)  the same + the two counts of the phase-2 time estimate
 // mode 2: sortAndMergeIntervals (:871-896 / Dtw :1021-1046)            merge overlaps and neighbours; sums and partitions dropped
 // (a merged interval keeps the MINIMUM of every sum, the upper ones included: Dtw :949-950)
-inline void norm_sort_merge(std::vector<NormIv>& v, int mode, std::vector<NormIv>& out, int64_t* cnt_disjoint, int64_t* cnt_offsets) {
-  out.clear();
-  if (cnt_disjoint) *cnt_disjoint = (int64_t)v.size();
-  if (cnt_offsets) *cnt_offsets = v.empty() ? 0 : (int64_t)v[0].right - v[0].left + 1;
-  if (v.size() <= 1) {
-    out = v;
+// `emit(const NormIv&)` receives the result in order; the input is read in place (no copy): already sorted lists (every
+// intersection output) are walked directly, the others through a permutation from a stable LSD radix sort of
+// (left, position) pairs — the lists are millions of 48-byte intervals at n = 1e8 and this is where T_1 goes.
+template <class Emit>
+inline void norm_sort_merge_core(const NormIv* v, size_t n, int mode, Emit&& emit_out, int64_t* cnt_disjoint, int64_t* cnt_offsets) {
+  if (cnt_disjoint) *cnt_disjoint = (int64_t)n;
+  if (cnt_offsets) *cnt_offsets = n == 0 ? 0 : (int64_t)v[0].right - v[0].left + 1;
+  if (n <= 1) {  // returned as is
+    if (n == 1) emit_out(v[0]);
     return;
   }
-  // List.sort(comparingInt(getLeft)) is a stable merge sort.  The lists are millions of 48-byte intervals at n = 1e8:
-  // already sorted ones (every intersection output) are left alone, the others are ordered through (left, position)
-  // pairs — unique keys, so any sort of them is the stable order — and gathered once.
-  if (!std::is_sorted(v.begin(), v.end(), [](const NormIv& a, const NormIv& b) { return a.left < b.left; })) {
-    std::vector<uint64_t> key(v.size());
-    for (size_t i = 0; i < v.size(); i++) key[i] = ((uint64_t)((uint32_t)v[i].left ^ 0x80000000u) << 32) | (uint64_t)i;
-    std::sort(key.begin(), key.end());
-    std::vector<NormIv> sorted(v.size());
-    for (size_t i = 0; i < v.size(); i++) sorted[i] = v[(size_t)(key[i] & 0xffffffffu)];
-    v.swap(sorted);
+  // List.sort(comparingInt(getLeft)) is a stable merge sort
+  bool sorted = true;
+  for (size_t i = 1; i < n && sorted; i++) sorted = v[i - 1].left <= v[i].left;
+  std::vector<uint64_t> key;
+  if (!sorted) {
+    key.resize(n);
+    std::vector<uint64_t> tmp(n);
+    for (size_t i = 0; i < n; i++) key[i] = ((uint64_t)((uint32_t)v[i].left ^ 0x80000000u) << 32) | (uint64_t)i;
+    for (int pass = 0; pass < 3; pass++) {  // bits 32..42, 43..53, 54..63 of the key: stable, so equal lefts keep their order
+      const int shift = 32 + 11 * pass, bits = pass == 2 ? 10 : 11;
+      const uint64_t mask = ((uint64_t)1 << bits) - 1;
+      std::vector<size_t> count(((size_t)1 << bits) + 1, 0);
+      for (size_t i = 0; i < n; i++) count[((key[i] >> shift) & mask) + 1]++;
+      for (size_t b = 1; b < count.size(); b++) count[b] += count[b - 1];
+      for (size_t i = 0; i < n; i++) tmp[count[(key[i] >> shift) & mask]++] = key[i];
+      key.swap(tmp);
+    }
   }
-  NormIv cur = v[0];
-  int64_t disjoint = (int64_t)v.size(), offsets = 0;
+  auto at = [&](size_t i) -> const NormIv& { return sorted ? v[i] : v[(size_t)(key[i] & 0xffffffffu)]; };
+  NormIv cur = at(0);
+  int64_t disjoint = (int64_t)n, offsets = 0;
   auto emit = [&]() {
-    out.push_back(mode == 2 ? NormIv{cur.left, cur.right, 0.0, 0.0, 0.0, 0.0, 0} : cur);
+    if (mode == 2) {
+      emit_out(NormIv{cur.left, cur.right, 0.0, 0.0, 0.0, 0.0, 0});
+    } else {
+      emit_out(cur);
+    }
     offsets += (int64_t)cur.right - cur.left + 1;
   };
-  for (size_t i = 1; i < v.size(); i++) {
-    const NormIv& c = v[i];
+  for (size_t i = 1; i < n; i++) {
+    const NormIv& c = at(i);
     const int64_t gap = (int64_t)c.left - 1;
     if (gap <= cur.right) disjoint--;
     const bool merge = (mode == 2) ? (gap <= cur.right)
@@ -186,17 +201,22 @@ inline void norm_sort_merge(std::vector<NormIv>& v, int mode, std::vector<NormIv
   if (cnt_offsets) *cnt_offsets = offsets;
 }
 
+inline void norm_sort_merge(const std::vector<NormIv>& v, int mode, std::vector<NormIv>& out, int64_t* cnt_disjoint, int64_t* cnt_offsets) {
+  out.clear();
+  norm_sort_merge_core(v.data(), v.size(), mode, [&](const NormIv& x) { out.push_back(x); }, cnt_disjoint, cnt_offsets);
+}
+
 // CS ∩ CS_i (:333-397 / Dtw :349-425) with ENABLE_BETA_PARTITION and ENABLE_STD_FILTER: an overlap survives when the two
 // sides share a beta partition and the smallest variance any window with these block sums can have stays within
 // (alpha * stdQ)^2.  pre_length = blocks of w0 points covered by the segments so far (this one included).  dtw = the
 // DTW engine's form: the same test from the lower sums, then — overwriting it — from the upper sums.
-inline void norm_intersect(const std::vector<NormIv>& cs, const std::vector<NormIv>& csi, int32_t pre_length, int32_t w0,
-                           int32_t query_length, double mean_q, double std_q, double alpha, double beta, int32_t delta_w, bool dtw,
-                           std::vector<NormIv>& out) {
-  out.clear();
+template <class Emit>
+inline void norm_intersect_core(const NormIv* cs, size_t n1, const NormIv* csi, size_t n2, int32_t pre_length, int32_t w0,
+                                int32_t query_length, double mean_q, double std_q, double alpha, double beta, int32_t delta_w, bool dtw,
+                                Emit&& emit_out) {
   const double limit = alpha * alpha * std_q * std_q;
   size_t i1 = 0, i2 = 0;
-  while (i1 < cs.size() && i2 < csi.size()) {
+  while (i1 < n1 && i2 < n2) {
     const NormIv& a = cs[i1];
     const NormIv& b = csi[i2];
     if (a.right < b.left) {
@@ -232,22 +252,31 @@ inline void norm_intersect(const std::vector<NormIv>& cs, const std::vector<Norm
       const bool keep = jcompare_le(std2, limit);
       const int32_t l = std::max(a.left, b.left) + delta_w;
       if (a.right < b.right) {
-        if (keep) out.push_back(NormIv{l, a.right + delta_w, sum_ex, sum_ex2, sum_exu, sum_ex2u, common});
+        if (keep) emit_out(NormIv{l, a.right + delta_w, sum_ex, sum_ex2, sum_exu, sum_ex2u, common});
         i1++;
       } else {
-        if (keep) out.push_back(NormIv{l, b.right + delta_w, sum_ex, sum_ex2, sum_exu, sum_ex2u, common});
+        if (keep) emit_out(NormIv{l, b.right + delta_w, sum_ex, sum_ex2, sum_exu, sum_ex2u, common});
         i2++;
       }
     }
   }
 }
 
-// The first segment's positions clamped to window starts inside the series (:313-332 / Dtw :326-348).
-inline void norm_first_segment(const std::vector<NormIv>& pos, int32_t order, int32_t w0, int32_t length, int32_t n, int32_t delta_w,
-                               std::vector<NormIv>& out) {
+inline void norm_intersect(const std::vector<NormIv>& cs, const std::vector<NormIv>& csi, int32_t pre_length, int32_t w0,
+                           int32_t query_length, double mean_q, double std_q, double alpha, double beta, int32_t delta_w, bool dtw,
+                           std::vector<NormIv>& out) {
   out.clear();
+  norm_intersect_core(cs.data(), cs.size(), csi.data(), csi.size(), pre_length, w0, query_length, mean_q, std_q, alpha, beta, delta_w, dtw,
+                      [&](const NormIv& x) { out.push_back(x); });
+}
+
+// The first segment's positions clamped to window starts inside the series (:313-332 / Dtw :326-348).
+template <class Emit>
+inline void norm_first_segment_core(const NormIv* pos, size_t n_pos, int32_t order, int32_t w0, int32_t length, int32_t n, int32_t delta_w,
+                                    Emit&& emit_out) {
   const int64_t sh = (int64_t)(order - 1) * w0;
-  for (const NormIv& p : pos) {
+  for (size_t i = 0; i < n_pos; i++) {
+    const NormIv& p = pos[i];
     NormIv o = p;
     if ((int64_t)p.right - sh + length - 1 > n) {
       if ((int64_t)p.left - sh + length - 1 > n) continue;
@@ -261,8 +290,14 @@ inline void norm_first_segment(const std::vector<NormIv>& pos, int32_t order, in
       o.left = p.left + delta_w;
       o.right = p.right + delta_w;
     }
-    out.push_back(o);
+    emit_out(o);
   }
+}
+
+inline void norm_first_segment(const std::vector<NormIv>& pos, int32_t order, int32_t w0, int32_t length, int32_t n, int32_t delta_w,
+                               std::vector<NormIv>& out) {
+  out.clear();
+  norm_first_segment_core(pos.data(), pos.size(), order, w0, length, n, delta_w, [&](const NormIv& x) { out.push_back(x); });
 }
 
 }  // namespace kvm_phase1

@@ -169,9 +169,23 @@ class QuerySegment:
     wu: int
 
 
+_KEYS_CACHE: dict = {}
+
+
+def _keys_of(stat):
+    """Row keys of a cumulative statistic table (built once per table: the plan DP looks them up hundreds of times)."""
+    hit = _KEYS_CACHE.get(id(stat))
+    if hit is None or hit[0] is not stat:
+        if len(_KEYS_CACHE) > 64:
+            _KEYS_CACHE.clear()
+        hit = (stat, [t[0] for t in stat])
+        _KEYS_CACHE[id(stat)] = hit
+    return hit[1]
+
+
 def _counts(stat, wu: int, mean: float, epsilon: float):
     """getCountsFromStatisticInfo :382-399 on the cumulative table of width wu."""
-    keys = [t[0] for t in stat]
+    keys = _keys_of(stat)
     rng = epsilon / math.sqrt(wu)
     begin, end = to_round(mean - rng), to_round(mean + rng)
 
@@ -320,7 +334,7 @@ BETA_PARTITION_WIDTH = 10.0   # :59
 
 
 def _norm_out(k):
-    return np.zeros(max(k, 1), dtype=NORM_IV)
+    return np.empty(max(k, 1), dtype=NORM_IV)
 
 
 def norm_sort_merge(ivs: np.ndarray, mode: int):
@@ -379,7 +393,7 @@ def norm_mean_range(mean: float, wu: int, epsilon: float, alpha: float, beta: fl
 
 def _counts_norm(stat, wu: int, mean: float, epsilon: float, alpha: float, beta: float, mean_q: float, std_q: float):
     """getCountsFromStatisticInfo :547-572 (both ends through the plain toRound)."""
-    keys = [t[0] for t in stat]
+    keys = _keys_of(stat)
     lo, hi = norm_mean_range(mean, wu, epsilon, alpha, beta, mean_q, std_q)
     begin, end = to_round(lo), to_round(hi)
 
@@ -509,7 +523,7 @@ def norm_mean_range_dtw(mean_min: float, mean_max: float, wu: int, epsilon: floa
 
 def _cumulative_counts(stat, begin: float, end: float):
     """The table lookups shared by every getCountsFromStatisticInfo (e.g. K/NormQueryEngineDtw.java:633-645)."""
-    keys = [t[0] for t in stat]
+    keys = _keys_of(stat)
 
     def search(key):
         return min(bisect.bisect_left(keys, key), len(stat) - 1)
