@@ -107,6 +107,8 @@ class IndexFile:
 
 
 # ---------------------------------------------------------------- interval algebra: the library's host functions
+# An interval list is (lr int32 [k, 2], eps float64 [k]) inside this module; the list-of-tuples forms below are the same
+# calls for small inputs (tests, notebooks).
 def _pack(ivs):
     k = len(ivs)
     lr = np.zeros((max(k, 1), 2), dtype=np.int32)
@@ -114,50 +116,71 @@ def _pack(ivs):
     for i, (l, r, e) in enumerate(ivs):
         lr[i] = (l, r)
         eps[i] = e
-    return lr, eps, k
+    return lr[:k], eps[:k]
 
 
-def _unpack(lr, eps, k):
-    return [(int(lr[i, 0]), int(lr[i, 1]), float(eps[i])) for i in range(k)]
+def _unpack(lr, eps):
+    return [(int(a), int(b), float(e)) for (a, b), e in zip(lr.tolist(), eps.tolist())]
+
+
+def _room(k):
+    return np.empty((max(k, 1), 2), dtype=np.int32), np.empty(max(k, 1))
+
+
+def sort_merge_arrays(lr, eps, mode: int):
+    """kvm_intervals_sort_merge on arrays -> (lr, eps, cnt_disjoint, cnt_offsets)."""
+    L = _lib.load()
+    lr, eps = np.ascontiguousarray(lr, dtype=np.int32), np.ascontiguousarray(eps, dtype=np.float64)
+    k = len(eps)
+    lo, eo = _room(k)
+    ko, cd, co = C.c_int64(), C.c_int64(), C.c_int64()
+    rc = L.kvm_intervals_sort_merge(lr.ctypes.data, eps.ctypes.data, k, mode, lo.ctypes.data, eo.ctypes.data, len(eo),
+                                    C.byref(ko), C.byref(cd), C.byref(co))
+    if rc:
+        raise _lib.KvmError(rc, "kvm_intervals_sort_merge")
+    return lo[:ko.value], eo[:ko.value], cd.value, co.value
+
+
+def intersect_arrays(cs_lr, cs_eps, csi_lr, csi_eps, eps2: float, delta_w: int):
+    """kvm_intervals_intersect on arrays -> (lr, eps, smallest summed bound kept)."""
+    L = _lib.load()
+    a, ae = np.ascontiguousarray(cs_lr, dtype=np.int32), np.ascontiguousarray(cs_eps, dtype=np.float64)
+    b, be = np.ascontiguousarray(csi_lr, dtype=np.int32), np.ascontiguousarray(csi_eps, dtype=np.float64)
+    lo, eo = _room(len(ae) + len(be))
+    ko, me = C.c_int64(), C.c_double()
+    rc = L.kvm_intervals_intersect(a.ctypes.data, ae.ctypes.data, len(ae), b.ctypes.data, be.ctypes.data, len(be), eps2, delta_w,
+                                   lo.ctypes.data, eo.ctypes.data, len(eo), C.byref(ko), C.byref(me))
+    if rc:
+        raise _lib.KvmError(rc, "kvm_intervals_intersect")
+    return lo[:ko.value], eo[:ko.value], me.value
+
+
+def first_segment_arrays(lr, eps, order: int, length: int, n: int, delta_w: int):
+    L = _lib.load()
+    a, ae = np.ascontiguousarray(lr, dtype=np.int32), np.ascontiguousarray(eps, dtype=np.float64)
+    lo, eo = _room(len(ae))
+    ko, me = C.c_int64(), C.c_double()
+    rc = L.kvm_intervals_first_segment(a.ctypes.data, ae.ctypes.data, len(ae), order, WU_LIST[0], length, n, delta_w, lo.ctypes.data,
+                                       eo.ctypes.data, len(eo), C.byref(ko), C.byref(me))
+    if rc:
+        raise _lib.KvmError(rc, "kvm_intervals_first_segment")
+    return lo[:ko.value], eo[:ko.value], me.value
 
 
 def sort_merge(ivs, mode: int):
     """kvm_intervals_sort_merge -> (intervals, cnt_disjoint, cnt_offsets)."""
-    L = _lib.load()
-    lr, eps, k = _pack(ivs)
-    lo, eo = np.zeros((max(k, 1), 2), dtype=np.int32), np.zeros(max(k, 1))
-    ko, cd, co = C.c_int64(), C.c_int64(), C.c_int64()
-    rc = L.kvm_intervals_sort_merge(lr.ctypes.data, eps.ctypes.data, k, mode, lo.ctypes.data, eo.ctypes.data, max(k, 1),
-                                    C.byref(ko), C.byref(cd), C.byref(co))
-    if rc:
-        raise _lib.KvmError(rc, "kvm_intervals_sort_merge")
-    return _unpack(lo, eo, ko.value), cd.value, co.value
+    lo, eo, cd, co = sort_merge_arrays(*_pack(ivs), mode)
+    return _unpack(lo, eo), cd, co
 
 
 def intersect(cs, csi, eps2: float, delta_w: int):
-    L = _lib.load()
-    a, ae, k1 = _pack(cs)
-    b, be, k2 = _pack(csi)
-    cap = max(k1 + k2, 1)
-    lo, eo = np.zeros((cap, 2), dtype=np.int32), np.zeros(cap)
-    ko, me = C.c_int64(), C.c_double()
-    rc = L.kvm_intervals_intersect(a.ctypes.data, ae.ctypes.data, k1, b.ctypes.data, be.ctypes.data, k2, eps2, delta_w,
-                                   lo.ctypes.data, eo.ctypes.data, cap, C.byref(ko), C.byref(me))
-    if rc:
-        raise _lib.KvmError(rc, "kvm_intervals_intersect")
-    return _unpack(lo, eo, ko.value), me.value
+    lo, eo, me = intersect_arrays(*_pack(cs), *_pack(csi), eps2, delta_w)
+    return _unpack(lo, eo), me
 
 
 def first_segment(pos, order: int, length: int, n: int, delta_w: int):
-    L = _lib.load()
-    a, ae, k = _pack(pos)
-    lo, eo = np.zeros((max(k, 1), 2), dtype=np.int32), np.zeros(max(k, 1))
-    ko, me = C.c_int64(), C.c_double()
-    rc = L.kvm_intervals_first_segment(a.ctypes.data, ae.ctypes.data, k, order, WU_LIST[0], length, n, delta_w, lo.ctypes.data,
-                                       eo.ctypes.data, max(k, 1), C.byref(ko), C.byref(me))
-    if rc:
-        raise _lib.KvmError(rc, "kvm_intervals_first_segment")
-    return _unpack(lo, eo, ko.value), me.value
+    lo, eo, me = first_segment_arrays(*_pack(pos), order, length, n, delta_w)
+    return _unpack(lo, eo), me
 
 
 # ---------------------------------------------------------------- phase 0: determineQueryPlan (K/QueryEngine.java:398-503)
@@ -285,47 +308,65 @@ def determine_query_plan(q, epsilon: float, stats, counts=None, bounds=None):
 
 
 # ---------------------------------------------------------------- phase 1 (K/QueryEngine.java:185-334)
+def _scan_rows(idx: IndexFile, begin: float, end: float, bound_of):
+    """Rows with begin <= key <= end + 0.01 as one interval list; bound_of(key, upper) = the row's distance lower bound."""
+    rows = idx.read_index_arrays(begin, end + 0.01)
+    lr = np.empty((sum(len(p) for _, p in rows), 2), dtype=np.int32)
+    eps = np.empty(len(lr))
+    at = 0
+    for key, positions in rows:
+        k = len(positions)
+        lr[at:at + k] = positions
+        eps[at:at + k] = bound_of(key, to_upper_stat(key, idx.stat_keys))
+        at += k
+    return lr, eps
+
+
 def scan_index(idx: IndexFile, seg: QuerySegment, begin: float, end: float):
-    """scanIndex :505-521 with getDistanceLowerBound :383-396: positions (left, right, wu * lower bound)."""
-    out = []
-    for key, positions in idx.read_indexes(begin, end + 0.01):
-        upper = to_upper_stat(key, idx.stat_keys)
+    """scanIndex :505-521 with getDistanceLowerBound :383-396: positions with wu * lower bound, as (lr, eps) arrays."""
+    def bound(key, upper):
         if key > seg.mean:
             delta = (key - seg.mean) * (key - seg.mean)
         elif upper < seg.mean:
             delta = (seg.mean - upper) * (seg.mean - upper)
         else:
             delta = 0.0
-        out.extend((l, r, seg.wu * delta) for l, r in positions)
-    return out
+        return seg.wu * delta
+    return _scan_rows(idx, begin, end, bound)
+
+
+def _rsm_loop(queries, epsilon: float, length: int, n: int, by_w, scan, seg_range, reset_last_min: bool):
+    """The phase-1 loop shared by K/QueryEngine.java:185-334 and K/QueryEngineDtw.java:195-347."""
+    v_lr, v_eps = np.empty((0, 2), dtype=np.int32), np.empty(0)
+    last_min = 0.0
+    range0 = epsilon * epsilon
+    for i, seg in enumerate(queries):
+        delta_w = 0 if i == len(queries) - 1 else (queries[i + 1].order - seg.order) * WU_LIST[0]
+        ix = by_w[seg.wu]
+        if reset_last_min and last_min > range0:   # K/QueryEngineDtw.java:210
+            last_min = 0.0
+        rng = math.sqrt((range0 - last_min) / seg.wu)
+        lo, hi = seg_range(seg)
+        begin = to_round_stat(lo - rng, ix.stat_keys)
+        end = to_round(hi + rng)
+        p_lr, p_eps, _, _ = sort_merge_arrays(*scan(ix, seg, begin, end), 0)
+        if i == 0:
+            n_lr, n_eps, last_min = first_segment_arrays(p_lr, p_eps, seg.order, length, n, delta_w)
+        else:
+            n_lr, n_eps, last_min = intersect_arrays(v_lr, v_eps, p_lr, p_eps, range0, delta_w)
+        v_lr, v_eps, _, _ = sort_merge_arrays(n_lr, n_eps, 1)
+        if len(v_eps) == 0:
+            break
+    m_lr, _, _, _ = sort_merge_arrays(v_lr, v_eps, 2)
+    return [(int(l), int(r)) for l, r in m_lr.tolist()], queries[-1].order, queries
 
 
 def phase1(q, epsilon: float, n: int, indexes):
     """Candidate intervals of an RSM-ED query: (valid_positions [(left, right)], last_segment, plan).  `indexes` = one
     IndexFile per width of WU_LIST."""
     by_w = dict(zip(WU_LIST, indexes))
-    length = len(q)
     queries = determine_query_plan(q, epsilon, {w: ix.stat for w, ix in by_w.items()})
-    valid = []
-    last_min = 0.0
-    range0 = epsilon * epsilon
-    for i, seg in enumerate(queries):
-        delta_w = 0 if i == len(queries) - 1 else (queries[i + 1].order - seg.order) * WU_LIST[0]
-        ix = by_w[seg.wu]
-        rng = math.sqrt((range0 - last_min) / seg.wu)
-        begin = to_round_stat(seg.mean - rng, ix.stat_keys)
-        end = to_round(seg.mean + rng)
-        positions, _, _ = sort_merge(scan_index(ix, seg, begin, end), 0)
-        if i == 0:
-            nxt, last_min = first_segment(positions, seg.order, length, n, delta_w)
-        else:
-            nxt, last_min = intersect(valid, positions, range0, delta_w)
-        valid, _, _ = sort_merge(nxt, 1)
-        if not valid:
-            break
-    last_segment = queries[-1].order
-    merged, _, _ = sort_merge(valid, 2)
-    return [(l, r) for l, r, _ in merged], last_segment, queries
+    return _rsm_loop(queries, epsilon, len(q), n, by_w, scan_index, lambda seg: (seg.mean, seg.mean), False)
 
 
 # ---------------------------------------------------------------- cNSM-ED: phases 0 / 1 of K/NormQueryEngine.java:177-430
@@ -601,47 +642,24 @@ def phase1_norm_dtw(q, epsilon: float, rho: int, alpha: float, beta: float, n: i
 # ---------------------------------------------------------------- RSM-DTW: phases 0 / 1 of K/QueryEngineDtw.java:172-347
 def scan_index_dtw(idx: IndexFile, seg: RangeQuerySegment, begin: float, end: float):
     """scanIndex :647-661 with getDistanceLowerBound :721-734: the row's mean range against the segment's mean range."""
-    out = []
-    for key, positions in idx.read_indexes(begin, end + 0.01):
-        upper = to_upper_stat(key, idx.stat_keys)
+    def bound(key, upper):
         if key > seg.mean_max:
             delta = (key - seg.mean_max) * (key - seg.mean_max)
         elif upper < seg.mean_min:
             delta = (seg.mean_min - upper) * (seg.mean_min - upper)
         else:
             delta = 0.0
-        out.extend((l, r, seg.wu * delta) for l, r in positions)
-    return out
+        return seg.wu * delta
+    return _scan_rows(idx, begin, end, bound)
 
 
 def phase1_dtw(q, epsilon: float, rho: int, n: int, indexes):
     """Candidate intervals of an RSM-DTW query: (valid_positions, last_segment, plan).  The RSM-ED loop over segments that
     carry the mean range of the query's envelope; the interval algebra is the same (kvm_intervals_*)."""
     by_w = dict(zip(WU_LIST, indexes))
-    length = len(q)
 
     def counts(stat, wu, mean_min, mean_max):   # getCountsFromStatisticInfo :471-491
         rng = epsilon / math.sqrt(wu)
         return _cumulative_counts(stat, to_round(mean_min - rng), to_round(mean_max + rng))
     queries = determine_query_plan(q, epsilon, {w: ix.stat for w, ix in by_w.items()}, counts=counts, bounds=query_envelope_padded(q, rho))
-    valid = []
-    last_min = 0.0
-    range0 = epsilon * epsilon
-    for i, seg in enumerate(queries):
-        delta_w = 0 if i == len(queries) - 1 else (queries[i + 1].order - seg.order) * WU_LIST[0]
-        ix = by_w[seg.wu]
-        if last_min > range0:   # :210
-            last_min = 0.0
-        rng = math.sqrt((range0 - last_min) / seg.wu)
-        begin = to_round_stat(seg.mean_min - rng, ix.stat_keys)
-        end = to_round(seg.mean_max + rng)
-        positions, _, _ = sort_merge(scan_index_dtw(ix, seg, begin, end), 0)
-        if i == 0:
-            nxt, last_min = first_segment(positions, seg.order, length, n, delta_w)
-        else:
-            nxt, last_min = intersect(valid, positions, range0, delta_w)
-        valid, _, _ = sort_merge(nxt, 1)
-        if not valid:
-            break
-    merged, _, _ = sort_merge(valid, 2)
-    return [(l, r) for l, r, _ in merged], queries[-1].order, queries
+    return _rsm_loop(queries, epsilon, len(q), n, by_w, scan_index_dtw, lambda seg: (seg.mean_min, seg.mean_max), True)

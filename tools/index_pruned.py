@@ -38,39 +38,46 @@ indexes = [phase1.IndexFile(images[w]) for w in phase1.WU_LIST]
 open_s = time.perf_counter() - t0
 full_iv = datagen.chain_intervals(n, m, bench.DEFAULT_CHUNK)
 rows = []
+RSM_EPS = 10.0
 for off in bench.query_offsets(n, m, bench.N_QUERIES)[:n_q]:
     q = s[off - 1:off - 1 + m].copy()
-    t0 = time.perf_counter()
-    valid, last_segment, plan = phase1.phase1_norm(q, eps, bench.ALPHA, bench.BETA, n, indexes)
-    t1_ms = 1e3 * (time.perf_counter() - t0)
-    iv = np.asarray(valid, dtype=np.int32).reshape(-1, 2)
-    shift = (last_segment - 1) * 25
-    g.verify_cnsm_ed(q, eps, bench.ALPHA, bench.BETA, iv, shift)
-    t0 = time.perf_counter()
-    r = g.verify_cnsm_ed(q, eps, bench.ALPHA, bench.BETA, iv, shift)
-    t2_ms = 1e3 * (time.perf_counter() - t0)
-    g.verify_cnsm_ed(q, eps, bench.ALPHA, bench.BETA, full_iv)
-    t0 = time.perf_counter()
-    f = g.verify_cnsm_ed(q, eps, bench.ALPHA, bench.BETA, full_iv)
-    tf_ms = 1e3 * (time.perf_counter() - t0)
-    assert r.offsets.tolist() == f.offsets.tolist(), off
-    assert off in r.offsets.tolist(), off
-    lens = iv[:, 1] - iv[:, 0] + 1
-    row = (off, len(plan), last_segment, t1_ms, len(iv), int(lens.sum()), int(lens.max()), r.kernel_ms, t2_ms, f.kernel_ms, tf_ms, r.count)
-    rows.append(row)
-    print(row, flush=True)
+    for engine in ("cNSM-ED", "RSM-ED"):
+        norm = engine == "cNSM-ED"
+        verify = (lambda I, sh=0: g.verify_cnsm_ed(q, eps, bench.ALPHA, bench.BETA, I, sh)) if norm else (lambda I, sh=0: g.verify_ed(q, RSM_EPS, I, sh))
+        t0 = time.perf_counter()
+        valid, last_segment, plan = phase1.phase1_norm(q, eps, bench.ALPHA, bench.BETA, n, indexes) if norm else phase1.phase1(q, RSM_EPS, n, indexes)
+        t1_ms = 1e3 * (time.perf_counter() - t0)
+        iv = np.asarray(valid, dtype=np.int32).reshape(-1, 2)
+        shift = (last_segment - 1) * 25
+        verify(iv, shift)
+        t0 = time.perf_counter()
+        r = verify(iv, shift)
+        t2_ms = 1e3 * (time.perf_counter() - t0)
+        scan_iv = full_iv if norm else np.array([[1, n - m + 1]], dtype=np.int32)
+        verify(scan_iv)
+        t0 = time.perf_counter()
+        f = verify(scan_iv)
+        tf_ms = 1e3 * (time.perf_counter() - t0)
+        assert r.offsets.tolist() == f.offsets.tolist(), (engine, off)
+        assert off in r.offsets.tolist(), (engine, off)
+        if not norm:
+            assert r.distances.tolist() == f.distances.tolist(), off   # no running statistics: bit-identical distances
+        lens = iv[:, 1] - iv[:, 0] + 1
+        row = (off, len(plan), last_segment, t1_ms, len(iv), int(lens.sum()), int(lens.max()), r.kernel_ms, t2_ms, f.kernel_ms, tf_ms, r.count, engine)
+        rows.append(row)
+        print(row, flush=True)
 with open(out, "w") as fh:
-    fh.write(f"# Index-pruned cNSM-ED queries (BASELINE configs[1] (ii)), n = {n}, m = {m}, eps = {eps}, alpha = {bench.ALPHA}, beta = {bench.BETA} (round 2)\n\n"
+    fh.write(f"# Index-pruned queries (BASELINE configs[1] (ii)), n = {n}, m = {m}; cNSM-ED: eps = {eps}, alpha = {bench.ALPHA}, beta = {bench.BETA}; RSM-ED: eps = {RSM_EPS} (round 2)\n\n"
              f"`python tools/index_pruned.py {n} {n_q} {eps}` on one B200.  Index build (five widths: one fused window-mean pass on the GPU, "
              f"runs to the host, step 2 + file images on the host, the five widths on five host threads): {build_s:.2f} s for the first build "
              f"(it allocates the pinned staging of the runs), {build2_s:.2f} s for a second one, of which the GPU pass is {kernel_ms:.2f} ms and the pass "
              f"with its runs copied out to numpy arrays {runs_s:.2f} s; {sum(len(b) for b in images.values()) / 1e6:.0f} MB of index files; "
              f"opening them (offset + statistic tables): {open_s:.2f} s.  T_1 = phases 0 / 1 on ONE host core (plan DP, index range scans, "
-             f"`kvm_norm_intervals_*`); T_2 = `kvm_verify_cnsm_ed` over the phase-1 interval list with host buffers (wall) and its CUDA-event "
-             f"kernel time; full scan = the same query over every window start (chains of {bench.DEFAULT_CHUNK}).  Every row: index-pruned answer "
+             f"`kvm_norm_intervals_*` / `kvm_intervals_*`); T_2 = `kvm_verify_cnsm_ed` / `kvm_verify_ed` over the phase-1 interval list with host buffers (wall) and its CUDA-event "
+             f"kernel time; full scan = the same query over every window start (cNSM: chains of {bench.DEFAULT_CHUNK}; RSM: one interval).  Every row: index-pruned answer "
              f"offsets == full-scan answer offsets.\n\n"
-             "| query offset | segments | lastSegment | T_1 host ms | intervals | candidates | longest interval | T_2 kernel ms | T_2 wall ms | full-scan kernel ms | full-scan wall ms | answers |\n"
-             "|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+             "| engine | query offset | segments | lastSegment | T_1 host ms | intervals | candidates | longest interval | T_2 kernel ms | T_2 wall ms | full-scan kernel ms | full-scan wall ms | answers |\n"
+             "|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
     for r in rows:
-        fh.write(f"| {r[0]} | {r[1]} | {r[2]} | {r[3]:.0f} | {r[4]} | {r[5]} ({100.0 * r[5] / n:.1f} % of n) | {r[6]} | {r[7]:.3f} | {r[8]:.3f} | {r[9]:.3f} | {r[10]:.3f} | {r[11]} |\n")
+        fh.write(f"| {r[12]} | {r[0]} | {r[1]} | {r[2]} | {r[3]:.0f} | {r[4]} | {r[5]} ({100.0 * r[5] / n:.2g} % of n) | {r[6]} | {r[7]:.3f} | {r[8]:.3f} | {r[9]:.3f} | {r[10]:.3f} | {r[11]} |\n")
 print(open(out).read())
