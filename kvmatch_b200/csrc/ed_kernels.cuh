@@ -15,6 +15,7 @@
 namespace kvm {
 
 constexpr int kEdThreads = 256;
+constexpr int kEdAhead = 64;
 constexpr int kEdTile = 4096;  // candidates per CTA (16 per thread): amortises the tile -> interval search
 
 struct EdParams {
@@ -27,6 +28,7 @@ struct EdParams {
   int m;
   double eps2;
   int32_t first_global;  // 1-based global offset of T[0]
+  int ahead;             // samples between a long-lived window's current round and the line it prefetches (kEdAhead; >= m: off)
   AnswerSink sink;
 };
 
@@ -42,6 +44,7 @@ __global__ void __launch_bounds__(kEdThreads) ed_verify_kernel(EdParams P) {
   const int m = P.m;
   const double eps2 = P.eps2;
   const double q0 = __ldg(q);
+  const int ahead = P.ahead;
   // On a scan almost every window is hopeless after its first sample, so a thread's work per window is one 8-byte load
   // and a compare: the kernel is bound by the bytes in flight.  The first samples of four of the thread's windows are
   // therefore requested together (4 x 256 B per warp in flight instead of one load and a dependent branch).
@@ -58,6 +61,9 @@ __global__ void __launch_bounds__(kEdThreads) ed_verify_kernel(EdParams P) {
       j = 4;
     }
     for (; j + 8 <= m && alive; j += 8) {
+      // A window that lives on (a match, or on smooth data its neighbours) is a chain of dependent rounds, each waiting
+      // for lines that left L1 long ago: ask for the line eight rounds ahead.
+      if (j + ahead < m) asm volatile("prefetch.global.L1 [%0];" ::"l"(w + j + ahead));
       double t[8];
 #pragma unroll
       for (int u = 0; u < 8; u++) t[u] = xsqdist(w[j + u], __ldg(q + j + u));

@@ -1965,6 +1965,8 @@ static int verify_ed_impl(kvm_ctx* ctx, const double* q, int32_t m, double epsil
     E.m = m;
     E.eps2 = epsilon * epsilon;
     E.first_global = (int32_t)ctx->first;
+    static const int ed_ahead = env_int("KVM_ED_AHEAD", kvm::kEdAhead);  // developer knob
+    E.ahead = ed_ahead > 0 ? ed_ahead : (1 << 30);
     E.sink = sink_of(ctx);
     KVM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     ed_verify_kernel<<<(unsigned)n_tiles, kEdThreads, 0, ctx->stream>>>(E);
