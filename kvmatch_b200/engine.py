@@ -351,7 +351,7 @@ class _EngineBase:
         """Phases 0 / 1 over index file images (kvmatch_b200/phase1.py): sets valid_positions / last_segment / phase1_ms."""
         from . import phase1
         t0 = time.perf_counter()
-        indexes = [phase1.IndexFile(self._images[w]) for w in WU_LIST]
+        indexes = [phase1.open_index(self._images[w]) for w in WU_LIST]
         valid, last_segment, _ = getattr(phase1, fn)(query_data, *args, self.series.n, indexes)
         self.phase1_ms = 1e3 * (time.perf_counter() - t0)
         self.valid_positions, self.last_segment = valid, last_segment
@@ -381,7 +381,7 @@ class QueryEngine(_EngineBase):
     def query_with_index(self, statistics, query_data, epsilon, index_images):
         from . import phase1
         t0 = time.perf_counter()
-        indexes = [phase1.IndexFile(index_images[w]) for w in WU_LIST]
+        indexes = [phase1.open_index(index_images[w]) for w in WU_LIST]
         valid, last_segment, _ = phase1.phase1(query_data, epsilon, self.series.n, indexes)
         self.phase1_ms = 1e3 * (time.perf_counter() - t0)
         self.valid_positions, self.last_segment = valid, last_segment
@@ -462,14 +462,29 @@ class IndexBuilder:
         keys, first, last, _, _ = self.series.window_mean_runs(w)
         return keys, first, last
 
-    def build_all(self, widths=WU_LIST):
+    def build_all(self, widths=WU_LIST, shards: int = 1):
         """The whole index build for every width (K/IndexBuilder.java:98-120): ONE window-mean pass on the GPU
-        (kvm_window_mean_runs_all), then step 2 and the file image per width on the host.  Returns {w: file bytes}."""
+        (kvm_window_mean_runs_all), then step 2 and the file image per width on the host.  Returns {w: file bytes}, or with
+        shards > 1 {w: [file bytes per shard]}: the per-shard layout (phase1.ShardedIndexFile), each file holding the
+        window starts of one contiguous range with the single-file index's keys and positions."""
+        from concurrent.futures import ThreadPoolExecutor   # widths and shards are independent; the library call drops the GIL
+        from . import phase1
         res = self.series.window_mean_runs_all(widths, copy=False)   # consumed right here
-        from concurrent.futures import ThreadPoolExecutor   # the widths are independent; the library call drops the GIL
-        with ThreadPoolExecutor(max_workers=len(res.widths)) as pool:
-            images = list(pool.map(lambda kfl: _lib.index_image_from_runs(*kfl)[0], res.runs))
-        return dict(zip(res.widths, images))
+        jobs = []
+        for w, (k, f, l) in zip(res.widths, res.runs):
+            if shards <= 1:
+                jobs.append((w, (k, f, l)))
+            else:
+                n_windows = int(l[-1]) if len(l) else 0
+                jobs.extend((w, piece) for piece in phase1.split_runs(k, f, l, phase1.shard_ranges(n_windows, shards)))
+        with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), 16))) as pool:
+            images = list(pool.map(lambda job: _lib.index_image_from_runs(*job[1])[0], jobs))
+        if shards <= 1:
+            return {w: img for (w, _), img in zip(jobs, images)}
+        out = {}
+        for (w, _), img in zip(jobs, images):
+            out.setdefault(w, []).append(img)
+        return out
 
     def build_rows(self, w: int):
         """{key: [(first, last), ...]} — what the reference's indexNodeMap holds after step 1."""

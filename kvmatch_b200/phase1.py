@@ -99,11 +99,68 @@ class IndexFile:
         hi = bisect.bisect_right(self.keys, key_to) - 1
         return [self.row(i) for i in range(lo, hi + 1)] if lo < self.n_rows and hi >= 0 else []
 
+    def parts(self):
+        """The files that make up this index (one; see ShardedIndexFile)."""
+        return [self]
+
     def read_index_arrays(self, key_from: float, key_to: float):
         """read_indexes with the positions as int32 arrays (the cNSM scans fill structured arrays from them)."""
         lo = bisect.bisect_left(self.keys, key_from)
         hi = bisect.bisect_right(self.keys, key_to) - 1
         return [self.row_array(i) for i in range(lo, hi + 1)] if lo < self.n_rows and hi >= 0 else []
+
+
+class ShardedIndexFile:
+    """One window width's index as SEVERAL files, each covering a contiguous range of window starts (the per-shard layout
+    of SURVEY 8(f) f2: a file's offset table holds int32 byte offsets, so one file ends at 2 GiB — about n = 1.5e9 for
+    w = 25 on the synthetic series; and one file per GPU shard is what a multi-GPU build writes).  Positions stay global
+    1-based window starts.  Every part keeps its own rows (step 2 merges rows per file), so range scans round the lower
+    end against each part's own keys; the statistic table the plan DP reads is the parts' tables added up on the union
+    of their keys (cumulative counts are sums over disjoint position ranges)."""
+
+    def __init__(self, images):
+        self._parts = [IndexFile(b) for b in images]
+        keys = sorted({k for p in self._parts for k in p.stat_keys})
+        self.stat = []
+        for k in keys:
+            iv = off = 0
+            for p in self._parts:
+                i = bisect.bisect_right(p.stat_keys, k) - 1
+                if i >= 0:
+                    iv += p.stat[i][1]
+                    off += p.stat[i][2]
+            self.stat.append((k, iv, off))
+        self.stat_keys = keys
+
+    def parts(self):
+        return self._parts
+
+
+def open_index(image):
+    """One width's index from its file image (bytes) or, for the per-shard layout, the list of its files' images."""
+    return IndexFile(image) if isinstance(image, (bytes, bytearray, memoryview)) else ShardedIndexFile(image)
+
+
+def shard_ranges(n_windows: int, shards: int):
+    """`shards` contiguous (lo, hi) ranges of 1-based window starts covering [1, n_windows]."""
+    per = -(-n_windows // shards)
+    return [(k * per + 1, min((k + 1) * per, n_windows)) for k in range(shards) if k * per < n_windows]
+
+
+def split_runs(keys, first, last, ranges):
+    """Step-1 runs of one width cut at shard boundaries: for each (lo, hi) range of 1-based window starts, the runs (or
+    pieces of runs) inside it, in position order.  Keys and positions are those of the single-file index."""
+    keys, first, last = np.asarray(keys), np.asarray(first), np.asarray(last)
+    out = []
+    for lo, hi in ranges:
+        a = int(np.searchsorted(last, lo, side="left"))     # first run ending at or after lo
+        b = int(np.searchsorted(first, hi, side="right"))   # one past the last run starting at or before hi
+        f, l = first[a:b].copy(), last[a:b].copy()
+        if len(f):
+            f[0] = max(int(f[0]), lo)
+            l[-1] = min(int(l[-1]), hi)
+        out.append((keys[a:b].copy(), f, l))
+    return out
 
 
 # ---------------------------------------------------------------- interval algebra: the library's host functions
@@ -308,16 +365,20 @@ def determine_query_plan(q, epsilon: float, stats, counts=None, bounds=None):
 
 
 # ---------------------------------------------------------------- phase 1 (K/QueryEngine.java:185-334)
-def _scan_rows(idx: IndexFile, begin: float, end: float, bound_of):
-    """Rows with begin <= key <= end + 0.01 as one interval list; bound_of(key, upper) = the row's distance lower bound."""
-    rows = idx.read_index_arrays(begin, end + 0.01)
-    lr = np.empty((sum(len(p) for _, p in rows), 2), dtype=np.int32)
+def _scan_rows(idx, lo_value: float, end: float, bound_of):
+    """Rows with toRound(lo_value, statisticInfo) <= key <= end + 0.01 as one interval list (every part of a sharded index
+    rounds against its own row keys); bound_of(key, upper) = the row's distance lower bound."""
+    rows = []
+    for part in idx.parts():
+        begin = to_round_stat(lo_value, part.stat_keys)
+        rows.extend((key, positions, to_upper_stat(key, part.stat_keys)) for key, positions in part.read_index_arrays(begin, end + 0.01))
+    lr = np.empty((sum(len(p) for _, p, _ in rows), 2), dtype=np.int32)
     eps = np.empty(len(lr))
     at = 0
-    for key, positions in rows:
+    for key, positions, upper in rows:
         k = len(positions)
         lr[at:at + k] = positions
-        eps[at:at + k] = bound_of(key, to_upper_stat(key, idx.stat_keys))
+        eps[at:at + k] = bound_of(key, upper)
         at += k
     return lr, eps
 
@@ -347,7 +408,7 @@ def _rsm_loop(queries, epsilon: float, length: int, n: int, by_w, scan, seg_rang
             last_min = 0.0
         rng = math.sqrt((range0 - last_min) / seg.wu)
         lo, hi = seg_range(seg)
-        begin = to_round_stat(lo - rng, ix.stat_keys)
+        begin = lo - rng        # (rounded against the statistic table inside the scan)
         end = to_round(hi + rng)
         p_lr, p_eps, _, _ = sort_merge_arrays(*scan(ix, seg, begin, end), 0)
         if i == 0:
@@ -449,7 +510,7 @@ def _counts_norm(stat, wu: int, mean: float, epsilon: float, alpha: float, beta:
     return upper1 - lower1, upper2 - lower2
 
 
-def beta_partitions(seg: QuerySegment, epsilon: float, alpha: float, beta: float, mean_q: float, std_q: float, stat_keys):
+def beta_partitions(seg: QuerySegment, epsilon: float, alpha: float, beta: float, mean_q: float, std_q: float):
     """:233-254: (int)(2 beta / 10) partitions (at most 64) of the beta range, each with its own rounded mean range.  beta < 5
     gives ZERO partitions, hence empty bit sets and — from the second segment on — an empty candidate set: the reference's
     behaviour, kept."""
@@ -458,7 +519,7 @@ def beta_partitions(seg: QuerySegment, epsilon: float, alpha: float, beta: float
     for idx in range(num):
         width = 2.0 * beta / num
         lo, hi = norm_mean_range(seg.mean, seg.wu, epsilon, alpha, beta, mean_q, std_q, width * idx, width * (idx + 1))
-        parts.append((to_round_stat(lo, stat_keys), to_round(hi)))
+        parts.append((lo, to_round(hi)))   # (the lower end is rounded against the statistic table inside the scan)
     return parts
 
 
@@ -468,28 +529,44 @@ def _java_int_shl1(idx: int) -> int:
     return v - (1 << 32) if v & 0x80000000 else v
 
 
-def scan_index_norm(idx: IndexFile, seg: QuerySegment, begin: float, end: float, parts) -> np.ndarray:
-    """scanIndex :673-701: positions with the row's lower block sums (key * blocks, key'^2 * blocks with key' = the row's
-    upper end for negative keys) and the beta partitions the row key falls into."""
-    blocks = seg.wu // WU_ALL[0]
-    rows = idx.read_index_arrays(begin, end + 0.01)
-    out = np.zeros(sum(len(p) for _, p in rows), dtype=NORM_IV)
+def _scan_rows_norm(idx, lo_value: float, end: float, parts, sums_of) -> np.ndarray:
+    """The cNSM scans: rows of every part of the index with their block sums (sums_of(key, upper) -> ex, ex2, exu, ex2u)
+    and the beta partitions the row key falls into.  `parts` = (unrounded lower end, rounded upper end) per partition;
+    lower ends are rounded against the statistic table of the file being scanned (toRound(value, statisticInfo))."""
+    rows = []
+    for part in idx.parts():
+        begin = to_round_stat(lo_value, part.stat_keys)
+        ranges = [(to_round_stat(p_lo, part.stat_keys), p_hi) for p_lo, p_hi in parts]
+        for key, positions in part.read_index_arrays(begin, end + 0.01):
+            bits = 0
+            for j, (p_lo, p_hi) in enumerate(ranges):
+                if p_lo > key:
+                    break
+                if p_lo <= key <= p_hi:
+                    bits |= _java_int_shl1(j)
+            rows.append((positions, sums_of(key, to_upper_stat(key, part.stat_keys)), bits))
+    out = np.zeros(sum(len(p) for p, _, _ in rows), dtype=NORM_IV)
     at = 0
-    for key, positions in rows:
-        key2 = to_upper_stat(key, idx.stat_keys) if key < 0 else key
-        bits = 0
-        for j, (p_lo, p_hi) in enumerate(parts):
-            if p_lo > key:
-                break
-            if p_lo <= key <= p_hi:
-                bits |= _java_int_shl1(j)
+    for positions, sums, bits in rows:
         k = len(positions)
         if k:
             blk = out[at:at + k]
             blk["left"], blk["right"] = positions[:, 0], positions[:, 1]
-            blk["ex"], blk["ex2"], blk["bp"] = key * blocks, key2 * key2 * blocks, bits
+            blk["ex"], blk["ex2"], blk["exu"], blk["ex2u"] = sums
+            blk["bp"] = bits
             at += k
     return out
+
+
+def scan_index_norm(idx, seg: QuerySegment, lo_value: float, end: float, parts) -> np.ndarray:
+    """scanIndex :673-701: positions with the row's lower block sums (key * blocks, key'^2 * blocks with key' = the row's
+    upper end for negative keys) and the beta partitions the row key falls into."""
+    blocks = seg.wu // WU_ALL[0]
+
+    def sums(key, upper):
+        key2 = upper if key < 0 else key
+        return key * blocks, key2 * key2 * blocks, 0.0, 0.0
+    return _scan_rows_norm(idx, lo_value, end, parts, sums)
 
 
 def query_statistics(q):
@@ -520,8 +597,8 @@ def phase1_norm(q, epsilon: float, alpha: float, beta: float, n: int, indexes):
         pre_length += seg.wu // WU_ALL[0]
         ix = by_w[seg.wu]
         lo, hi = norm_mean_range(seg.mean, seg.wu, epsilon, alpha, beta, mean_q, std_q)
-        begin, end = to_round_stat(lo, ix.stat_keys), to_round(hi)
-        parts = beta_partitions(seg, epsilon, alpha, beta, mean_q, std_q, ix.stat_keys)
+        begin, end = lo, to_round(hi)
+        parts = beta_partitions(seg, epsilon, alpha, beta, mean_q, std_q)
         positions, _, _ = norm_sort_merge(scan_index_norm(ix, seg, begin, end, parts), 0)
         if i == 0:
             nxt = norm_first_segment(positions, seg.order, length, n, delta_w)
@@ -577,29 +654,15 @@ def _cumulative_counts(stat, begin: float, end: float):
     return upper1 - lower1, upper2 - lower2
 
 
-def scan_index_norm_dtw(idx: IndexFile, seg: RangeQuerySegment, begin: float, end: float, parts) -> np.ndarray:
+def scan_index_norm_dtw(idx, seg: RangeQuerySegment, lo_value: float, end: float, parts) -> np.ndarray:
     """scanIndex :802-833: like the ED engine's, plus the row's upper block sums (upper = the next row key)."""
     blocks = seg.wu // WU_ALL[0]
-    rows = idx.read_index_arrays(begin, end + 0.01)
-    out = np.zeros(sum(len(p) for _, p in rows), dtype=NORM_IV)
-    at = 0
-    for key, positions in rows:
-        upper = to_upper_stat(key, idx.stat_keys)
+
+    def sums(key, upper):
         sq_lower = upper * upper if key < 0 else key * key
         sq_upper = key * key if upper < 0 else upper * upper
-        bits = 0
-        for j, (p_lo, p_hi) in enumerate(parts):
-            if p_lo > key:
-                break
-            if p_lo <= key <= p_hi:
-                bits |= _java_int_shl1(j)
-        k = len(positions)
-        if k:
-            blk = out[at:at + k]
-            blk["left"], blk["right"] = positions[:, 0], positions[:, 1]
-            blk["ex"], blk["ex2"], blk["exu"], blk["ex2u"], blk["bp"] = key * blocks, sq_lower * blocks, upper * blocks, sq_upper * blocks, bits
-            at += k
-    return out
+        return key * blocks, sq_lower * blocks, upper * blocks, sq_upper * blocks
+    return _scan_rows_norm(idx, lo_value, end, parts, sums)
 
 
 def phase1_norm_dtw(q, epsilon: float, rho: int, alpha: float, beta: float, n: int, indexes):
@@ -620,13 +683,13 @@ def phase1_norm_dtw(q, epsilon: float, rho: int, alpha: float, beta: float, n: i
         pre_length += seg.wu // WU_ALL[0]
         ix = by_w[seg.wu]
         lo, hi = rng(seg.mean_min, seg.mean_max, seg.wu)
-        begin, end = to_round_stat(lo, ix.stat_keys), to_round(hi)
+        begin, end = lo, to_round(hi)
         num = min(int(2.0 * beta / BETA_PARTITION_WIDTH), 64)   # :246-268
         parts = []
         for j in range(num):
             width = 2.0 * beta / num
             p_lo, p_hi = rng(seg.mean_min, seg.mean_max, seg.wu, width * j, width * (j + 1))
-            parts.append((to_round_stat(p_lo, ix.stat_keys), to_round(p_hi)))
+            parts.append((p_lo, to_round(p_hi)))
         positions, _, _ = norm_sort_merge(scan_index_norm_dtw(ix, seg, begin, end, parts), 0)
         if i == 0:
             nxt = norm_first_segment(positions, seg.order, length, n, delta_w)

@@ -110,3 +110,26 @@ def test_cnsm_dtw_index_pruned_query_equals_full_scan(world, oracle, off, length
     assert eng.last.offsets.tolist() == same_list.offsets.tolist() and eng.last.distances.tolist() == same_list.distances.tolist()
     full = oracle.verify_cnsm_dtw(s, q, eps, rho, alpha, beta, [(1, len(s) - length + 1)])
     assert eng.last.offsets.tolist() == full.offsets.tolist() and off in full.offsets.tolist()
+
+
+def test_per_shard_index_layout_end_to_end(world, oracle):
+    """build_all(shards=3): three files per width from the same fused GPU pass (the per-shard layout of SURVEY 8(f) f2);
+    index-pruned queries over them return what the single-file indexes return."""
+    import kvmatch_b200
+    s, g, images = world
+    sharded = kvmatch_b200.IndexBuilder(g).build_all(shards=3)
+    assert all(len(sharded[w]) == 3 for w in phase1.WU_LIST)
+    for w in (25, 400):
+        one, many = phase1.IndexFile(images[w]), phase1.ShardedIndexFile(sharded[w])
+        assert many.stat[-1][2] == one.stat[-1][2] == len(s) - w + 1
+    off, length = 333_000, 1024          # (a shard boundary of the w = 25 index lies at 333 326: the match straddles it)
+    q = s[off - 1:off - 1 + length].copy()
+    eng = kvmatch_b200.NormQueryEngine(g)
+    assert eng.query_with_index(None, q, 5.0, 1.5, 5.0, sharded) is True
+    full = oracle.verify_cnsm_ed(s, q, 5.0, 1.5, 5.0, [(1, len(s) - length + 1)])
+    assert eng.last.offsets.tolist() == full.offsets.tolist() and off in full.offsets.tolist()
+    rsm = kvmatch_b200.QueryEngine(g)
+    assert rsm.query_with_index(None, q, 10.0, sharded) is True
+    full = oracle.verify_ed(s, q, 10.0, [(1, len(s) - length + 1)])
+    assert rsm.last.offsets.tolist() == full.offsets.tolist() and rsm.last.distances.tolist() == full.distances.tolist()
+    assert rsm.answers[0] == (off, 0.0)

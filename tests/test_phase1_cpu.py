@@ -251,3 +251,69 @@ def test_rsm_dtw_phase1_has_no_false_dismissals(small_world, off, length, eps, r
     assert pruned.offsets.tolist() == full.offsets.tolist() and pruned.distances.tolist() == full.distances.tolist()
     n_cand = sum(r - l + 1 for l, r in valid)
     assert n_cand < 0.5 * n
+
+
+# ---------------------------------------------------------------- per-shard index layout
+@pytest.fixture(scope="module")
+def sharded_world(small_world):
+    from oracle import kvm_oracle
+    s, single = small_world
+    sharded = []
+    for w in phase1.WU_LIST:
+        k, f, l = kvm_oracle.window_mean_runs(s, w)
+        pieces = phase1.split_runs(k, f, l, phase1.shard_ranges(int(l[-1]), 3))
+        sharded.append(phase1.ShardedIndexFile([_lib.index_image_from_runs(*p)[0] for p in pieces]))
+    return s, single, sharded
+
+
+def test_sharded_index_holds_the_same_positions(sharded_world):
+    s, single, sharded = sharded_world
+    for one, many in zip(single, sharded):
+        assert len(many.parts()) == 3
+        cover_one = sorted(p for i in range(one.n_rows) for p in one.row(i)[1])
+        cover_many = sorted(p for part in many.parts() for i in range(part.n_rows) for p in part.row(i)[1])
+        total = sum(r - l + 1 for l, r in cover_one)
+        assert sum(r - l + 1 for l, r in cover_many) == total == many.stat[-1][2] == one.stat[-1][2]
+        for (l1, r1), (l2, r2) in zip(cover_many, cover_many[1:]):
+            assert r1 < l2                                    # no window start in two files
+        # every part covers one contiguous range of window starts
+        spans = [(min(p[0] for i in range(part.n_rows) for p in part.row(i)[1]), max(p[1] for i in range(part.n_rows) for p in part.row(i)[1]))
+                 for part in many.parts()]
+        assert spans[0][0] == 1 and all(a[1] + 1 == b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] == total
+        # the aggregated table is cumulative in both counts
+        assert all(a[1] <= b[1] and a[2] <= b[2] for a, b in zip(many.stat, many.stat[1:]))
+
+
+@pytest.mark.parametrize("off,length,eps", [(30_000, 512, 3.0), (77_777, 1024, 6.0), (41_000, 256, 2.0)])
+def test_sharded_index_queries_equal_full_scan(sharded_world, off, length, eps):
+    """All four engines' phase 1 over the per-shard layout: no false dismissals, and never fewer candidates than what the
+    true answers need (a query cut across a shard boundary at 40 000 / 80 000 included)."""
+    from oracle import kvm_oracle
+    s, single, sharded = sharded_world
+    n = len(s)
+    q = s[off - 1:off - 1 + length].copy()
+    v, last, _ = phase1.phase1(q, eps * 3, n, sharded)
+    full = kvm_oracle.verify_ed(s, q, eps * 3, [(1, n - length + 1)])
+    got = kvm_oracle.verify_ed(s, q, eps * 3, v, (last - 1) * 25)
+    assert got.offsets.tolist() == full.offsets.tolist() and got.distances.tolist() == full.distances.tolist() and off in got.offsets.tolist()
+    v, last, _ = phase1.phase1_norm(q, eps, 1.5, 5.0, n, sharded)
+    full = kvm_oracle.verify_cnsm_ed(s, q, eps, 1.5, 5.0, [(1, n - length + 1)])
+    assert kvm_oracle.verify_cnsm_ed(s, q, eps, 1.5, 5.0, v, (last - 1) * 25).offsets.tolist() == full.offsets.tolist()
+    rho = length // 20
+    v, last, _ = phase1.phase1_dtw(q, eps * 3, rho, n, sharded)
+    full = kvm_oracle.verify_dtw(s, q, eps * 3, rho, [(1, n - length + 1)])
+    assert kvm_oracle.verify_dtw(s, q, eps * 3, rho, v, (last - 1) * 25).offsets.tolist() == full.offsets.tolist()
+    v, last, _ = phase1.phase1_norm_dtw(q, eps, rho, 1.5, 5.0, n, sharded)
+    full = kvm_oracle.verify_cnsm_dtw(s, q, eps, rho, 1.5, 5.0, [(1, n - length + 1)])
+    assert kvm_oracle.verify_cnsm_dtw(s, q, eps, rho, 1.5, 5.0, v, (last - 1) * 25).offsets.tolist() == full.offsets.tolist()
+
+
+def test_split_runs_cuts_straddling_runs():
+    keys = np.array([0.5, 1.0, 0.5, 2.0])
+    first = np.array([1, 11, 31, 41], dtype=np.int32)
+    last = np.array([10, 30, 40, 50], dtype=np.int32)
+    a, b, c = phase1.split_runs(keys, first, last, [(1, 20), (21, 35), (36, 50)])
+    assert (a[0].tolist(), a[1].tolist(), a[2].tolist()) == ([0.5, 1.0], [1, 11], [10, 20])
+    assert (b[0].tolist(), b[1].tolist(), b[2].tolist()) == ([1.0, 0.5], [21, 31], [30, 35])
+    assert (c[0].tolist(), c[1].tolist(), c[2].tolist()) == ([0.5, 2.0], [36, 41], [40, 50])
+    assert phase1.shard_ranges(50, 3) == [(1, 17), (18, 34), (35, 50)] and phase1.shard_ranges(2, 3) == [(1, 1), (2, 2)]
