@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KVM_ABI_VERSION 3
+#define KVM_ABI_VERSION 4 /* 4: + kvm_norm_intervals_*, kvm_index_row_positions (additions only) */
 
 enum {
   KVM_OK = 0,

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert set(names) == set(_lib.EXPORTS)
     for name in names:
         assert hasattr(L, name), name
-    assert L.kvm_abi_version() == 3
+    assert L.kvm_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_device():
