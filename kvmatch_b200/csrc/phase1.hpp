@@ -134,6 +134,14 @@ inline bool jcompare_le(double a, double b) {
   return !(std::signbit(b) && !std::signbit(a));
 }
 
+// Math.min(double, double): NaN if either is NaN, -0.0 below +0.0
+inline double jmin(double a, double b) {
+  if (a != a) return a;
+  if (b != b) return b;
+  if (a == 0.0 && b == 0.0) return std::signbit(a) ? a : b;
+  return a <= b ? a : b;
+}
+
 // mode 0: sortButNotMergeIntervals (:788-823 / Dtw :926-967)          merge overlaps, or neighbours with bit-equal LOWER sums
 // mode 1: sortButNotMergeIntervalsAndCount (:825-869 / Dtw :969-1019)  the same + the two counts of the phase-2 time estimate
 // mode 2: sortAndMergeIntervals (:871-896 / Dtw :1021-1046)            merge overlaps and neighbours; sums and partitions dropped
@@ -186,10 +194,10 @@ inline void norm_sort_merge_core(const NormIv* v, size_t n, int mode, Emit&& emi
                                    : (gap < cur.right || (gap == cur.right && jcompare_eq(c.ex, cur.ex) && jcompare_eq(c.ex2, cur.ex2)));
     if (merge) {
       cur.right = std::max(c.right, cur.right);
-      cur.ex = std::min(c.ex, cur.ex);  // (Math.min; the sums are finite products of row keys)
-      cur.ex2 = std::min(c.ex2, cur.ex2);
-      cur.exu = std::min(c.exu, cur.exu);
-      cur.ex2u = std::min(c.ex2u, cur.ex2u);
+      cur.ex = jmin(c.ex, cur.ex);
+      cur.ex2 = jmin(c.ex2, cur.ex2);
+      cur.exu = jmin(c.exu, cur.exu);
+      cur.ex2u = jmin(c.ex2u, cur.ex2u);
       cur.bp |= c.bp;
     } else {
       emit();

@@ -93,6 +93,14 @@ def _same_double(a, b):  # Double.compare(a, b) == 0
     return _struct.pack(">d", a) == _struct.pack(">d", b) or (a != a and b != b)
 
 
+def _java_min(a, b):  # Math.min: NaN wins, then -0.0 < +0.0
+    if a != a or b != b:
+        return float("nan")
+    if a == 0.0 and b == 0.0:
+        return a if _struct.pack(">d", a)[0] & 0x80 else b
+    return a if a <= b else b
+
+
 def norm_sort_but_not_merge(ivs, count=False):  # :788-823 / :825-869
     if len(ivs) <= 1:
         out = list(ivs)
@@ -105,8 +113,8 @@ def norm_sort_but_not_merge(ivs, count=False):  # :788-823 / :825-869
             disjoint -= 1
         if left - 1 < end or (left - 1 == end and _same_double(cex, ex) and _same_double(cex2, ex2)):
             end = max(right, end)
-            ex, ex2 = min(cex, ex), min(cex2, ex2)
-            exu, ex2u = min(cexu, exu), min(cex2u, ex2u)   # Math.min for the upper sums too (Dtw :949-950)
+            ex, ex2 = _java_min(cex, ex), _java_min(cex2, ex2)
+            exu, ex2u = _java_min(cexu, exu), _java_min(cex2u, ex2u)   # Math.min for the upper sums too (Dtw :949-950)
             bp |= cbp
         else:
             out.append((start, end, ex, ex2, exu, ex2u, bp))

@@ -317,3 +317,52 @@ def test_split_runs_cuts_straddling_runs():
     assert (b[0].tolist(), b[1].tolist(), b[2].tolist()) == ([1.0, 0.5], [21, 31], [30, 35])
     assert (c[0].tolist(), c[1].tolist(), c[2].tolist()) == ([0.5, 2.0], [36, 41], [40, 50])
     assert phase1.shard_ranges(50, 3) == [(1, 17), (18, 34), (35, 50)] and phase1.shard_ranges(2, 3) == [(1, 1), (2, 2)]
+
+
+# ---------------------------------------------------------------- adversarial small cases (hypothesis): ties on `left`,
+# adjacency, nested intervals, signed zeros and NaN sums, bit 31 / bit 63 partition sets
+from hypothesis import given, settings, strategies as st
+
+_sum = st.sampled_from([0.0, -0.0, 1.5, 1.5000000000000002, -7.25, 1e300, float("nan")])
+_bp = st.sampled_from([0, 1, 2, 3, -(1 << 31), (1 << 62), -1])
+_norm_iv = st.tuples(st.integers(1, 60), st.integers(0, 12), _sum, _sum, _sum, _sum, _bp).map(
+    lambda t: (t[0], t[0] + t[1], t[2], t[3], t[4], t[5], t[6]))
+
+
+def _same(a, b):
+    """Tuple lists equal with NaN == NaN and -0.0 != 0.0 (what Double.compare sees)."""
+    import struct
+    key = lambda lst: [tuple(struct.pack(">d", x) if isinstance(x, float) else x for x in t) for t in lst]
+    norm = lambda lst: [tuple((float("nan") if isinstance(x, float) and x != x else x) for x in t) for t in lst]
+    ka, kb = key(norm(a)), key(norm(b))
+    return ka == kb
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(_norm_iv, max_size=14), st.integers(0, 2))
+def test_norm_sort_merge_small_adversarial(ivs, mode):
+    got, cd, co = phase1.norm_sort_merge(_norm_array(ivs), mode)
+    if mode == 2:
+        exp, ed, eo = po.norm_sort_and_merge(ivs), None, None
+    else:
+        exp, ed, eo = po.norm_sort_but_not_merge(ivs, count=True)
+    assert _same(_norm_tuples(got), exp)
+    if mode == 1:
+        assert (cd, co) == (ed, eo)
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(_norm_iv, max_size=10), st.lists(_norm_iv, max_size=10), st.integers(1, 6), st.sampled_from([-3.0, 0.0, 2.0]),
+       st.sampled_from([0.5, 2.0, float("nan")]), st.sampled_from([1.0, 1.5]), st.sampled_from([0.0, 5.0]), st.integers(-50, 50), st.booleans())
+def test_norm_intersect_small_adversarial(cs, csi, pre, mean_q, std_q, alpha, beta, dw, dtw):
+    # the engine hands over lists that are sorted by left and internally disjoint: make them so
+    def disjoint(lst):
+        out, end = [], 0
+        for t in sorted(lst, key=lambda t: t[0]):
+            if t[0] > end:
+                out.append(t)
+                end = t[1]
+        return out
+    cs, csi = disjoint(cs), disjoint(csi)
+    got = phase1.norm_intersect(_norm_array(cs), _norm_array(csi), pre, 400, mean_q, std_q, alpha, beta, dw, dtw)
+    assert _same(_norm_tuples(got), po.norm_intersect(cs, csi, pre, 25, 400, mean_q, std_q, alpha, beta, dw, dtw))
