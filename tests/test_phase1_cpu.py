@@ -366,3 +366,37 @@ def test_norm_intersect_small_adversarial(cs, csi, pre, mean_q, std_q, alpha, be
     cs, csi = disjoint(cs), disjoint(csi)
     got = phase1.norm_intersect(_norm_array(cs), _norm_array(csi), pre, 400, mean_q, std_q, alpha, beta, dw, dtw)
     assert _same(_norm_tuples(got), po.norm_intersect(cs, csi, pre, 25, 400, mean_q, std_q, alpha, beta, dw, dtw))
+
+
+_rsm_iv = st.tuples(st.integers(1, 60), st.integers(0, 12), st.sampled_from([0.0, 0.25, 0.999, 1.0, 1.25, 7.5, 100.0])).map(
+    lambda t: (t[0], t[0] + t[1], t[2]))
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(_rsm_iv, max_size=14), st.integers(0, 2))
+def test_rsm_sort_merge_small_adversarial(ivs, mode):
+    """Ties on `left`, adjacency with |eps difference| around the merge threshold 1 (K/QueryEngine.java:607), nested intervals."""
+    got, cd, co = phase1.sort_merge(ivs, mode)
+    if mode == 2:
+        assert got == po.sort_and_merge(ivs)
+    else:
+        exp, ed, eo = po.sort_but_not_merge(ivs, count=True)
+        assert got == exp
+        if mode == 1:
+            assert (cd, co) == (ed, eo)
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(_rsm_iv, max_size=10), st.lists(_rsm_iv, max_size=10), st.sampled_from([0.5, 1.25, 8.0, 200.0]), st.integers(-50, 50))
+def test_rsm_intersect_small_adversarial(cs, csi, eps2, dw):
+    def disjoint(lst):
+        out, end = [], 0
+        for t in sorted(lst, key=lambda t: t[0]):
+            if t[0] > end:
+                out.append(t)
+                end = t[1]
+        return out
+    cs, csi = disjoint(cs), disjoint(csi)
+    got, gm = phase1.intersect(cs, csi, eps2, dw)
+    exp, em = po.intersect(cs, csi, eps2, dw)
+    assert got == exp and gm == em
