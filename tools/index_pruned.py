@@ -39,13 +39,24 @@ open_s = time.perf_counter() - t0
 full_iv = datagen.chain_intervals(n, m, bench.DEFAULT_CHUNK)
 rows = []
 RSM_EPS = 10.0
+DTW_NORM_EPS = 2.0
 for off in bench.query_offsets(n, m, bench.N_QUERIES)[:n_q]:
     q = s[off - 1:off - 1 + m].copy()
-    for engine in ("cNSM-ED", "RSM-ED"):
-        norm = engine == "cNSM-ED"
-        verify = (lambda I, sh=0: g.verify_cnsm_ed(q, eps, bench.ALPHA, bench.BETA, I, sh)) if norm else (lambda I, sh=0: g.verify_ed(q, RSM_EPS, I, sh))
+    rho = int(0.05 * m)
+    rsm_iv = datagen.chain_intervals(n, m, 100_000 - m + 1)
+    engines = {
+        "cNSM-ED": (lambda I, sh=0: g.verify_cnsm_ed(q, eps, bench.ALPHA, bench.BETA, I, sh),
+                    lambda: phase1.phase1_norm(q, eps, bench.ALPHA, bench.BETA, n, indexes), full_iv),
+        "RSM-ED": (lambda I, sh=0: g.verify_ed(q, RSM_EPS, I, sh), lambda: phase1.phase1(q, RSM_EPS, n, indexes),
+                   np.array([[1, n - m + 1]], dtype=np.int32)),
+        "cNSM-DTW": (lambda I, sh=0: g.verify_cnsm_dtw(q, DTW_NORM_EPS, rho, bench.ALPHA, bench.BETA, I, sh),
+                     lambda: phase1.phase1_norm_dtw(q, DTW_NORM_EPS, rho, bench.ALPHA, bench.BETA, n, indexes), full_iv),
+        "RSM-DTW": (lambda I, sh=0: g.verify_dtw(q, RSM_EPS, rho, I, sh), lambda: phase1.phase1_dtw(q, RSM_EPS, rho, n, indexes), rsm_iv),
+    }
+    for engine, (verify, run_phase1, scan_iv) in engines.items():
+        norm = engine.startswith("cNSM")
         t0 = time.perf_counter()
-        valid, last_segment, plan = phase1.phase1_norm(q, eps, bench.ALPHA, bench.BETA, n, indexes) if norm else phase1.phase1(q, RSM_EPS, n, indexes)
+        valid, last_segment, plan = run_phase1()
         t1_ms = 1e3 * (time.perf_counter() - t0)
         iv = np.asarray(valid, dtype=np.int32).reshape(-1, 2)
         shift = (last_segment - 1) * 25
@@ -53,7 +64,6 @@ for off in bench.query_offsets(n, m, bench.N_QUERIES)[:n_q]:
         t0 = time.perf_counter()
         r = verify(iv, shift)
         t2_ms = 1e3 * (time.perf_counter() - t0)
-        scan_iv = full_iv if norm else np.array([[1, n - m + 1]], dtype=np.int32)
         verify(scan_iv)
         t0 = time.perf_counter()
         f = verify(scan_iv)
@@ -67,14 +77,14 @@ for off in bench.query_offsets(n, m, bench.N_QUERIES)[:n_q]:
         rows.append(row)
         print(row, flush=True)
 with open(out, "w") as fh:
-    fh.write(f"# Index-pruned queries (BASELINE configs[1] (ii)), n = {n}, m = {m}; cNSM-ED: eps = {eps}, alpha = {bench.ALPHA}, beta = {bench.BETA}; RSM-ED: eps = {RSM_EPS} (round 2)\n\n"
+    fh.write(f"# Index-pruned queries (BASELINE configs[1] (ii)), n = {n}, m = {m}; cNSM-ED: eps = {eps}, alpha = {bench.ALPHA}, beta = {bench.BETA}; cNSM-DTW: eps = {DTW_NORM_EPS}, rho = {int(0.05 * m)}; RSM-ED / RSM-DTW: eps = {RSM_EPS} (round 2)\n\n"
              f"`python tools/index_pruned.py {n} {n_q} {eps}` on one B200.  Index build (five widths: one fused window-mean pass on the GPU, "
              f"runs to the host, step 2 + file images on the host, the five widths on five host threads): {build_s:.2f} s for the first build "
              f"(it allocates the pinned staging of the runs), {build2_s:.2f} s for a second one, of which the GPU pass is {kernel_ms:.2f} ms and the pass "
              f"with its runs copied out to numpy arrays {runs_s:.2f} s; {sum(len(b) for b in images.values()) / 1e6:.0f} MB of index files; "
              f"opening them (offset + statistic tables): {open_s:.2f} s.  T_1 = phases 0 / 1 on ONE host core (plan DP, index range scans, "
-             f"`kvm_norm_intervals_*` / `kvm_intervals_*`); T_2 = `kvm_verify_cnsm_ed` / `kvm_verify_ed` over the phase-1 interval list with host buffers (wall) and its CUDA-event "
-             f"kernel time; full scan = the same query over every window start (cNSM: chains of {bench.DEFAULT_CHUNK}; RSM: one interval).  Every row: index-pruned answer "
+             f"`kvm_norm_intervals_*` / `kvm_intervals_*`); T_2 = `kvm_verify_*` over the phase-1 interval list with host buffers (wall) and its CUDA-event "
+             f"kernel time; full scan = the same query over every window start (cNSM: chains of {bench.DEFAULT_CHUNK}; RSM-ED: one interval; RSM-DTW: chains of 100000 - m + 1).  Every row: index-pruned answer "
              f"offsets == full-scan answer offsets.\n\n"
              "| engine | query offset | segments | lastSegment | T_1 host ms | intervals | candidates | longest interval | T_2 kernel ms | T_2 wall ms | full-scan kernel ms | full-scan wall ms | answers |\n"
              "|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
