@@ -580,6 +580,17 @@ def query_statistics(q):
     return mean_q, math.sqrt(ex2 / len(q) - mean_q * mean_q)
 
 
+PROBE_THREADS = 4   # host threads probing the index for the segments of one cNSM query (the library calls drop the GIL)
+
+
+def _probe_all(probe, queries):
+    if PROBE_THREADS <= 1 or len(queries) <= 1:
+        return [probe(seg) for seg in queries]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(PROBE_THREADS, len(queries))) as pool:
+        return list(pool.map(probe, queries))
+
+
 def phase1_norm(q, epsilon: float, alpha: float, beta: float, n: int, indexes):
     """Candidate intervals of a cNSM-ED query: (valid_positions [(left, right)], last_segment, plan).  Same deviations as
     phase1(): the index is scanned directly (the reference's incremental-visiting cache returns the same rows where its
@@ -590,16 +601,17 @@ def phase1_norm(q, epsilon: float, alpha: float, beta: float, n: int, indexes):
     mean_q, std_q = query_statistics(q)
     queries = determine_query_plan(q, epsilon, {w: ix.stat for w, ix in by_w.items()},
                                    counts=lambda stat, wu, mean: _counts_norm(stat, wu, mean, epsilon, alpha, beta, mean_q, std_q))
+    def probe(seg):   # CS_i of one segment: depends on the segment only, so the segments are probed side by side
+        lo, hi = norm_mean_range(seg.mean, seg.wu, epsilon, alpha, beta, mean_q, std_q)
+        parts = beta_partitions(seg, epsilon, alpha, beta, mean_q, std_q)
+        return norm_sort_merge(scan_index_norm(by_w[seg.wu], seg, lo, to_round(hi), parts), 0)[0]
+    probed = _probe_all(probe, queries)
     valid = np.zeros(0, dtype=NORM_IV)
     pre_length = 0
     for i, seg in enumerate(queries):
         delta_w = 0 if i == len(queries) - 1 else (queries[i + 1].order - seg.order) * WU_LIST[0]
         pre_length += seg.wu // WU_ALL[0]
-        ix = by_w[seg.wu]
-        lo, hi = norm_mean_range(seg.mean, seg.wu, epsilon, alpha, beta, mean_q, std_q)
-        begin, end = lo, to_round(hi)
-        parts = beta_partitions(seg, epsilon, alpha, beta, mean_q, std_q)
-        positions, _, _ = norm_sort_merge(scan_index_norm(ix, seg, begin, end, parts), 0)
+        positions = probed[i]
         if i == 0:
             nxt = norm_first_segment(positions, seg.order, length, n, delta_w)
         else:
@@ -676,21 +688,22 @@ def phase1_norm_dtw(q, epsilon: float, rho: int, alpha: float, beta: float, n: i
         lo, hi = rng(mean_min, mean_max, wu)
         return _cumulative_counts(stat, to_round(lo), to_round(hi))
     queries = determine_query_plan(q, epsilon, {w: ix.stat for w, ix in by_w.items()}, counts=counts, bounds=query_envelope_padded(q, rho))
-    valid = np.zeros(0, dtype=NORM_IV)
-    pre_length = 0
-    for i, seg in enumerate(queries):
-        delta_w = 0 if i == len(queries) - 1 else (queries[i + 1].order - seg.order) * WU_LIST[0]
-        pre_length += seg.wu // WU_ALL[0]
-        ix = by_w[seg.wu]
+    def probe(seg):
         lo, hi = rng(seg.mean_min, seg.mean_max, seg.wu)
-        begin, end = lo, to_round(hi)
         num = min(int(2.0 * beta / BETA_PARTITION_WIDTH), 64)   # :246-268
         parts = []
         for j in range(num):
             width = 2.0 * beta / num
             p_lo, p_hi = rng(seg.mean_min, seg.mean_max, seg.wu, width * j, width * (j + 1))
             parts.append((p_lo, to_round(p_hi)))
-        positions, _, _ = norm_sort_merge(scan_index_norm_dtw(ix, seg, begin, end, parts), 0)
+        return norm_sort_merge(scan_index_norm_dtw(by_w[seg.wu], seg, lo, to_round(hi), parts), 0)[0]
+    probed = _probe_all(probe, queries)
+    valid = np.zeros(0, dtype=NORM_IV)
+    pre_length = 0
+    for i, seg in enumerate(queries):
+        delta_w = 0 if i == len(queries) - 1 else (queries[i + 1].order - seg.order) * WU_LIST[0]
+        pre_length += seg.wu // WU_ALL[0]
+        positions = probed[i]
         if i == 0:
             nxt = norm_first_segment(positions, seg.order, length, n, delta_w)
         else:

@@ -82,7 +82,7 @@ with open(out, "w") as fh:
              f"runs to the host, step 2 + file images on the host, the five widths on five host threads): {build_s:.2f} s for the first build "
              f"(it allocates the pinned staging of the runs), {build2_s:.2f} s for a second one, of which the GPU pass is {kernel_ms:.2f} ms and the pass "
              f"with its runs copied out to numpy arrays {runs_s:.2f} s; {sum(len(b) for b in images.values()) / 1e6:.0f} MB of index files; "
-             f"opening them (offset + statistic tables): {open_s:.2f} s.  T_1 = phases 0 / 1 on ONE host core (plan DP, index range scans, "
+             f"opening them (offset + statistic tables): {open_s:.2f} s.  T_1 = phases 0 / 1 on the host (plan DP on one core, a cNSM query's segments probed on up to four threads, "
              f"`kvm_norm_intervals_*` / `kvm_intervals_*`); T_2 = `kvm_verify_*` over the phase-1 interval list with host buffers (wall) and its CUDA-event "
              f"kernel time; full scan = the same query over every window start (cNSM: chains of {bench.DEFAULT_CHUNK}; RSM-ED: one interval; RSM-DTW: chains of 100000 - m + 1).  Every row: index-pruned answer "
              f"offsets == full-scan answer offsets.\n\n"
