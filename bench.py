@@ -542,7 +542,7 @@ def window_mean_block(kvmatch_b200, peak):
 
 def index_pruned_block(kvmatch_b200, g, s, n, n_queries=3):
     """The reference's whole query() for cNSM-ED: the five indexes built from the fused window-mean pass (+ host step 2 and
-    file images), phases 0 / 1 on one host core (kvmatch_b200/phase1.py over kvm_norm_intervals_*), phase 2 on the GPU over
+    file images), phases 0 / 1 on the host (kvmatch_b200/phase1.py over kvm_norm_intervals_*), phase 2 on the GPU over
     the phase-1 interval list; beside it the same query as a full scan, whose answer offsets it must reproduce."""
     from kvmatch_b200 import phase1
     t0 = time.perf_counter()
@@ -570,7 +570,7 @@ def index_pruned_block(kvmatch_b200, g, s, n, n_queries=3):
                      "phase2_kernel_ms": r.kernel_ms, "phase2_wall_ms": t2_ms, "full_scan_kernel_ms": f.kernel_ms,
                      "answers": int(r.count), "same_answer_offsets_as_full_scan": bool(r.offsets.tolist() == f.offsets.tolist())})
     return {"index_build_s": build_s, "index_bytes": int(sum(len(b) for b in images.values())), "queries": rows,
-            "note": "phase 1 = one host core; incremental index visiting and wall-clock early termination off (DESIGN 1, row f1)"}
+            "note": "phase 1 on the host (plan on one core, segments probed on up to four threads); incremental index visiting and wall-clock early termination off (DESIGN 1, row f1)"}
 
 
 if __name__ == "__main__":
