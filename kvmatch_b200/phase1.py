@@ -587,6 +587,7 @@ def _probe_all(probe, queries):
     if PROBE_THREADS <= 1 or len(queries) <= 1:
         return [probe(seg) for seg in queries]
     from concurrent.futures import ThreadPoolExecutor
+    _lib.load()   # (resolve the library once, before the threads ask for it)
     with ThreadPoolExecutor(max_workers=min(PROBE_THREADS, len(queries))) as pool:
         return list(pool.map(probe, queries))
 
